@@ -1,0 +1,8 @@
+"""fmtuner_sdr_b200 — B200-native channel-batched FM stereo + RDS engine.
+
+Python is plumbing only: `Engine` is a ctypes view of the C ABI in include/fmgpu.h
+(libfmgpu.so, hand-written sm_100a CUDA). There is no CPU fallback; creating an
+engine without a CUDA device raises.
+"""
+from .engine import (Engine, EngineError, SynthParams, GROUP_DTYPE, STATUS_DTYPE, lib_path,  # noqa: F401
+                     load_library, make_config, synth_iq)

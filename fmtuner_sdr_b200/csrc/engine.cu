@@ -1,0 +1,1463 @@
+// engine.cu — host side of the engine and the C ABI (include/fmgpu.h).
+//
+// Owns the device buffers described in engine.h, the per-channel settings the
+// reference keeps inside its objects (FMDemod / StereoDecoder / AFPostProcessor /
+// RDSDecoder members), and the launch sequence that restates the per-block body of
+// the reference's main loop (src/main.cpp:1232-1308) for C channels at once.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "design.h"
+#include "kernels.h"
+
+using namespace fmgpu;
+
+namespace {
+
+std::string g_create_error;
+
+size_t roundUp(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+struct StageTimer {
+  std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+};
+
+}  // namespace
+
+struct fmgpu_engine {
+  fmgpu_config cfg{};
+  int C = 0, device = 0, fs = 0, N = 0, M = 1, maxBlocks = 1;
+  size_t nmax = 0;    // DSP-rate samples per call
+  size_t pitch = 0;   // nmax rounded up
+  size_t iqPitch = 0; // bytes per channel in the internal IQ staging buffer
+  size_t acap = 0;    // audio frames per channel per call
+  size_t gcap = 0;    // groups per channel per call
+  size_t bitsCap = 0;
+  EngineConst k{};
+  std::recursive_mutex mu;  // reset() may arrive from another host thread
+
+  // designs
+  std::vector<float> decTaps;
+  TapsParam decParam{}, decParamRaw{}, pilParam{}, audParam{};
+  int decPp = 0, decL = 0, pilLp = 0, pilL = 0, audLp = 0, audL = 0;
+  float decScale = 1.0f;
+  std::vector<float> pilTaps, audTaps, rdsLpf;
+  fmdesign::ResamplerDesign audRs, rdsRs;
+  fmdesign::SymSyncDesign ss;
+
+  // channel filter table
+  struct ChanFilter {
+    std::vector<float> taps;
+    float scale;
+    int lp;
+  };
+  std::vector<ChanFilter> filters;
+  std::map<std::tuple<unsigned, float, float>, int> filterIndex;
+  std::vector<ChanParams> hParams;
+  bool paramsDirty = true;
+
+  // device memory
+  uint8_t *dIq = nullptr, *dHistIq = nullptr;
+  int *dHistValid = nullptr;
+  float2 *dX1 = nullptr, *dX2 = nullptr, *dY = nullptr, *dRing = nullptr;
+  float *dMpx = nullptr, *dPilot = nullptr, *dLraw = nullptr, *dRraw = nullptr, *dLf = nullptr,
+        *dRf = nullptr, *dAudio = nullptr, *dRdsHist = nullptr, *dMonoHist = nullptr;
+  float *dChanTaps = nullptr, *dChanScale = nullptr, *dAudBank = nullptr, *dRdsBank = nullptr,
+        *dRdsLpf = nullptr, *dMf = nullptr, *dDmf = nullptr;
+  int *dChanLp = nullptr;
+  ChanParams *dParams = nullptr;
+  DemodState *dDemod = nullptr;
+  StereoState *dStereo = nullptr;
+  AudioState *dAudioSt = nullptr;
+  RdsState *dRds = nullptr;
+  fmgpu_rds_group *dGroups = nullptr;
+  fmgpu_block_status *dStatus = nullptr;
+  uint32_t *dNAudio = nullptr, *dNGroups = nullptr;
+  uint8_t *dBits = nullptr;
+  size_t x2Pitch = 0, yPitch = 0, mpxPitch = 0, lrPitch = 0, lfPitch = 0;
+  cudaStream_t stream = nullptr;
+
+  int lastN = 0;  // DSP-rate samples of the last call (debug reads)
+  uint64_t launches = 0;
+  std::string lastError;
+
+  bool timing = false;
+  std::vector<std::tuple<const char *, cudaEvent_t, cudaEvent_t>> spans;
+  std::vector<std::pair<const char *, float>> lastTimes;
+};
+
+namespace {
+
+#define CK(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      e->lastError = std::string(#expr) + ": " + cudaGetErrorString(err__);              \
+      return (err__ == cudaErrorMemoryAllocation) ? FMGPU_ENOMEM : FMGPU_ENODEV;         \
+    }                                                                                    \
+  } while (0)
+
+template <typename T> cudaError_t devAlloc(T **p, size_t count) {
+  cudaError_t err = cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(1, count) * sizeof(T));
+  if (err == cudaSuccess) {
+    err = cudaMemset(*p, 0, std::max<size_t>(1, count) * sizeof(T));
+  }
+  return err;
+}
+
+TapsParam padFront(const std::vector<float> &hrev, int lp) {
+  TapsParam t{};
+  const int L = static_cast<int>(hrev.size());
+  for (int i = 0; i < L; i++) {
+    t.h[lp - L + i] = hrev[i];
+  }
+  return t;
+}
+
+std::vector<float> reversed(const std::vector<float> &h) {
+  return std::vector<float>(h.rbegin(), h.rend());
+}
+
+DemodState defaultDemod() {
+  DemodState s{};
+  s.agc_g = 1.0f;
+  s.agc_y2 = 1.0f;
+  return s;
+}
+
+StereoState defaultStereo(const EngineConst &k) {
+  StereoState s{};
+  s.dtheta = k.pll_dtheta0;
+  s.pll_freq = k.nominal_pll;
+  return s;
+}
+
+void resetRdsLoops(RdsState &s, const EngineConst &k) {
+  // SubcarrierSet::reset (subcarrier.cpp:108-114) + fresh BlockStream (rds_decoder.cpp:23-27)
+  for (auto &w : s.wmf) {
+    w = make_float2(0.0f, 0.0f);
+  }
+  s.tau = 0.0f;
+  s.rate = 3.0f;
+  s.del = 3.0f;
+  s.q_hat = 0.0f;
+  s.sos_v1 = 0.0f;
+  s.b = 0;
+  s.decim_counter = 0;
+  s.theta = 0;
+  s.dtheta = k.rds_dtheta0;
+  s.since_reset = 0;
+  s.realign = 1;
+  s.bitcount = 0;
+  s.until = 1;
+  s.reg = 0;
+  s.bits_since_lost = 0;
+  s.expected = 0;
+  s.in_sync = 0;
+  s.err_ptr = 0;
+  s.err_mask = 0;
+  s.cur_recv = 0;
+  s.cur_err = 0;
+  for (int i = 0; i < 4; i++) {
+    s.cur_data[i] = 0;
+    s.pulse_pos[i] = 0;
+    s.pulse_off[i] = 5;
+  }
+}
+
+RdsState defaultRds(const EngineConst &k) {
+  RdsState s{};
+  s.agc_g = 0.08f;
+  s.agc_y2 = 1.0f;
+  resetRdsLoops(s, k);
+  s.realign = 0;
+  return s;
+}
+
+int filterSlot(fmgpu_engine *e, unsigned len, float cutoff, float atten) {
+  const auto key = std::make_tuple(len, cutoff, atten);
+  auto it = e->filterIndex.find(key);
+  if (it != e->filterIndex.end()) {
+    return it->second;
+  }
+  if (static_cast<int>(e->filters.size()) >= MAX_CHAN_FILTERS) {
+    return -1;
+  }
+  fmgpu_engine::ChanFilter f;
+  f.taps = fmdesign::kaiserLowpass(len, cutoff, atten, 0.0f);
+  f.scale = 2.0f * cutoff;
+  f.lp = static_cast<int>(roundUp(len, 8));
+  const int slot = static_cast<int>(e->filters.size());
+  std::vector<float> row(CHAN_TAPS_PITCH, 0.0f);
+  const std::vector<float> hrev = reversed(f.taps);
+  for (unsigned i = 0; i < len; i++) {
+    row[CHAN_TAPS_PITCH - len + i] = hrev[i];
+  }
+  cudaMemcpy(e->dChanTaps + static_cast<size_t>(slot) * CHAN_TAPS_PITCH, row.data(),
+             CHAN_TAPS_PITCH * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(e->dChanLp + slot, &f.lp, sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(e->dChanScale + slot, &f.scale, sizeof(float), cudaMemcpyHostToDevice);
+  e->filters.push_back(std::move(f));
+  e->filterIndex[key] = slot;
+  return slot;
+}
+
+int uploadParams(fmgpu_engine *e) {
+  if (!e->paramsDirty) {
+    return FMGPU_OK;
+  }
+  CK(cudaMemcpyAsync(e->dParams, e->hParams.data(), e->hParams.size() * sizeof(ChanParams),
+                     cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->paramsDirty = false;
+  return FMGPU_OK;
+}
+
+void deemphCoeffs(int tau_us, int rate, int *on, float *b0, float *a1) {
+  // fm_demod.cpp:50-62 / af_post_processor.cpp:31-45
+  if (tau_us <= 0) {
+    *on = 0;
+    return;
+  }
+  *on = 1;
+  const float tau = static_cast<float>(tau_us) * 1e-6f;
+  const float dt = 1.0f / static_cast<float>(rate);
+  const float alpha = dt / (tau + dt);
+  *b0 = alpha / 1.0f;
+  *a1 = (-(1.0f - alpha)) / 1.0f;
+}
+
+template <typename F> int forChannels(fmgpu_engine *e, int channel, F &&f) {
+  if (!e || channel < -1 || channel >= e->C) {
+    return FMGPU_EINVAL;
+  }
+  const int lo = (channel < 0) ? 0 : channel;
+  const int hi = (channel < 0) ? e->C : channel + 1;
+  for (int c = lo; c < hi; c++) {
+    const int rc = f(c);
+    if (rc != FMGPU_OK) {
+      return rc;
+    }
+  }
+  return FMGPU_OK;
+}
+
+struct Span {
+  fmgpu_engine *e;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Span(fmgpu_engine *e_, const char *name, cudaStream_t s_) : e(e_), s(s_) {
+    if (e->timing) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+      e->spans.emplace_back(name, a, b);
+    }
+  }
+  ~Span() {
+    if (e->timing) {
+      cudaEventRecord(b, s);
+    }
+  }
+};
+
+// zero a [C][pitch] region [0, count) of channel c (or all)
+template <typename T>
+void zeroPrefix(T *buf, size_t pitch, size_t count, int lo, int hi, cudaStream_t s) {
+  cudaMemset2DAsync(buf + static_cast<size_t>(lo) * pitch, pitch * sizeof(T), 0, count * sizeof(T),
+                    static_cast<size_t>(hi - lo), s);
+}
+
+// ---------------------------------------------------------------------------
+// pipeline stages on channels [ch0, ch0 + nch)
+// ---------------------------------------------------------------------------
+void stageDecimate(fmgpu_engine *e, const uint8_t *iq, size_t stride, int n_out, int ch0, int nch,
+                   cudaStream_t s) {
+  Span sp(e, "decimate", s);
+  if (e->M == 1) {
+    launchConvertU8(iq, stride, e->dX1, e->pitch, n_out, ch0, nch, s);
+    e->launches += 1;
+    return;
+  }
+  launchDecim(e->M, iq, stride, e->dHistIq, e->dHistValid, e->dX1, e->pitch, n_out, ch0, nch, e->decPp, e->decL,
+              e->decScale, e->decParam, e->decParamRaw, s);
+  launchCarryIq(e->dHistIq, e->dHistValid, iq, stride, static_cast<long>(n_out) * e->M, ch0, nch, s);
+  e->launches += 2;
+}
+
+// x1 (or raw u8) -> mpx
+void stageDemod(fmgpu_engine *e, const uint8_t *iq_u8, size_t stride, fmgpu_block_status *status,
+                int nblk, int blk_len, int n, int ch0, int nch, cudaStream_t s) {
+  {
+    Span sp(e, "dcblock", s);
+    launchDcBlock(iq_u8 ? nullptr : e->dX1, e->pitch, iq_u8, stride, e->dX2, e->x2Pitch, e->dDemod,
+                  status, nblk, nblk, blk_len, n, ch0, nch, e->k.dc_a1_iq, s);
+  }
+  {
+    Span sp(e, "chanfir", s);
+    launchChanFir(e->dX2, e->x2Pitch, e->dY, e->yPitch, e->dChanTaps, e->dChanLp, e->dChanScale,
+                  e->dParams, n, ch0, nch, s);
+  }
+  bool anyAgc = false;
+  for (int c = ch0; c < ch0 + nch; c++) {
+    anyAgc = anyAgc || e->hParams[c].agc_mode != 0;
+  }
+  if (anyAgc) {
+    Span sp(e, "agc", s);
+    launchAgc(e->dY, e->yPitch, e->dDemod, e->dParams, n, ch0, nch, s);
+    e->launches += 1;
+  }
+  {
+    Span sp(e, "freqdem", s);
+    launchFreqDem(e->dY, e->yPitch, e->dMpx, e->mpxPitch, n, ch0, nch, e->k.fd_ref, s);
+    launchCarryF2(e->dY, e->yPitch, 1, n, ch0, nch, s);
+    launchCarryF2(e->dX2, e->x2Pitch, H_X2, n, ch0, nch, s);
+  }
+  e->launches += 5;
+}
+
+// mpx -> lf/rf (DSP-rate stereo) ; carries the stereo decoder's halos
+void stageStereo(fmgpu_engine *e, fmgpu_block_status *status, int nblk, int blk_len, int n, int ch0,
+                 int nch, cudaStream_t s) {
+  {
+    Span sp(e, "pilot_fir", s);
+    FirRealJob j{};
+    j.in[0] = e->dMpx;
+    j.out[0] = e->dPilot;
+    j.in_pitch = e->mpxPitch;
+    j.out_pitch = e->pitch;
+    j.in_off = H_MPX;
+    j.out_off = 0;
+    j.n_total = n;
+    j.Lp = e->pilLp;
+    j.scale = 1.0f;
+    j.ch0 = ch0;
+    launchFirReal(j, 1, nch, e->pilParam, s);
+  }
+  {
+    Span sp(e, "stereo_pll", s);
+    launchStereo(e->dMpx, e->mpxPitch, e->dPilot, e->pitch, e->dLraw, e->dRraw, e->lrPitch,
+                 e->dStereo, e->dParams, status, nblk, nblk, blk_len, n, ch0, nch, e->k, s);
+  }
+  {
+    Span sp(e, "audio_lpf", s);
+    FirRealJob j{};
+    j.in[0] = e->dLraw;
+    j.in[1] = e->dRraw;
+    j.out[0] = e->dLf;
+    j.out[1] = e->dRf;
+    j.in_pitch = e->lrPitch;
+    j.out_pitch = e->lfPitch;
+    j.in_off = H_LR;
+    j.out_off = H_LF;
+    j.n_total = n;
+    j.Lp = e->audLp;
+    j.scale = e->k.aud_scale;
+    j.ch0 = ch0;
+    launchFirReal(j, 2, nch, e->audParam, s);
+    launchCarryF32(e->dLraw, e->lrPitch, H_LR, n, ch0, nch, s);
+    launchCarryF32(e->dRraw, e->lrPitch, H_LR, n, ch0, nch, s);
+    launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, ch0, nch, s);
+  }
+  e->launches += 6;
+}
+
+// lf/rf -> audio rows (resample + de-emphasis + DC block [+ clamp])
+void stageAfPost(fmgpu_engine *e, int n, int clamp, int ch0, int nch, cudaStream_t s) {
+  Span sp(e, "afpost", s);
+  const int maxOut = static_cast<int>(std::min<size_t>(
+      e->acap, static_cast<size_t>((static_cast<double>(n) * 16777216.0) / e->k.aud_step) + 2));
+  launchResample(e->dLf, e->dRf, e->lfPitch, H_LF, nullptr, 0, e->dAudio, e->acap, e->dAudBank,
+                 AUD_RS_LEN, e->k.aud_step, e->dAudioSt, 0, maxOut, ch0, nch, s);
+  launchAudioIir(e->dAudio, e->acap, e->dAudioSt, e->dParams, ch0, nch, e->k.dc_a1_af, 0, clamp, 0,
+                 s);
+  launchCarryF32(e->dLf, e->lfPitch, H_LF, n, ch0, nch, s);
+  launchCarryF32(e->dRf, e->lfPitch, H_LF, n, ch0, nch, s);
+  e->launches += 4;
+}
+
+// FMDemod mono chain: mpx -> audio row 0 (fm_demod.cpp:210-226)
+void stageMono(fmgpu_engine *e, int n, int clamp, int dup, int ch0, int nch, cudaStream_t s) {
+  Span sp(e, "mono", s);
+  const int maxOut = static_cast<int>(std::min<size_t>(
+      e->acap, static_cast<size_t>((static_cast<double>(n) * 16777216.0) / e->k.aud_step) + 2));
+  launchResample(e->dMpx, nullptr, e->mpxPitch, H_MPX, e->dMonoHist, 32, e->dAudio, e->acap,
+                 e->dAudBank, AUD_RS_LEN, e->k.aud_step, e->dAudioSt, 1, maxOut, ch0, nch, s);
+  launchAudioIir(e->dAudio, e->acap, e->dAudioSt, e->dParams, ch0, nch, e->k.mono_dc_a1, 1, clamp,
+                 dup, s);
+  launchSaveTail(e->dMpx, e->mpxPitch, H_MPX, e->dMonoHist, 32, AUD_RS_LEN - 1, n, ch0, nch, s);
+  e->launches += 3;
+}
+
+void stageRds(fmgpu_engine *e, fmgpu_rds_group *groups, uint32_t gcap, fmgpu_block_status *status,
+              int nblk, int blk_len, int n, int ch0, int nch, cudaStream_t s) {
+  Span sp(e, "rds", s);
+  launchRds(e->dMpx, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
+            e->dMf, e->dDmf, groups, gcap, e->dBits, static_cast<uint32_t>(e->bitsCap), status, nblk,
+            nblk, blk_len, n, ch0, nch, e->k, s);
+  launchSaveTail(e->dMpx, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_RS_LEN - 1, n, ch0, nch, s);
+  e->launches += 2;
+}
+
+void collectTimes(fmgpu_engine *e) {
+  if (!e->timing) {
+    return;
+  }
+  e->lastTimes.clear();
+  for (auto &sp : e->spans) {
+    float ms = 0.0f;
+    cudaEventSynchronize(std::get<2>(sp));
+    cudaEventElapsedTime(&ms, std::get<1>(sp), std::get<2>(sp));
+    bool merged = false;
+    for (auto &t : e->lastTimes) {
+      if (std::strcmp(t.first, std::get<0>(sp)) == 0) {
+        t.second += ms;
+        merged = true;
+      }
+    }
+    if (!merged) {
+      e->lastTimes.emplace_back(std::get<0>(sp), ms);
+    }
+    cudaEventDestroy(std::get<1>(sp));
+    cudaEventDestroy(std::get<2>(sp));
+  }
+  e->spans.clear();
+}
+
+int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks, float *audio_dev,
+             size_t audio_cap, uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
+             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, cudaStream_t s) {
+  if (!iq_dev || n_blocks < 1 || n_blocks > e->maxBlocks) {
+    e->lastError = "process: n_blocks out of range or null input";
+    return FMGPU_EINVAL;
+  }
+  if ((reinterpret_cast<uintptr_t>(iq_dev) & 15u) || (stride & 15u) ||
+      stride < static_cast<size_t>(n_blocks) * e->N * e->M * 2) {
+    e->lastError = "process: iq buffer must be 16-byte aligned with a 16-byte aligned stride >= bytes per channel";
+    return FMGPU_EINVAL;
+  }
+  const int n = n_blocks * e->N;
+  const size_t needAudio = static_cast<size_t>((static_cast<double>(n) * 16777216.0) / e->k.aud_step) + 2;
+  if (audio_dev && audio_cap < needAudio) {
+    e->lastError = "process: audio capacity too small";
+    return FMGPU_ERANGE;
+  }
+  int rc = uploadParams(e);
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
+  const int C = e->C;
+  const bool stereo = e->cfg.stereo != 0;
+  fmgpu_block_status *status = status_dev ? status_dev : e->dStatus;
+  fmgpu_rds_group *groups = groups_dev ? groups_dev : e->dGroups;
+  const uint32_t gcap = static_cast<uint32_t>(groups_dev ? group_cap : e->gcap);
+  // audio is produced in the engine's buffer when the caller's capacity differs
+  float *audioSaved = e->dAudio;
+  const size_t acapSaved = e->acap;
+  if (audio_dev) {
+    e->dAudio = audio_dev;
+    e->acap = audio_cap;
+  }
+  {
+    Span sp(e, "prepare", s);
+    launchPrepare(e->dAudioSt, e->dRds, status, n_blocks, n_blocks, e->N, n, 0, C, e->k.aud_step,
+                  e->k.rds_step, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
+    e->launches += 1;
+  }
+  if (e->M > 1) {
+    stageDecimate(e, iq_dev, stride, n, 0, C, s);
+    stageDemod(e, nullptr, 0, status, n_blocks, e->N, n, 0, C, s);
+  } else {
+    stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, 0, C, s);
+  }
+  stageRds(e, groups, gcap, status, n_blocks, e->N, n, 0, C, s);
+  if (stereo) {
+    stageStereo(e, status, n_blocks, e->N, n, 0, C, s);
+    stageAfPost(e, n, 1, 0, C, s);
+  } else {
+    stageMono(e, n, 1, 1, 0, C, s);
+    launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, 0, C, s);
+    e->launches += 1;
+  }
+  {
+    Span sp(e, "commit", s);
+    launchStoreCounts(e->dAudioSt, e->dRds, n_audio_dev ? n_audio_dev : e->dNAudio,
+                      n_groups_dev ? n_groups_dev : e->dNGroups, 0, C, stereo ? 0 : 1,
+                      static_cast<uint32_t>(e->acap), gcap, s);
+    launchCommit(e->dAudioSt, e->dRds, 0, C, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
+    e->launches += 2;
+  }
+  e->dAudio = audioSaved;
+  e->acap = acapSaved;
+  e->lastN = n;
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    e->lastError = std::string("kernel launch: ") + cudaGetErrorString(err);
+    return FMGPU_ENODEV;
+  }
+  return FMGPU_OK;
+}
+
+// All design-time work of the reference constructors; touches no CUDA state.
+int computeDesigns(fmgpu_engine *e) {
+  try {
+    EngineConst &k = e->k;
+    k.C = e->C;
+    k.N = e->N;
+    k.M = e->M;
+    k.fs = e->fs;
+    k.fsf = static_cast<float>(e->fs);
+    const int rate = e->fs;
+    const int outRate = e->cfg.output_rate;
+    // --- ComplexDecimator::init (liquid_primitives.cpp:370-403, main.cpp:670-674)
+    if (e->M > 1) {
+      const uint32_t f = static_cast<uint32_t>(e->M);
+      const uint32_t tpp = std::max<uint32_t>(4, (f >= 8U) ? 28U : ((f >= 4U) ? 20U : 12U));
+      const float cutoff = std::clamp(0.45f / static_cast<float>(f), 0.01f, 0.45f);
+      e->decTaps = fmdesign::kaiserLowpass(f * tpp, cutoff, 80.0f, 0.0f);
+      e->decL = static_cast<int>(f * tpp);
+      e->decPp = static_cast<int>(roundUp(tpp, 4));
+      e->decScale = 2.0f * cutoff;
+      if (e->decPp * e->M - 1 > H_IQ || e->decPp * e->M > MAX_TAPS) {
+        e->lastError = "decimator too long for the IQ history";
+        return FMGPU_EINVAL;
+      }
+      const std::vector<float> hrev = reversed(e->decTaps);
+      e->decParam = padFront(hrev, e->decPp * e->M);
+      e->decParamRaw = padFront(hrev, e->decL);
+      k.dec_lp = e->decPp * e->M;
+      k.dec_scale = e->decScale;
+    }
+    // --- StereoDecoder ctor (stereo_decoder.cpp:25-63)
+    int pilotTapCount = static_cast<int>(std::ceil(3.8 * static_cast<double>(rate) / 3000.0));
+    pilotTapCount = std::clamp(pilotTapCount, 63, 511);
+    if ((pilotTapCount % 2) == 0) {
+      pilotTapCount++;
+    }
+    const float pilotCenterNorm = std::clamp(19000.0f / static_cast<float>(rate), 0.001f, 0.49f);
+    const float pilotCutoffNorm = std::clamp(250.0f / static_cast<float>(rate), 0.0005f, 0.45f);
+    e->pilTaps = fmdesign::shiftedBandpass(static_cast<unsigned>(pilotTapCount), pilotCutoffNorm,
+                                           60.0f, pilotCenterNorm);
+    e->pilL = pilotTapCount;
+    e->pilLp = static_cast<int>(roundUp(pilotTapCount, 8));
+    e->pilParam = padFront(reversed(e->pilTaps), e->pilLp);
+    const float audioCutoffNorm = std::clamp(15000.0f / static_cast<float>(rate), 0.01f, 0.45f);
+    e->audTaps = fmdesign::kaiserLowpass(121, audioCutoffNorm, 60.0f, 0.0f);
+    e->audL = 121;
+    e->audLp = 128;
+    e->audParam = padFront(reversed(e->audTaps), e->audLp);
+    k.pil_lp = e->pilLp;
+    k.aud_lp = e->audLp;
+    k.aud_scale = 2.0f * audioCutoffNorm;
+    k.delay = std::max(0, (pilotTapCount - 1) / 2) + 1;
+    constexpr float kPi = 3.14159265358979323846f;
+    k.nominal_pll = 2.0f * kPi * 19000.0f / static_cast<float>(rate);
+    k.pll_min = 2.0f * kPi * 18750.0f / static_cast<float>(rate);
+    k.pll_max = 2.0f * kPi * 19250.0f / static_cast<float>(rate);
+    k.pll_alpha = 0.01f;
+    k.pll_beta = std::sqrt(0.01f);
+    k.pll_dtheta0 = fmdesign::ncoConstrain(k.nominal_pll);
+    const float attack[3] = {0.090f, 0.120f, 0.180f};
+    const float release[3] = {0.040f, 0.030f, 0.015f};
+    const float gate[3] = {0.75f, 0.85f, 0.95f};
+    for (int m = 0; m < 3; m++) {
+      k.blend_attack[m] = 1.0f - std::exp(-1.0f / (attack[m] * static_cast<float>(rate)));
+      k.blend_release[m] = 1.0f - std::exp(-1.0f / (release[m] * static_cast<float>(rate)));
+      k.gate[m] = gate[m];
+    }
+    // --- resamplers (af_post_processor.cpp:7-18, fm_demod.cpp:40-42)
+    const float ratio = static_cast<float>(outRate) / static_cast<float>(rate);
+    if (ratio < 0.005f || ratio > 8.0f) {
+      e->lastError = "resampler ratio is out of supported range";
+      return FMGPU_EINVAL;
+    }
+    e->audRs = fmdesign::resampler(ratio, 12, 0.47f, 60.0f, 32);
+    k.aud_step = e->audRs.step;
+    k.mono_dc_a1 = -1.0f + 0.0008f;
+    k.dc_a1_iq = -1.0f + 0.0005f;
+    k.dc_a1_af = -1.0f + 0.005f;
+    // --- freqdem (fm_demod.cpp:64-71)
+    const float kf = static_cast<float>(75000.0 / static_cast<double>(rate));
+    k.fd_ref = static_cast<float>(1.0 / (2.0 * M_PI * static_cast<double>(kf)));
+    // --- RDS (subcarrier.cpp:37-45,94-106)
+    const float kTarget = 171000.f;
+    const float rdsRatio = kTarget / static_cast<float>(rate);
+    if (rdsRatio < 0.005f || rdsRatio > 2.0f) {
+      e->lastError = "RDS: can't support this sample rate";
+      return FMGPU_EINVAL;
+    }
+    e->rdsRs = fmdesign::resampler(1.f, 13, 0.47f, 60.0f, 32);
+    e->rdsRs.step = fmdesign::resamplerStep(rdsRatio);
+    k.rds_step = e->rdsRs.step;
+    const float lpfFc = 2400.0f / kTarget;
+    e->rdsLpf = fmdesign::kaiserLowpass(255, lpfFc, 60.0f, 0.0f);
+    k.rds_lpf_scale = 2.0f * lpfFc;
+    k.rds_agc_alpha = 500.0f / kTarget;
+    e->ss = fmdesign::symsyncRrc(3, 3, 0.8f, 32, 2200.0f / kTarget);
+    k.ss_b0 = e->ss.sosB0;
+    k.ss_a1 = e->ss.sosA1;
+    k.ss_rate_adj = e->ss.rateAdjustment;
+    k.rds_dtheta0 = fmdesign::ncoConstrain(57000.f * (2.f * kPi) / kTarget);
+    k.rds_pll_alpha = 0.03f / kTarget;
+    k.rds_pll_beta = std::sqrt(k.rds_pll_alpha);
+    if (e->rdsRs.subLen != RDS_RS_LEN || e->audRs.subLen != AUD_RS_LEN || e->ss.subLen != SS_LEN) {
+      e->lastError = "internal: unexpected polyphase sub-filter length";
+      return FMGPU_EINVAL;
+    }
+  } catch (const std::exception &ex) {
+    e->lastError = ex.what();
+    return FMGPU_EINVAL;
+  }
+
+  return FMGPU_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmgpu_engine **out) {
+  if (!cfg || !out || n_channels < 1 || cfg->iq_rate < 1 || cfg->decimation < 1 ||
+      cfg->block_samples < 1 || cfg->max_blocks < 1) {
+    g_create_error = "fmgpu_engine_create: invalid arguments";
+    return FMGPU_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_create_error = "fmgpu_engine_create: no CUDA device (the engine has no CPU fallback)";
+    cudaGetLastError();
+    return FMGPU_ENODEV;
+  }
+  fmgpu_engine *e = new (std::nothrow) fmgpu_engine();
+  if (!e) {
+    return FMGPU_ENOMEM;
+  }
+  auto fail = [&](int rc) {
+    g_create_error = e->lastError;
+    fmgpu_engine_destroy(e);
+    return rc;
+  };
+#define CKC(expr)                                                                  \
+  do {                                                                             \
+    cudaError_t err__ = (expr);                                                    \
+    if (err__ != cudaSuccess) {                                                    \
+      e->lastError = std::string(#expr) + ": " + cudaGetErrorString(err__);        \
+      return fail(err__ == cudaErrorMemoryAllocation ? FMGPU_ENOMEM : FMGPU_ENODEV); \
+    }                                                                              \
+  } while (0)
+
+  e->cfg = *cfg;
+  if (e->cfg.output_rate <= 0) {
+    e->cfg.output_rate = 32000;
+  }
+  e->C = n_channels;
+  e->device = device;
+  e->M = cfg->decimation;
+  e->fs = cfg->iq_rate / cfg->decimation;
+  e->N = cfg->block_samples;
+  e->maxBlocks = cfg->max_blocks;
+  e->nmax = static_cast<size_t>(e->N) * e->maxBlocks;
+  e->pitch = roundUp(e->nmax, 32);
+  e->x2Pitch = H_X2 + e->pitch;
+  e->yPitch = 32 + e->pitch;
+  e->mpxPitch = H_MPX + e->pitch;
+  e->lrPitch = H_LR + e->pitch;
+  e->lfPitch = H_LF + e->pitch;
+  e->iqPitch = roundUp(e->nmax * e->M * 2, 16);
+  CKC(cudaSetDevice(device));
+
+  {
+    const int drc = computeDesigns(e);
+    if (drc != FMGPU_OK) {
+      return fail(drc);
+    }
+  }
+
+  const size_t C = static_cast<size_t>(e->C);
+  e->acap = static_cast<size_t>((static_cast<double>(e->nmax) * 16777216.0) / e->k.aud_step) + 8;
+  e->gcap = e->nmax * 12 / static_cast<size_t>(std::max(1, e->fs)) + 8;  // 11.4 groups/s
+  e->bitsCap = e->nmax / 100 + 64;
+  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(initRdsTables());
+  CKC(devAlloc(&e->dIq, C * e->iqPitch));
+  CKC(devAlloc(&e->dHistIq, C * 2 * H_IQ));
+  CKC(devAlloc(&e->dHistValid, C));
+  CKC(devAlloc(&e->dX1, C * e->pitch));
+  CKC(devAlloc(&e->dX2, C * e->x2Pitch));
+  CKC(devAlloc(&e->dY, C * e->yPitch));
+  CKC(devAlloc(&e->dMpx, C * e->mpxPitch));
+  CKC(devAlloc(&e->dPilot, C * e->pitch));
+  CKC(devAlloc(&e->dLraw, C * e->lrPitch));
+  CKC(devAlloc(&e->dRraw, C * e->lrPitch));
+  CKC(devAlloc(&e->dLf, C * e->lfPitch));
+  CKC(devAlloc(&e->dRf, C * e->lfPitch));
+  CKC(devAlloc(&e->dAudio, C * 2 * e->acap));
+  CKC(devAlloc(&e->dRing, C * RDS_RING));
+  CKC(devAlloc(&e->dRdsHist, C * 32));
+  CKC(devAlloc(&e->dMonoHist, C * 32));
+  CKC(devAlloc(&e->dChanTaps, static_cast<size_t>(MAX_CHAN_FILTERS) * CHAN_TAPS_PITCH));
+  CKC(devAlloc(&e->dChanScale, MAX_CHAN_FILTERS));
+  CKC(devAlloc(&e->dChanLp, MAX_CHAN_FILTERS));
+  CKC(devAlloc(&e->dAudBank, e->audRs.bank.size()));
+  CKC(devAlloc(&e->dRdsBank, e->rdsRs.bank.size()));
+  CKC(devAlloc(&e->dRdsLpf, 256));
+  CKC(devAlloc(&e->dMf, e->ss.mf.size()));
+  CKC(devAlloc(&e->dDmf, e->ss.dmf.size()));
+  CKC(devAlloc(&e->dParams, C));
+  CKC(devAlloc(&e->dDemod, C));
+  CKC(devAlloc(&e->dStereo, C));
+  CKC(devAlloc(&e->dAudioSt, C));
+  CKC(devAlloc(&e->dRds, C));
+  CKC(devAlloc(&e->dGroups, C * e->gcap));
+  CKC(devAlloc(&e->dStatus, C * static_cast<size_t>(e->maxBlocks)));
+  CKC(devAlloc(&e->dNAudio, C));
+  CKC(devAlloc(&e->dNGroups, C));
+  CKC(devAlloc(&e->dBits, C * e->bitsCap));
+  CKC(cudaMemcpy(e->dAudBank, e->audRs.bank.data(), e->audRs.bank.size() * sizeof(float),
+                 cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(e->dRdsBank, e->rdsRs.bank.data(), e->rdsRs.bank.size() * sizeof(float),
+                 cudaMemcpyHostToDevice));
+  {
+    const std::vector<float> hrev = reversed(e->rdsLpf);
+    CKC(cudaMemcpy(e->dRdsLpf, hrev.data(), hrev.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  CKC(cudaMemcpy(e->dMf, e->ss.mf.data(), e->ss.mf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(e->dDmf, e->ss.dmf.data(), e->ss.dmf.size() * sizeof(float),
+                 cudaMemcpyHostToDevice));
+
+  // per-channel defaults: FMDemod ctor filter (fm_demod.cpp:36-37), then the calls main.cpp makes
+  const float ctorCut = std::clamp(110000.0f / static_cast<float>(e->fs), 0.01f, 0.45f);
+  const int slot0 = filterSlot(e, 81, ctorCut, 60.0f);
+  ChanParams p{};
+  p.filt = slot0;
+  p.bandwidth_mode = 0;
+  p.w0_hz = 194000;
+  p.blend_mode = 1;
+  e->hParams.assign(C, p);
+  {
+    std::vector<DemodState> d(C, defaultDemod());
+    std::vector<StereoState> st(C, defaultStereo(e->k));
+    std::vector<RdsState> r(C, defaultRds(e->k));
+    CKC(cudaMemcpy(e->dDemod, d.data(), C * sizeof(DemodState), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(e->dStereo, st.data(), C * sizeof(StereoState), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(e->dRds, r.data(), C * sizeof(RdsState), cudaMemcpyHostToDevice));
+  }
+  *out = e;
+  // constructor defaults of the reference objects, then main.cpp:641-710
+  fmgpu_set_deemphasis_us(e, -1, 75);
+  fmgpu_set_w0_bandwidth_hz(e, -1, cfg->w0_bandwidth_hz);
+  fmgpu_set_agc_mode(e, -1, cfg->dsp_agc);
+  fmgpu_set_blend_mode(e, -1, cfg->stereo_blend);
+  fmgpu_set_deemphasis_us(e, -1, cfg->deemphasis == 0 ? 50 : (cfg->deemphasis == 1 ? 75 : 0));
+  fmgpu_set_force_mono(e, -1, cfg->force_mono);
+  fmgpu_set_bandwidth_hz(e, -1, cfg->bandwidth_hz);
+  const int rc = uploadParams(e);
+  if (rc != FMGPU_OK) {
+    *out = nullptr;
+    return fail(rc);
+  }
+  return FMGPU_OK;
+#undef CKC
+}
+
+void fmgpu_engine_destroy(fmgpu_engine *e) {
+  if (!e) {
+    return;
+  }
+  cudaSetDevice(e->device);
+  if (e->stream) {
+    cudaStreamSynchronize(e->stream);
+  }
+  void *ptrs[] = {e->dIq,      e->dHistIq, e->dX1,     e->dX2,      e->dY,       e->dMpx,
+                  e->dPilot,   e->dLraw,   e->dRraw,   e->dLf,      e->dRf,      e->dAudio,
+                  e->dRing,    e->dRdsHist, e->dMonoHist, e->dChanTaps, e->dChanScale, e->dChanLp,
+                  e->dAudBank, e->dRdsBank, e->dRdsLpf, e->dMf,     e->dDmf,     e->dParams,
+                  e->dDemod,   e->dStereo, e->dAudioSt, e->dRds,    e->dGroups,  e->dStatus,
+                  e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid};
+  for (void *p : ptrs) {
+    if (p) {
+      cudaFree(p);
+    }
+  }
+  if (e->stream) {
+    cudaStreamDestroy(e->stream);
+  }
+  delete e;
+}
+
+const char *fmgpu_last_error(const fmgpu_engine *e) {
+  return e ? e->lastError.c_str() : g_create_error.c_str();
+}
+int fmgpu_n_channels(const fmgpu_engine *e) { return e ? e->C : 0; }
+int fmgpu_dsp_rate(const fmgpu_engine *e) { return e ? e->fs : 0; }
+
+// ---- settings --------------------------------------------------------------
+int fmgpu_set_w0_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
+  return forChannels(e, channel, [&](int c) {
+    e->hParams[c].w0_hz = std::clamp(bw_hz, 0, 400000);
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_set_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  return forChannels(e, channel, [&](int c) {
+    ChanParams &p = e->hParams[c];
+    const fmdesign::ChannelFilterSpec spec = fmdesign::channelFilterSpec(bw_hz, p.w0_hz, e->fs);
+    if (spec.index == p.bandwidth_mode) {
+      return FMGPU_OK;  // fm_demod.cpp:114-116
+    }
+    const int slot = filterSlot(e, spec.length, spec.cutoff, spec.atten);
+    if (slot < 0) {
+      e->lastError = "channel filter table full";
+      return FMGPU_ENOMEM;
+    }
+    p.bandwidth_mode = spec.index;
+    p.filt = slot;
+    e->paramsDirty = true;
+    // the FIR is re-created with an empty window (fm_demod.cpp:134); r_prev is kept
+    zeroPrefix(e->dX2, e->x2Pitch, H_X2, c, c + 1, e->stream);
+    cudaStreamSynchronize(e->stream);
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_set_bandwidth_mode(fmgpu_engine *e, int channel, int mode) {
+  return fmgpu_set_bandwidth_hz(e, channel, fmdesign::tefBandwidthHz(mode));
+}
+
+int fmgpu_set_agc_mode(fmgpu_engine *e, int channel, int mode) {
+  if (!e || mode < 0 || mode > 2) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  return forChannels(e, channel, [&](int c) {
+    ChanParams &p = e->hParams[c];
+    p.agc_mode = mode;
+    e->paramsDirty = true;
+    if (mode != 0) {
+      // AGC::init re-creates the object: gain 1, energy 1 (fm_demod.cpp:146-147)
+      p.agc_alpha = (mode == 1) ? 0.01f : 0.001f;
+      const float init[2] = {1.0f, 1.0f};
+      cudaMemcpyAsync(&e->dDemod[c].agc_g, init, sizeof(init), cudaMemcpyHostToDevice, e->stream);
+      cudaStreamSynchronize(e->stream);
+    }
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_set_deemphasis_us(fmgpu_engine *e, int channel, int tau_us) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  return forChannels(e, channel, [&](int c) {
+    ChanParams &p = e->hParams[c];
+    deemphCoeffs(tau_us, e->cfg.output_rate, &p.deemph_on, &p.de_b0, &p.de_a1);
+    deemphCoeffs(tau_us, e->cfg.output_rate, &p.mono_deemph_on, &p.mono_de_b0, &p.mono_de_a1);
+    e->paramsDirty = true;
+    if (tau_us > 0) {
+      // IIRFilterReal::init creates fresh filters: state cleared
+      const float z[2] = {0.0f, 0.0f};
+      cudaMemcpyAsync(e->dAudioSt[c].de_v1, z, sizeof(z), cudaMemcpyHostToDevice, e->stream);
+      cudaMemcpyAsync(&e->dAudioSt[c].mono_de_v1, z, sizeof(float), cudaMemcpyHostToDevice,
+                      e->stream);
+      cudaStreamSynchronize(e->stream);
+    }
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
+  if (mode < 0 || mode > 2) {
+    return FMGPU_EINVAL;
+  }
+  return forChannels(e, channel, [&](int c) {
+    e->hParams[c].blend_mode = mode;
+    e->paramsDirty = true;
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on) {
+  return forChannels(e, channel, [&](int c) {
+    e->hParams[c].force_mono = on ? 1 : 0;
+    e->paramsDirty = true;
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on) {
+  return forChannels(e, channel, [&](int c) {
+    e->hParams[c].force_stereo = on ? 1 : 0;
+    e->paramsDirty = true;
+    return FMGPU_OK;
+  });
+}
+
+int fmgpu_reset(fmgpu_engine *e, int channel, unsigned what) {
+  if (!e || channel < -1 || channel >= e->C) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  const int lo = (channel < 0) ? 0 : channel;
+  const int hi = (channel < 0) ? e->C : channel + 1;
+  const size_t cnt = static_cast<size_t>(hi - lo);
+  cudaStream_t s = e->stream;
+  CK(cudaStreamSynchronize(s));
+  if (what & FMGPU_RESET_DECIM) {
+    if (e->M > 1) {
+      CK(cudaMemsetAsync(e->dHistIq + static_cast<size_t>(lo) * 2 * H_IQ, 0, cnt * 2 * H_IQ, s));
+      CK(cudaMemsetAsync(e->dHistValid + lo, 0, cnt * sizeof(int), s));
+    }
+  }
+  if (what & FMGPU_RESET_DEMOD) {
+    // fm_demod.cpp:73-88
+    zeroPrefix(e->dX2, e->x2Pitch, H_X2, lo, hi, s);
+    zeroPrefix(e->dY, e->yPitch, 1, lo, hi, s);
+    zeroPrefix(e->dMonoHist, 32, 32, lo, hi, s);
+    std::vector<DemodState> d(cnt, defaultDemod());
+    CK(cudaMemcpyAsync(e->dDemod + lo, d.data(), cnt * sizeof(DemodState), cudaMemcpyHostToDevice, s));
+    std::vector<AudioState> a(cnt);
+    CK(cudaMemcpyAsync(a.data(), e->dAudioSt + lo, cnt * sizeof(AudioState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < cnt; i++) {
+      if (e->hParams[lo + i].mono_deemph_on) {
+        a[i].mono_de_v1 = 0.0f;
+      }
+      a[i].mono_dc_v1 = 0.0f;
+      a[i].mono_phase = 0;
+      a[i].mono_phase_next = 0;
+    }
+    CK(cudaMemcpyAsync(e->dAudioSt + lo, a.data(), cnt * sizeof(AudioState), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (what & FMGPU_RESET_STEREO) {
+    // stereo_decoder.cpp:67-86
+    zeroPrefix(e->dMpx, e->mpxPitch, H_MPX, lo, hi, s);
+    zeroPrefix(e->dLraw, e->lrPitch, H_LR, lo, hi, s);
+    zeroPrefix(e->dRraw, e->lrPitch, H_LR, lo, hi, s);
+    std::vector<StereoState> st(cnt, defaultStereo(e->k));
+    CK(cudaMemcpyAsync(e->dStereo + lo, st.data(), cnt * sizeof(StereoState), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (what & FMGPU_RESET_AFPOST) {
+    // af_post_processor.cpp:20-29
+    zeroPrefix(e->dLf, e->lfPitch, H_LF, lo, hi, s);
+    zeroPrefix(e->dRf, e->lfPitch, H_LF, lo, hi, s);
+    std::vector<AudioState> a(cnt);
+    CK(cudaMemcpyAsync(a.data(), e->dAudioSt + lo, cnt * sizeof(AudioState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < cnt; i++) {
+      a[i].rs_phase = 0;
+      a[i].rs_phase_next = 0;
+      a[i].dc_v1[0] = a[i].dc_v1[1] = 0.0f;
+      if (e->hParams[lo + i].deemph_on) {
+        a[i].de_v1[0] = a[i].de_v1[1] = 0.0f;
+      }
+    }
+    CK(cudaMemcpyAsync(e->dAudioSt + lo, a.data(), cnt * sizeof(AudioState), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (what & FMGPU_RESET_RDS) {
+    std::vector<RdsState> r(cnt);
+    CK(cudaMemcpyAsync(r.data(), e->dRds + lo, cnt * sizeof(RdsState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (auto &st : r) {
+      resetRdsLoops(st, e->k);
+    }
+    CK(cudaMemcpyAsync(e->dRds + lo, r.data(), cnt * sizeof(RdsState), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return FMGPU_OK;
+}
+
+// ---- observables -------------------------------------------------------------
+static int readStereo(fmgpu_engine *e, int channel, StereoState *out) {
+  if (!e || channel < 0 || channel >= e->C) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(out, e->dStereo + channel, sizeof(StereoState), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return FMGPU_OK;
+}
+static int readDemod(fmgpu_engine *e, int channel, DemodState *out) {
+  if (!e || channel < 0 || channel >= e->C) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(out, e->dDemod + channel, sizeof(DemodState), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return FMGPU_OK;
+}
+int fmgpu_is_stereo(fmgpu_engine *e, int channel) {
+  StereoState s{};
+  return readStereo(e, channel, &s) == FMGPU_OK ? s.stereo : 0;
+}
+int fmgpu_pilot_tenths(fmgpu_engine *e, int channel) {
+  StereoState s{};
+  return readStereo(e, channel, &s) == FMGPU_OK ? s.pilot_tenths : 0;
+}
+float fmgpu_clip_ratio(fmgpu_engine *e, int channel) {
+  DemodState s{};
+  return readDemod(e, channel, &s) == FMGPU_OK ? s.clip_ratio : 0.0f;
+}
+int fmgpu_is_clipping(fmgpu_engine *e, int channel) {
+  DemodState s{};
+  return readDemod(e, channel, &s) == FMGPU_OK ? s.clipping : 0;
+}
+
+// ---- batched paths -------------------------------------------------------------
+int fmgpu_process_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
+                        int n_blocks, float *audio_dev, size_t audio_cap, uint32_t *n_audio_dev,
+                        fmgpu_rds_group *groups_dev, size_t group_cap, uint32_t *n_groups_dev,
+                        fmgpu_block_status *status_dev, void *stream) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  const int rc = runBatch(e, iq_dev, iq_stride_bytes, n_blocks, audio_dev, audio_cap, n_audio_dev,
+                          groups_dev, group_cap, n_groups_dev, status_dev, s);
+  if (rc == FMGPU_OK && e->timing) {
+    CK(cudaStreamSynchronize(s));
+    collectTimes(e);
+  }
+  return rc;
+}
+
+int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_bytes,
+                       int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
+                       fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
+                       fmgpu_block_status *status_host) {
+  if (!e || !iq_host || n_blocks < 1 || n_blocks > e->maxBlocks) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  const size_t C = static_cast<size_t>(e->C);
+  const size_t bytes = static_cast<size_t>(n_blocks) * e->N * e->M * 2;
+  if (iq_stride_bytes < bytes) {
+    e->lastError = "process_host: stride smaller than the bytes per channel";
+    return FMGPU_EINVAL;
+  }
+  if (iq_stride_bytes == e->iqPitch) {
+    CK(cudaMemcpyAsync(e->dIq, iq_host, C * e->iqPitch, cudaMemcpyHostToDevice, s));
+  } else {
+    CK(cudaMemcpy2DAsync(e->dIq, e->iqPitch, iq_host, iq_stride_bytes, bytes, C,
+                         cudaMemcpyHostToDevice, s));
+  }
+  const int rc = runBatch(e, e->dIq, e->iqPitch, n_blocks, nullptr, 0, nullptr, nullptr, 0, nullptr,
+                          nullptr, s);
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
+  const size_t n = static_cast<size_t>(n_blocks) * e->N;
+  const size_t frames = std::min(e->acap, static_cast<size_t>((static_cast<double>(n) * 16777216.0) /
+                                                               e->k.aud_step) + 2);
+  if (audio_host) {
+    if (audio_cap < frames) {
+      e->lastError = "process_host: audio capacity too small";
+      return FMGPU_ERANGE;
+    }
+    CK(cudaMemcpy2DAsync(audio_host, audio_cap * sizeof(float), e->dAudio, e->acap * sizeof(float),
+                         frames * sizeof(float), C * 2, cudaMemcpyDeviceToHost, s));
+  }
+  if (n_audio_host) {
+    CK(cudaMemcpyAsync(n_audio_host, e->dNAudio, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  }
+  if (groups_host) {
+    const size_t g = std::min(group_cap, e->gcap);
+    CK(cudaMemcpy2DAsync(groups_host, group_cap * sizeof(fmgpu_rds_group), e->dGroups,
+                         e->gcap * sizeof(fmgpu_rds_group), g * sizeof(fmgpu_rds_group), C,
+                         cudaMemcpyDeviceToHost, s));
+  }
+  if (n_groups_host) {
+    CK(cudaMemcpyAsync(n_groups_host, e->dNGroups, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  }
+  if (status_host) {
+    CK(cudaMemcpy2DAsync(status_host, n_blocks * sizeof(fmgpu_block_status), e->dStatus,
+                         n_blocks * sizeof(fmgpu_block_status),
+                         n_blocks * sizeof(fmgpu_block_status), C, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  if (n_groups_host && groups_host) {
+    for (size_t c = 0; c < C; c++) {
+      n_groups_host[c] = std::min<uint32_t>(n_groups_host[c], static_cast<uint32_t>(group_cap));
+    }
+  }
+  collectTimes(e);
+  return FMGPU_OK;
+}
+
+// ---- stage-level entry points ------------------------------------------------------
+#define STAGE_PROLOGUE(cond)                                                    \
+  if (!e || channel < 0 || channel >= e->C || !(cond)) {                        \
+    return 0;                                                                   \
+  }                                                                             \
+  std::lock_guard<std::recursive_mutex> lk(e->mu);                              \
+  if (cudaSetDevice(e->device) != cudaSuccess || uploadParams(e) != FMGPU_OK) { \
+    return 0;                                                                   \
+  }                                                                             \
+  cudaStream_t s = e->stream;
+
+static bool stageFail(fmgpu_engine *e, const char *what) {
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    e->lastError = std::string(what) + ": " + cudaGetErrorString(err);
+    return true;
+  }
+  return false;
+}
+
+size_t fmgpu_decimate(fmgpu_engine *e, int channel, const uint8_t *iq, size_t in_samples,
+                      float *out_cf32, size_t out_capacity) {
+  STAGE_PROLOGUE(iq && out_cf32 && in_samples > 0 && out_capacity > 0)
+  const size_t n_out = std::min({in_samples / static_cast<size_t>(e->M), out_capacity});
+  if (n_out == 0) {
+    return 0;
+  }
+  if (n_out > e->nmax) {
+    e->lastError = "decimate: more samples than the engine was sized for";
+    return 0;
+  }
+  uint8_t *dst = e->dIq + static_cast<size_t>(channel) * e->iqPitch;
+  cudaMemcpyAsync(dst, iq, n_out * e->M * 2, cudaMemcpyHostToDevice, s);
+  stageDecimate(e, e->dIq, e->iqPitch, static_cast<int>(n_out), channel, 1, s);
+  cudaMemcpyAsync(out_cf32, e->dX1 + static_cast<size_t>(channel) * e->pitch, n_out * sizeof(float2),
+                  cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  e->lastN = static_cast<int>(n_out);
+  return stageFail(e, "decimate") ? 0 : n_out;
+}
+
+static size_t demodCommon(fmgpu_engine *e, int channel, const uint8_t *iq_u8, const float *iq_cf32,
+                          float *mpx_out, float *mono_out, size_t n, cudaStream_t s) {
+  if (n > e->nmax) {
+    e->lastError = "demod: more samples than the engine was sized for";
+    return 0;
+  }
+  const int ni = static_cast<int>(n);
+  if (iq_u8) {
+    uint8_t *dst = e->dIq + static_cast<size_t>(channel) * e->iqPitch;
+    cudaMemcpyAsync(dst, iq_u8, n * 2, cudaMemcpyHostToDevice, s);
+  } else {
+    cudaMemcpyAsync(e->dX1 + static_cast<size_t>(channel) * e->pitch, iq_cf32, n * sizeof(float2),
+                    cudaMemcpyHostToDevice, s);
+  }
+  if (mono_out) {
+    launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
+                  e->k.rds_step, 0, 1, 0, s);
+  }
+  stageDemod(e, iq_u8 ? e->dIq : nullptr, e->iqPitch, nullptr, 1, ni, ni, channel, 1, s);
+  if (mpx_out) {
+    cudaMemcpyAsync(mpx_out, e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX,
+                    n * sizeof(float), cudaMemcpyDeviceToHost, s);
+  }
+  size_t produced = 0;
+  if (mono_out) {
+    stageMono(e, ni, 0, 0, channel, 1, s);
+    launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, s);
+    AudioState a{};
+    cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    produced = std::min<size_t>(a.mono_n_out, e->acap);
+    cudaMemcpyAsync(mono_out, e->dAudio + static_cast<size_t>(channel) * 2 * e->acap,
+                    produced * sizeof(float), cudaMemcpyDeviceToHost, s);
+  }
+  cudaStreamSynchronize(s);
+  e->lastN = ni;
+  return stageFail(e, "demod") ? 0 : produced;
+}
+
+size_t fmgpu_demod_u8(fmgpu_engine *e, int channel, const uint8_t *iq, float *mpx_out,
+                      float *mono_out, size_t n) {
+  STAGE_PROLOGUE(iq && n > 0)
+  return demodCommon(e, channel, iq, nullptr, mpx_out, mono_out, n, s);
+}
+
+size_t fmgpu_demod_cf32(fmgpu_engine *e, int channel, const float *iq_cf32, float *mpx_out,
+                        float *mono_out, size_t n) {
+  STAGE_PROLOGUE(iq_cf32 && n > 0)
+  return demodCommon(e, channel, nullptr, iq_cf32, mpx_out, mono_out, n, s);
+}
+
+size_t fmgpu_stereo(fmgpu_engine *e, int channel, const float *mpx, float *left, float *right,
+                    size_t n) {
+  STAGE_PROLOGUE(mpx && left && right && n > 0)
+  if (n > e->nmax) {
+    e->lastError = "stereo: more samples than the engine was sized for";
+    return 0;
+  }
+  const int ni = static_cast<int>(n);
+  cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
+                  n * sizeof(float), cudaMemcpyHostToDevice, s);
+  stageStereo(e, nullptr, 1, ni, ni, channel, 1, s);
+  cudaMemcpyAsync(left, e->dLf + static_cast<size_t>(channel) * e->lfPitch + H_LF, n * sizeof(float),
+                  cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(right, e->dRf + static_cast<size_t>(channel) * e->lfPitch + H_LF,
+                  n * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  e->lastN = ni;
+  return stageFail(e, "stereo") ? 0 : n;
+}
+
+size_t fmgpu_afpost(fmgpu_engine *e, int channel, const float *in_left, const float *in_right,
+                    size_t n, float *out_left, float *out_right, size_t out_capacity) {
+  STAGE_PROLOGUE(in_left && in_right && out_left && out_right && n > 0 && out_capacity > 0)
+  if (n > e->nmax) {
+    e->lastError = "afpost: more samples than the engine was sized for";
+    return 0;
+  }
+  // honour outCapacity as the reference loop does (af_post_processor.cpp:56): stop
+  // consuming input once out_capacity frames exist.
+  AudioState a{};
+  cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  size_t n_eff = n;
+  {
+    const unsigned long long num = static_cast<unsigned long long>(n) << 24;
+    unsigned long long cnt = 0;
+    if (num > a.rs_phase) {
+      cnt = (num - a.rs_phase + e->k.aud_step - 1) / e->k.aud_step;
+    }
+    if (cnt > out_capacity) {
+      // input index that emits output #(out_capacity-1)
+      const unsigned long long P =
+          static_cast<unsigned long long>(a.rs_phase) + (out_capacity - 1) * 1ull * e->k.aud_step;
+      n_eff = static_cast<size_t>(P >> 24) + 1;
+    }
+  }
+  const int ni = static_cast<int>(n_eff);
+  cudaMemcpyAsync(e->dLf + static_cast<size_t>(channel) * e->lfPitch + H_LF, in_left,
+                  n_eff * sizeof(float), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(e->dRf + static_cast<size_t>(channel) * e->lfPitch + H_LF, in_right,
+                  n_eff * sizeof(float), cudaMemcpyHostToDevice, s);
+  launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
+                e->k.rds_step, 1, 0, 0, s);
+  stageAfPost(e, ni, 0, channel, 1, s);
+  launchCommit(e->dAudioSt, e->dRds, channel, 1, 1, 0, 0, s);
+  cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  const size_t produced = std::min<size_t>({a.n_out, out_capacity, e->acap});
+  cudaMemcpyAsync(out_left, e->dAudio + (static_cast<size_t>(channel) * 2 + 0) * e->acap,
+                  produced * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(out_right, e->dAudio + (static_cast<size_t>(channel) * 2 + 1) * e->acap,
+                  produced * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  e->launches += 2;
+  return stageFail(e, "afpost") ? 0 : produced;
+}
+
+size_t fmgpu_rds(fmgpu_engine *e, int channel, const float *mpx, size_t n, fmgpu_rds_group *out,
+                 size_t cap) {
+  STAGE_PROLOGUE(mpx && n > 0)
+  if (n > e->nmax) {
+    e->lastError = "rds: more samples than the engine was sized for";
+    return 0;
+  }
+  const int ni = static_cast<int>(n);
+  cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
+                  n * sizeof(float), cudaMemcpyHostToDevice, s);
+  launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
+                e->k.rds_step, 0, 0, 1, s);
+  stageRds(e, e->dGroups, static_cast<uint32_t>(e->gcap), nullptr, 1, ni, ni, channel, 1, s);
+  launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 0, 1, s);
+  e->launches += 2;
+  RdsState r{};
+  cudaMemcpyAsync(&r, e->dRds + channel, sizeof(r), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  const size_t ng = r.n_groups;
+  const size_t copy = std::min({ng, cap, e->gcap});
+  if (out && copy > 0) {
+    cudaMemcpyAsync(out, e->dGroups + static_cast<size_t>(channel) * e->gcap,
+                    copy * sizeof(fmgpu_rds_group), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+  }
+  e->lastN = ni;
+  return stageFail(e, "rds") ? 0 : ng;
+}
+
+// ---- introspection ------------------------------------------------------------------
+size_t fmgpu_get_design(fmgpu_engine *e, int which, int channel, float *out, size_t cap,
+                        float *scale) {
+  if (!e) {
+    return 0;
+  }
+  std::vector<float> v;
+  float sc = 1.0f;
+  switch (which) {
+  case 0: v = e->decTaps; sc = e->decScale; break;
+  case 1: {
+    if (channel < 0 || channel >= e->C) {
+      return 0;
+    }
+    const auto &f = e->filters[e->hParams[channel].filt];
+    v = f.taps;
+    sc = f.scale;
+    break;
+  }
+  case 2: v = e->pilTaps; sc = 1.0f; break;
+  case 3: v = e->audTaps; sc = e->k.aud_scale; break;
+  case 4: v = e->audRs.bank; sc = static_cast<float>(e->audRs.step); break;
+  case 5: v = e->rdsLpf; sc = e->k.rds_lpf_scale; break;
+  case 6: v = e->ss.mf; sc = e->ss.sosB0; break;
+  case 7: v = e->ss.dmf; sc = e->ss.sosA1; break;
+  case 8: v = e->rdsRs.bank; sc = static_cast<float>(e->rdsRs.step); break;
+  default: return 0;
+  }
+  if (scale) {
+    *scale = sc;
+  }
+  if (out) {
+    std::memcpy(out, v.data(), std::min(cap, v.size()) * sizeof(float));
+  }
+  return v.size();
+}
+
+size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, size_t cap) {
+  if (!e || !out || channel < 0 || channel >= e->C) {
+    return 0;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  const size_t c = static_cast<size_t>(channel);
+  const size_t n = static_cast<size_t>(e->lastN);
+  const float *src = nullptr;
+  size_t count = n;
+  switch (which) {
+  case 0: src = reinterpret_cast<const float *>(e->dX1 + c * e->pitch); count = 2 * n; break;
+  case 1: src = e->dMpx + c * e->mpxPitch + H_MPX; break;
+  case 2: src = e->dLf + c * e->lfPitch + H_LF; break;
+  case 3: src = e->dRf + c * e->lfPitch + H_LF; break;
+  case 4: src = e->dPilot + c * e->pitch; break;
+  default: return 0;
+  }
+  // NOTE: mpx / lf / rf halos have already been carried; the data region is intact.
+  count = std::min(count, cap);
+  cudaMemcpyAsync(out, src, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  cudaStreamSynchronize(e->stream);
+  return count;
+}
+
+size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t cap) {
+  if (!e || channel < 0 || channel >= e->C) {
+    return 0;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  RdsState r{};
+  cudaMemcpyAsync(&r, e->dRds + channel, sizeof(r), cudaMemcpyDeviceToHost, e->stream);
+  cudaStreamSynchronize(e->stream);
+  const size_t n = std::min<size_t>(r.n_bits, e->bitsCap);
+  if (out) {
+    cudaMemcpyAsync(out, e->dBits + static_cast<size_t>(channel) * e->bitsCap, std::min(n, cap),
+                    cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+  }
+  return n;
+}
+
+uint64_t fmgpu_launch_count(const fmgpu_engine *e) { return e ? e->launches : 0; }
+
+int fmgpu_enable_stage_timing(fmgpu_engine *e, int on) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  e->timing = on != 0;
+  return FMGPU_OK;
+}
+
+int fmgpu_get_stage_times(fmgpu_engine *e, const char **names, float *ms, int cap) {
+  if (!e) {
+    return 0;
+  }
+  int n = 0;
+  for (auto &t : e->lastTimes) {
+    if (n < cap) {
+      names[n] = t.first;
+      ms[n] = t.second;
+    }
+    n++;
+  }
+  return n;
+}
+
+size_t fmgpu_design_host(const fmgpu_config *cfg, int which, int bw_hz, float *out, size_t cap,
+                         float *scale) {
+  if (!cfg || cfg->iq_rate < 1 || cfg->decimation < 1) {
+    return 0;
+  }
+  fmgpu_engine tmp;
+  tmp.cfg = *cfg;
+  if (tmp.cfg.output_rate <= 0) {
+    tmp.cfg.output_rate = 32000;
+  }
+  tmp.M = cfg->decimation;
+  tmp.fs = cfg->iq_rate / cfg->decimation;
+  if (computeDesigns(&tmp) != FMGPU_OK) {
+    return 0;
+  }
+  std::vector<float> v;
+  float sc = 1.0f;
+  switch (which) {
+  case 0: v = tmp.decTaps; sc = tmp.decScale; break;
+  case 1: {
+    // FMDemod ctor filter, then setW0BandwidthHz(cfg->w0), setBandwidthHz(bw_hz)
+    unsigned len = 81;
+    float cut = std::clamp(110000.0f / static_cast<float>(tmp.fs), 0.01f, 0.45f);
+    float as = 60.0f;
+    const fmdesign::ChannelFilterSpec spec =
+        fmdesign::channelFilterSpec(bw_hz, std::clamp(cfg->w0_bandwidth_hz, 0, 400000), tmp.fs);
+    if (spec.index != 0) {
+      len = spec.length;
+      cut = spec.cutoff;
+      as = spec.atten;
+    }
+    v = fmdesign::kaiserLowpass(len, cut, as, 0.0f);
+    sc = 2.0f * cut;
+    break;
+  }
+  case 2: v = tmp.pilTaps; sc = 1.0f; break;
+  case 3: v = tmp.audTaps; sc = tmp.k.aud_scale; break;
+  case 4: v = tmp.audRs.bank; sc = static_cast<float>(tmp.audRs.step); break;
+  case 5: v = tmp.rdsLpf; sc = tmp.k.rds_lpf_scale; break;
+  case 6: v = tmp.ss.mf; sc = tmp.ss.sosB0; break;
+  case 7: v = tmp.ss.dmf; sc = tmp.ss.sosA1; break;
+  case 8: v = tmp.rdsRs.bank; sc = static_cast<float>(tmp.rdsRs.step); break;
+  default: return 0;
+  }
+  if (scale) {
+    *scale = sc;
+  }
+  if (out) {
+    std::memcpy(out, v.data(), std::min(cap, v.size()) * sizeof(float));
+  }
+  return v.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,1439 @@
+// kernels.cu — sm_100a kernels of the FM stereo + RDS engine.
+//
+// Two kinds of kernels:
+//  * "tile" kernels: the FIRs and element-wise stages. One CTA per (tile of
+//    outputs, channel); inputs staged in shared memory with their halo, outputs
+//    register-tiled so every FFMA has one shared-memory operand at most. Dot
+//    products are ONE accumulator per output, oldest sample first, fused
+//    multiply-add — the order the CPU oracle uses — so results are bit-identical.
+//  * "lane" kernels: the serial recursions (DC blockers, AGC, 19 kHz pilot PLL
+//    and blend, de-emphasis, the whole RDS demodulator and block synchroniser).
+//    One lane per channel, state in registers, one warp per CTA so channels
+//    spread over all SMs.
+// Compiled with -fmad=false: only explicit fmaf() fuses.
+#include "kernels.h"
+
+#include "fm_math.h"
+
+namespace fmgpu {
+
+// ---------------------------------------------------------------------------
+// constant tables of the RDS (26,16) code, filled by initRdsTables()
+// ---------------------------------------------------------------------------
+__constant__ uint32_t c_syn_mask[10];   // syndrome bit r = parity(word & c_syn_mask[r])
+__constant__ uint32_t c_err_syn[52];    // syndromes of the correctable error bursts
+__constant__ uint32_t c_err_vec[52];    // the bursts themselves (1-bit then 2-bit, shift 0..25)
+__constant__ uint32_t c_off_word[5];    // offset words A, B, C, C', D
+
+namespace {
+
+const uint32_t kParity[26] = {
+    0b1000000000, 0b0100000000, 0b0010000000, 0b0001000000, 0b0000100000, 0b0000010000,
+    0b0000001000, 0b0000000100, 0b0000000010, 0b0000000001, 0b1011011100, 0b0101101110,
+    0b0010110111, 0b1010000111, 0b1110011111, 0b1100010011, 0b1101010101, 0b1101110110,
+    0b0110111011, 0b1000000001, 0b1111011100, 0b0111101110, 0b0011110111, 0b1010100111,
+    0b1110001111, 0b1100011011};
+
+uint32_t hostSyndrome(uint32_t v) {
+  uint32_t r = 0;
+  for (int k = 0; k < 26; k++) {
+    if ((v >> k) & 1u) {
+      r ^= kParity[25 - k];
+    }
+  }
+  return r;
+}
+
+}  // namespace
+
+cudaError_t initRdsTables() {
+  uint32_t mask[10];
+  for (int r = 0; r < 10; r++) {
+    mask[r] = 0;
+    for (int k = 0; k < 26; k++) {
+      if ((kParity[25 - k] >> r) & 1u) {
+        mask[r] |= (1u << k);
+      }
+    }
+  }
+  uint32_t esyn[52], evec[52];
+  int n = 0;
+  for (uint32_t eb : {1u, 3u}) {
+    for (uint32_t sh = 0; sh < 26; sh++) {
+      evec[n] = (eb << sh) & 0x3ffffffu;
+      esyn[n] = hostSyndrome(evec[n]);
+      n++;
+    }
+  }
+  const uint32_t offw[5] = {0b0011111100, 0b0110011000, 0b0101101000, 0b1101010000, 0b0110110100};
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_syn_mask, mask, sizeof(mask))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_err_syn, esyn, sizeof(esyn))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_err_vec, evec, sizeof(evec))) != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_off_word, offw, sizeof(offw));
+}
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ncoConstrainDev(float theta) {
+  const float p = (float)((double)theta * 0.159154943091895);
+  float fpart = p - (float)((long long)p);
+  if (fpart < 0.0f) {
+    fpart = fpart + 1.0f;
+  }
+  const float scaled = fpart * 4294967296.0f;
+  return (uint32_t)((unsigned long long)scaled);
+}
+
+__device__ __forceinline__ float ncoPhaseDev(uint32_t theta) {
+  return (float)(6.283185307179586 * (double)((float)theta) / 4294967296.0);
+}
+
+__device__ __forceinline__ float unwrapDev(float p) {
+  const float kPi = 3.14159265358979323846f;
+  const float k2Pi = 2.f * kPi;
+  if (p > kPi) {
+    return p - k2Pi;
+  }
+  if (p < -kPi) {
+    return p + k2Pi;
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// history carry: buf[c][0..H) <- buf[c][n..n+H)   (the last H samples of hist ++ new)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_carry(T *buf, size_t pitch, int H, size_t n, int ch0) {
+  T *row = buf + (size_t)(blockIdx.x + ch0) * pitch;
+  const int e = threadIdx.x;
+  T v{};
+  if (e < H) {
+    v = row[n + e];
+  }
+  __syncthreads();
+  if (e < H) {
+    row[e] = v;
+  }
+}
+
+// IQ history: hist[c] <- last H_IQ samples of (hist[c] ++ in[c][0..n_in))
+__global__ void k_carry_iq(uchar2 *hist, int *hist_valid, const uint8_t *iq, size_t iq_stride,
+                           long n_in, int ch0) {
+  const int c = blockIdx.x + ch0;
+  if (threadIdx.x == 0) {
+    // samples older than `valid` are the zero-initialised window of a fresh firdecim
+    hist_valid[c] = (int)min((long)H_IQ, (long)hist_valid[c] + n_in);
+  }
+  uchar2 *h = hist + (size_t)c * H_IQ;
+  const uchar2 *in = reinterpret_cast<const uchar2 *>(iq + (size_t)c * iq_stride);
+  const int e = threadIdx.x;  // blockDim == H_IQ
+  const long src = n_in - H_IQ + e;
+  const uchar2 v = (src >= 0) ? in[src] : h[e + n_in];
+  __syncthreads();
+  h[e] = v;
+}
+
+// hist[c][0..H) <- last H samples of (hist[c] ++ src[c][src_off .. src_off+n)); H <= 32.
+// Used for windows that belong to a stage other than the owner of the buffer's own
+// halo (RDS resampler and FMDemod mono resampler both read the MPX buffer).
+__global__ void k_save_tail(const float *src, size_t src_pitch, int src_off, float *hist,
+                            int hist_pitch, int H, long n, int ch0) {
+  const int c = blockIdx.x + ch0;
+  const int e = threadIdx.x;
+  float v = 0.0f;
+  if (e < H) {
+    const long si = n - H + e;
+    v = (si >= 0) ? src[(size_t)c * src_pitch + src_off + si] : hist[(size_t)c * hist_pitch + e + n];
+  }
+  __syncthreads();
+  if (e < H) {
+    hist[(size_t)c * hist_pitch + e] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: uint8 IQ -> float, polyphase-ordered decimating FIR (firdecim_crcf)
+//   y[n] = scale * sum_i hrev[i] * x[n*M - (L-1) + i]      (newest sample = n*M)
+// Taps are front-padded with zeros to Pp*M (Pp multiple of 4). 128 threads x 4
+// consecutive outputs; the tile (converted to float2) sits in shared memory with a
+// one-word skew per 4*M samples so the per-thread stride is odd (no bank conflicts).
+// Input bytes are fetched as 128-bit words from the 16-byte aligned virtual stream
+// hist ++ input.
+// ---------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(128)
+k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
+        const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
+        int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
+  constexpr int R = 4;
+  constexpr int T = 128 * R;
+  constexpr int RM = R * M;
+  extern __shared__ float2 xs[];
+  const int c = blockIdx.y + ch0;
+  const int n0 = blockIdx.x * T;
+  const int t = threadIdx.x;
+  const long o = (long)(n0 - Pp) * M + 1;  // stream index of tile element 0
+  const int tile_len = (T + Pp - 1) * M;
+  const long v0 = o + H_IQ;                // virtual index (history first)
+  const long ck0 = v0 >> 3;
+  const long ck1 = (v0 + tile_len - 1) >> 3;
+  const long n_in = (long)n_out * M;
+  const uint8_t *in_c = iq + (size_t)c * iq_stride;
+  const uint8_t *hist_c = hist + (size_t)c * (2 * H_IQ);
+  const long v_first_valid = H_IQ - hist_valid[c];
+  constexpr float kScale = 1.0f / 127.5f;
+
+  for (long ck = ck0 + t; ck <= ck1; ck += 128) {
+    const long v = ck << 3;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (v < H_IQ) {
+      raw = *reinterpret_cast<const uint4 *>(hist_c + 2 * v);
+    } else if (v - H_IQ < n_in) {
+      raw = __ldg(reinterpret_cast<const uint4 *>(in_c + 2 * (v - H_IQ)));
+    }
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const long a = v + e - v0;
+      if (a >= 0 && a < tile_len) {
+        const uint32_t word = w[e >> 1] >> ((e & 1) * 16);
+        float fi = ((float)(word & 0xffu) - 127.5f) * kScale;
+        float fq = ((float)((word >> 8) & 0xffu) - 127.5f) * kScale;
+        if (v + e < v_first_valid) {
+          fi = 0.0f;
+          fq = 0.0f;
+        }
+        const int ai = (int)a;
+        xs[ai + ai / RM] = make_float2(fi, fq);
+      }
+    }
+  }
+  __syncthreads();
+
+  float2 acc[R];
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    acc[j] = make_float2(0.0f, 0.0f);
+  }
+  float2 seg[R][M];
+  const int tbase = t * (RM + 1);
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+      seg[u][r] = xs[tbase + u * M + r];  // u < 4: no skew word yet
+    }
+  }
+  for (int pp = 0; pp < Pp; pp += 4) {
+#pragma unroll
+    for (int ps = 0; ps < 4; ps++) {
+      const int u = pp + ps + 3;
+      const int sb = tbase + u * M + (u >> 2);
+#pragma unroll
+      for (int r = 0; r < M; r++) {
+        seg[(ps + 3) & 3][r] = xs[sb + r];
+      }
+#pragma unroll
+      for (int r = 0; r < M; r++) {
+        const float h = taps.h[(pp + ps) * M + r];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          acc[j].x = fmaf(h, seg[(j + ps) & 3][r].x, acc[j].x);
+          acc[j].y = fmaf(h, seg[(j + ps) & 3][r].y, acc[j].y);
+        }
+      }
+    }
+  }
+  float2 *out = x1 + (size_t)c * x1_pitch;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int n = n0 + R * t + j;
+    if (n < n_out) {
+      out[n] = make_float2(acc[j].x * scale, acc[j].y * scale);
+    }
+  }
+}
+
+// generic fallback for decimation factors without an instantiation
+__global__ void k_decim_generic(const uint8_t *__restrict__ iq, size_t iq_stride,
+                                const uint8_t *__restrict__ hist,
+                                const int *__restrict__ hist_valid, float2 *__restrict__ x1,
+                                size_t x1_pitch, int n_out, int ch0, int M, int L, float scale,
+                                const __grid_constant__ TapsParam taps) {
+  const int c = blockIdx.y + ch0;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_out) {
+    return;
+  }
+  const uchar2 *in_c = reinterpret_cast<const uchar2 *>(iq + (size_t)c * iq_stride);
+  const uchar2 *hist_c = reinterpret_cast<const uchar2 *>(hist + (size_t)c * (2 * H_IQ));
+  constexpr float kScale = 1.0f / 127.5f;
+  float ar = 0.0f, ai = 0.0f;
+  for (int i = 0; i < L; i++) {
+    const long s = (long)n * M - (L - 1) + i;
+    const uchar2 b = (s >= 0) ? in_c[s] : hist_c[H_IQ + s];
+    float fi = ((float)b.x - 127.5f) * kScale;
+    float fq = ((float)b.y - 127.5f) * kScale;
+    if (s < -(long)hist_valid[c]) {
+      fi = 0.0f;
+      fq = 0.0f;
+    }
+    ar = fmaf(taps.h[i], fi, ar);
+    ai = fmaf(taps.h[i], fq, ai);
+  }
+  x1[(size_t)c * x1_pitch + n] = make_float2(ar * scale, ai * scale);
+}
+
+// M == 1 through ComplexDecimator::executeComplex: a pure convert (liquid_primitives.cpp:468-478)
+__global__ void k_convert_u8(const uint8_t *__restrict__ iq, size_t iq_stride,
+                             float2 *__restrict__ x1, size_t x1_pitch, int n, int ch0) {
+  const int c = blockIdx.y + ch0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  constexpr float kScale = 1.0f / 127.5f;
+  const uchar2 b = reinterpret_cast<const uchar2 *>(iq + (size_t)c * iq_stride)[i];
+  x1[(size_t)c * x1_pitch + i] =
+      make_float2(((float)b.x - 127.5f) * kScale, ((float)b.y - 127.5f) * kScale);
+}
+
+// ---------------------------------------------------------------------------
+// S1: I/Q DC blockers (iirfilt dc_blocker, alpha = 0.0005) + clip statistics.
+// One lane per channel; fm_demod.cpp:150-208.
+// ---------------------------------------------------------------------------
+__global__ void k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch,
+                          const uint8_t *__restrict__ iq_u8, size_t iq_stride,
+                          float2 *__restrict__ x2, size_t x2_pitch, DemodState *st,
+                          fmgpu_block_status *status, int status_pitch, int nblk, int blk_len,
+                          int n_total, int ch0, int nch, float a1) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  DemodState s = st[c];
+  float vi = s.dc_i, vq = s.dc_q;
+  const float2 *in = x1 ? x1 + (size_t)c * x1_pitch : nullptr;
+  const uchar2 *inb = iq_u8 ? reinterpret_cast<const uchar2 *>(iq_u8 + (size_t)c * iq_stride) : nullptr;
+  float2 *out = x2 + (size_t)c * x2_pitch + H_X2;
+  for (int b = 0; b < nblk; b++) {
+    const int beg = b * blk_len;
+    const int len = min(blk_len, n_total - beg);
+    int clip = 0;
+    for (int i = 0; i < len; i++) {
+      float ir, qr;
+      if (inb) {
+        const uchar2 v = inb[beg + i];
+        if (v.x == 0 || v.x == 255 || v.y == 0 || v.y == 255) {
+          clip++;
+        }
+        ir = ((float)v.x - 127.0f) / 127.5f;
+        qr = ((float)v.y - 127.0f) / 127.5f;
+      } else {
+        const float2 v = in[beg + i];
+        ir = v.x;
+        qr = v.y;
+        if (fabsf(ir) >= 0.995f || fabsf(qr) >= 0.995f) {
+          clip++;
+        }
+      }
+      const float v0i = ir - (a1 * vi);
+      const float yi = v0i - vi;
+      vi = v0i;
+      const float v0q = qr - (a1 * vq);
+      const float yq = v0q - vq;
+      vq = v0q;
+      out[beg + i] = make_float2(yi, yq);
+    }
+    s.clipping = (clip > 0) ? 1 : 0;
+    s.clip_ratio = (len > 0) ? ((float)clip / (float)len) : 0.0f;
+    if (status) {
+      status[(size_t)c * status_pitch + b].clip_ratio = s.clip_ratio;
+    }
+  }
+  s.dc_i = vi;
+  s.dc_q = vq;
+  st[c] = s;
+}
+
+// ---------------------------------------------------------------------------
+// K2: channel filter (firfilt_crcf, 81/121 real taps on complex data, per-channel
+// bandwidth). 128 threads x 8 consecutive complex outputs, sliding register window.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ ybuf,
+          size_t y_pitch, const float *__restrict__ chan_taps, const int *__restrict__ chan_lp,
+          const float *__restrict__ chan_scale, const ChanParams *__restrict__ cp, int n_total,
+          int ch0) {
+  constexpr int R = 8;
+  constexpr int T = 128 * R;
+  __shared__ float hs[CHAN_TAPS_PITCH];
+  extern __shared__ float2 xs[];
+  const int c = blockIdx.y + ch0;
+  const int n0 = blockIdx.x * T;
+  const int t = threadIdx.x;
+  const int f = cp[c].filt;
+  const int Lp = chan_lp[f];
+  const float scale = chan_scale[f];
+  if (t < Lp) {
+    hs[t] = chan_taps[f * CHAN_TAPS_PITCH + (CHAN_TAPS_PITCH - Lp) + t];
+  }
+  const float2 *row = x2 + (size_t)c * x2_pitch + H_X2;
+  const int b0 = n0 - (Lp - 1);
+  const int tile_len = T + Lp - 1 + R;
+  for (int a = t; a < tile_len; a += 128) {
+    const int s = b0 + a;
+    xs[a + (a >> 3)] = (s < n_total) ? row[s] : make_float2(0.0f, 0.0f);
+  }
+  __syncthreads();
+  float2 acc[R], win[R];
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    acc[j] = make_float2(0.0f, 0.0f);
+    const int a = t * R + j;
+    win[j] = xs[a + (a >> 3)];
+  }
+  for (int i = 0; i < Lp; i += R) {
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+      const float h = hs[i + u];
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        acc[j].x = fmaf(h, win[(j + u) & (R - 1)].x, acc[j].x);
+        acc[j].y = fmaf(h, win[(j + u) & (R - 1)].y, acc[j].y);
+      }
+      const int a = t * R + i + u + R;
+      win[u] = xs[a + (a >> 3)];
+    }
+  }
+  float2 *out = ybuf + (size_t)c * y_pitch + 1;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int n = n0 + t * R + j;
+    if (n < n_total) {
+      out[n] = make_float2(acc[j].x * scale, acc[j].y * scale);
+    }
+  }
+}
+
+// S2: pre-discriminator AGC (agc_crcf; fm_demod.cpp:170-172,196-198), in place, lanes with AGC on
+__global__ void k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp,
+                      int n_total, int ch0, int nch) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  if (cp[c].agc_mode == 0) {
+    return;
+  }
+  const float alpha = cp[c].agc_alpha;
+  float g = st[c].agc_g, y2 = st[c].agc_y2;
+  float2 *y = ybuf + (size_t)c * y_pitch + 1;
+  for (int n = 0; n < n_total; n++) {
+    const float2 x = y[n];
+    const float2 o = make_float2(x.x * g, x.y * g);
+    const float e = (o.x * o.x) + (o.y * o.y);
+    y2 = ((1.0f - alpha) * y2) + (alpha * e);
+    if (y2 > 1e-6f) {
+      g = g * fm_expf((-0.5f * alpha) * fm_logf(y2));
+    }
+    if (g > 1e6f) {
+      g = 1e6f;
+    }
+    y[n] = o;
+  }
+  st[c].agc_g = g;
+  st[c].agc_y2 = y2;
+}
+
+// K2b: quadrature discriminator, arg(conj(y[n-1]) * y[n]) / (2 pi kf)   (freqdem)
+__global__ void k_freqdem(const float2 *__restrict__ ybuf, size_t y_pitch, float *__restrict__ mpx,
+                          size_t mpx_pitch, int n_total, int ch0, float ref) {
+  const int c = blockIdx.y + ch0;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_total) {
+    return;
+  }
+  const float2 *y = ybuf + (size_t)c * y_pitch;
+  const float2 p = y[n];
+  const float2 r = y[n + 1];
+  const float re = (p.x * r.x) + (p.y * r.y);
+  const float im = (p.x * r.y) - (p.y * r.x);
+  mpx[(size_t)c * mpx_pitch + H_MPX + n] = fm_atan2f(im, re) * ref;
+}
+
+// ---------------------------------------------------------------------------
+// K3 / K5: real FIR with taps in the kernel-parameter constant bank
+// (pilot band-pass 305/325 taps; 2 x 121-tap 15 kHz low-pass via gridDim.z = 2)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
+  constexpr int R = 8;
+  constexpr int T = 128 * R;
+  extern __shared__ float fs_x[];
+  const int c = blockIdx.y + job.ch0;
+  const int z = blockIdx.z;
+  const int n0 = blockIdx.x * T;
+  const int t = threadIdx.x;
+  const int Lp = job.Lp;
+  const float *row = job.in[z] + (size_t)c * job.in_pitch + job.in_off;
+  const int b0 = n0 - (Lp - 1);
+  const int tile_len = T + Lp - 1 + R;
+  for (int a = t; a < tile_len; a += 128) {
+    const int s = b0 + a;
+    fs_x[a + (a >> 3)] = (s < job.n_total) ? row[s] : 0.0f;
+  }
+  __syncthreads();
+  float acc[R], win[R];
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    acc[j] = 0.0f;
+    const int a = t * R + j;
+    win[j] = fs_x[a + (a >> 3)];
+  }
+  for (int i = 0; i < Lp; i += R) {
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+      const float h = taps.h[i + u];
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        acc[j] = fmaf(h, win[(j + u) & (R - 1)], acc[j]);
+      }
+      const int a = t * R + i + u + R;
+      win[u] = fs_x[a + (a >> 3)];
+    }
+  }
+  float *out = job.out[z] + (size_t)c * job.out_pitch + job.out_off;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int n = n0 + t * R + j;
+    if (n < job.n_total) {
+      out[n] = acc[j] * job.scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// S4: 19 kHz pilot PLL, quality metrics, blend, L-R matrix, per-block lock logic
+// (stereo_decoder.cpp:92-286). One lane per channel.
+// ---------------------------------------------------------------------------
+__global__ void k_stereo(const float *__restrict__ mpx, size_t mpx_pitch,
+                         const float *__restrict__ pilot, size_t pilot_pitch,
+                         float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
+                         StereoState *st, const ChanParams *cp, fmgpu_block_status *status,
+                         int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch,
+                         EngineConst k) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  constexpr float kPi = 3.14159265358979323846f;
+  constexpr float kMatrixScale = 0.5f;
+  constexpr float kPilotRatioAcquire = 0.040f, kPilotRatioHold = 0.022f;
+  constexpr float kMpxMinAcquire = 0.005f, kMpxMinHold = 0.0028f;
+  constexpr float kPilotCoherenceAcquire = 0.18f, kPilotCoherenceHold = 0.11f;
+  constexpr float kPllLockAcquireHz = 180.0f, kPllLockHoldHz = 320.0f;
+  constexpr float kSmooth = 0.9995f;
+  constexpr float kInject = 1.0f - kSmooth;
+
+  StereoState s = st[c];
+  const ChanParams p = cp[c];
+  const int mode = p.blend_mode;
+  const float blendAttack = k.blend_attack[mode];
+  const float blendRelease = k.blend_release[mode];
+  const float gate = k.gate[mode];
+  const float ratioDen = fmaxf(kPilotRatioAcquire - kPilotRatioHold, 1e-4f);
+  const float cohDen = fmaxf(kPilotCoherenceAcquire - kPilotCoherenceHold, 1e-4f);
+  const float pllDen = fmaxf(kPllLockHoldHz - kPllLockAcquireHz, 1e-3f);
+
+  const float *mrow = mpx + (size_t)c * mpx_pitch + H_MPX;
+  const float *prow = pilot + (size_t)c * pilot_pitch;
+  float *lrow = lraw + (size_t)c * lr_pitch + H_LR;
+  float *rrow = rraw + (size_t)c * lr_pitch + H_LR;
+
+  uint32_t theta = s.theta, dtheta = s.dtheta;
+  float pbm = s.pbm, mm = s.mm, pilotI = s.pilot_i, pilotQ = s.pilot_q, blend = s.blend;
+  float pllFreq = s.pll_freq;
+  float phaseNow = ncoPhaseDev(theta);
+  float vcoQ, vcoI;
+  fm_sincosf(phaseNow, &vcoQ, &vcoI);
+
+  for (int b = 0; b < nblk; b++) {
+    const int beg = b * blk_len;
+    const int len = min(blk_len, n_total - beg);
+    const bool stereoDetected = s.stereo != 0;
+    for (int i = 0; i < len; i++) {
+      const int n = beg + i;
+      const float x = mrow[n];
+      const float pil = prow[n];
+      const float dm = mrow[n - k.delay];
+      pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
+      mm = (mm * kSmooth) + (fabsf(x) * kInject);
+      const float error = pil * vcoQ;
+      dtheta += ncoConstrainDev(error * k.pll_alpha);
+      theta += ncoConstrainDev(error * k.pll_beta);
+      theta += dtheta;
+      const float phaseNext = ncoPhaseDev(theta);
+      float dphi = phaseNext - phaseNow;
+      if (dphi > kPi) {
+        dphi -= 2.0f * kPi;
+      } else if (dphi < -kPi) {
+        dphi += 2.0f * kPi;
+      }
+      pllFreq = fm_clampf(dphi, k.pll_min, k.pll_max);
+      pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
+      pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
+
+      float target = 0.0f;
+      if (p.force_mono) {
+        target = 0.0f;
+      } else if (p.force_stereo) {
+        target = 1.0f;
+      } else if (stereoDetected) {
+        const float pilotMagNow = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
+        const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
+        const float pilotCoherence = pilotMagNow / fmaxf(pbm, 1e-4f);
+        const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
+        const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
+        const float cohQ = fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
+        const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
+        const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
+        float shaped = quality * quality;
+        if (mode == 0) {
+          shaped = FM_SQRT(fmaxf(0.0f, quality));
+        } else if (mode == 2) {
+          shaped = quality * quality * quality;
+        }
+        if (pilotRatio < (kPilotRatioHold * gate) || pilotCoherence < (kPilotCoherenceHold * gate) ||
+            pllErrHz > (kPllLockHoldHz * 1.10f)) {
+          target = 0.0f;
+        } else {
+          target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
+        }
+      }
+
+      float pllIm, pllRe;
+      fm_sincosf(phaseNext, &pllIm, &pllRe);
+      const float monoNorm = dm * kMatrixScale;
+      const float cos2 = (pllRe * pllRe) - (pllIm * pllIm);
+      const float lr = 2.0f * dm * cos2;
+      const float stereoLeft = (dm + lr) * kMatrixScale;
+      const float stereoRight = (dm - lr) * kMatrixScale;
+      const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
+      blend += (target - blend) * blendAlpha;
+      lrow[n] = monoNorm + ((stereoLeft - monoNorm) * blend);
+      rrow[n] = monoNorm + ((stereoRight - monoNorm) * blend);
+
+      phaseNow = phaseNext;
+      vcoQ = pllIm;
+      vcoI = pllRe;
+    }
+    // per-block tail (stereo_decoder.cpp:243-286)
+    const float pilotMag = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
+    s.pilot_mag = (s.pilot_mag * 0.9f) + (pilotMag * 0.1f);
+    const bool det = s.stereo != 0;
+    const float mpxThreshold = det ? kMpxMinHold : kMpxMinAcquire;
+    const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
+    const float pilotCoherence = s.pilot_mag / fmaxf(pbm, 1e-4f);
+    const float ratioThreshold = det ? kPilotRatioHold : kPilotRatioAcquire;
+    const float coherenceThreshold = det ? kPilotCoherenceHold : kPilotCoherenceAcquire;
+    const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
+    const float pllThreshold = det ? kPllLockHoldHz : kPllLockAcquireHz;
+    const bool pilotPresent = (mm > mpxThreshold) && (pilotRatio > ratioThreshold) &&
+                              (pilotCoherence > coherenceThreshold) && (pllErrHz < pllThreshold);
+    if (!p.force_stereo) {
+      if (!det) {
+        if (pilotPresent) {
+          s.pilot_count++;
+          s.loss_count = 0;
+          if (s.pilot_count >= 6) {
+            s.stereo = 1;
+          }
+        } else {
+          s.pilot_count = 0;
+        }
+      } else if (pilotPresent) {
+        s.loss_count = 0;
+      } else if (++s.loss_count >= 24) {
+        s.stereo = 0;
+        s.pilot_count = 0;
+        s.loss_count = 0;
+      }
+    }
+    const float calibrated = s.pilot_mag * 8.0f;
+    s.pilot_tenths = min(750, max(0, (int)fm_roundf(calibrated * 750.0f)));
+    if (status) {
+      fmgpu_block_status *o = &status[(size_t)c * status_pitch + b];
+      o->stereo = s.stereo;
+      o->pilot_tenths = s.pilot_tenths;
+    }
+  }
+  s.theta = theta;
+  s.dtheta = dtheta;
+  s.pbm = pbm;
+  s.mm = mm;
+  s.pilot_i = pilotI;
+  s.pilot_q = pilotQ;
+  s.blend = blend;
+  s.pll_freq = pllFreq;
+  st[c] = s;
+}
+
+// ---------------------------------------------------------------------------
+// per-call bookkeeping of the fixed-point resamplers (resamp_rrrf, Appendix A.6):
+// outputs produced by n inputs from phase p0:  ceil((n*2^24 - p0) / step)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t resampCount(uint32_t phase0, uint32_t step, long n,
+                                                uint32_t *phase_next) {
+  const unsigned long long num = (unsigned long long)n << 24;
+  unsigned long long cnt = 0;
+  if (num > phase0) {
+    cnt = (num - phase0 + step - 1) / step;
+  }
+  *phase_next = (uint32_t)(phase0 + cnt * step - num);
+  return (uint32_t)cnt;
+}
+
+__global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *status,
+                          int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch,
+                          uint32_t aud_step, uint32_t rds_step, int do_audio, int do_mono,
+                          int do_rds) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  if (do_audio || do_mono) {
+    AudioState *a = &au[c];
+    uint32_t nx;
+    const uint32_t p0 = do_mono ? a->mono_phase : a->rs_phase;
+    const uint32_t total = resampCount(p0, aud_step, n_total, &nx);
+    if (do_mono) {
+      a->mono_n_out = total;
+      a->mono_phase_next = nx;
+    } else {
+      a->n_out = total;
+      a->rs_phase_next = nx;
+    }
+    if (status) {
+      uint32_t prev = 0;
+      for (int b = 0; b < nblk; b++) {
+        const long upto = min((long)(b + 1) * blk_len, (long)n_total);
+        uint32_t dummy;
+        const uint32_t cum = resampCount(p0, aud_step, upto, &dummy);
+        status[(size_t)c * status_pitch + b].n_audio = (int)(cum - prev);
+        prev = cum;
+      }
+    }
+  }
+  if (do_rds) {
+    RdsState *r = &rds[c];
+    uint32_t nx;
+    r->n171 = resampCount(r->rs_phase, rds_step, n_total, &nx);
+    r->rs_phase_next = nx;
+    r->n_groups = 0;
+    r->n_bits = 0;
+  }
+}
+
+__global__ void k_commit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
+                         int do_rds) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  if (do_audio) {
+    au[c].rs_phase = au[c].rs_phase_next;
+  }
+  if (do_mono) {
+    au[c].mono_phase = au[c].mono_phase_next;
+  }
+  if (do_rds) {
+    rds[c].rs_phase = rds[c].rs_phase_next;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5b: arbitrary-rate polyphase resampler to 32 kHz (one thread per output frame)
+// ---------------------------------------------------------------------------
+__global__ void k_resample(const float *__restrict__ in0, const float *__restrict__ in1,
+                           size_t in_pitch, int in_off, const float *__restrict__ hist,
+                           int hist_pitch, float *__restrict__ out, size_t acap,
+                           const float *__restrict__ bank, int sub_len, uint32_t step,
+                           const AudioState *au, int mono, int ch0) {
+  extern __shared__ float bk[];
+  for (int i = threadIdx.x; i < 32 * sub_len; i += blockDim.x) {
+    bk[i] = bank[i];
+  }
+  __syncthreads();
+  const int c = blockIdx.y + ch0;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_out = mono ? au[c].mono_n_out : au[c].n_out;
+  if (j >= n_out || j >= acap) {
+    return;
+  }
+  const uint32_t phase0 = mono ? au[c].mono_phase : au[c].rs_phase;
+  const unsigned long long P = (unsigned long long)phase0 + (unsigned long long)j * step;
+  const long i = (long)(P >> 24);
+  const int br = (int)((P & 0xffffffull) >> 19);
+  const float *h = bk + br * sub_len;
+  const float *a = in0 + (size_t)c * in_pitch + in_off + i - (sub_len - 1);
+  float acc0 = 0.0f;
+  if (hist && i < sub_len - 1) {
+    // window reaches before this call: those samples live in the stage's own history
+    const float *hc = hist + (size_t)c * hist_pitch;
+    const int H = sub_len - 1;
+    for (int q = 0; q < sub_len; q++) {
+      const long si = i - (sub_len - 1) + q;
+      const float x = (si >= 0) ? a[q] : hc[H + si];
+      acc0 = fmaf(h[q], x, acc0);
+    }
+  } else {
+    for (int q = 0; q < sub_len; q++) {
+      acc0 = fmaf(h[q], a[q], acc0);
+    }
+  }
+  out[((size_t)c * 2 + 0) * acap + j] = acc0;
+  if (in1) {
+    const float *b = in1 + (size_t)c * in_pitch + in_off + i - (sub_len - 1);
+    float acc1 = 0.0f;
+    for (int q = 0; q < sub_len; q++) {
+      acc1 = fmaf(h[q], b[q], acc1);
+    }
+    out[((size_t)c * 2 + 1) * acap + j] = acc1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// S6: de-emphasis + DC blocker at 32 kHz (af_post_processor.cpp:66-71), in place;
+// optional +-1 clamp (main.cpp:1305-1308). Lanes = (channel, side).
+// mono = 1: FMDemod mono chain (fm_demod.cpp:216-222) on row 0, then optionally
+// x0.5 duplicated to both rows (main.cpp:1275-1278).
+// ---------------------------------------------------------------------------
+__global__ void k_audio_iir(float *audio, size_t acap, AudioState *au, const ChanParams *cp,
+                            int ch0, int nch, float dc_a1, int mono, int clamp, int mono_dup) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lanes = mono ? nch : 2 * nch;
+  if (lane >= lanes) {
+    return;
+  }
+  const int c = ch0 + (mono ? lane : lane / 2);
+  const int side = mono ? 0 : (lane & 1);
+  AudioState *a = &au[c];
+  const ChanParams p = cp[c];
+  const uint32_t n = min((uint32_t)acap, mono ? a->mono_n_out : a->n_out);
+  float *row = audio + ((size_t)c * 2 + side) * acap;
+  float *row2 = audio + ((size_t)c * 2 + 1) * acap;
+  const bool de = mono ? (p.mono_deemph_on != 0) : (p.deemph_on != 0);
+  const float b0 = mono ? p.mono_de_b0 : p.de_b0;
+  const float a1 = mono ? p.mono_de_a1 : p.de_a1;
+  float dv = mono ? a->mono_de_v1 : a->de_v1[side];
+  float cv = mono ? a->mono_dc_v1 : a->dc_v1[side];
+  for (uint32_t i = 0; i < n; i++) {
+    float x = row[i];
+    if (de) {
+      const float v0 = x - (a1 * dv);
+      x = b0 * v0;
+      dv = v0;
+    }
+    const float v0 = x - (dc_a1 * cv);
+    float y = v0 - cv;
+    cv = v0;
+    if (mono_dup) {
+      y = y * 0.5f;
+    }
+    if (clamp) {
+      y = fm_clampf(y, -1.0f, 1.0f);
+    }
+    row[i] = y;
+    if (mono_dup) {
+      row2[i] = y;
+    }
+  }
+  if (mono) {
+    a->mono_de_v1 = dv;
+    a->mono_dc_v1 = cv;
+  } else {
+    a->de_v1[side] = dv;
+    a->dc_v1[side] = cv;
+  }
+}
+
+__global__ void k_store_counts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,
+                               uint32_t *n_groups, int ch0, int nch, int mono, uint32_t acap,
+                               uint32_t gcap) {
+  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  if (n_audio) {
+    n_audio[c] = min(acap, mono ? au[c].mono_n_out : au[c].n_out);
+  }
+  if (n_groups) {
+    n_groups[c] = min(gcap, rds[c].n_groups);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// S7: the RDS branch, one lane per channel (redsea_port subcarrier.cpp:117-235,
+// liquid_wrappers.cpp:98-147, block_sync.cpp:235-313, rds_decoder.cpp:29-58):
+//   resample to 171 kHz -> 57 kHz NCO mix-down -> 255-tap low-pass evaluated only
+//   at the /24 instants (running accumulators, oldest sample first) -> AGC ->
+//   polyphase symbol synchroniser -> BPSK PLL -> biphase -> differential decode ->
+//   (26,16) block synchroniser with burst error correction -> groups.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rdsSyndromeDev(uint32_t v) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int q = 0; q < 10; q++) {
+    r |= (uint32_t)(__popc(v & c_syn_mask[q]) & 1) << q;
+  }
+  return r;
+}
+
+__device__ __forceinline__ int rdsOffsetForSyndromeDev(uint32_t s) {
+  switch (s) {
+  case 0b1111011000: return 0;  // A
+  case 0b1111010100: return 1;  // B
+  case 0b1001011100: return 2;  // C
+  case 0b1111001100: return 3;  // C'
+  case 0b1001011000: return 4;  // D
+  default: return 5;            // invalid
+  }
+}
+
+__device__ __forceinline__ int rdsBlockNumberDev(int off) {
+  return (off == 0) ? 0 : (off == 1) ? 1 : (off == 2 || off == 3) ? 2 : (off == 4) ? 3 : 0;
+}
+
+__device__ __forceinline__ int rdsNextOffsetDev(int off) {
+  return (off == 0) ? 1 : (off == 1) ? 2 : (off == 2 || off == 3) ? 4 : 0;
+}
+
+__device__ __forceinline__ bool rdsCouldFollow(int off, uint32_t pos, int ooff, uint32_t opos) {
+  const uint32_t d = pos - opos;
+  return d % 26 == 0 && d / 26 <= 6 && off != 5 && ooff != 5 &&
+         ((uint32_t)rdsBlockNumberDev(ooff) + d / 26) % 4 == (uint32_t)rdsBlockNumberDev(off);
+}
+
+__device__ void rdsPushBit(RdsState &s, bool bit, fmgpu_rds_group *groups, uint32_t gcap,
+                           uint32_t block_index) {
+  s.reg = (s.reg << 1) + (bit ? 1u : 0u);
+  s.until--;
+  s.bitcount++;
+  if (s.until != 0) {
+    return;
+  }
+  // findBlockInInputRegister
+  const uint32_t raw = s.reg & 0x3ffffffu;
+  const uint32_t syn = rdsSyndromeDev(raw);
+  int off = rdsOffsetForSyndromeDev(syn);
+  if (!s.in_sync) {
+    s.bits_since_lost++;
+    if (off != 5) {
+      for (int i = 0; i < 3; i++) {
+        s.pulse_pos[i] = s.pulse_pos[i + 1];
+        s.pulse_off[i] = s.pulse_off[i + 1];
+      }
+      s.pulse_pos[3] = s.bitcount;
+      s.pulse_off[3] = off;
+      bool found = false;
+      for (int i1 = 0; i1 < 2 && !found; i1++) {
+        for (int i2 = i1 + 1; i2 < 3 && !found; i2++) {
+          if (rdsCouldFollow(s.pulse_off[3], s.pulse_pos[3], s.pulse_off[i2], s.pulse_pos[i2]) &&
+              rdsCouldFollow(s.pulse_off[i2], s.pulse_pos[i2], s.pulse_off[i1], s.pulse_pos[i1])) {
+            found = true;
+          }
+        }
+      }
+      if (found) {
+        s.in_sync = 1;
+        s.expected = off;
+        s.cur_recv = 0;
+        s.cur_err = 0;
+        s.bits_since_lost = 0;
+      }
+    }
+  }
+  if (s.in_sync) {
+    if (s.expected == 2 && off == 3) {
+      s.expected = 3;
+    }
+    const bool had_errors = (off != s.expected);
+    const unsigned long long bitm = 1ull << s.err_ptr;
+    s.err_mask = had_errors ? (s.err_mask | bitm) : (s.err_mask & ~bitm);
+    s.err_ptr = (s.err_ptr + 1) % 50;
+    if (__popcll(s.err_mask) > 42) {
+      s.in_sync = 0;
+      s.err_mask = 0;
+    } else {
+      uint32_t data = raw >> 10;
+      if (had_errors) {
+        const uint32_t want = syn ^ rdsSyndromeDev(c_off_word[s.expected]);
+        for (int q = 0; q < 52; q++) {
+          if (c_err_syn[q] == want) {
+            data = (raw ^ c_err_vec[q]) >> 10;
+            off = s.expected;
+            break;
+          }
+        }
+      }
+      if (off == s.expected) {
+        const int bn = rdsBlockNumberDev(s.expected);
+        s.cur_data[bn] = (uint16_t)data;
+        s.cur_recv |= (1u << bn);
+        s.cur_err = had_errors ? (s.cur_err | (1u << bn)) : (s.cur_err & ~(1u << bn));
+      }
+      const int next = rdsNextOffsetDev(s.expected);
+      if (next == 0) {
+        if (groups && s.n_groups < gcap) {
+          fmgpu_rds_group g;
+          uint8_t e = 0;
+          uint16_t w[4];
+          for (int q = 0; q < 4; q++) {
+            const bool rc = (s.cur_recv >> q) & 1u;
+            w[q] = rc ? s.cur_data[q] : 0;
+            const uint8_t code = !rc ? 3 : (((s.cur_err >> q) & 1u) ? 1 : 0);
+            e = (uint8_t)((e << 2) | code);
+          }
+          g.a = w[0];
+          g.b = w[1];
+          g.c = w[2];
+          g.d = w[3];
+          g.errors = e;
+          g.pad[0] = g.pad[1] = g.pad[2] = 0;
+          g.block_index = block_index;
+          groups[s.n_groups] = g;
+        }
+        s.n_groups++;
+        s.cur_recv = 0;
+        s.cur_err = 0;
+      }
+      s.expected = next;
+    }
+  }
+  s.until = s.in_sync ? 26 : 1;
+}
+
+__global__ void __launch_bounds__(32)
+k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
+      int hist_pitch, RdsState *st, float2 *ring,
+      const float *__restrict__ g_bank, const float *__restrict__ g_lpf,
+      const float *__restrict__ g_mf, const float *__restrict__ g_dmf, fmgpu_rds_group *groups,
+      uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap, fmgpu_block_status *status,
+      int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
+  __shared__ float s_bank[32 * RDS_RS_LEN];
+  __shared__ float s_lpf[RDS_LPF_LEN + 1];
+  __shared__ float s_mf[32 * SS_LEN];
+  __shared__ float s_dmf[32 * SS_LEN];
+  __shared__ float2 s_wmf[SS_LEN][32];
+  __shared__ float2 s_wdmf[SS_LEN][32];
+  const int tl = threadIdx.x;
+  for (int i = tl; i < 32 * RDS_RS_LEN; i += 32) {
+    s_bank[i] = g_bank[i];
+  }
+  for (int i = tl; i < RDS_LPF_LEN; i += 32) {
+    s_lpf[i] = g_lpf[i];
+  }
+  for (int i = tl; i < 32 * SS_LEN; i += 32) {
+    s_mf[i] = g_mf[i];
+    s_dmf[i] = g_dmf[i];
+  }
+  __syncwarp();
+  const int lane = blockIdx.x * 32 + tl;
+  if (lane >= nch) {
+    return;
+  }
+  const int c = ch0 + lane;
+  constexpr float kPi = 3.14159265358979323846f;
+  RdsState s = st[c];
+  for (int q = 0; q < SS_LEN; q++) {
+    s_wmf[q][tl] = s.wmf[q];
+    s_wdmf[q][tl] = s.wdmf[q];
+  }
+  int sp = 0;  // ring position of the oldest symsync window element
+  float2 *ringc = ring + (size_t)c * RDS_RING;
+  fmgpu_rds_group *gout = groups ? groups + (size_t)c * gcap : nullptr;
+  uint8_t *bout = bits_dbg ? bits_dbg + (size_t)c * bits_cap : nullptr;
+
+  float2 acc[RDS_NACC];
+#pragma unroll
+  for (int j = 0; j < RDS_NACC; j++) {
+    acc[j] = s.acc[j];
+  }
+  if (s.realign) {
+    // SubcarrierSet::reset() moved the /24 phase: rebuild the pending sums from the
+    // last 254 mixed samples (the low-pass itself is not reset, subcarrier.cpp:108-114)
+    const uint32_t u0 = s.ring_pos;  // absolute index of the next sample
+#pragma unroll
+    for (int j = 0; j < RDS_NACC; j++) {
+      float ar = 0.0f, ai = 0.0f;
+      const int dj = 24 * j;  // instant t_j = u0 + 24 j
+      for (int back = 254 - dj; back >= 1; back--) {
+        // sample u = u0 - back contributes with window index 254 - (t_j - u)
+        const int idx = 254 - (dj + back);
+        if (idx >= 0) {
+          const float2 x = ringc[(u0 - (uint32_t)back) & (RDS_RING - 1)];
+          ar = fmaf(s_lpf[idx], x.x, ar);
+          ai = fmaf(s_lpf[idx], x.y, ai);
+        }
+      }
+      acc[j] = make_float2(ar, ai);
+    }
+    s.realign = 0;
+  }
+
+  const float *mrow = mpx + (size_t)c * mpx_pitch + H_MPX;
+  const float *hrow = hist + (size_t)c * hist_pitch;
+  uint32_t phase = s.rs_phase;
+  uint32_t produced = 0;
+  const uint32_t n171 = s.n171;
+
+  for (int blk = 0; blk < nblk; blk++) {
+    const int beg = blk * blk_len;
+    const int len = min(blk_len, n_total - beg);
+    const uint32_t groups_before = s.n_groups;
+    for (int ii = 0; ii < len; ii++) {
+      const int n = beg + ii;
+      while (phase < (1u << 24)) {
+        const int br = (int)(phase >> 19);
+        const float *h = s_bank + br * RDS_RS_LEN;
+        const float *w = mrow + n - (RDS_RS_LEN - 1);
+        float smp = 0.0f;
+        if (n >= RDS_RS_LEN - 1) {
+#pragma unroll
+          for (int q = 0; q < RDS_RS_LEN; q++) {
+            smp = fmaf(h[q], w[q], smp);
+          }
+        } else {
+          // the resampler window is RDS state of its own (not reset with the stereo path)
+          for (int q = 0; q < RDS_RS_LEN; q++) {
+            const int si = n - (RDS_RS_LEN - 1) + q;
+            const float x = (si >= 0) ? mrow[si] : hrow[(RDS_RS_LEN - 1) + si];
+            smp = fmaf(h[q], x, smp);
+          }
+        }
+        phase += k.rds_step;
+        // ---- one 171 kHz sample -------------------------------------------------
+        float sn, cs;
+        fm_sincosf(-s.phase0, &sn, &cs);
+        const float2 bb = make_float2(smp * cs, smp * sn);
+        if (n171 - produced <= (uint32_t)RDS_RING) {
+          ringc[s.ring_pos & (RDS_RING - 1)] = bb;
+        }
+        s.ring_pos++;
+        produced++;
+        const uint32_t ph = s.since_reset % 24u;
+        const int d0 = (ph == 0) ? 0 : (int)(24u - ph);
+#pragma unroll
+        for (int j = 0; j < RDS_NACC; j++) {
+          const int idx = 254 - d0 - 24 * j;
+          if (idx >= 0) {
+            const float hh = s_lpf[idx];
+            acc[j].x = fmaf(hh, bb.x, acc[j].x);
+            acc[j].y = fmaf(hh, bb.y, acc[j].y);
+          }
+        }
+        if (ph == 0) {
+          const float2 lo = make_float2(acc[0].x * k.rds_lpf_scale, acc[0].y * k.rds_lpf_scale);
+#pragma unroll
+          for (int j = 0; j < RDS_NACC - 1; j++) {
+            acc[j] = acc[j + 1];
+          }
+          acc[RDS_NACC - 1] = make_float2(0.0f, 0.0f);
+          // agc_crcf
+          const float2 y = make_float2(lo.x * s.agc_g, lo.y * s.agc_g);
+          const float e = (y.x * y.x) + (y.y * y.y);
+          s.agc_y2 = ((1.0f - k.rds_agc_alpha) * s.agc_y2) + (k.rds_agc_alpha * e);
+          if (s.agc_y2 > 1e-6f) {
+            s.agc_g = s.agc_g * fm_expf((-0.5f * k.rds_agc_alpha) * fm_logf(s.agc_y2));
+          }
+          if (s.agc_g > 1e6f) {
+            s.agc_g = 1e6f;
+          }
+          // symsync_crcf step
+          s_wmf[sp][tl] = y;
+          s_wdmf[sp][tl] = y;
+          sp = (sp + 1 == SS_LEN) ? 0 : sp + 1;
+          int n_out = 0;
+          float2 sym = make_float2(0.0f, 0.0f);
+          while (s.b < 32) {
+            float mr = 0.0f, mi = 0.0f;
+            const float *hm = s_mf + s.b * SS_LEN;
+            int wp = sp;
+            for (int q = 0; q < SS_LEN; q++) {
+              const float2 wv = s_wmf[wp][tl];
+              mr = fmaf(hm[q], wv.x, mr);
+              mi = fmaf(hm[q], wv.y, mi);
+              wp = (wp + 1 == SS_LEN) ? 0 : wp + 1;
+            }
+            if (n_out == 0) {
+              sym = make_float2(mr / 3.0f, mi / 3.0f);
+            }
+            if (s.decim_counter == 1u) {
+              s.decim_counter = 0;
+              float dr = 0.0f, di = 0.0f;
+              const float *hd = s_dmf + s.b * SS_LEN;
+              wp = sp;
+              for (int q = 0; q < SS_LEN; q++) {
+                const float2 wv = s_wdmf[wp][tl];
+                dr = fmaf(hd[q], wv.x, dr);
+                di = fmaf(hd[q], wv.y, di);
+                wp = (wp + 1 == SS_LEN) ? 0 : wp + 1;
+              }
+              float qe = (mr * dr) + (mi * di);
+              if (qe > 1.0f) {
+                qe = 1.0f;
+              } else if (qe < -1.0f) {
+                qe = -1.0f;
+              }
+              const float v0 = qe - (k.ss_a1 * s.sos_v1);
+              s.q_hat = k.ss_b0 * v0;
+              s.sos_v1 = v0;
+              s.rate = s.rate + (k.ss_rate_adj * s.q_hat);
+              s.del = s.rate + s.q_hat;
+            }
+            s.decim_counter++;
+            s.tau = s.tau + s.del;
+            const float bf = s.tau * 32.0f;
+            s.b = (int)fm_roundf(bf);
+            n_out++;
+          }
+          s.tau = s.tau - 1.0f;
+          s.b -= 32;
+          if (n_out == 1) {
+            const float pe_raw = (sym.x > 0.0f) ? sym.y : -sym.y;
+            const float pe = fm_clampf(pe_raw, -kPi, kPi);
+            const float dphi = pe * 12.0f;
+            s.dtheta += ncoConstrainDev(dphi * k.rds_pll_alpha);
+            s.theta += ncoConstrainDev(dphi * k.rds_pll_beta);
+            // biphase
+            const float bre = (sym.x - s.bi_prev_re) * 0.5f;
+            const bool bval = bre >= 0.0f;
+            const bool has = ((s.bi_clock & 1u) == s.bi_polarity);
+            s.bi_prev_re = sym.x;
+            if (s.bi_clock & 1u) {
+              s.bi_odd += fabsf(bre);
+            } else {
+              s.bi_even += fabsf(bre);
+            }
+            s.bi_clock++;
+            if (s.bi_clock == 128u) {
+              if (s.bi_even > s.bi_odd) {
+                s.bi_polarity = 0;
+              } else if (s.bi_odd > s.bi_even) {
+                s.bi_polarity = 1;
+              }
+              s.bi_even = 0.0f;
+              s.bi_odd = 0.0f;
+              s.bi_clock = 0;
+            }
+            if (has) {
+              const bool bit = (bval != (s.delta_prev != 0));
+              s.delta_prev = bval ? 1 : 0;
+              if (bout && s.n_bits < bits_cap) {
+                bout[s.n_bits] = bit ? 1 : 0;
+              }
+              s.n_bits++;
+              rdsPushBit(s, bit, gout, gcap, (uint32_t)blk);
+            }
+          }
+        }
+        // NCO::step (liquid_wrappers.cpp:125-139)
+        s.theta += s.dtheta;
+        const float pn = ncoPhaseDev(s.theta);
+        const float delta = unwrapDev(pn - s.prev_f0_phase);
+        s.prev_f0_phase = pn;
+        s.phase0 = unwrapDev(s.phase0 + ((delta * 57000.f) / 57000.f));
+        s.since_reset++;
+      }
+      phase -= (1u << 24);
+    }
+    if (status) {
+      status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - groups_before);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RDS_NACC; j++) {
+    s.acc[j] = acc[j];
+  }
+  for (int q = 0; q < SS_LEN; q++) {
+    s.wmf[q] = s_wmf[sp][tl];
+    s.wdmf[q] = s_wdmf[sp][tl];
+    sp = (sp + 1 == SS_LEN) ? 0 : sp + 1;
+  }
+  st[c] = s;
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+#define FMGPU_DECIM_CASE(MM)                                                                     \
+  case MM: {                                                                                     \
+    constexpr int T = 512;                                                                       \
+    const int tile_len = (T + Pp - 1) * MM;                                                      \
+    const size_t smem = (size_t)(tile_len + tile_len / (4 * MM) + 2) * sizeof(float2);           \
+    static bool attr_done = false;                                                               \
+    if (!attr_done) {                                                                            \
+      cudaFuncSetAttribute(k_decim<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
+      attr_done = true;                                                                          \
+    }                                                                                            \
+    dim3 grid((n_out + T - 1) / T, nch);                                                         \
+    k_decim<MM><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1, x1_pitch, n_out, \
+                                             ch0, Pp, scale, taps);                              \
+    break;                                                                                       \
+  }
+
+void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
+                 const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
+                 const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream) {
+  switch (M) {
+    FMGPU_DECIM_CASE(2)
+    FMGPU_DECIM_CASE(4)
+    FMGPU_DECIM_CASE(5)
+    FMGPU_DECIM_CASE(8)
+    FMGPU_DECIM_CASE(10)
+    FMGPU_DECIM_CASE(16)
+  default: {
+    dim3 grid((n_out + 127) / 128, nch);
+    k_decim_generic<<<grid, 128, 0, stream>>>(iq, iq_stride, hist, hist_valid, x1, x1_pitch, n_out,
+                                              ch0, M, L, scale, taps_unpadded);
+    break;
+  }
+  }
+}
+
+void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_pitch, int n,
+                     int ch0, int nch, cudaStream_t stream) {
+  dim3 grid((n + 255) / 256, nch);
+  k_convert_u8<<<grid, 256, 0, stream>>>(iq, iq_stride, x1, x1_pitch, n, ch0);
+}
+
+void launchCarryIq(uint8_t *hist, int *hist_valid, const uint8_t *iq, size_t iq_stride, long n_in,
+                   int ch0, int nch, cudaStream_t stream) {
+  k_carry_iq<<<nch, H_IQ, 0, stream>>>(reinterpret_cast<uchar2 *>(hist), hist_valid, iq, iq_stride,
+                                       n_in, ch0);
+}
+
+void launchCarryF32(float *buf, size_t pitch, int H, size_t n, int ch0, int nch,
+                    cudaStream_t stream) {
+  k_carry<float><<<nch, 512, 0, stream>>>(buf, pitch, H, n, ch0);
+}
+
+void launchCarryF2(float2 *buf, size_t pitch, int H, size_t n, int ch0, int nch,
+                   cudaStream_t stream) {
+  k_carry<float2><<<nch, 512, 0, stream>>>(buf, pitch, H, n, ch0);
+}
+
+void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size_t iq_stride,
+                   float2 *x2, size_t x2_pitch, DemodState *st, fmgpu_block_status *status,
+                   int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, float a1,
+                   cudaStream_t stream) {
+  k_dcblock<<<(nch + 31) / 32, 32, 0, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
+                                               status, status_pitch, nblk, blk_len, n_total, ch0,
+                                               nch, a1);
+}
+
+void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pitch,
+                   const float *chan_taps, const int *chan_lp, const float *chan_scale,
+                   const ChanParams *cp, int n_total, int ch0, int nch, cudaStream_t stream) {
+  constexpr int T = 1024;
+  const int tile_len = T + CHAN_TAPS_PITCH - 1 + 8;
+  const size_t smem = (size_t)(tile_len + (tile_len >> 3) + 2) * sizeof(float2);
+  dim3 grid((n_total + T - 1) / T, nch);
+  k_chanfir<<<grid, 128, smem, stream>>>(x2, x2_pitch, ybuf, y_pitch, chan_taps, chan_lp,
+                                         chan_scale, cp, n_total, ch0);
+}
+
+void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total,
+               int ch0, int nch, cudaStream_t stream) {
+  k_agc<<<(nch + 31) / 32, 32, 0, stream>>>(ybuf, y_pitch, st, cp, n_total, ch0, nch);
+}
+
+void launchFreqDem(const float2 *ybuf, size_t y_pitch, float *mpx, size_t mpx_pitch, int n_total,
+                   int ch0, int nch, float ref, cudaStream_t stream) {
+  dim3 grid((n_total + 255) / 256, nch);
+  k_freqdem<<<grid, 256, 0, stream>>>(ybuf, y_pitch, mpx, mpx_pitch, n_total, ch0, ref);
+}
+
+void launchFirReal(const FirRealJob &job, int nsig, int nch, const TapsParam &taps,
+                   cudaStream_t stream) {
+  constexpr int T = 1024;
+  const int tile_len = T + job.Lp - 1 + 8;
+  const size_t smem = (size_t)(tile_len + (tile_len >> 3) + 2) * sizeof(float);
+  dim3 grid((job.n_total + T - 1) / T, nch, nsig);
+  k_fir_real<<<grid, 128, smem, stream>>>(job, taps);
+}
+
+void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t pilot_pitch,
+                  float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
+                  fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
+                  int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+  k_stereo<<<(nch + 31) / 32, 32, 0, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
+                                              lr_pitch, st, cp, status, status_pitch, nblk, blk_len,
+                                              n_total, ch0, nch, k);
+}
+
+void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
+                   int nblk, int blk_len, int n_total, int ch0, int nch, uint32_t aud_step,
+                   uint32_t rds_step, int do_audio, int do_mono, int do_rds, cudaStream_t stream) {
+  k_prepare<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, status, status_pitch, nblk, blk_len,
+                                                  n_total, ch0, nch, aud_step, rds_step, do_audio,
+                                                  do_mono, do_rds);
+}
+
+void launchCommit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
+                  int do_rds, cudaStream_t stream) {
+  k_commit<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, ch0, nch, do_audio, do_mono, do_rds);
+}
+
+void launchResample(const float *in0, const float *in1, size_t in_pitch, int in_off,
+                    const float *hist, int hist_pitch, float *out, size_t acap, const float *bank,
+                    int sub_len, uint32_t step, const AudioState *au, int mono, int max_out,
+                    int ch0, int nch, cudaStream_t stream) {
+  if (max_out <= 0) {
+    return;
+  }
+  dim3 grid((max_out + 127) / 128, nch);
+  k_resample<<<grid, 128, 32 * sub_len * sizeof(float), stream>>>(
+      in0, in1, in_pitch, in_off, hist, hist_pitch, out, acap, bank, sub_len, step, au, mono, ch0);
+}
+
+void launchSaveTail(const float *src, size_t src_pitch, int src_off, float *hist, int hist_pitch,
+                    int H, long n, int ch0, int nch, cudaStream_t stream) {
+  k_save_tail<<<nch, 32, 0, stream>>>(src, src_pitch, src_off, hist, hist_pitch, H, n, ch0);
+}
+
+void launchAudioIir(float *audio, size_t acap, AudioState *au, const ChanParams *cp, int ch0,
+                    int nch, float dc_a1, int mono, int clamp, int mono_dup, cudaStream_t stream) {
+  const int lanes = mono ? nch : 2 * nch;
+  k_audio_iir<<<(lanes + 31) / 32, 32, 0, stream>>>(audio, acap, au, cp, ch0, nch, dc_a1, mono,
+                                                   clamp, mono_dup);
+}
+
+void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,
+                       uint32_t *n_groups, int ch0, int nch, int mono, uint32_t acap, uint32_t gcap,
+                       cudaStream_t stream) {
+  k_store_counts<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, n_audio, n_groups, ch0, nch, mono,
+                                                       acap, gcap);
+}
+
+void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
+               float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
+               fmgpu_rds_group *groups, uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap,
+               fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
+               int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+  k_rds<<<(nch + 31) / 32, 32, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, ring, bank, lpf,
+                                           mf, dmf, groups, gcap, bits_dbg, bits_cap, status,
+                                           status_pitch, nblk, blk_len, n_total, ch0, nch, k);
+}
+
+}  // namespace fmgpu

@@ -1,0 +1,79 @@
+// kernels.h — host-callable launchers of the engine's kernels (kernels.cu).
+#ifndef FMGPU_KERNELS_H_
+#define FMGPU_KERNELS_H_
+
+#include "engine.h"
+
+namespace fmgpu {
+
+struct FirRealJob {
+  const float *in[2];
+  float *out[2];
+  size_t in_pitch, out_pitch;
+  int in_off, out_off;
+  int n_total;
+  int Lp;
+  float scale;
+  int ch0;
+};
+
+cudaError_t initRdsTables();
+
+void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
+                 const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
+                 const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream);
+void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_pitch, int n,
+                     int ch0, int nch, cudaStream_t stream);
+void launchCarryIq(uint8_t *hist, int *hist_valid, const uint8_t *iq, size_t iq_stride, long n_in,
+                   int ch0, int nch, cudaStream_t stream);
+void launchCarryF32(float *buf, size_t pitch, int H, size_t n, int ch0, int nch,
+                    cudaStream_t stream);
+void launchCarryF2(float2 *buf, size_t pitch, int H, size_t n, int ch0, int nch,
+                   cudaStream_t stream);
+void launchSaveTail(const float *src, size_t src_pitch, int src_off, float *hist, int hist_pitch,
+                    int H, long n, int ch0, int nch, cudaStream_t stream);
+void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size_t iq_stride,
+                   float2 *x2, size_t x2_pitch, DemodState *st, fmgpu_block_status *status,
+                   int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, float a1,
+                   cudaStream_t stream);
+void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pitch,
+                   const float *chan_taps, const int *chan_lp, const float *chan_scale,
+                   const ChanParams *cp, int n_total, int ch0, int nch, cudaStream_t stream);
+void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total,
+               int ch0, int nch, cudaStream_t stream);
+void launchFreqDem(const float2 *ybuf, size_t y_pitch, float *mpx, size_t mpx_pitch, int n_total,
+                   int ch0, int nch, float ref, cudaStream_t stream);
+void launchFirReal(const FirRealJob &job, int nsig, int nch, const TapsParam &taps,
+                   cudaStream_t stream);
+void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t pilot_pitch,
+                  float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
+                  fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
+                  int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
+                   int nblk, int blk_len, int n_total, int ch0, int nch, uint32_t aud_step,
+                   uint32_t rds_step, int do_audio, int do_mono, int do_rds, cudaStream_t stream);
+void launchCommit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
+                  int do_rds, cudaStream_t stream);
+void launchResample(const float *in0, const float *in1, size_t in_pitch, int in_off,
+                    const float *hist, int hist_pitch, float *out, size_t acap, const float *bank,
+                    int sub_len, uint32_t step, const AudioState *au, int mono, int max_out,
+                    int ch0, int nch, cudaStream_t stream);
+void launchAudioIir(float *audio, size_t acap, AudioState *au, const ChanParams *cp, int ch0,
+                    int nch, float dc_a1, int mono, int clamp, int mono_dup, cudaStream_t stream);
+void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,
+                       uint32_t *n_groups, int ch0, int nch, int mono, uint32_t acap, uint32_t gcap,
+                       cudaStream_t stream);
+void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
+               float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
+               fmgpu_rds_group *groups, uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap,
+               fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
+               int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+
+// synth.cu
+cudaError_t launchSynth(const fmgpu_synth_params *params_dev, const int8_t *chips_dev,
+                        int chips_per_channel, int n_channels, double fs_iq, size_t n_samples,
+                        uint8_t *iq_dev, size_t iq_stride_bytes, cudaStream_t stream);
+
+}  // namespace fmgpu
+
+#endif  // FMGPU_KERNELS_H_

@@ -1,0 +1,201 @@
+// synth.cu — on-device synthetic FM-stereo + RDS multiplex generator (bench input).
+//
+// The reference has no signal generator. bench.py needs
+// thousands of distinct uint8 IQ channels resident in HBM without crossing PCIe, so
+// the multiplex of Appendix C is synthesised here, one lane per channel:
+//   m(t) = 0.43(L+R) + 0.43(L-R) sin(2wp t) + a_p sin(wp t) + a_r d(t) sin(3wp t)
+//   iq   = A exp(j 2 pi dev * integral(m)) + AWGN  -> round(127.5 + 127.5 x)
+// d(t): biphase RDS chips at 2375/s shaped by a root-raised-cosine (beta 0.8) table.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "kernels.h"
+
+namespace fmgpu {
+
+namespace {
+
+constexpr int kSpan = 4;   // pulse support +-4 chips
+constexpr int kOver = 64;  // table points per chip
+constexpr int kTable = 2 * kSpan * kOver + 2;
+
+__constant__ float c_rrc[kTable];
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+
+__global__ void k_synth(const fmgpu_synth_params *params, const int8_t *chips, int n_chips, int C,
+                        double fs, size_t n, uint8_t *iq, size_t stride) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) {
+    return;
+  }
+  const fmgpu_synth_params p = params[c];
+  const int8_t *ch = chips + (size_t)c * n_chips;
+  uchar2 *out = reinterpret_cast<uchar2 *>(iq + (size_t)c * stride);
+  const double dt = 1.0 / fs;
+  const double twoPi = 6.283185307179586;
+  const double wp = twoPi * 19000.0;
+  const float sigma =
+      (p.snr_db >= 200.0f) ? 0.0f : p.iq_amp * sqrtf(0.5f / exp10f(p.snr_db / 10.0f));
+  double phi = 0.0;
+  for (size_t kk = 0; kk < n; kk++) {
+    const double t = (double)kk * dt;
+    const float l = p.tone_l_amp * (float)sin(twoPi * p.tone_l_hz * t);
+    const float r = p.tone_r_amp * (float)sin(twoPi * p.tone_r_hz * t);
+    const double pt = wp * t;
+    float m = 0.43f * (l + r) + 0.43f * (l - r) * (float)sin(2.0 * pt) + p.pilot_amp * (float)sin(pt);
+    if (n_chips > 0 && p.rds_amp != 0.0f) {
+      const double u = t * 2375.0;
+      const long c0 = (long)floor(u);
+      const float fr0 = (float)(u - (double)c0);
+      float d = 0.0f;
+#pragma unroll
+      for (int j = -kSpan + 1; j <= kSpan; j++) {
+        const float z = fr0 - (float)j;  // in (-kSpan, kSpan]
+        const float pos = (z + (float)kSpan) * (float)kOver;
+        const int ip = (int)pos;
+        const float fr = pos - (float)ip;
+        const float pv = c_rrc[ip] * (1.0f - fr) + c_rrc[ip + 1] * fr;
+        long cm = (c0 + j) % n_chips;
+        if (cm < 0) {
+          cm += n_chips;
+        }
+        d += (float)ch[cm] * pv;
+      }
+      m += p.rds_amp * d * (float)sin(3.0 * pt);
+    }
+    phi += twoPi * (double)p.deviation_hz * (double)m * dt;
+    if (phi > 3.141592653589793) {
+      phi -= twoPi;
+    } else if (phi < -3.141592653589793) {
+      phi += twoPi;
+    }
+    float sn, cs;
+    sincosf((float)phi, &sn, &cs);
+    float xi = p.iq_amp * cs;
+    float xq = p.iq_amp * sn;
+    if (sigma > 0.0f) {
+      const uint32_t h1 = hash32((uint32_t)kk * 2654435761U ^ hash32(p.seed * 2u + 1u));
+      const uint32_t h2 = hash32(h1 ^ 0x9e3779b9U ^ (uint32_t)(kk >> 32));
+      const float u1 = ((float)(h1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float u2 = ((float)(h2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float s2, c2;
+      sincosf(6.2831853f * u2, &s2, &c2);
+      xi += sigma * rad * c2;
+      xq += sigma * rad * s2;
+    }
+    const float bi = fminf(255.0f, fmaxf(0.0f, rintf(127.5f + 127.5f * xi)));
+    const float bq = fminf(255.0f, fmaxf(0.0f, rintf(127.5f + 127.5f * xq)));
+    out[kk] = make_uchar2((unsigned char)bi, (unsigned char)bq);
+  }
+}
+
+double rrcHost(double z, double beta) {
+  if (std::fabs(z) < 1e-9) {
+    return 1.0 - beta + 4.0 * beta / M_PI;
+  }
+  const double g = 1.0 - 16.0 * beta * beta * z * z;
+  if (std::fabs(g) < 1e-9) {
+    return beta / std::sqrt(2.0) *
+           ((1.0 + 2.0 / M_PI) * std::sin(0.25 * M_PI / beta) +
+            (1.0 - 2.0 / M_PI) * std::cos(0.25 * M_PI / beta));
+  }
+  return (std::sin(M_PI * z * (1.0 - beta)) + 4.0 * beta * z * std::cos(M_PI * z * (1.0 + beta))) /
+         (M_PI * z * g);
+}
+
+// (26,16) RDS block: data || (crc10(data) ^ offset), g(x) = x^10+x^8+x^7+x^5+x^4+x^3+1
+uint32_t encodeBlock(uint16_t data, int offIdx) {
+  static const uint32_t offs[5] = {0x0FC, 0x198, 0x168, 0x350, 0x1B4};
+  uint32_t reg = static_cast<uint32_t>(data) << 10;
+  for (int i = 25; i >= 10; i--) {
+    if (reg & (1u << i)) {
+      reg ^= (0x5B9u << (i - 10));
+    }
+  }
+  return (static_cast<uint32_t>(data) << 10) | ((reg & 0x3FFu) ^ offs[offIdx]);
+}
+
+}  // namespace
+
+cudaError_t launchSynth(const fmgpu_synth_params *params_dev, const int8_t *chips_dev,
+                        int chips_per_channel, int n_channels, double fs_iq, size_t n_samples,
+                        uint8_t *iq_dev, size_t iq_stride_bytes, cudaStream_t stream) {
+  float tab[kTable];
+  for (int i = 0; i < kTable; i++) {
+    tab[i] = static_cast<float>(rrcHost(static_cast<double>(i) / kOver - kSpan, 0.8));
+  }
+  cudaError_t e = cudaMemcpyToSymbol(c_rrc, tab, sizeof(tab));
+  if (e != cudaSuccess) {
+    return e;
+  }
+  k_synth<<<(n_channels + 31) / 32, 32, 0, stream>>>(params_dev, chips_dev, chips_per_channel,
+                                                    n_channels, fs_iq, n_samples, iq_dev,
+                                                    iq_stride_bytes);
+  return cudaGetLastError();
+}
+
+}  // namespace fmgpu
+
+extern "C" int fmgpu_synth_iq(int device, const fmgpu_synth_params *params_host, int n_channels,
+                              double fs_iq, size_t n_samples, uint8_t *iq_dev,
+                              size_t iq_stride_bytes, void *stream) {
+  if (!params_host || n_channels < 1 || !iq_dev || iq_stride_bytes < 2 * n_samples) {
+    return FMGPU_EINVAL;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    return FMGPU_ENODEV;
+  }
+  // four 0A groups carrying PS "CHnnnn  " (nnnn = seed mod 10000)
+  constexpr int kBits = 4 * 104;
+  constexpr int kChips = 2 * kBits;
+  std::vector<int8_t> chips(static_cast<size_t>(n_channels) * kChips);
+  for (int c = 0; c < n_channels; c++) {
+    char ps[16];
+    std::snprintf(ps, sizeof(ps), "CH%04u  ", params_host[c].seed % 10000u);
+    int e = 0;
+    size_t w = static_cast<size_t>(c) * kChips;
+    for (int seg = 0; seg < 4; seg++) {
+      const uint16_t blocks[4] = {
+          params_host[c].pi,
+          static_cast<uint16_t>((10u << 5) | (1u << 3) | static_cast<unsigned>(seg)), 0xE0CD,
+          static_cast<uint16_t>((static_cast<unsigned char>(ps[2 * seg]) << 8) |
+                                static_cast<unsigned char>(ps[2 * seg + 1]))};
+      const int offIdx[4] = {0, 1, 2, 4};
+      for (int b = 0; b < 4; b++) {
+        const uint32_t word = fmgpu::encodeBlock(blocks[b], offIdx[b]);
+        for (int i = 25; i >= 0; i--) {
+          e ^= static_cast<int>((word >> i) & 1u);
+          chips[w++] = static_cast<int8_t>(e ? 1 : -1);
+          chips[w++] = static_cast<int8_t>(e ? -1 : 1);
+        }
+      }
+    }
+  }
+  fmgpu_synth_params *dp = nullptr;
+  int8_t *dc = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMalloc(&dp, n_channels * sizeof(fmgpu_synth_params)) != cudaSuccess ||
+      cudaMalloc(&dc, chips.size()) != cudaSuccess) {
+    cudaFree(dp);
+    return FMGPU_ENOMEM;
+  }
+  cudaMemcpyAsync(dp, params_host, n_channels * sizeof(fmgpu_synth_params), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dc, chips.data(), chips.size(), cudaMemcpyHostToDevice, s);
+  const cudaError_t err = fmgpu::launchSynth(dp, dc, kChips, n_channels, fs_iq, n_samples, iq_dev,
+                                             iq_stride_bytes, s);
+  cudaStreamSynchronize(s);
+  cudaFree(dp);
+  cudaFree(dc);
+  return err == cudaSuccess ? FMGPU_OK : FMGPU_ENODEV;
+}

@@ -1,0 +1,193 @@
+/* fmgpu.h — C ABI of the B200 channel-batched FM stereo + RDS engine.
+ *
+ * This is the drop-in boundary for the reference's IQ -> audio + RDS hot path
+ * (SURVEY.md §8(b)). Every entry point below replaces one method of the
+ * reference's block-processing classes; the C++ classes in
+ * fmtuner_sdr_b200/dropin/ (same names and signatures as the reference headers)
+ * are thin wrappers over these calls, so the reference's src/main.cpp compiles
+ * unchanged against them.
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross this boundary.
+ * Functions returning int return 0 on success and a negative FMGPU_E* code on
+ * failure (fmgpu_last_error gives the text). Functions mirroring a reference
+ * method that returns a sample count return that count and 0 for null / empty
+ * arguments, as the reference does (stereo_decoder.cpp:94-96,
+ * af_post_processor.cpp:50-53, rds_decoder.cpp:76-78, liquid_primitives.cpp:465-467).
+ * There is no CPU fallback: every call fails with FMGPU_ENODEV without a CUDA device.
+ */
+#ifndef FMGPU_H_
+#define FMGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMGPU_OK 0
+#define FMGPU_EINVAL (-1)  /* bad argument */
+#define FMGPU_ENODEV (-2)  /* no CUDA device / CUDA runtime error */
+#define FMGPU_ENOMEM (-3)  /* device allocation failed */
+#define FMGPU_ERANGE (-4)  /* a caller-supplied capacity is too small */
+
+typedef struct fmgpu_engine fmgpu_engine;
+
+/* Parameters the reference takes from its constructors and config keys
+ * (processing.* and tuner.deemphasis; src/main.cpp:640-710). */
+typedef struct fmgpu_config {
+  int32_t iq_rate;         /* IQ sample rate in: 256000|1024000|2048000 (main.cpp:391-396) or 240000|2400000 */
+  int32_t decimation;      /* ComplexDecimator factor: 1, 4, 8 (main.cpp:670-674) or 10 */
+  int32_t output_rate;     /* audio rate, 32000 (main.cpp OUTPUT_RATE) */
+  int32_t block_samples;   /* processing.dsp_block_samples at the DSP rate, 1024..32768 (default 8192) */
+  int32_t max_blocks;      /* logical blocks accepted per fmgpu_process_* call (>= 1) */
+  int32_t w0_bandwidth_hz; /* processing.w0_bandwidth_hz (default 194000) */
+  int32_t bandwidth_hz;    /* initial FMDemod::setBandwidthHz argument (0 => W0), main.cpp:710 */
+  int32_t dsp_agc;         /* FMDemod::DspAgcMode: 0 off, 1 fast, 2 slow */
+  int32_t stereo_blend;    /* StereoDecoder::BlendMode: 0 soft, 1 normal, 2 aggressive */
+  int32_t deemphasis;      /* tuner.deemphasis: 0 = 50 us, 1 = 75 us, 2 = off (include/config.h:37) */
+  int32_t stereo;          /* processing.stereo (0 => mono path, main.cpp:1266-1279) */
+  int32_t force_mono;      /* StereoDecoder::setForceMono */
+} fmgpu_config;
+
+/* RDSGroup (include/rds_decoder.h:9-15) plus the logical block that emitted it. */
+typedef struct fmgpu_rds_group {
+  uint16_t a, b, c, d;
+  uint8_t errors; /* A<<6|B<<4|C<<2|D ; 0 clean, 1 corrected/had errors, 3 missing (rds_decoder.cpp:29-41) */
+  uint8_t pad[3];
+  uint32_t block_index;
+} fmgpu_rds_group;
+
+/* Per logical block observables the caller reads after each block
+ * (main.cpp:1294-1303: isStereo, getPilotLevelTenthsKHz; fm_demod.h:35-36). */
+typedef struct fmgpu_block_status {
+  int32_t n_audio;      /* 32 kHz frames produced by this block */
+  int32_t stereo;       /* StereoDecoder::isStereo() after the block */
+  int32_t pilot_tenths; /* StereoDecoder::getPilotLevelTenthsKHz() */
+  float clip_ratio;     /* FMDemod::getClippingRatio() */
+  int32_t n_groups;     /* RDS groups emitted during this block */
+} fmgpu_block_status;
+
+#define FMGPU_RESET_DECIM 1u  /* ComplexDecimator::reset  liquid_primitives.cpp:405-420 */
+#define FMGPU_RESET_DEMOD 2u  /* FMDemod::reset           fm_demod.cpp:73-88 */
+#define FMGPU_RESET_STEREO 4u /* StereoDecoder::reset     stereo_decoder.cpp:67-86 */
+#define FMGPU_RESET_AFPOST 8u /* AFPostProcessor::reset   af_post_processor.cpp:20-29 */
+#define FMGPU_RESET_RDS 16u   /* RDSDecoder::reset        rds_decoder.cpp:23-27 */
+#define FMGPU_RESET_DSP 15u   /* the dspRuntime reset handler, main.cpp:686-691 */
+#define FMGPU_RESET_ALL 31u
+
+/* ---- lifetime ------------------------------------------------------------ */
+/* Replaces the constructors at main.cpp:640-674,895. n_channels independent
+ * channels share one configuration; per-channel settings can be changed below. */
+int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmgpu_engine **out);
+void fmgpu_engine_destroy(fmgpu_engine *e);
+const char *fmgpu_last_error(const fmgpu_engine *e); /* e may be NULL: last creation error */
+int fmgpu_n_channels(const fmgpu_engine *e);
+int fmgpu_dsp_rate(const fmgpu_engine *e); /* iq_rate / decimation */
+
+/* ---- per-channel settings; channel = -1 applies to every channel ---------- */
+int fmgpu_set_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz);   /* FMDemod::setBandwidthHz   fm_demod.cpp:99-135 */
+int fmgpu_set_bandwidth_mode(fmgpu_engine *e, int channel, int mode);  /* FMDemod::setBandwidthMode fm_demod.cpp:90-97 */
+int fmgpu_set_w0_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz);/* FMDemod::setW0BandwidthHz fm_demod.cpp:137-139 */
+int fmgpu_set_agc_mode(fmgpu_engine *e, int channel, int mode);        /* FMDemod::setDspAgcMode    fm_demod.cpp:141-148 */
+int fmgpu_set_deemphasis_us(fmgpu_engine *e, int channel, int tau_us); /* FMDemod/AFPostProcessor::setDeemphasis */
+int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode);      /* StereoDecoder::setBlendMode */
+int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on);        /* StereoDecoder::setForceMono */
+int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on);      /* StereoDecoder::setForceStereo */
+int fmgpu_reset(fmgpu_engine *e, int channel, unsigned what_mask);     /* the reset() methods, see FMGPU_RESET_* */
+
+/* ---- observables ------------------------------------------------------------ */
+int fmgpu_is_stereo(fmgpu_engine *e, int channel);       /* StereoDecoder::isStereo */
+int fmgpu_pilot_tenths(fmgpu_engine *e, int channel);    /* StereoDecoder::getPilotLevelTenthsKHz */
+float fmgpu_clip_ratio(fmgpu_engine *e, int channel);    /* FMDemod::getClippingRatio */
+int fmgpu_is_clipping(fmgpu_engine *e, int channel);     /* FMDemod::isClipping */
+
+/* ---- batched whole-pipeline path (the per-block body of main.cpp:1232-1308) ----
+ * All channels, n_blocks logical blocks each. Device pointers, asynchronous on
+ * `stream` (a cudaStream_t, may be NULL for the default stream).
+ *   iq_dev      [C][iq_stride_bytes] uint8 I,Q pairs; each channel holds
+ *               n_blocks*block_samples*decimation pairs; base and stride 16-byte aligned
+ *   audio_dev   [C][2][audio_cap] float, left row then right row, clamped to +-1
+ *   n_audio_dev [C] frames written per channel
+ *   groups_dev  [C][group_cap], n_groups_dev [C]
+ *   status_dev  [C][n_blocks]
+ * Any output pointer may be NULL to skip that output. */
+int fmgpu_process_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
+                        int n_blocks, float *audio_dev, size_t audio_cap, uint32_t *n_audio_dev,
+                        fmgpu_rds_group *groups_dev, size_t group_cap, uint32_t *n_groups_dev,
+                        fmgpu_block_status *status_dev, void *stream);
+
+/* Same work with HOST buffers: copies the IQ bytes host->device, runs the batch,
+ * copies audio / groups / status back and synchronises. Layouts as above. */
+int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_bytes,
+                       int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
+                       fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
+                       fmgpu_block_status *status_host);
+
+/* ---- stage-level entry points, one per reference method; HOST buffers, synchronous ----
+ * They run the same kernels as the batch path on one channel's state. */
+/* ComplexDecimator::executeComplex  liquid_primitives.cpp:461-499 ; out = interleaved re,im */
+size_t fmgpu_decimate(fmgpu_engine *e, int channel, const uint8_t *iq, size_t in_samples,
+                      float *out_cf32, size_t out_capacity);
+/* FMDemod::processSplit (uint8 IQ at the DSP rate)  fm_demod.cpp:245-259 */
+size_t fmgpu_demod_u8(fmgpu_engine *e, int channel, const uint8_t *iq, float *mpx_out,
+                      float *mono_out, size_t n);
+/* FMDemod::processSplitComplex  fm_demod.cpp:261-274 */
+size_t fmgpu_demod_cf32(fmgpu_engine *e, int channel, const float *iq_cf32, float *mpx_out,
+                        float *mono_out, size_t n);
+/* StereoDecoder::processAudio  stereo_decoder.cpp:92-286 */
+size_t fmgpu_stereo(fmgpu_engine *e, int channel, const float *mpx, float *left, float *right,
+                    size_t n);
+/* AFPostProcessor::process  af_post_processor.cpp:47-78 */
+size_t fmgpu_afpost(fmgpu_engine *e, int channel, const float *in_left, const float *in_right,
+                    size_t n, float *out_left, float *out_right, size_t out_capacity);
+/* RDSDecoder::process  rds_decoder.cpp:74-93 ; returns the number of groups (written up to cap) */
+size_t fmgpu_rds(fmgpu_engine *e, int channel, const float *mpx, size_t n, fmgpu_rds_group *out,
+                 size_t cap);
+
+/* ---- introspection used by tests/ ---------------------------------------------- */
+/* Filter designs the engine computed for itself (compared against the oracle's).
+ * which: 0 decimator taps, 1 channel filter of `channel`, 2 pilot band-pass,
+ * 3 audio low-pass, 4 audio resampler bank [32][24], 5 RDS low-pass,
+ * 6 symsync MF bank, 7 symsync dMF bank, 8 RDS resampler bank [32][26].
+ * *scale receives the filter's output scale (which 4/8: the phase step). */
+size_t fmgpu_get_design(fmgpu_engine *e, int which, int channel, float *out, size_t cap,
+                        float *scale);
+/* The same designs computed WITHOUT a device or an engine (host only): `which` as above,
+ * with 1 = the channel filter FMDemod(cfg rate) holds after setW0BandwidthHz(cfg->w0_bandwidth_hz)
+ * and setBandwidthHz(bw_hz). */
+size_t fmgpu_design_host(const fmgpu_config *cfg, int which, int bw_hz, float *out, size_t cap,
+                         float *scale);
+/* Intermediate device buffers of the last fmgpu_process_* call, copied to the host:
+ * which: 0 decimated cf32 (2 floats/sample), 1 MPX, 2 stereo left at the DSP rate,
+ * 3 stereo right, 4 pilot band-pass output. Returns floats written. */
+size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, size_t cap);
+/* Every RDS bit demodulated by `channel` during the last call (before block sync). */
+size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t cap);
+/* Number of kernels this engine has launched so far. */
+uint64_t fmgpu_launch_count(const fmgpu_engine *e);
+/* Device time (ms) spent per pipeline stage during the last fmgpu_process_batch when
+ * stage timing was enabled with fmgpu_enable_stage_timing; names[i] are static strings. */
+int fmgpu_enable_stage_timing(fmgpu_engine *e, int on);
+int fmgpu_get_stage_times(fmgpu_engine *e, const char **names, float *ms, int cap);
+
+/* ---- on-device synthetic multiplex generator (bench.py input) ---- */
+typedef struct fmgpu_synth_params {
+  float deviation_hz;   /* 22500..75000 */
+  float tone_l_hz, tone_l_amp, tone_r_hz, tone_r_amp;
+  float pilot_amp, rds_amp, iq_amp;
+  float snr_db;         /* >= 200 => no noise */
+  uint32_t seed;
+  uint16_t pi;          /* RDS PI; PS is "CHnnnn  " from the low 16 bits of seed */
+  uint16_t pad;
+} fmgpu_synth_params;
+/* params_host [C]; writes n_samples IQ pairs per channel into iq_dev [C][iq_stride_bytes]. */
+int fmgpu_synth_iq(int device, const fmgpu_synth_params *params_host, int n_channels,
+                   double fs_iq, size_t n_samples, uint8_t *iq_dev, size_t iq_stride_bytes,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FMGPU_H_ */
