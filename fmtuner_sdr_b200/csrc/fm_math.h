@@ -12,7 +12,7 @@
 //
 // Accuracy (measured in tests/test_fm_math.py against libm in float64):
 //   fm_sincosf  |x| <= 16     : <= 2 ulp      (Cody-Waite pi/2 3-term + Cephes minimax)
-//   fm_atan2f                 : <= 3 ulp      (Cephes atanf on min/max quotient)
+//   fm_atan2f                 : <= 4 ulp      (Cephes atanf on min/max quotient)
 //   fm_expf     |x| <= 87     : <= 2 ulp
 //   fm_logf     x normal > 0  : <= 2 ulp
 #ifndef FMGPU_FM_MATH_H_

@@ -1,0 +1,122 @@
+"""The CPU oracle against (1) its committed golden fixtures, (2) physics-level expectations
+for the synthetic multiplex and (3) itself across the two
+transcendental flavours (libm — faithful to the reference call sites — vs fm_math, the
+flavour the engine is compared with bit for bit)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from tests.common import groups_equal, rates, snr_db
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,rate", [("config1_240k", "240k"), ("config1_256k", "256k")])
+def test_golden_fixture(orc_fm, name, rate):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    iq_rate, decim = rates(rate)
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(12 * 8192 * decim)
+    assert np.array_equal(iq[:64], g["iq_head"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8),
+                          g["iq_sha256"])
+    ch = orc.Channel(orc_fm, orc.make_config(iq_rate=iq_rate, decimation=decim))
+    r = ch.process(iq, debug=True)
+    assert np.array_equal(r.left, g["left"]) and np.array_equal(r.right, g["right"])
+    assert np.array_equal(r.mpx[::64], g["mpx_every64"])
+    assert np.array_equal(r.status, g["status"])
+    assert groups_equal(r.groups, g["groups"])
+    assert np.array_equal(ch.rds_bits(), g["rds_bits"])
+
+
+@pytest.fixture(scope="module")
+def config1(orc_libm):
+    iq_rate, decim = rates("240k")
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(40 * 8192 * decim)
+    ch = orc.Channel(orc_libm, orc.make_config(iq_rate=iq_rate, decimation=decim))
+    return iq, ch.process(iq, debug=True)
+
+
+def test_mpx_scale_and_pilot_lock(config1):
+    _, r = config1
+    # +-75 kHz deviation <-> MPX +-1: the composite peaks at 0.43+0.43+0.10+0.04 ~ 1
+    assert 0.85 < np.abs(r.mpx[20000:]).max() < 1.05
+    # stereo flag needs 6 good blocks (stereo_decoder.cpp:6,263-270): lock at block 6..8
+    first = int(np.flatnonzero(r.status["stereo"])[0])
+    assert 6 <= first <= 8
+    assert r.status["stereo"][first:].all()
+    assert (r.status["n_audio"].sum() == r.left.size) and abs(r.left.size - 40 * 8192 * 32000 / 240000) < 2
+    assert (np.diff(r.status["pilot_tenths"][first:]) >= -1).all()   # settles monotonically
+
+
+def test_left_only_tone_separation(config1):
+    _, r = config1
+    l, rr = r.left[-16000:], r.right[-16000:]
+    sep_db = 20 * np.log10(np.sqrt((l ** 2).mean()) / np.sqrt((rr ** 2).mean()))
+    assert sep_db > 20.0        # Appendix B.2: finite separation from the (N-1)/2 + 1 delay
+    spec = np.abs(np.fft.rfft(l * np.hanning(l.size)))
+    assert abs(np.argmax(spec) * 32000 / l.size - 1000.0) < 4.0
+
+
+def test_rds_payload_decodes(config1):
+    _, r = config1
+    assert len(r.groups) >= 10
+    assert orc.decode_ps_rt(r.groups) == (0x1234, "B200TEST", "FM ON B200")
+    assert (r.groups["errors"][1:] == 0).all()
+
+
+def test_deemphasis_corner(orc_libm):
+    # 50 us: alpha = dt/(tau+dt) at 32 kHz = 0.384615; 10 kHz tone ~ -9.6 dB vs 400 Hz
+    amp = {}
+    for f in (400.0, 10000.0):
+        sig = orc.Signal(fs_iq=2_400_000, tone_l_hz=f, tone_l_amp=0.5, tone_r_hz=f, tone_r_amp=0.5,
+                         rds_amp=0.0)
+        iq = sig.generate(14 * 81920)
+        r = orc.Channel(orc_libm, orc.make_config()).process(iq)
+        amp[f] = np.sqrt((r.left[-8000:] ** 2).mean())
+    ratio_db = 20 * np.log10(amp[10000.0] / amp[400.0])
+    assert -12.0 < ratio_db < -8.0
+
+
+@pytest.mark.parametrize("rate", ["240k", "256k"])
+def test_libm_and_fm_flavours_agree(orc_libm, orc_fm, rate):
+    """The only deviation of the engine-comparable oracle from the libm-faithful one is the
+    transcendental kernels; end to end that costs < 1e-4 of full scale and no RDS bit."""
+    iq_rate, decim = rates(rate)
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(24 * 8192 * decim)
+    a = orc.Channel(orc_libm, orc.make_config(iq_rate=iq_rate, decimation=decim))
+    b = orc.Channel(orc_fm, orc.make_config(iq_rate=iq_rate, decimation=decim))
+    ra, rb = a.process(iq, debug=True), b.process(iq, debug=True)
+    assert np.abs(ra.mpx - rb.mpx).max() < 2e-6
+    assert np.abs(ra.left - rb.left).max() < 1e-4 and np.abs(ra.right - rb.right).max() < 1e-4
+    assert snr_db(ra.left[8000:], rb.left[8000:]) > 90.0
+    assert np.array_equal(ra.status["stereo"], rb.status["stereo"])
+    assert np.abs(ra.status["pilot_tenths"] - rb.status["pilot_tenths"]).max() <= 1
+    assert np.array_equal(a.rds_bits(), b.rds_bits())
+    assert groups_equal(ra.groups, rb.groups)
+
+
+def test_block_boundaries_are_the_callers(orc_fm):
+    """Appendix B.12: results depend on the logical block length only through the per-block
+    stereo logic; FIR / IIR / RDS outputs do not depend on how the stream is cut."""
+    iq_rate, decim = rates("240k")
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(8 * 8192 * decim)
+    a = orc.Channel(orc_fm, orc.make_config(block_samples=8192)).process(iq, debug=True)
+    b = orc.Channel(orc_fm, orc.make_config(block_samples=4096)).process(iq, debug=True)
+    assert np.array_equal(a.mpx, b.mpx)
+    assert np.array_equal(a.groups[["a", "b", "c", "d", "errors"]], b.groups[["a", "b", "c", "d", "errors"]])
+
+
+def test_empty_and_null_arguments(orc_libm):
+    L = orc_libm.lib
+    d = L.orc_decim_create(8, 28, 80.0)
+    assert L.orc_decim_execute_complex(d, None, 0, None, 0) == 0
+    L.orc_decim_destroy(d)
+    s = L.orc_stereo_create(256000)
+    assert L.orc_stereo_process(s, None, None, None, 0) == 0
+    L.orc_stereo_destroy(s)
+    a = L.orc_afpost_create(256000, 32000)
+    assert L.orc_afpost_process(a, None, None, 0, None, None, 0) == 0
+    L.orc_afpost_destroy(a)
