@@ -84,6 +84,8 @@ struct fmgpu_engine {
   uint8_t *dBits = nullptr;
   size_t x2Pitch = 0, yPitch = 0, mpxPitch = 0, lrPitch = 0, lfPitch = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // the RDS branch runs beside the stereo branch
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
 
   int lastN = 0;  // DSP-rate samples of the last call (debug reads)
   uint64_t launches = 0;
@@ -318,7 +320,7 @@ void stageDemod(fmgpu_engine *e, const uint8_t *iq_u8, size_t stride, fmgpu_bloc
   {
     Span sp(e, "freqdem", s);
     launchFreqDem(e->dY, e->yPitch, e->dMpx, e->mpxPitch, n, ch0, nch, e->k.fd_ref, s);
-    launchCarryF2(e->dY, e->yPitch, 1, n, ch0, nch, s);
+    launchCarryF2(e->dY, e->yPitch, Y_OFF, n, ch0, nch, s);  // slot Y_OFF-1 <- last output
     launchCarryF2(e->dX2, e->x2Pitch, H_X2, n, ch0, nch, s);
   }
   e->launches += 5;
@@ -403,7 +405,7 @@ void stageRds(fmgpu_engine *e, fmgpu_rds_group *groups, uint32_t gcap, fmgpu_blo
   launchRds(e->dMpx, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
             e->dMf, e->dDmf, groups, gcap, e->dBits, static_cast<uint32_t>(e->bitsCap), status, nblk,
             nblk, blk_len, n, ch0, nch, e->k, s);
-  launchSaveTail(e->dMpx, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_RS_LEN - 1, n, ch0, nch, s);
+  launchSaveTail(e->dMpx, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, n, ch0, nch, s);
   e->launches += 2;
 }
 
@@ -478,7 +480,12 @@ int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks
   } else {
     stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, 0, C, s);
   }
-  stageRds(e, groups, gcap, status, n_blocks, e->N, n, 0, C, s);
+  // MPX is complete: the RDS branch (reads MPX data + its own window) runs on a second
+  // stream beside the stereo/audio branch; both only read the MPX data region.
+  cudaEventRecord(e->evFork, s);
+  cudaStreamWaitEvent(e->stream2, e->evFork, 0);
+  stageRds(e, groups, gcap, status, n_blocks, e->N, n, 0, C, e->stream2);
+  cudaEventRecord(e->evJoin, e->stream2);
   if (stereo) {
     stageStereo(e, status, n_blocks, e->N, n, 0, C, s);
     stageAfPost(e, n, 1, 0, C, s);
@@ -487,6 +494,7 @@ int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks
     launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, 0, C, s);
     e->launches += 1;
   }
+  cudaStreamWaitEvent(s, e->evJoin, 0);
   {
     Span sp(e, "commit", s);
     launchStoreCounts(e->dAudioSt, e->dRds, n_audio_dev ? n_audio_dev : e->dNAudio,
@@ -689,6 +697,9 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   e->gcap = e->nmax * 12 / static_cast<size_t>(std::max(1, e->fs)) + 8;  // 11.4 groups/s
   e->bitsCap = e->nmax / 100 + 64;
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   CKC(initRdsTables());
   CKC(devAlloc(&e->dIq, C * e->iqPitch));
   CKC(devAlloc(&e->dHistIq, C * 2 * H_IQ));
@@ -792,6 +803,16 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
   }
   if (e->stream) {
     cudaStreamDestroy(e->stream);
+  }
+  if (e->stream2) {
+    cudaStreamSynchronize(e->stream2);
+    cudaStreamDestroy(e->stream2);
+  }
+  if (e->evFork) {
+    cudaEventDestroy(e->evFork);
+  }
+  if (e->evJoin) {
+    cudaEventDestroy(e->evJoin);
   }
   delete e;
 }
@@ -932,7 +953,7 @@ int fmgpu_reset(fmgpu_engine *e, int channel, unsigned what) {
   if (what & FMGPU_RESET_DEMOD) {
     // fm_demod.cpp:73-88
     zeroPrefix(e->dX2, e->x2Pitch, H_X2, lo, hi, s);
-    zeroPrefix(e->dY, e->yPitch, 1, lo, hi, s);
+    zeroPrefix(e->dY, e->yPitch, Y_OFF, lo, hi, s);
     zeroPrefix(e->dMonoHist, 32, 32, lo, hi, s);
     std::vector<DemodState> d(cnt, defaultDemod());
     CK(cudaMemcpyAsync(e->dDemod + lo, d.data(), cnt * sizeof(DemodState), cudaMemcpyHostToDevice, s));
@@ -1039,7 +1060,7 @@ int fmgpu_process_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream
   const int rc = runBatch(e, iq_dev, iq_stride_bytes, n_blocks, audio_dev, audio_cap, n_audio_dev,
                           groups_dev, group_cap, n_groups_dev, status_dev, s);
   if (rc == FMGPU_OK && e->timing) {

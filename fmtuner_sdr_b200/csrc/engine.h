@@ -39,6 +39,8 @@ constexpr int RDS_RING = 256;
 constexpr int SS_LEN = 18;   // symsync sub-filter length
 constexpr int RDS_RS_LEN = 26;
 constexpr int AUD_RS_LEN = 24;
+constexpr int RDS_HIST = 28;  // RDS resampler window history kept per channel (>= 25, multiple of 4)
+constexpr int Y_OFF = 2;      // ybuf: data starts at float2 index 2 (16-byte aligned), r_prev at 1
 
 struct TapsParam {  // passed by value: lives in the kernel-parameter constant bank
   float h[MAX_TAPS];

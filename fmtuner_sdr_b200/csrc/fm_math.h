@@ -98,24 +98,12 @@ FM_HD void fm_sincosf(float x, float *s, float *c) {
   float pc = FM_FMA(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
   pc = FM_FMA(pc, z, 4.166664568298827e-2f);
   const float cr = FM_FMA(FM_MUL(pc, z), z, FM_FMA(z, -0.5f, 1.0f));
-  switch (k & 3) {
-  case 0:
-    *s = sr;
-    *c = cr;
-    break;
-  case 1:
-    *s = cr;
-    *c = -sr;
-    break;
-  case 2:
-    *s = -sr;
-    *c = -cr;
-    break;
-  default:
-    *s = -cr;
-    *c = sr;
-    break;
-  }
+  // quadrant selection without branches (lanes of a warp sit in different quadrants)
+  const bool swap = (k & 1) != 0;
+  const float s0 = swap ? cr : sr;
+  const float c0 = swap ? sr : cr;
+  *s = (k & 2) ? -s0 : s0;
+  *c = ((k + 1) & 2) ? -c0 : c0;
 }
 
 FM_HD float fm_sinf(float x) {

@@ -78,12 +78,13 @@ cudaError_t initRdsTables() {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ncoConstrainDev(float theta) {
   const float p = (float)((double)theta * 0.159154943091895);
-  float fpart = p - (float)((long long)p);
+  float fpart = p - truncf(p);  // == p - (float)(long)p for every |p| < 2^63
   if (fpart < 0.0f) {
     fpart = fpart + 1.0f;
   }
-  const float scaled = fpart * 4294967296.0f;
-  return (uint32_t)((unsigned long long)scaled);
+  const float scaled = fpart * 4294967296.0f;  // in [0, 2^32]
+  // (uint32_t)(uint64_t)scaled: 2^32 wraps to 0, everything else fits 32 bits
+  return (scaled >= 4294967296.0f) ? 0u : __float2uint_rz(scaled);
 }
 
 __device__ __forceinline__ float ncoPhaseDev(uint32_t theta) {
@@ -100,6 +101,57 @@ __device__ __forceinline__ float unwrapDev(float p) {
     return p + k2Pi;
   }
   return p;
+}
+
+// ---------------------------------------------------------------------------
+// warp tiles for the lane kernels. A lane kernel walks one channel per lane, so a
+// warp touches 32 rows of a [C][time] buffer at once; reading them lane-by-lane is
+// 32 cache lines per instruction. Instead the warp moves a [32 rows][LT samples]
+// tile between global and shared memory cooperatively (each instruction covers 128
+// contiguous bytes of ONE row; loads are cp.async so the next tile streams in while
+// the current one is processed) and every lane then reads its own row from shared
+// memory. Row pitches are multiples of 4 floats so rows move as 16-byte transfers; the
+// 4-way bank conflict that costs a lane kernel is noise next to its dependent-issue latency.
+// ---------------------------------------------------------------------------
+constexpr int LT = 64;  // samples per tile row
+
+__device__ __forceinline__ void cpAsync16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem)),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// tile[r][k] <- base[(c0 + r) * pitch + start + k],  r < nrows, k < len, as 16-byte
+// cp.async transfers: start, pitch and the row pitch TP are multiples of 4 floats; len is
+// rounded up to 4 (the over-read stays inside the row's padding). One warp.
+template <int TP>
+__device__ __forceinline__ void tileLoadAsync(float *tile, const float *base, size_t pitch, int c0,
+                                              int nrows, long start, int len, int lane) {
+  const int cpr = (len + 3) >> 2;  // 16-byte chunks per row
+  const int total = nrows * cpr;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / cpr;
+    const int q = idx - r * cpr;
+    cpAsync16(tile + r * TP + 4 * q, base + (size_t)(c0 + r) * pitch + start + 4 * q);
+  }
+}
+
+template <int TP>
+__device__ __forceinline__ void tileStore(const float *tile, float *base, size_t pitch, int c0,
+                                          int nrows, long start, int len, int lane) {
+  const int cpr = (len + 3) >> 2;
+  const int total = nrows * cpr;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / cpr;
+    const int q = idx - r * cpr;
+    const float4 v = *reinterpret_cast<const float4 *>(tile + r * TP + 4 * q);
+    *reinterpret_cast<float4 *>(base + (size_t)(c0 + r) * pitch + start + 4 * q) = v;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -305,59 +357,117 @@ __global__ void k_convert_u8(const uint8_t *__restrict__ iq, size_t iq_stride,
 // S1: I/Q DC blockers (iirfilt dc_blocker, alpha = 0.0005) + clip statistics.
 // One lane per channel; fm_demod.cpp:150-208.
 // ---------------------------------------------------------------------------
-__global__ void k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch,
-                          const uint8_t *__restrict__ iq_u8, size_t iq_stride,
-                          float2 *__restrict__ x2, size_t x2_pitch, DemodState *st,
-                          fmgpu_block_status *status, int status_pitch, int nblk, int blk_len,
-                          int n_total, int ch0, int nch, float a1) {
-  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= nch) {
-    return;
+__global__ void __launch_bounds__(64)
+k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restrict__ iq_u8,
+          size_t iq_stride, float2 *__restrict__ x2, size_t x2_pitch, DemodState *st,
+          fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total, int ch0,
+          int nch, float a1) {
+  // warp 0 moves tiles (global <-> shared), warp 1 runs the recursions: one lane per channel
+  constexpr int TP = 2 * LT + 4;  // interleaved re,im; 16-byte aligned rows
+  extern __shared__ float sm_dc[];
+  float *tin[2] = {sm_dc, sm_dc + 32 * TP};
+  float *tout[2] = {sm_dc + 2 * 32 * TP, sm_dc + 3 * 32 * TP};
+  const int lane = threadIdx.x & 31;
+  const bool io = threadIdx.x < 32;
+  const int c0 = ch0 + blockIdx.x * 32;
+  const int nrows = min(32, ch0 + nch - c0);
+  const bool active = !io && lane < nrows;
+  const int c = c0 + min(lane, nrows - 1);
+  DemodState s{};
+  if (active) {
+    s = st[c];
   }
-  const int c = ch0 + lane;
-  DemodState s = st[c];
   float vi = s.dc_i, vq = s.dc_q;
-  const float2 *in = x1 ? x1 + (size_t)c * x1_pitch : nullptr;
-  const uchar2 *inb = iq_u8 ? reinterpret_cast<const uchar2 *>(iq_u8 + (size_t)c * iq_stride) : nullptr;
-  float2 *out = x2 + (size_t)c * x2_pitch + H_X2;
-  for (int b = 0; b < nblk; b++) {
-    const int beg = b * blk_len;
-    const int len = min(blk_len, n_total - beg);
-    int clip = 0;
-    for (int i = 0; i < len; i++) {
-      float ir, qr;
-      if (inb) {
-        const uchar2 v = inb[beg + i];
-        if (v.x == 0 || v.x == 255 || v.y == 0 || v.y == 255) {
-          clip++;
+  const uchar2 *inb =
+      (iq_u8 && active) ? reinterpret_cast<const uchar2 *>(iq_u8 + (size_t)c * iq_stride) : nullptr;
+  const float *x1f = reinterpret_cast<const float *>(x1);
+  float *x2f = reinterpret_cast<float *>(x2);
+  const int nchunks = (n_total + LT - 1) / LT;
+  if (io && !iq_u8) {
+    tileLoadAsync<TP>(tin[0], x1f, 2 * x1_pitch, c0, nrows, 0, 2 * min(LT, n_total), lane);
+    cpAsyncCommit();
+    cpAsyncWait<0>();
+  }
+  __syncthreads();
+  int b = 0, in_blk = 0, clip = 0;
+  int cur_len = min(blk_len, n_total);
+  for (int ck = 0; ck < nchunks; ck++) {
+    const int n0 = ck * LT;
+    const int len = min(LT, n_total - n0);
+    if (io) {
+      if (!iq_u8 && ck + 1 < nchunks) {
+        tileLoadAsync<TP>(tin[(ck + 1) & 1], x1f, 2 * x1_pitch, c0, nrows, 2L * (n0 + LT),
+                          2 * min(LT, n_total - n0 - LT), lane);
+        cpAsyncCommit();
+      }
+      if (ck > 0) {
+        tileStore<TP>(tout[(ck - 1) & 1], x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0 - LT),
+                      2 * LT, lane);
+      }
+      cpAsyncWait<0>();
+    } else if (active) {
+      const float *ti = tin[ck & 1] + lane * TP;
+      float *to = tout[ck & 1] + lane * TP;
+      int i = 0;
+      while (i < len) {
+        const int run = min(len - i, cur_len - in_blk);
+        if (inb) {
+          for (int j = 0; j < run; j++, i++) {
+            const uchar2 v = inb[n0 + i];
+            if (v.x == 0 || v.x == 255 || v.y == 0 || v.y == 255) {
+              clip++;
+            }
+            const float ir = ((float)v.x - 127.0f) / 127.5f;
+            const float qr = ((float)v.y - 127.0f) / 127.5f;
+            const float v0i = ir - (a1 * vi);
+            to[2 * i] = v0i - vi;
+            vi = v0i;
+            const float v0q = qr - (a1 * vq);
+            to[2 * i + 1] = v0q - vq;
+            vq = v0q;
+          }
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < run; j++, i++) {
+            const float ir = ti[2 * i];
+            const float qr = ti[2 * i + 1];
+            if (fabsf(ir) >= 0.995f || fabsf(qr) >= 0.995f) {
+              clip++;
+            }
+            const float v0i = ir - (a1 * vi);
+            to[2 * i] = v0i - vi;
+            vi = v0i;
+            const float v0q = qr - (a1 * vq);
+            to[2 * i + 1] = v0q - vq;
+            vq = v0q;
+          }
         }
-        ir = ((float)v.x - 127.0f) / 127.5f;
-        qr = ((float)v.y - 127.0f) / 127.5f;
-      } else {
-        const float2 v = in[beg + i];
-        ir = v.x;
-        qr = v.y;
-        if (fabsf(ir) >= 0.995f || fabsf(qr) >= 0.995f) {
-          clip++;
+        in_blk += run;
+        if (in_blk == cur_len) {
+          s.clipping = (clip > 0) ? 1 : 0;
+          s.clip_ratio = (float)clip / (float)cur_len;
+          if (status) {
+            status[(size_t)c * status_pitch + b].clip_ratio = s.clip_ratio;
+          }
+          b++;
+          in_blk = 0;
+          clip = 0;
+          cur_len = min(blk_len, n_total - b * blk_len);
         }
       }
-      const float v0i = ir - (a1 * vi);
-      const float yi = v0i - vi;
-      vi = v0i;
-      const float v0q = qr - (a1 * vq);
-      const float yq = v0q - vq;
-      vq = v0q;
-      out[beg + i] = make_float2(yi, yq);
     }
-    s.clipping = (clip > 0) ? 1 : 0;
-    s.clip_ratio = (len > 0) ? ((float)clip / (float)len) : 0.0f;
-    if (status) {
-      status[(size_t)c * status_pitch + b].clip_ratio = s.clip_ratio;
-    }
+    __syncthreads();
   }
-  s.dc_i = vi;
-  s.dc_q = vq;
-  st[c] = s;
+  if (io) {
+    const int n0 = (nchunks - 1) * LT;
+    tileStore<TP>(tout[(nchunks - 1) & 1], x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0),
+                  2 * (n_total - n0), lane);
+  }
+  if (active) {
+    s.dc_i = vi;
+    s.dc_q = vq;
+    st[c] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -410,7 +520,7 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
       win[u] = xs[a + (a >> 3)];
     }
   }
-  float2 *out = ybuf + (size_t)c * y_pitch + 1;
+  float2 *out = ybuf + (size_t)c * y_pitch + Y_OFF;
 #pragma unroll
   for (int j = 0; j < R; j++) {
     const int n = n0 + t * R + j;
@@ -421,34 +531,86 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
 }
 
 // S2: pre-discriminator AGC (agc_crcf; fm_demod.cpp:170-172,196-198), in place, lanes with AGC on
-__global__ void k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp,
-                      int n_total, int ch0, int nch) {
-  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= nch) {
-    return;
-  }
-  const int c = ch0 + lane;
-  if (cp[c].agc_mode == 0) {
-    return;
-  }
-  const float alpha = cp[c].agc_alpha;
-  float g = st[c].agc_g, y2 = st[c].agc_y2;
-  float2 *y = ybuf + (size_t)c * y_pitch + 1;
-  for (int n = 0; n < n_total; n++) {
-    const float2 x = y[n];
-    const float2 o = make_float2(x.x * g, x.y * g);
-    const float e = (o.x * o.x) + (o.y * o.y);
-    y2 = ((1.0f - alpha) * y2) + (alpha * e);
-    if (y2 > 1e-6f) {
-      g = g * fm_expf((-0.5f * alpha) * fm_logf(y2));
+__global__ void __launch_bounds__(64)
+k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total, int ch0,
+      int nch) {
+  // warp 0 moves tiles, warp 1 runs the AGC recursion in place on the tile (3 rotating tiles:
+  // one loading, one computing, one storing)
+  constexpr int TP = 2 * LT + 4;
+  extern __shared__ float sm_agc[];
+  float *tb[3] = {sm_agc, sm_agc + 32 * TP, sm_agc + 2 * 32 * TP};
+  __shared__ int any_agc;
+  const int lane = threadIdx.x & 31;
+  const bool io = threadIdx.x < 32;
+  const int c0 = ch0 + blockIdx.x * 32;
+  const int nrows = min(32, ch0 + nch - c0);
+  const int c = c0 + min(lane, nrows - 1);
+  const bool has_agc = lane < nrows && cp[c].agc_mode != 0;
+  if (io) {
+    const unsigned m = __ballot_sync(0xffffffffu, has_agc);
+    if (lane == 0) {
+      any_agc = (m != 0u) ? 1 : 0;
     }
-    if (g > 1e6f) {
-      g = 1e6f;
-    }
-    y[n] = o;
   }
-  st[c].agc_g = g;
-  st[c].agc_y2 = y2;
+  __syncthreads();
+  if (!any_agc) {
+    return;  // no channel of this block runs an AGC
+  }
+  const bool active = !io && has_agc;
+  const float alpha = active ? cp[c].agc_alpha : 0.0f;
+  float g = active ? st[c].agc_g : 1.0f;
+  float y2 = active ? st[c].agc_y2 : 1.0f;
+  float *yf = reinterpret_cast<float *>(ybuf);
+  const int nchunks = (n_total + LT - 1) / LT;
+  if (io) {
+    tileLoadAsync<TP>(tb[0], yf, 2 * y_pitch, c0, nrows, 2 * Y_OFF, 2 * min(LT, n_total), lane);
+    cpAsyncCommit();
+    cpAsyncWait<0>();
+  }
+  __syncthreads();
+  for (int ck = 0; ck < nchunks; ck++) {
+    const int n0 = ck * LT;
+    const int len = min(LT, n_total - n0);
+    if (io) {
+      if (ck + 1 < nchunks) {
+        tileLoadAsync<TP>(tb[(ck + 1) % 3], yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 + LT),
+                          2 * min(LT, n_total - n0 - LT), lane);
+        cpAsyncCommit();
+      }
+      if (ck > 0) {
+        tileStore<TP>(tb[(ck - 1) % 3], yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 - LT), 2 * LT,
+                      lane);
+      }
+      cpAsyncWait<0>();
+    } else if (active) {
+      float *t = tb[ck % 3] + lane * TP;
+      for (int i = 0; i < len; i++) {
+        const float ox = t[2 * i] * g;
+        const float oy = t[2 * i + 1] * g;
+        const float e = (ox * ox) + (oy * oy);
+        y2 = ((1.0f - alpha) * y2) + (alpha * e);
+        if (y2 > 1e-6f) {
+          g = g * fm_expf((-0.5f * alpha) * fm_logf(y2));
+        }
+        if (g > 1e6f) {
+          g = 1e6f;
+        }
+        t[2 * i] = ox;
+        t[2 * i + 1] = oy;
+      }
+    }
+    __syncthreads();
+  }
+  if (io) {
+    const int n0 = (nchunks - 1) * LT;
+    // rows without an AGC are written back unchanged
+    tileStore<TP>(tb[(nchunks - 1) % 3], yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0),
+                  2 * (n_total - n0), lane);
+  }
+  if (active) {
+    st[c].agc_g = g;
+    st[c].agc_y2 = y2;
+  }
 }
 
 // K2b: quadrature discriminator, arg(conj(y[n-1]) * y[n]) / (2 pi kf)   (freqdem)
@@ -459,7 +621,7 @@ __global__ void k_freqdem(const float2 *__restrict__ ybuf, size_t y_pitch, float
   if (n >= n_total) {
     return;
   }
-  const float2 *y = ybuf + (size_t)c * y_pitch;
+  const float2 *y = ybuf + (size_t)c * y_pitch + (Y_OFF - 1);
   const float2 p = y[n];
   const float2 r = y[n + 1];
   const float re = (p.x * r.x) + (p.y * r.y);
@@ -522,17 +684,25 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
 // S4: 19 kHz pilot PLL, quality metrics, blend, L-R matrix, per-block lock logic
 // (stereo_decoder.cpp:92-286). One lane per channel.
 // ---------------------------------------------------------------------------
-__global__ void k_stereo(const float *__restrict__ mpx, size_t mpx_pitch,
-                         const float *__restrict__ pilot, size_t pilot_pitch,
-                         float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
-                         StereoState *st, const ChanParams *cp, fmgpu_block_status *status,
-                         int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch,
-                         EngineConst k) {
-  const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= nch) {
-    return;
-  }
-  const int c = ch0 + lane;
+__global__ void __launch_bounds__(64)
+k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ pilot,
+         size_t pilot_pitch, float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
+         StereoState *st, const ChanParams *cp, fmgpu_block_status *status, int status_pitch,
+         int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
+  constexpr int TP = LT + 8;  // 16-byte aligned rows; the delayed tile needs up to 3 extra
+  extern __shared__ float sm_st[];
+  float *t_mpx[2] = {sm_st, sm_st + 32 * TP};
+  float *t_pil[2] = {sm_st + 2 * 32 * TP, sm_st + 3 * 32 * TP};
+  float *t_dly[2] = {sm_st + 4 * 32 * TP, sm_st + 5 * 32 * TP};
+  float *t_l[2] = {sm_st + 6 * 32 * TP, sm_st + 7 * 32 * TP};
+  float *t_r[2] = {sm_st + 8 * 32 * TP, sm_st + 9 * 32 * TP};
+  // warp 0 moves tiles (global <-> shared), warp 1 runs the loop: one lane per channel
+  const int lane = threadIdx.x & 31;
+  const bool io = threadIdx.x < 32;
+  const int c0 = ch0 + blockIdx.x * 32;
+  const int nrows = min(32, ch0 + nch - c0);
+  const bool active = !io && lane < nrows;
+  const int c = c0 + min(lane, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   constexpr float kMatrixScale = 0.5f;
   constexpr float kPilotRatioAcquire = 0.040f, kPilotRatioHold = 0.022f;
@@ -552,11 +722,6 @@ __global__ void k_stereo(const float *__restrict__ mpx, size_t mpx_pitch,
   const float cohDen = fmaxf(kPilotCoherenceAcquire - kPilotCoherenceHold, 1e-4f);
   const float pllDen = fmaxf(kPllLockHoldHz - kPllLockAcquireHz, 1e-3f);
 
-  const float *mrow = mpx + (size_t)c * mpx_pitch + H_MPX;
-  const float *prow = pilot + (size_t)c * pilot_pitch;
-  float *lrow = lraw + (size_t)c * lr_pitch + H_LR;
-  float *rrow = rraw + (size_t)c * lr_pitch + H_LR;
-
   uint32_t theta = s.theta, dtheta = s.dtheta;
   float pbm = s.pbm, mm = s.mm, pilotI = s.pilot_i, pilotQ = s.pilot_q, blend = s.blend;
   float pllFreq = s.pll_freq;
@@ -564,115 +729,167 @@ __global__ void k_stereo(const float *__restrict__ mpx, size_t mpx_pitch,
   float vcoQ, vcoI;
   fm_sincosf(phaseNow, &vcoQ, &vcoI);
 
-  for (int b = 0; b < nblk; b++) {
-    const int beg = b * blk_len;
-    const int len = min(blk_len, n_total - beg);
-    const bool stereoDetected = s.stereo != 0;
-    for (int i = 0; i < len; i++) {
-      const int n = beg + i;
-      const float x = mrow[n];
-      const float pil = prow[n];
-      const float dm = mrow[n - k.delay];
-      pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
-      mm = (mm * kSmooth) + (fabsf(x) * kInject);
-      const float error = pil * vcoQ;
-      dtheta += ncoConstrainDev(error * k.pll_alpha);
-      theta += ncoConstrainDev(error * k.pll_beta);
-      theta += dtheta;
-      const float phaseNext = ncoPhaseDev(theta);
-      float dphi = phaseNext - phaseNow;
-      if (dphi > kPi) {
-        dphi -= 2.0f * kPi;
-      } else if (dphi < -kPi) {
-        dphi += 2.0f * kPi;
+  const int nchunks = (n_total + LT - 1) / LT;
+  const int delay4 = (k.delay + 3) & ~3;  // aligned start of the delayed-MPX tile
+  const int dskew = delay4 - k.delay;
+  auto prefetch = [&](int ck) {
+    const int n0 = ck * LT;
+    const int len = min(LT, n_total - n0);
+    tileLoadAsync<TP>(t_mpx[ck & 1], mpx, mpx_pitch, c0, nrows, H_MPX + n0, len, lane);
+    tileLoadAsync<TP>(t_pil[ck & 1], pilot, pilot_pitch, c0, nrows, n0, len, lane);
+    tileLoadAsync<TP>(t_dly[ck & 1], mpx, mpx_pitch, c0, nrows, H_MPX + n0 - delay4, len + 4, lane);
+  };
+  if (io) {
+    prefetch(0);
+    cpAsyncCommit();
+    cpAsyncWait<0>();
+  }
+  __syncthreads();
+  int b = 0, in_blk = 0;
+  int cur_len = min(blk_len, n_total);
+  bool stereoDetected = s.stereo != 0;
+  for (int ck = 0; ck < nchunks; ck++) {
+    const int n0 = ck * LT;
+    const int len = min(LT, n_total - n0);
+    if (io) {
+      if (ck + 1 < nchunks) {
+        prefetch(ck + 1);
+        cpAsyncCommit();
       }
-      pllFreq = fm_clampf(dphi, k.pll_min, k.pll_max);
-      pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
-      pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
-
-      float target = 0.0f;
-      if (p.force_mono) {
-        target = 0.0f;
-      } else if (p.force_stereo) {
-        target = 1.0f;
-      } else if (stereoDetected) {
-        const float pilotMagNow = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
-        const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
-        const float pilotCoherence = pilotMagNow / fmaxf(pbm, 1e-4f);
-        const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
-        const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
-        const float cohQ = fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
-        const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
-        const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
-        float shaped = quality * quality;
-        if (mode == 0) {
-          shaped = FM_SQRT(fmaxf(0.0f, quality));
-        } else if (mode == 2) {
-          shaped = quality * quality * quality;
+      if (ck > 0) {
+        tileStore<TP>(t_l[(ck - 1) & 1], lraw, lr_pitch, c0, nrows, H_LR + n0 - LT, LT, lane);
+        tileStore<TP>(t_r[(ck - 1) & 1], rraw, lr_pitch, c0, nrows, H_LR + n0 - LT, LT, lane);
+      }
+      cpAsyncWait<0>();
+    } else if (active) {
+      const float *tm = t_mpx[ck & 1] + lane * TP;
+      const float *tp = t_pil[ck & 1] + lane * TP;
+      const float *td = t_dly[ck & 1] + lane * TP + dskew;
+      float *tl = t_l[ck & 1] + lane * TP;
+      float *tr = t_r[ck & 1] + lane * TP;
+      int i = 0;
+      while (i < len) {
+      const int run = min(len - i, cur_len - in_blk);
+#pragma unroll 2
+      for (int j = 0; j < run; j++, i++) {
+        const float x = tm[i];
+        const float pil = tp[i];
+        const float dm = td[i];
+        pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
+        mm = (mm * kSmooth) + (fabsf(x) * kInject);
+        const float error = pil * vcoQ;
+        dtheta += ncoConstrainDev(error * k.pll_alpha);
+        theta += ncoConstrainDev(error * k.pll_beta);
+        theta += dtheta;
+        const float phaseNext = ncoPhaseDev(theta);
+        float dphi = phaseNext - phaseNow;
+        if (dphi > kPi) {
+          dphi -= 2.0f * kPi;
+        } else if (dphi < -kPi) {
+          dphi += 2.0f * kPi;
         }
-        if (pilotRatio < (kPilotRatioHold * gate) || pilotCoherence < (kPilotCoherenceHold * gate) ||
-            pllErrHz > (kPllLockHoldHz * 1.10f)) {
+        pllFreq = fm_clampf(dphi, k.pll_min, k.pll_max);
+        pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
+        pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
+
+        float target = 0.0f;
+        if (p.force_mono) {
           target = 0.0f;
-        } else {
-          target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
-        }
-      }
-
-      float pllIm, pllRe;
-      fm_sincosf(phaseNext, &pllIm, &pllRe);
-      const float monoNorm = dm * kMatrixScale;
-      const float cos2 = (pllRe * pllRe) - (pllIm * pllIm);
-      const float lr = 2.0f * dm * cos2;
-      const float stereoLeft = (dm + lr) * kMatrixScale;
-      const float stereoRight = (dm - lr) * kMatrixScale;
-      const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
-      blend += (target - blend) * blendAlpha;
-      lrow[n] = monoNorm + ((stereoLeft - monoNorm) * blend);
-      rrow[n] = monoNorm + ((stereoRight - monoNorm) * blend);
-
-      phaseNow = phaseNext;
-      vcoQ = pllIm;
-      vcoI = pllRe;
-    }
-    // per-block tail (stereo_decoder.cpp:243-286)
-    const float pilotMag = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
-    s.pilot_mag = (s.pilot_mag * 0.9f) + (pilotMag * 0.1f);
-    const bool det = s.stereo != 0;
-    const float mpxThreshold = det ? kMpxMinHold : kMpxMinAcquire;
-    const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
-    const float pilotCoherence = s.pilot_mag / fmaxf(pbm, 1e-4f);
-    const float ratioThreshold = det ? kPilotRatioHold : kPilotRatioAcquire;
-    const float coherenceThreshold = det ? kPilotCoherenceHold : kPilotCoherenceAcquire;
-    const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
-    const float pllThreshold = det ? kPllLockHoldHz : kPllLockAcquireHz;
-    const bool pilotPresent = (mm > mpxThreshold) && (pilotRatio > ratioThreshold) &&
-                              (pilotCoherence > coherenceThreshold) && (pllErrHz < pllThreshold);
-    if (!p.force_stereo) {
-      if (!det) {
-        if (pilotPresent) {
-          s.pilot_count++;
-          s.loss_count = 0;
-          if (s.pilot_count >= 6) {
-            s.stereo = 1;
+        } else if (p.force_stereo) {
+          target = 1.0f;
+        } else if (stereoDetected) {
+          const float pilotMagNow = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
+          const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
+          const float pilotCoherence = pilotMagNow / fmaxf(pbm, 1e-4f);
+          const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
+          const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
+          const float cohQ = fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
+          const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
+          const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
+          float shaped = quality * quality;
+          if (mode == 0) {
+            shaped = FM_SQRT(fmaxf(0.0f, quality));
+          } else if (mode == 2) {
+            shaped = quality * quality * quality;
           }
-        } else {
-          s.pilot_count = 0;
+          if (pilotRatio < (kPilotRatioHold * gate) || pilotCoherence < (kPilotCoherenceHold * gate) ||
+              pllErrHz > (kPllLockHoldHz * 1.10f)) {
+            target = 0.0f;
+          } else {
+            target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
+          }
         }
-      } else if (pilotPresent) {
-        s.loss_count = 0;
-      } else if (++s.loss_count >= 24) {
-        s.stereo = 0;
-        s.pilot_count = 0;
-        s.loss_count = 0;
+
+        float pllIm, pllRe;
+        fm_sincosf(phaseNext, &pllIm, &pllRe);
+        const float monoNorm = dm * kMatrixScale;
+        const float cos2 = (pllRe * pllRe) - (pllIm * pllIm);
+        const float lr = 2.0f * dm * cos2;
+        const float stereoLeft = (dm + lr) * kMatrixScale;
+        const float stereoRight = (dm - lr) * kMatrixScale;
+        const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
+        blend += (target - blend) * blendAlpha;
+        tl[i] = monoNorm + ((stereoLeft - monoNorm) * blend);
+        tr[i] = monoNorm + ((stereoRight - monoNorm) * blend);
+
+        phaseNow = phaseNext;
+        vcoQ = pllIm;
+        vcoI = pllRe;
+      }
+      in_blk += run;
+        if (in_blk == cur_len) {
+          // per-block tail (stereo_decoder.cpp:243-286)
+          const float pilotMag = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
+          s.pilot_mag = (s.pilot_mag * 0.9f) + (pilotMag * 0.1f);
+          const bool det = s.stereo != 0;
+          const float mpxThreshold = det ? kMpxMinHold : kMpxMinAcquire;
+          const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
+          const float pilotCoherence = s.pilot_mag / fmaxf(pbm, 1e-4f);
+          const float ratioThreshold = det ? kPilotRatioHold : kPilotRatioAcquire;
+          const float coherenceThreshold = det ? kPilotCoherenceHold : kPilotCoherenceAcquire;
+          const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
+          const float pllThreshold = det ? kPllLockHoldHz : kPllLockAcquireHz;
+          const bool pilotPresent = (mm > mpxThreshold) && (pilotRatio > ratioThreshold) &&
+                                    (pilotCoherence > coherenceThreshold) && (pllErrHz < pllThreshold);
+          if (!p.force_stereo) {
+            if (!det) {
+              if (pilotPresent) {
+                s.pilot_count++;
+                s.loss_count = 0;
+                if (s.pilot_count >= 6) {
+                  s.stereo = 1;
+                }
+              } else {
+                s.pilot_count = 0;
+              }
+            } else if (pilotPresent) {
+              s.loss_count = 0;
+            } else if (++s.loss_count >= 24) {
+              s.stereo = 0;
+              s.pilot_count = 0;
+              s.loss_count = 0;
+            }
+          }
+          const float calibrated = s.pilot_mag * 8.0f;
+          s.pilot_tenths = min(750, max(0, (int)fm_roundf(calibrated * 750.0f)));
+          if (status) {
+            fmgpu_block_status *o = &status[(size_t)c * status_pitch + b];
+            o->stereo = s.stereo;
+            o->pilot_tenths = s.pilot_tenths;
+          }
+          b++;
+          in_blk = 0;
+          cur_len = min(blk_len, n_total - b * blk_len);
+          stereoDetected = s.stereo != 0;
+        }
       }
     }
-    const float calibrated = s.pilot_mag * 8.0f;
-    s.pilot_tenths = min(750, max(0, (int)fm_roundf(calibrated * 750.0f)));
-    if (status) {
-      fmgpu_block_status *o = &status[(size_t)c * status_pitch + b];
-      o->stereo = s.stereo;
-      o->pilot_tenths = s.pilot_tenths;
-    }
+    __syncthreads();
+  }
+  if (io) {
+    const int n0 = (nchunks - 1) * LT;
+    tileStore<TP>(t_l[(nchunks - 1) & 1], lraw, lr_pitch, c0, nrows, H_LR + n0, n_total - n0, lane);
+    tileStore<TP>(t_r[(nchunks - 1) & 1], rraw, lr_pitch, c0, nrows, H_LR + n0, n_total - n0, lane);
   }
   s.theta = theta;
   s.dtheta = dtheta;
@@ -682,7 +899,9 @@ __global__ void k_stereo(const float *__restrict__ mpx, size_t mpx_pitch,
   s.pilot_q = pilotQ;
   s.blend = blend;
   s.pll_freq = pllFreq;
-  st[c] = s;
+  if (active) {
+    st[c] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1023,7 +1242,7 @@ __device__ void rdsPushBit(RdsState &s, bool bit, fmgpu_rds_group *groups, uint3
   s.until = s.in_sync ? 26 : 1;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
       int hist_pitch, RdsState *st, float2 *ring,
       const float *__restrict__ g_bank, const float *__restrict__ g_lpf,
@@ -1036,28 +1255,34 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
   __shared__ float s_dmf[32 * SS_LEN];
   __shared__ float2 s_wmf[SS_LEN][32];
   __shared__ float2 s_wdmf[SS_LEN][32];
-  const int tl = threadIdx.x;
-  for (int i = tl; i < 32 * RDS_RS_LEN; i += 32) {
+  // warp 0 streams MPX tiles into shared memory, warp 1 runs the demodulator (lane = channel)
+  const int tl = threadIdx.x & 31;
+  const bool io = threadIdx.x < 32;
+  for (int i = threadIdx.x; i < 32 * RDS_RS_LEN; i += 64) {
     s_bank[i] = g_bank[i];
   }
-  for (int i = tl; i < RDS_LPF_LEN; i += 32) {
+  for (int i = threadIdx.x; i < RDS_LPF_LEN; i += 64) {
     s_lpf[i] = g_lpf[i];
   }
-  for (int i = tl; i < 32 * SS_LEN; i += 32) {
+  for (int i = threadIdx.x; i < 32 * SS_LEN; i += 64) {
     s_mf[i] = g_mf[i];
     s_dmf[i] = g_dmf[i];
   }
-  __syncwarp();
-  const int lane = blockIdx.x * 32 + tl;
-  if (lane >= nch) {
-    return;
-  }
-  const int c = ch0 + lane;
+  __syncthreads();
+  constexpr int TPR = LT + RDS_HIST;  // tile element q <-> MPX sample n0 - RDS_HIST + q
+  extern __shared__ float sm_rds[];
+  float *t_in[2] = {sm_rds, sm_rds + 32 * TPR};
+  const int c0 = ch0 + blockIdx.x * 32;
+  const int nrows = min(32, ch0 + nch - c0);
+  const bool active = !io && tl < nrows;
+  const int c = c0 + min(tl, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   RdsState s = st[c];
-  for (int q = 0; q < SS_LEN; q++) {
-    s_wmf[q][tl] = s.wmf[q];
-    s_wdmf[q][tl] = s.wdmf[q];
+  if (!io) {
+    for (int q = 0; q < SS_LEN; q++) {
+      s_wmf[q][tl] = s.wmf[q];
+      s_wdmf[q][tl] = s.wdmf[q];
+    }
   }
   int sp = 0;  // ring position of the oldest symsync window element
   float2 *ringc = ring + (size_t)c * RDS_RING;
@@ -1069,7 +1294,7 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
   for (int j = 0; j < RDS_NACC; j++) {
     acc[j] = s.acc[j];
   }
-  if (s.realign) {
+  if (active && s.realign) {
     // SubcarrierSet::reset() moved the /24 phase: rebuild the pending sums from the
     // last 254 mixed samples (the low-pass itself is not reset, subcarrier.cpp:108-114)
     const uint32_t u0 = s.ring_pos;  // absolute index of the next sample
@@ -1091,35 +1316,55 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
     s.realign = 0;
   }
 
-  const float *mrow = mpx + (size_t)c * mpx_pitch + H_MPX;
-  const float *hrow = hist + (size_t)c * hist_pitch;
   uint32_t phase = s.rs_phase;
   uint32_t produced = 0;
   const uint32_t n171 = s.n171;
+  const int nchunks = (n_total + LT - 1) / LT;
+  // tile element k of chunk ck <-> MPX sample ck*LT - 25 + k; samples before this call come
+  // from the RDS resampler's own window (it is not reset with the stereo path)
+  auto prefetch = [&](int ck) {
+    const int n0 = ck * LT;
+    const int cpr = (min(LT, n_total - n0) + RDS_HIST + 3) >> 2;
+    const int total = nrows * cpr;
+    for (int idx = tl; idx < total; idx += 32) {
+      const int r = idx / cpr;
+      const int q4 = 4 * (idx - r * cpr);
+      const int si = n0 - RDS_HIST + q4;  // multiple of 4: a chunk never straddles sample 0
+      const float *src = (si >= 0)
+                             ? mpx + (size_t)(c0 + r) * mpx_pitch + H_MPX + si
+                             : hist + (size_t)(c0 + r) * hist_pitch + RDS_HIST + si;
+      cpAsync16(t_in[ck & 1] + r * TPR + q4, src);
+    }
+  };
+  if (io) {
+    prefetch(0);
+    cpAsyncCommit();
+    cpAsyncWait<0>();
+  }
+  __syncthreads();
+  int blk = 0, in_blk = 0;
+  int cur_len = min(blk_len, n_total);
+  uint32_t groups_before = s.n_groups;
 
-  for (int blk = 0; blk < nblk; blk++) {
-    const int beg = blk * blk_len;
-    const int len = min(blk_len, n_total - beg);
-    const uint32_t groups_before = s.n_groups;
-    for (int ii = 0; ii < len; ii++) {
-      const int n = beg + ii;
+  for (int ck = 0; ck < nchunks; ck++) {
+    const int clen = min(LT, n_total - ck * LT);
+    if (io) {
+      if (ck + 1 < nchunks) {
+        prefetch(ck + 1);
+        cpAsyncCommit();
+      }
+      cpAsyncWait<0>();
+    }
+    const float *trow = t_in[ck & 1] + tl * TPR;
+    for (int ii = 0; active && ii < clen; ii++) {
       while (phase < (1u << 24)) {
         const int br = (int)(phase >> 19);
         const float *h = s_bank + br * RDS_RS_LEN;
-        const float *w = mrow + n - (RDS_RS_LEN - 1);
+        const float *w = trow + ii + (RDS_HIST - (RDS_RS_LEN - 1));
         float smp = 0.0f;
-        if (n >= RDS_RS_LEN - 1) {
 #pragma unroll
-          for (int q = 0; q < RDS_RS_LEN; q++) {
-            smp = fmaf(h[q], w[q], smp);
-          }
-        } else {
-          // the resampler window is RDS state of its own (not reset with the stereo path)
-          for (int q = 0; q < RDS_RS_LEN; q++) {
-            const int si = n - (RDS_RS_LEN - 1) + q;
-            const float x = (si >= 0) ? mrow[si] : hrow[(RDS_RS_LEN - 1) + si];
-            smp = fmaf(h[q], x, smp);
-          }
+        for (int q = 0; q < RDS_RS_LEN; q++) {
+          smp = fmaf(h[q], w[q], smp);
         }
         phase += k.rds_step;
         // ---- one 171 kHz sample -------------------------------------------------
@@ -1256,10 +1501,20 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
         s.since_reset++;
       }
       phase -= (1u << 24);
+      if (++in_blk == cur_len) {
+        if (status) {
+          status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - groups_before);
+        }
+        groups_before = s.n_groups;
+        blk++;
+        in_blk = 0;
+        cur_len = min(blk_len, n_total - blk * blk_len);
+      }
     }
-    if (status) {
-      status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - groups_before);
-    }
+    __syncthreads();
+  }
+  if (!active) {
+    return;
   }
 #pragma unroll
   for (int j = 0; j < RDS_NACC; j++) {
@@ -1337,7 +1592,13 @@ void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size
                    float2 *x2, size_t x2_pitch, DemodState *st, fmgpu_block_status *status,
                    int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, float a1,
                    cudaStream_t stream) {
-  k_dcblock<<<(nch + 31) / 32, 32, 0, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
+  constexpr size_t smem = 4 * 32 * (2 * LT + 4) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_dcblock, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  k_dcblock<<<(nch + 31) / 32, 64, smem, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
                                                status, status_pitch, nblk, blk_len, n_total, ch0,
                                                nch, a1);
 }
@@ -1355,7 +1616,13 @@ void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pit
 
 void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total,
                int ch0, int nch, cudaStream_t stream) {
-  k_agc<<<(nch + 31) / 32, 32, 0, stream>>>(ybuf, y_pitch, st, cp, n_total, ch0, nch);
+  constexpr size_t smem = 3 * 32 * (2 * LT + 4) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_agc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  k_agc<<<(nch + 31) / 32, 64, smem, stream>>>(ybuf, y_pitch, st, cp, n_total, ch0, nch);
 }
 
 void launchFreqDem(const float2 *ybuf, size_t y_pitch, float *mpx, size_t mpx_pitch, int n_total,
@@ -1377,7 +1644,13 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  k_stereo<<<(nch + 31) / 32, 32, 0, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
+  constexpr size_t smem = 10 * 32 * (LT + 8) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  k_stereo<<<(nch + 31) / 32, 64, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
                                               lr_pitch, st, cp, status, status_pitch, nblk, blk_len,
                                               n_total, ch0, nch, k);
 }
@@ -1431,7 +1704,8 @@ void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_p
                fmgpu_rds_group *groups, uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap,
                fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  k_rds<<<(nch + 31) / 32, 32, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, ring, bank, lpf,
+  constexpr size_t smem = 2 * 32 * (LT + RDS_HIST) * sizeof(float);
+  k_rds<<<(nch + 31) / 32, 64, smem, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, ring, bank, lpf,
                                            mf, dmf, groups, gcap, bits_dbg, bits_cap, status,
                                            status_pitch, nblk, blk_len, n_total, ch0, nch, k);
 }
