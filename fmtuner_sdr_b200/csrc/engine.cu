@@ -528,9 +528,13 @@ int computeDesigns(fmgpu_engine *e) {
     // --- ComplexDecimator::init (liquid_primitives.cpp:370-403, main.cpp:670-674)
     if (e->M > 1) {
       const uint32_t f = static_cast<uint32_t>(e->M);
-      const uint32_t tpp = std::max<uint32_t>(4, (f >= 8U) ? 28U : ((f >= 4U) ? 20U : 12U));
+      const uint32_t tppArg = e->cfg.decim_taps_per_phase > 0
+                                  ? static_cast<uint32_t>(e->cfg.decim_taps_per_phase)
+                                  : ((f >= 8U) ? 28U : ((f >= 4U) ? 20U : 12U));
+      const uint32_t tpp = std::max<uint32_t>(4, tppArg);
+      const float atten = e->cfg.decim_atten_db > 0 ? static_cast<float>(e->cfg.decim_atten_db) : 80.0f;
       const float cutoff = std::clamp(0.45f / static_cast<float>(f), 0.01f, 0.45f);
-      e->decTaps = fmdesign::kaiserLowpass(f * tpp, cutoff, 80.0f, 0.0f);
+      e->decTaps = fmdesign::kaiserLowpass(f * tpp, cutoff, atten, 0.0f);
       e->decL = static_cast<int>(f * tpp);
       e->decPp = static_cast<int>(roundUp(tpp, 4));
       e->decScale = 2.0f * cutoff;
@@ -906,6 +910,20 @@ int fmgpu_set_deemphasis_us(fmgpu_engine *e, int channel, int tau_us) {
   });
 }
 
+int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz) {
+  if (!e || !(deviation_hz > 0.0)) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  // freqdem is re-created: new reference gain, r_prev cleared (fm_demod.cpp:64-71)
+  const float kf = static_cast<float>(deviation_hz / static_cast<double>(e->fs));
+  e->k.fd_ref = static_cast<float>(1.0 / (2.0 * M_PI * static_cast<double>(kf)));
+  zeroPrefix(e->dY, e->yPitch, Y_OFF, 0, e->C, e->stream);
+  CK(cudaStreamSynchronize(e->stream));
+  return FMGPU_OK;
+}
+
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
   if (mode < 0 || mode > 2) {
     return FMGPU_EINVAL;
@@ -1227,6 +1245,31 @@ size_t fmgpu_demod_cf32(fmgpu_engine *e, int channel, const float *iq_cf32, floa
   return demodCommon(e, channel, nullptr, iq_cf32, mpx_out, mono_out, n, s);
 }
 
+size_t fmgpu_downsample_mono(fmgpu_engine *e, int channel, const float *mpx, float *audio_out,
+                             size_t n) {
+  STAGE_PROLOGUE(mpx && audio_out && n > 0)
+  if (n > e->nmax) {
+    e->lastError = "downsample: more samples than the engine was sized for";
+    return 0;
+  }
+  const int ni = static_cast<int>(n);
+  cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
+                  n * sizeof(float), cudaMemcpyHostToDevice, s);
+  launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
+                e->k.rds_step, 0, 1, 0, s);
+  stageMono(e, ni, 0, 0, channel, 1, s);
+  launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, s);
+  e->launches += 2;
+  AudioState a{};
+  cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  const size_t produced = std::min<size_t>(a.mono_n_out, e->acap);
+  cudaMemcpyAsync(audio_out, e->dAudio + static_cast<size_t>(channel) * 2 * e->acap,
+                  produced * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return stageFail(e, "downsample") ? 0 : produced;
+}
+
 size_t fmgpu_stereo(fmgpu_engine *e, int channel, const float *mpx, float *left, float *right,
                     size_t n) {
   STAGE_PROLOGUE(mpx && left && right && n > 0)
@@ -1266,8 +1309,9 @@ size_t fmgpu_afpost(fmgpu_engine *e, int channel, const float *in_left, const fl
     if (num > a.rs_phase) {
       cnt = (num - a.rs_phase + e->k.aud_step - 1) / e->k.aud_step;
     }
-    if (cnt > out_capacity) {
-      // input index that emits output #(out_capacity-1)
+    if (cnt >= out_capacity) {
+      // the reference loop also stops when the count EQUALS the capacity: inputs after the one
+      // that emitted output #(out_capacity-1) are never pushed
       const unsigned long long P =
           static_cast<unsigned long long>(a.rs_phase) + (out_capacity - 1) * 1ull * e->k.aud_step;
       n_eff = static_cast<size_t>(P >> 24) + 1;

@@ -30,14 +30,17 @@ class EngineError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "iq_rate", "decimation", "output_rate", "block_samples", "max_blocks", "w0_bandwidth_hz",
-        "bandwidth_hz", "dsp_agc", "stereo_blend", "deemphasis", "stereo", "force_mono")]
+        "bandwidth_hz", "dsp_agc", "stereo_blend", "deemphasis", "stereo", "force_mono",
+        "decim_taps_per_phase", "decim_atten_db")]
 
 
 def make_config(iq_rate=2_400_000, decimation=10, output_rate=32000, block_samples=8192,
                 max_blocks=4, w0_bandwidth_hz=194000, bandwidth_hz=0, dsp_agc=0, stereo_blend=1,
-                deemphasis=0, stereo=1, force_mono=0) -> Config:
+                deemphasis=0, stereo=1, force_mono=0, decim_taps_per_phase=0,
+                decim_atten_db=0) -> Config:
     return Config(iq_rate, decimation, output_rate, block_samples, max_blocks, w0_bandwidth_hz,
-                  bandwidth_hz, dsp_agc, stereo_blend, deemphasis, stereo, force_mono)
+                  bandwidth_hz, dsp_agc, stereo_blend, deemphasis, stereo, force_mono,
+                  decim_taps_per_phase, decim_atten_db)
 
 
 class SynthParams(C.Structure):
@@ -88,6 +91,9 @@ def load_library(build: bool = True):
     L.fmgpu_demod_u8.argtypes = [vp, i32, u8p, f32p, f32p, sz]
     L.fmgpu_demod_cf32.restype = sz
     L.fmgpu_demod_cf32.argtypes = [vp, i32, f32p, f32p, f32p, sz]
+    L.fmgpu_downsample_mono.restype = sz
+    L.fmgpu_downsample_mono.argtypes = [vp, i32, f32p, f32p, sz]
+    L.fmgpu_set_deviation_hz.argtypes = [vp, C.c_double]
     L.fmgpu_stereo.restype = sz
     L.fmgpu_stereo.argtypes = [vp, i32, f32p, f32p, f32p, sz]
     L.fmgpu_afpost.restype = sz
@@ -265,6 +271,15 @@ class Engine:
         mono = np.zeros(n, np.float32) if want_mono else None
         k = self.L.fmgpu_demod_cf32(self.h, channel, _ptr(iq), _ptr(mpx), _ptr(mono), n)
         return mpx, (mono[:k] if want_mono else None)
+
+    def downsampleAudio(self, mpx: np.ndarray, channel=0) -> np.ndarray:
+        mpx = np.ascontiguousarray(mpx, np.float32).reshape(-1)
+        out = np.zeros(mpx.size, np.float32)
+        n = self.L.fmgpu_downsample_mono(self.h, channel, _ptr(mpx), _ptr(out), mpx.size)
+        return out[:n]
+
+    def set_deviation_hz(self, hz: float):
+        self._check(self.L.fmgpu_set_deviation_hz(self.h, float(hz)), "set_deviation_hz")
 
     def processAudio(self, mpx: np.ndarray, channel=0):
         mpx = np.ascontiguousarray(mpx, np.float32).reshape(-1)

@@ -48,6 +48,8 @@ typedef struct fmgpu_config {
   int32_t deemphasis;      /* tuner.deemphasis: 0 = 50 us, 1 = 75 us, 2 = off (include/config.h:37) */
   int32_t stereo;          /* processing.stereo (0 => mono path, main.cpp:1266-1279) */
   int32_t force_mono;      /* StereoDecoder::setForceMono */
+  int32_t decim_taps_per_phase; /* ComplexDecimator::init tapsPerPhase; 0 => main.cpp:672-673 (12/20/28) */
+  int32_t decim_atten_db;       /* ComplexDecimator::init stopBandAtten; 0 => 80 dB (main.cpp:674) */
 } fmgpu_config;
 
 /* RDSGroup (include/rds_decoder.h:9-15) plus the logical block that emitted it. */
@@ -91,6 +93,7 @@ int fmgpu_set_bandwidth_mode(fmgpu_engine *e, int channel, int mode);  /* FMDemo
 int fmgpu_set_w0_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz);/* FMDemod::setW0BandwidthHz fm_demod.cpp:137-139 */
 int fmgpu_set_agc_mode(fmgpu_engine *e, int channel, int mode);        /* FMDemod::setDspAgcMode    fm_demod.cpp:141-148 */
 int fmgpu_set_deemphasis_us(fmgpu_engine *e, int channel, int tau_us); /* FMDemod/AFPostProcessor::setDeemphasis */
+int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz);      /* FMDemod::setDeviation fm_demod.cpp:64-71 (all channels) */
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode);      /* StereoDecoder::setBlendMode */
 int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on);        /* StereoDecoder::setForceMono */
 int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on);      /* StereoDecoder::setForceStereo */
@@ -135,6 +138,9 @@ size_t fmgpu_demod_u8(fmgpu_engine *e, int channel, const uint8_t *iq, float *mp
 /* FMDemod::processSplitComplex  fm_demod.cpp:261-274 */
 size_t fmgpu_demod_cf32(fmgpu_engine *e, int channel, const float *iq_cf32, float *mpx_out,
                         float *mono_out, size_t n);
+/* FMDemod::downsampleAudio  fm_demod.cpp:210-226 (mono chain on caller-supplied MPX) */
+size_t fmgpu_downsample_mono(fmgpu_engine *e, int channel, const float *mpx, float *audio_out,
+                             size_t n);
 /* StereoDecoder::processAudio  stereo_decoder.cpp:92-286 */
 size_t fmgpu_stereo(fmgpu_engine *e, int channel, const float *mpx, float *left, float *right,
                     size_t n);

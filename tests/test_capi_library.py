@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(fm.engine.Config) == 12 * 4
+    assert C.sizeof(fm.engine.Config) == 14 * 4
     assert fm.GROUP_DTYPE.itemsize == 16 and fm.STATUS_DTYPE.itemsize == 20
     assert C.sizeof(fm.SynthParams) == 44
 
