@@ -6,8 +6,9 @@ count = value / 2.4. One "step" = one pass of the whole pipeline (decimate, disc
 pilot PLL + stereo matrix, 15 kHz low-pass, resample to 32 kHz, de-emphasis, RDS down to
 groups) over `blocks` logical blocks (8192 samples @ 240 kHz each) of every channel.
 
-Workload: BASELINE config 5 sharded over 8 GPUs -> 1250 channels per GPU (weak scaling:
-channels-per-GPU fixed), 2.4 MS/s uint8 IQ / 10 -> 240 kHz, SNR 10-40 dB, blend mode c%3,
+Workload: BASELINE config 5 — the 10,000-channel weak-signal sweep — resident on ONE GPU
+(it fits: 3.3 GB of IQ per step), weak-scaled to N GPUs (channels-per-GPU fixed, every rank a
+differently seeded sweep): 2.4 MS/s uint8 IQ / 10 -> 240 kHz, SNR 10-40 dB, blend mode c%3,
 dsp_agc fast, synthetic multiplexes generated on the device from per-channel seeds. Channels
 are independent: they are sharded across ranks with no collective on the data path.
 
@@ -46,8 +47,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--channels", type=int, default=1250, help="channels per GPU")
-    ap.add_argument("--blocks", type=int, default=4, help="logical blocks per step")
+    ap.add_argument("--channels", type=int, default=10000, help="channels per GPU")
+    ap.add_argument("--blocks", type=int, default=2, help="logical blocks per step")
+    ap.add_argument("--groups", type=int, default=4, help="pipeline groups (streams) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -189,10 +191,11 @@ def run_reference(args, rank: int):
 
 def workload_config(args, channels_this_arm: int) -> dict:
     return {
-        "workload": "BASELINE config 5 (10,000-channel weak-signal sweep) sharded by channel: "
-                    f"{args.channels} channels/GPU, 2.4 MS/s uint8 IQ /10 -> 240 kHz, SNR 10-40 dB, "
-                    "blend soft/normal/aggressive by c%3, dsp_agc fast, stereo + RDS",
+        "workload": "BASELINE config 5 (10,000-channel weak-signal sweep) per GPU, sharded by "
+                    f"channel: {args.channels} channels/GPU, 2.4 MS/s uint8 IQ /10 -> 240 kHz, "
+                    "SNR 10-40 dB, blend soft/normal/aggressive by c%3, dsp_agc fast, stereo + RDS",
         "channels_per_gpu": args.channels, "blocks_per_step": args.blocks,
+        "pipeline_groups": args.groups,
         "block_samples": BLOCK, "iq_rate": IQ_RATE, "decimation": DECIM,
         "channels_in_this_arm": channels_this_arm,
         "l2_policy": "inputs larger than L2 (no flush): "
@@ -210,6 +213,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     import torch.distributed as dist
 
     import fmtuner_sdr_b200 as fm
+    from fmtuner_sdr_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
@@ -221,6 +225,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
 
     eng = fm.Engine(fm.make_config(iq_rate=IQ_RATE, decimation=DECIM, max_blocks=B, dsp_agc=1), C,
                     local_rank)
+    eng.set_pipeline_groups(args.groups)
     for c in range(C):
         if (rank * C + c) % 3 != 1:
             eng.set_blend_mode((rank * C + c) % 3, c)
@@ -229,8 +234,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     iq_dev = torch.empty((C, stride), dtype=torch.uint8, device=dev)
     rng = np.random.default_rng(1234 + rank)
     params = []
-    for c in range(C):
-        g = rank * C + c
+    for c, g in enumerate(shard.channels_of_rank(rank, world, C)):
         params.append(fm.SynthParams(
             float(rng.choice([22_500.0, 37_500.0, 50_000.0, 60_000.0, 75_000.0])),
             400.0 + 37.0 * (g % 200), 0.8, 700.0 + 53.0 * (g % 150), 0.8, 0.10, 0.04, 0.5,
@@ -277,13 +281,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     w1 = time.time()
     launches = eng.launch_count() - l0
     clocks = sampler.stop(w0, w1)
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = shard.max_over_ranks(ev0.elapsed_time(ev1), dev)
     samples_per_step_rank = C * n_iq
-    value = world * samples_per_step_rank * args.steps / (ms * 1e-3) / 1e6   # MS/s, whole job
+    value = shard.aggregate_throughput(samples_per_step_rank, args.steps, world, ms)  # MS/s, whole job
 
     # sanity: the run really decoded (stereo flags + RDS groups present)
     st_host = status.cpu().numpy().view(fm.STATUS_DTYPE).reshape(C, B)
@@ -333,11 +333,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         for _ in range(args.steps):
             estep()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = shard.max_over_ranks(time.perf_counter() - t0, dev)
         frames = int(na_host.max().item())
         e2e = {"value": world * samples_per_step_rank * args.steps / dt / 1e6, "unit": "MS/s",
                "h2d_bytes_per_step": int(C * 2 * n_iq),

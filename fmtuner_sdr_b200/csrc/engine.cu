@@ -86,6 +86,13 @@ struct fmgpu_engine {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // the RDS branch runs beside the stereo branch
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  // optional channel groups: each group runs the whole pipeline on its own pair of streams so
+  // that one group's lane kernels overlap another group's FIR kernels and host copies
+  static constexpr int kMaxGroups = 8;
+  int nGroups = 1;
+  cudaStream_t gStream[kMaxGroups] = {}, gStream2[kMaxGroups] = {};
+  cudaEvent_t gFork[kMaxGroups] = {}, gJoin[kMaxGroups] = {}, gDone[kMaxGroups] = {};
+  cudaEvent_t evStart = nullptr;
 
   int lastN = 0;  // DSP-rate samples of the last call (debug reads)
   uint64_t launches = 0;
@@ -434,78 +441,123 @@ void collectTimes(fmgpu_engine *e) {
   e->spans.clear();
 }
 
-int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks, float *audio_dev,
-             size_t audio_cap, uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
-             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, cudaStream_t s) {
-  if (!iq_dev || n_blocks < 1 || n_blocks > e->maxBlocks) {
+// the per-block body of main.cpp:1232-1308 for channels [ch0, ch0+nch) on stream s (RDS on s2)
+void runRange(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks,
+              uint32_t *n_audio, fmgpu_rds_group *groups, uint32_t gcap, uint32_t *n_groups,
+              fmgpu_block_status *status, int ch0, int nch, cudaStream_t s, cudaStream_t s2,
+              cudaEvent_t evFork, cudaEvent_t evJoin) {
+  const int n = n_blocks * e->N;
+  const bool stereo = e->cfg.stereo != 0;
+  {
+    Span sp(e, "prepare", s);
+    launchPrepare(e->dAudioSt, e->dRds, status, n_blocks, n_blocks, e->N, n, ch0, nch,
+                  e->k.aud_step, e->k.rds_step, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
+    e->launches += 1;
+  }
+  if (e->M > 1) {
+    stageDecimate(e, iq_dev, stride, n, ch0, nch, s);
+    stageDemod(e, nullptr, 0, status, n_blocks, e->N, n, ch0, nch, s);
+  } else {
+    stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, ch0, nch, s);
+  }
+  // MPX is complete: the RDS branch (reads MPX data + its own window) runs on a second
+  // stream beside the stereo/audio branch; both only read the MPX data region.
+  cudaEventRecord(evFork, s);
+  cudaStreamWaitEvent(s2, evFork, 0);
+  stageRds(e, groups, gcap, status, n_blocks, e->N, n, ch0, nch, s2);
+  cudaEventRecord(evJoin, s2);
+  if (stereo) {
+    stageStereo(e, status, n_blocks, e->N, n, ch0, nch, s);
+    stageAfPost(e, n, 1, ch0, nch, s);
+  } else {
+    stageMono(e, n, 1, 1, ch0, nch, s);
+    launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, ch0, nch, s);
+    e->launches += 1;
+  }
+  cudaStreamWaitEvent(s, evJoin, 0);
+  {
+    Span sp(e, "commit", s);
+    launchStoreCounts(e->dAudioSt, e->dRds, n_audio, n_groups, ch0, nch, stereo ? 0 : 1,
+                      static_cast<uint32_t>(e->acap), gcap, s);
+    launchCommit(e->dAudioSt, e->dRds, ch0, nch, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
+    e->launches += 2;
+  }
+}
+
+// channel range of pipeline group g (multiples of 32 channels: one warp of lane kernels)
+void groupRange(const fmgpu_engine *e, int g, int *ch0, int *nch) {
+  const int per = static_cast<int>(roundUp((e->C + e->nGroups - 1) / e->nGroups, 32));
+  *ch0 = std::min(e->C, g * per);
+  *nch = std::min(e->C, (g + 1) * per) - *ch0;
+}
+
+int checkBatchArgs(fmgpu_engine *e, const void *iq, size_t stride, int n_blocks, bool device,
+                   const float *audio, size_t audio_cap) {
+  if (!iq || n_blocks < 1 || n_blocks > e->maxBlocks) {
     e->lastError = "process: n_blocks out of range or null input";
     return FMGPU_EINVAL;
   }
-  if ((reinterpret_cast<uintptr_t>(iq_dev) & 15u) || (stride & 15u) ||
-      stride < static_cast<size_t>(n_blocks) * e->N * e->M * 2) {
-    e->lastError = "process: iq buffer must be 16-byte aligned with a 16-byte aligned stride >= bytes per channel";
+  if (device && ((reinterpret_cast<uintptr_t>(iq) & 15u) || (stride & 15u))) {
+    e->lastError = "process: iq buffer and stride must be 16-byte aligned";
     return FMGPU_EINVAL;
   }
-  const int n = n_blocks * e->N;
+  if (stride < static_cast<size_t>(n_blocks) * e->N * e->M * 2) {
+    e->lastError = "process: stride smaller than the bytes per channel";
+    return FMGPU_EINVAL;
+  }
+  const size_t n = static_cast<size_t>(n_blocks) * e->N;
   const size_t needAudio = static_cast<size_t>((static_cast<double>(n) * 16777216.0) / e->k.aud_step) + 2;
-  if (audio_dev && audio_cap < needAudio) {
+  if (audio && audio_cap < needAudio) {
     e->lastError = "process: audio capacity too small";
     return FMGPU_ERANGE;
   }
-  int rc = uploadParams(e);
+  return FMGPU_OK;
+}
+
+int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks, float *audio_dev,
+             size_t audio_cap, uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
+             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, cudaStream_t s) {
+  int rc = checkBatchArgs(e, iq_dev, stride, n_blocks, true, audio_dev, audio_cap);
   if (rc != FMGPU_OK) {
     return rc;
   }
-  const int C = e->C;
-  const bool stereo = e->cfg.stereo != 0;
+  rc = uploadParams(e);
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
   fmgpu_block_status *status = status_dev ? status_dev : e->dStatus;
   fmgpu_rds_group *groups = groups_dev ? groups_dev : e->dGroups;
   const uint32_t gcap = static_cast<uint32_t>(groups_dev ? group_cap : e->gcap);
-  // audio is produced in the engine's buffer when the caller's capacity differs
+  uint32_t *n_audio = n_audio_dev ? n_audio_dev : e->dNAudio;
+  uint32_t *n_groups = n_groups_dev ? n_groups_dev : e->dNGroups;
+  // audio is produced straight into the caller's buffer when one is given
   float *audioSaved = e->dAudio;
   const size_t acapSaved = e->acap;
   if (audio_dev) {
     e->dAudio = audio_dev;
     e->acap = audio_cap;
   }
-  {
-    Span sp(e, "prepare", s);
-    launchPrepare(e->dAudioSt, e->dRds, status, n_blocks, n_blocks, e->N, n, 0, C, e->k.aud_step,
-                  e->k.rds_step, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
-    e->launches += 1;
-  }
-  if (e->M > 1) {
-    stageDecimate(e, iq_dev, stride, n, 0, C, s);
-    stageDemod(e, nullptr, 0, status, n_blocks, e->N, n, 0, C, s);
+  if (e->nGroups <= 1) {
+    runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, 0, e->C, s,
+             e->stream2, e->evFork, e->evJoin);
   } else {
-    stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, 0, C, s);
-  }
-  // MPX is complete: the RDS branch (reads MPX data + its own window) runs on a second
-  // stream beside the stereo/audio branch; both only read the MPX data region.
-  cudaEventRecord(e->evFork, s);
-  cudaStreamWaitEvent(e->stream2, e->evFork, 0);
-  stageRds(e, groups, gcap, status, n_blocks, e->N, n, 0, C, e->stream2);
-  cudaEventRecord(e->evJoin, e->stream2);
-  if (stereo) {
-    stageStereo(e, status, n_blocks, e->N, n, 0, C, s);
-    stageAfPost(e, n, 1, 0, C, s);
-  } else {
-    stageMono(e, n, 1, 1, 0, C, s);
-    launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, 0, C, s);
-    e->launches += 1;
-  }
-  cudaStreamWaitEvent(s, e->evJoin, 0);
-  {
-    Span sp(e, "commit", s);
-    launchStoreCounts(e->dAudioSt, e->dRds, n_audio_dev ? n_audio_dev : e->dNAudio,
-                      n_groups_dev ? n_groups_dev : e->dNGroups, 0, C, stereo ? 0 : 1,
-                      static_cast<uint32_t>(e->acap), gcap, s);
-    launchCommit(e->dAudioSt, e->dRds, 0, C, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
-    e->launches += 2;
+    cudaEventRecord(e->evStart, s);
+    for (int g = 0; g < e->nGroups; g++) {
+      int ch0, nch;
+      groupRange(e, g, &ch0, &nch);
+      if (nch <= 0) {
+        continue;
+      }
+      cudaStreamWaitEvent(e->gStream[g], e->evStart, 0);
+      runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, ch0, nch,
+               e->gStream[g], e->gStream2[g], e->gFork[g], e->gJoin[g]);
+      cudaEventRecord(e->gDone[g], e->gStream[g]);
+      cudaStreamWaitEvent(s, e->gDone[g], 0);
+    }
   }
   e->dAudio = audioSaved;
   e->acap = acapSaved;
-  e->lastN = n;
+  e->lastN = n_blocks * e->N;
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     e->lastError = std::string("kernel launch: ") + cudaGetErrorString(err);
@@ -704,6 +756,14 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   CKC(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&e->evStart, cudaEventDisableTiming));
+  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
+    CKC(cudaStreamCreateWithFlags(&e->gStream[g], cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&e->gStream2[g], cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&e->gFork[g], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->gJoin[g], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->gDone[g], cudaEventDisableTiming));
+  }
   CKC(initRdsTables());
   CKC(devAlloc(&e->dIq, C * e->iqPitch));
   CKC(devAlloc(&e->dHistIq, C * 2 * H_IQ));
@@ -817,6 +877,24 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
   }
   if (e->evJoin) {
     cudaEventDestroy(e->evJoin);
+  }
+  if (e->evStart) {
+    cudaEventDestroy(e->evStart);
+  }
+  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
+    if (e->gStream[g]) {
+      cudaStreamSynchronize(e->gStream[g]);
+      cudaStreamDestroy(e->gStream[g]);
+    }
+    if (e->gStream2[g]) {
+      cudaStreamSynchronize(e->gStream2[g]);
+      cudaStreamDestroy(e->gStream2[g]);
+    }
+    for (cudaEvent_t ev : {e->gFork[g], e->gJoin[g], e->gDone[g]}) {
+      if (ev) {
+        cudaEventDestroy(ev);
+      }
+    }
   }
   delete e;
 }
@@ -1092,64 +1170,93 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
                        int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
                        fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
                        fmgpu_block_status *status_host) {
-  if (!e || !iq_host || n_blocks < 1 || n_blocks > e->maxBlocks) {
+  if (!e) {
     return FMGPU_EINVAL;
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  cudaStream_t s = e->stream;
-  const size_t C = static_cast<size_t>(e->C);
-  const size_t bytes = static_cast<size_t>(n_blocks) * e->N * e->M * 2;
-  if (iq_stride_bytes < bytes) {
-    e->lastError = "process_host: stride smaller than the bytes per channel";
-    return FMGPU_EINVAL;
-  }
-  if (iq_stride_bytes == e->iqPitch) {
-    CK(cudaMemcpyAsync(e->dIq, iq_host, C * e->iqPitch, cudaMemcpyHostToDevice, s));
-  } else {
-    CK(cudaMemcpy2DAsync(e->dIq, e->iqPitch, iq_host, iq_stride_bytes, bytes, C,
-                         cudaMemcpyHostToDevice, s));
-  }
-  const int rc = runBatch(e, e->dIq, e->iqPitch, n_blocks, nullptr, 0, nullptr, nullptr, 0, nullptr,
-                          nullptr, s);
+  int rc = checkBatchArgs(e, iq_host, iq_stride_bytes, n_blocks, false, audio_host, audio_cap);
   if (rc != FMGPU_OK) {
     return rc;
   }
+  rc = uploadParams(e);
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
+  const size_t bytes = static_cast<size_t>(n_blocks) * e->N * e->M * 2;
   const size_t n = static_cast<size_t>(n_blocks) * e->N;
   const size_t frames = std::min(e->acap, static_cast<size_t>((static_cast<double>(n) * 16777216.0) /
                                                                e->k.aud_step) + 2);
-  if (audio_host) {
-    if (audio_cap < frames) {
-      e->lastError = "process_host: audio capacity too small";
-      return FMGPU_ERANGE;
+  const int G = std::max(1, e->nGroups);
+  // every group: host->device copy of its rows, the pipeline, device->host copy of its results,
+  // all on the group's own stream, so copies of one group overlap kernels of the others
+  for (int g = 0; g < G; g++) {
+    int ch0 = 0, nch = e->C;
+    cudaStream_t s = e->stream, s2 = e->stream2;
+    cudaEvent_t evF = e->evFork, evJ = e->evJoin;
+    if (G > 1) {
+      groupRange(e, g, &ch0, &nch);
+      if (nch <= 0) {
+        continue;
+      }
+      s = e->gStream[g];
+      s2 = e->gStream2[g];
+      evF = e->gFork[g];
+      evJ = e->gJoin[g];
     }
-    CK(cudaMemcpy2DAsync(audio_host, audio_cap * sizeof(float), e->dAudio, e->acap * sizeof(float),
-                         frames * sizeof(float), C * 2, cudaMemcpyDeviceToHost, s));
-  }
-  if (n_audio_host) {
-    CK(cudaMemcpyAsync(n_audio_host, e->dNAudio, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  }
-  if (groups_host) {
-    const size_t g = std::min(group_cap, e->gcap);
-    CK(cudaMemcpy2DAsync(groups_host, group_cap * sizeof(fmgpu_rds_group), e->dGroups,
-                         e->gcap * sizeof(fmgpu_rds_group), g * sizeof(fmgpu_rds_group), C,
+    const size_t c0 = static_cast<size_t>(ch0), cn = static_cast<size_t>(nch);
+    CK(cudaMemcpy2DAsync(e->dIq + c0 * e->iqPitch, e->iqPitch, iq_host + c0 * iq_stride_bytes,
+                         iq_stride_bytes, bytes, cn, cudaMemcpyHostToDevice, s));
+    runRange(e, e->dIq, e->iqPitch, n_blocks, e->dNAudio, e->dGroups, static_cast<uint32_t>(e->gcap),
+             e->dNGroups, e->dStatus, ch0, nch, s, s2, evF, evJ);
+    if (audio_host) {
+      CK(cudaMemcpy2DAsync(audio_host + c0 * 2 * audio_cap, audio_cap * sizeof(float),
+                           e->dAudio + c0 * 2 * e->acap, e->acap * sizeof(float),
+                           frames * sizeof(float), cn * 2, cudaMemcpyDeviceToHost, s));
+    }
+    if (n_audio_host) {
+      CK(cudaMemcpyAsync(n_audio_host + c0, e->dNAudio + c0, cn * sizeof(uint32_t),
                          cudaMemcpyDeviceToHost, s));
+    }
+    if (groups_host) {
+      const size_t gw = std::min(group_cap, e->gcap);
+      CK(cudaMemcpy2DAsync(groups_host + c0 * group_cap, group_cap * sizeof(fmgpu_rds_group),
+                           e->dGroups + c0 * e->gcap, e->gcap * sizeof(fmgpu_rds_group),
+                           gw * sizeof(fmgpu_rds_group), cn, cudaMemcpyDeviceToHost, s));
+    }
+    if (n_groups_host) {
+      CK(cudaMemcpyAsync(n_groups_host + c0, e->dNGroups + c0, cn * sizeof(uint32_t),
+                         cudaMemcpyDeviceToHost, s));
+    }
+    if (status_host) {
+      CK(cudaMemcpyAsync(status_host + c0 * n_blocks, e->dStatus + c0 * n_blocks,
+                         cn * n_blocks * sizeof(fmgpu_block_status), cudaMemcpyDeviceToHost, s));
+    }
   }
-  if (n_groups_host) {
-    CK(cudaMemcpyAsync(n_groups_host, e->dNGroups, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  for (int g = 0; g < G; g++) {
+    CK(cudaStreamSynchronize(G > 1 ? e->gStream[g] : e->stream));
   }
-  if (status_host) {
-    CK(cudaMemcpy2DAsync(status_host, n_blocks * sizeof(fmgpu_block_status), e->dStatus,
-                         n_blocks * sizeof(fmgpu_block_status),
-                         n_blocks * sizeof(fmgpu_block_status), C, cudaMemcpyDeviceToHost, s));
+  e->lastN = static_cast<int>(n);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    e->lastError = std::string("process_host: ") + cudaGetErrorString(err);
+    return FMGPU_ENODEV;
   }
-  CK(cudaStreamSynchronize(s));
   if (n_groups_host && groups_host) {
-    for (size_t c = 0; c < C; c++) {
+    for (int c = 0; c < e->C; c++) {
       n_groups_host[c] = std::min<uint32_t>(n_groups_host[c], static_cast<uint32_t>(group_cap));
     }
   }
   collectTimes(e);
+  return FMGPU_OK;
+}
+
+int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups) {
+  if (!e || groups < 1 || groups > fmgpu_engine::kMaxGroups) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  e->nGroups = groups;
   return FMGPU_OK;
 }
 

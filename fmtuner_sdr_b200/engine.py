@@ -78,6 +78,7 @@ def load_library(build: bool = True):
                  "set_deemphasis_us", "set_blend_mode", "set_force_mono", "set_force_stereo"):
         getattr(L, f"fmgpu_{name}").argtypes = [vp, i32, i32]
     L.fmgpu_reset.argtypes = [vp, i32, C.c_uint]
+    L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
     L.fmgpu_is_stereo.argtypes = [vp, i32]
     L.fmgpu_pilot_tenths.argtypes = [vp, i32]
     L.fmgpu_clip_ratio.argtypes = [vp, i32]
@@ -191,6 +192,9 @@ class Engine:
 
     def set_force_stereo(self, on, channel=-1):
         self._check(self.L.fmgpu_set_force_stereo(self.h, channel, int(on)), "set_force_stereo")
+
+    def set_pipeline_groups(self, groups: int):
+        self._check(self.L.fmgpu_set_pipeline_groups(self.h, groups), "set_pipeline_groups")
 
     def reset(self, what=RESET_ALL, channel=-1):
         self._check(self.L.fmgpu_reset(self.h, channel, what), "reset")

@@ -127,6 +127,11 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
                        fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
                        fmgpu_block_status *status_host);
 
+/* Split the channels into `groups` (1..8) ranges that run the pipeline on separate streams:
+ * one range's serial (one-lane-per-channel) kernels then overlap another range's FIR kernels
+ * and, in fmgpu_process_host, its host<->device copies. Results do not depend on it. */
+int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups);
+
 /* ---- stage-level entry points, one per reference method; HOST buffers, synchronous ----
  * They run the same kernels as the batch path on one channel's state. */
 /* ComplexDecimator::executeComplex  liquid_primitives.cpp:461-499 ; out = interleaved re,im */

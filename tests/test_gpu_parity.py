@@ -68,6 +68,29 @@ def test_blocks_per_call_do_not_change_results(orc_fm):
         assert np.array_equal(st, outs[0][2])
 
 
+def test_pipeline_groups_do_not_change_results():
+    """Channel groups on separate streams (overlap of lane / FIR kernels and host copies)."""
+    iq_rate, decim = rates("240k")
+    C, nblk = 70, 4
+    rng = np.random.default_rng(11)
+    base = np.stack([orc.config3_signal(300 + c, fs_iq=iq_rate).generate(nblk * 8192 * decim)
+                     for c in range(6)])
+    iq = base[rng.integers(0, 6, C)]
+    ref = None
+    for groups in (1, 2, 3, 8):
+        eng = fm.Engine(fm.make_config(max_blocks=2, dsp_agc=1), C, 0)
+        eng.set_pipeline_groups(groups)
+        out = run_engine_chunks(eng, iq, nblk, 2)
+        eng.close()
+        if ref is None:
+            ref = out
+            continue
+        for c in range(C):
+            assert np.array_equal(out[0][c], ref[0][c]), (groups, c)
+            assert groups_equal(out[1][c], ref[1][c]), (groups, c)
+        assert np.array_equal(out[2], ref[2])
+
+
 def test_config3_varied_channels_bit_exact(orc_fm):
     """BASELINE config 3 (reduced to 24 channels x 8 blocks so the oracle finishes in seconds):
     varied deviation / SNR / tones / RDS payload per channel, batched on one GPU."""
