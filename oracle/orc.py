@@ -19,16 +19,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present) if stale."""
-    libs = ("liboracle_libm.so", "liboracle_fm.so", "libsiggen.so")
-    srcs = ("oracle_capi.cpp", "pipeline.hpp", "liquid_restated.hpp", "siggen.cpp", "Makefile",
-            os.path.join("..", "fmtuner_sdr_b200", "csrc", "fm_math.h"))
-    newest = max(os.path.getmtime(os.path.join(HERE, f)) for f in srcs)
-    stale = force or any(
-        not os.path.exists(os.path.join(HERE, f)) or os.path.getmtime(os.path.join(HERE, f)) < newest
-        for f in libs)
+    def mtime(f):
+        return os.path.getmtime(os.path.join(HERE, f))
+
+    def stale(target, deps):
+        return (not os.path.exists(os.path.join(HERE, target))) or mtime(target) < max(map(mtime, deps))
+
+    oracle_deps = ("oracle_capi.cpp", "pipeline.hpp", "liquid_restated.hpp", "Makefile",
+                   os.path.join("..", "fmtuner_sdr_b200", "csrc", "fm_math.h"))
+    need = force or stale("liboracle_libm.so", oracle_deps) or stale("liboracle_fm.so", oracle_deps) \
+        or stale("libsiggen.so", ("siggen.cpp", "Makefile"))
     have_ref_src = os.path.isdir("/root/reference/src/redsea_port")
     ref_missing = have_ref_src and not os.path.exists(os.path.join(HERE, "_ref", "libredsea_ref.so"))
-    if stale or ref_missing:
+    if need or ref_missing:
         subprocess.run(["make", "-C", HERE, "--no-print-directory"], check=True,
                        stdout=subprocess.DEVNULL)
 
