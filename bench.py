@@ -30,6 +30,9 @@ import sys
 import threading
 import time
 
+# the engine drives up to 3 streams per pipeline group: give them their own hardware queues
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -85,13 +85,15 @@ struct fmgpu_engine {
   size_t x2Pitch = 0, yPitch = 0, mpxPitch = 0, lrPitch = 0, lfPitch = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // the RDS branch runs beside the stereo branch
+  cudaStream_t laneStream = nullptr;  // high priority: lane kernels jump ahead of queued FIR CTAs
+  cudaEvent_t evHop = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   // optional channel groups: each group runs the whole pipeline on its own pair of streams so
   // that one group's lane kernels overlap another group's FIR kernels and host copies
   static constexpr int kMaxGroups = 8;
   int nGroups = 1;
-  cudaStream_t gStream[kMaxGroups] = {}, gStream2[kMaxGroups] = {};
-  cudaEvent_t gFork[kMaxGroups] = {}, gJoin[kMaxGroups] = {}, gDone[kMaxGroups] = {};
+  cudaStream_t gStream[kMaxGroups] = {}, gStream2[kMaxGroups] = {}, gLane[kMaxGroups] = {};
+  cudaEvent_t gFork[kMaxGroups] = {}, gJoin[kMaxGroups] = {}, gDone[kMaxGroups] = {}, gHop[kMaxGroups] = {};
   cudaEvent_t evStart = nullptr;
 
   int lastN = 0;  // DSP-rate samples of the last call (debug reads)
@@ -302,14 +304,30 @@ void stageDecimate(fmgpu_engine *e, const uint8_t *iq, size_t stride, int n_out,
   e->launches += 2;
 }
 
+// Lane kernels (one warp per 32 channels, latency-bound) go to a HIGH-PRIORITY stream so that
+// their few CTAs are scheduled ahead of the thousands of queued CTAs of other groups' FIR
+// kernels; `hop` chains the two streams with an event. lane == s means: no split.
+static void hop(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
+  if (from != to) {
+    cudaEventRecord(ev, from);
+    cudaStreamWaitEvent(to, ev, 0);
+  }
+}
+
 // x1 (or raw u8) -> mpx
 void stageDemod(fmgpu_engine *e, const uint8_t *iq_u8, size_t stride, fmgpu_block_status *status,
-                int nblk, int blk_len, int n, int ch0, int nch, cudaStream_t s) {
-  {
-    Span sp(e, "dcblock", s);
-    launchDcBlock(iq_u8 ? nullptr : e->dX1, e->pitch, iq_u8, stride, e->dX2, e->x2Pitch, e->dDemod,
-                  status, nblk, nblk, blk_len, n, ch0, nch, e->k.dc_a1_iq, s);
+                int nblk, int blk_len, int n, int ch0, int nch, cudaStream_t s,
+                cudaStream_t lane = nullptr, cudaEvent_t ev = nullptr) {
+  if (!lane) {
+    lane = s;
   }
+  {
+    hop(s, lane, ev);
+    Span sp(e, "dcblock", lane);
+    launchDcBlock(iq_u8 ? nullptr : e->dX1, e->pitch, iq_u8, stride, e->dX2, e->x2Pitch, e->dDemod,
+                  status, nblk, nblk, blk_len, n, ch0, nch, e->k.dc_a1_iq, lane);
+  }
+  hop(lane, s, ev);
   {
     Span sp(e, "chanfir", s);
     launchChanFir(e->dX2, e->x2Pitch, e->dY, e->yPitch, e->dChanTaps, e->dChanLp, e->dChanScale,
@@ -320,8 +338,12 @@ void stageDemod(fmgpu_engine *e, const uint8_t *iq_u8, size_t stride, fmgpu_bloc
     anyAgc = anyAgc || e->hParams[c].agc_mode != 0;
   }
   if (anyAgc) {
-    Span sp(e, "agc", s);
-    launchAgc(e->dY, e->yPitch, e->dDemod, e->dParams, n, ch0, nch, s);
+    hop(s, lane, ev);
+    {
+      Span sp(e, "agc", lane);
+      launchAgc(e->dY, e->yPitch, e->dDemod, e->dParams, n, ch0, nch, lane);
+    }
+    hop(lane, s, ev);
     e->launches += 1;
   }
   {
@@ -335,7 +357,10 @@ void stageDemod(fmgpu_engine *e, const uint8_t *iq_u8, size_t stride, fmgpu_bloc
 
 // mpx -> lf/rf (DSP-rate stereo) ; carries the stereo decoder's halos
 void stageStereo(fmgpu_engine *e, fmgpu_block_status *status, int nblk, int blk_len, int n, int ch0,
-                 int nch, cudaStream_t s) {
+                 int nch, cudaStream_t s, cudaStream_t lane = nullptr, cudaEvent_t ev = nullptr) {
+  if (!lane) {
+    lane = s;
+  }
   {
     Span sp(e, "pilot_fir", s);
     FirRealJob j{};
@@ -351,11 +376,13 @@ void stageStereo(fmgpu_engine *e, fmgpu_block_status *status, int nblk, int blk_
     j.ch0 = ch0;
     launchFirReal(j, 1, nch, e->pilParam, s);
   }
+  hop(s, lane, ev);
   {
-    Span sp(e, "stereo_pll", s);
+    Span sp(e, "stereo_pll", lane);
     launchStereo(e->dMpx, e->mpxPitch, e->dPilot, e->pitch, e->dLraw, e->dRraw, e->lrPitch,
-                 e->dStereo, e->dParams, status, nblk, nblk, blk_len, n, ch0, nch, e->k, s);
+                 e->dStereo, e->dParams, status, nblk, nblk, blk_len, n, ch0, nch, e->k, lane);
   }
+  hop(lane, s, ev);
   {
     Span sp(e, "audio_lpf", s);
     FirRealJob j{};
@@ -445,7 +472,7 @@ void collectTimes(fmgpu_engine *e) {
 void runRange(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks,
               uint32_t *n_audio, fmgpu_rds_group *groups, uint32_t gcap, uint32_t *n_groups,
               fmgpu_block_status *status, int ch0, int nch, cudaStream_t s, cudaStream_t s2,
-              cudaEvent_t evFork, cudaEvent_t evJoin) {
+              cudaEvent_t evFork, cudaEvent_t evJoin, cudaStream_t lane, cudaEvent_t evHop) {
   const int n = n_blocks * e->N;
   const bool stereo = e->cfg.stereo != 0;
   {
@@ -456,9 +483,9 @@ void runRange(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_block
   }
   if (e->M > 1) {
     stageDecimate(e, iq_dev, stride, n, ch0, nch, s);
-    stageDemod(e, nullptr, 0, status, n_blocks, e->N, n, ch0, nch, s);
+    stageDemod(e, nullptr, 0, status, n_blocks, e->N, n, ch0, nch, s, lane, evHop);
   } else {
-    stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, ch0, nch, s);
+    stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, ch0, nch, s, lane, evHop);
   }
   // MPX is complete: the RDS branch (reads MPX data + its own window) runs on a second
   // stream beside the stereo/audio branch; both only read the MPX data region.
@@ -467,7 +494,7 @@ void runRange(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_block
   stageRds(e, groups, gcap, status, n_blocks, e->N, n, ch0, nch, s2);
   cudaEventRecord(evJoin, s2);
   if (stereo) {
-    stageStereo(e, status, n_blocks, e->N, n, ch0, nch, s);
+    stageStereo(e, status, n_blocks, e->N, n, ch0, nch, s, lane, evHop);
     stageAfPost(e, n, 1, ch0, nch, s);
   } else {
     stageMono(e, n, 1, 1, ch0, nch, s);
@@ -539,7 +566,7 @@ int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks
   }
   if (e->nGroups <= 1) {
     runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, 0, e->C, s,
-             e->stream2, e->evFork, e->evJoin);
+             e->stream2, e->evFork, e->evJoin, e->laneStream, e->evHop);
   } else {
     cudaEventRecord(e->evStart, s);
     for (int g = 0; g < e->nGroups; g++) {
@@ -550,7 +577,7 @@ int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks
       }
       cudaStreamWaitEvent(e->gStream[g], e->evStart, 0);
       runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, ch0, nch,
-               e->gStream[g], e->gStream2[g], e->gFork[g], e->gJoin[g]);
+               e->gStream[g], e->gStream2[g], e->gFork[g], e->gJoin[g], e->gLane[g], e->gHop[g]);
       cudaEventRecord(e->gDone[g], e->gStream[g]);
       cudaStreamWaitEvent(s, e->gDone[g], 0);
     }
@@ -753,13 +780,19 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   e->gcap = e->nmax * 12 / static_cast<size_t>(std::max(1, e->fs)) + 8;  // 11.4 groups/s
   e->bitsCap = e->nmax / 100 + 64;
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CKC(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  int prLo = 0, prHi = 0;
+  CKC(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));  // prHi = numerically smallest = highest
+  CKC(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, prHi));
+  CKC(cudaStreamCreateWithPriority(&e->laneStream, cudaStreamNonBlocking, prHi));
+  CKC(cudaEventCreateWithFlags(&e->evHop, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->evStart, cudaEventDisableTiming));
   for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
     CKC(cudaStreamCreateWithFlags(&e->gStream[g], cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&e->gStream2[g], cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithPriority(&e->gStream2[g], cudaStreamNonBlocking, prHi));
+    CKC(cudaStreamCreateWithPriority(&e->gLane[g], cudaStreamNonBlocking, prHi));
+    CKC(cudaEventCreateWithFlags(&e->gHop[g], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->gFork[g], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->gJoin[g], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->gDone[g], cudaEventDisableTiming));
@@ -881,6 +914,13 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
   if (e->evStart) {
     cudaEventDestroy(e->evStart);
   }
+  if (e->laneStream) {
+    cudaStreamSynchronize(e->laneStream);
+    cudaStreamDestroy(e->laneStream);
+  }
+  if (e->evHop) {
+    cudaEventDestroy(e->evHop);
+  }
   for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
     if (e->gStream[g]) {
       cudaStreamSynchronize(e->gStream[g]);
@@ -890,7 +930,11 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
       cudaStreamSynchronize(e->gStream2[g]);
       cudaStreamDestroy(e->gStream2[g]);
     }
-    for (cudaEvent_t ev : {e->gFork[g], e->gJoin[g], e->gDone[g]}) {
+    if (e->gLane[g]) {
+      cudaStreamSynchronize(e->gLane[g]);
+      cudaStreamDestroy(e->gLane[g]);
+    }
+    for (cudaEvent_t ev : {e->gFork[g], e->gJoin[g], e->gDone[g], e->gHop[g]}) {
       if (ev) {
         cudaEventDestroy(ev);
       }
@@ -1192,8 +1236,8 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
   // all on the group's own stream, so copies of one group overlap kernels of the others
   for (int g = 0; g < G; g++) {
     int ch0 = 0, nch = e->C;
-    cudaStream_t s = e->stream, s2 = e->stream2;
-    cudaEvent_t evF = e->evFork, evJ = e->evJoin;
+    cudaStream_t s = e->stream, s2 = e->stream2, sl = e->laneStream;
+    cudaEvent_t evF = e->evFork, evJ = e->evJoin, evH = e->evHop;
     if (G > 1) {
       groupRange(e, g, &ch0, &nch);
       if (nch <= 0) {
@@ -1203,12 +1247,14 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
       s2 = e->gStream2[g];
       evF = e->gFork[g];
       evJ = e->gJoin[g];
+      sl = e->gLane[g];
+      evH = e->gHop[g];
     }
     const size_t c0 = static_cast<size_t>(ch0), cn = static_cast<size_t>(nch);
     CK(cudaMemcpy2DAsync(e->dIq + c0 * e->iqPitch, e->iqPitch, iq_host + c0 * iq_stride_bytes,
                          iq_stride_bytes, bytes, cn, cudaMemcpyHostToDevice, s));
     runRange(e, e->dIq, e->iqPitch, n_blocks, e->dNAudio, e->dGroups, static_cast<uint32_t>(e->gcap),
-             e->dNGroups, e->dStatus, ch0, nch, s, s2, evF, evJ);
+             e->dNGroups, e->dStatus, ch0, nch, s, s2, evF, evJ, sl, evH);
     if (audio_host) {
       CK(cudaMemcpy2DAsync(audio_host + c0 * 2 * audio_cap, audio_cap * sizeof(float),
                            e->dAudio + c0 * 2 * e->acap, e->acap * sizeof(float),

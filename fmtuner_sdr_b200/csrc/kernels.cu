@@ -113,7 +113,7 @@ __device__ __forceinline__ float unwrapDev(float p) {
 // memory. Row pitches are multiples of 4 floats so rows move as 16-byte transfers; the
 // 4-way bank conflict that costs a lane kernel is noise next to its dependent-issue latency.
 // ---------------------------------------------------------------------------
-constexpr int LT = 64;  // samples per tile row
+constexpr int LT = 32;  // samples per tile row (small tiles keep >= 4 lane CTAs resident per SM)
 
 __device__ __forceinline__ void cpAsync16(void *smem, const void *gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
@@ -798,25 +798,39 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
         } else if (p.force_stereo) {
           target = 1.0f;
         } else if (stereoDetected) {
-          const float pilotMagNow = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
-          const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
-          const float pilotCoherence = pilotMagNow / fmaxf(pbm, 1e-4f);
-          const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
-          const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
-          const float cohQ = fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
-          const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
-          const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
-          float shaped = quality * quality;
-          if (mode == 0) {
-            shaped = FM_SQRT(fmaxf(0.0f, quality));
-          } else if (mode == 2) {
-            shaped = quality * quality * quality;
-          }
-          if (pilotRatio < (kPilotRatioHold * gate) || pilotCoherence < (kPilotCoherenceHold * gate) ||
-              pllErrHz > (kPllLockHoldHz * 1.10f)) {
-            target = 0.0f;
+          const float mx = fmaxf(mm, 1e-3f);
+          const float pm = fmaxf(pbm, 1e-4f);
+          const float s2 = (pilotI * pilotI) + (pilotQ * pilotQ);
+          const float dfs = fabsf(pllFreq - k.nominal_pll) * k.fsf;
+          const float tB = 0.1803f * pm;
+          if (pbm >= 0.0402f * mx && s2 >= tB * tB && dfs <= 1130.0f) {
+            // Clean pilot: with ratio >= 0.0402, coherence >= 0.1803 and |f error| <= 179.9 Hz each
+            // of the three quality terms below clamps to exactly 1 (margins of >= 1e-4 against
+            // rounding errors of ~1e-7) and no gate trips, so target == 1.0f in every blend mode.
+            // Skipping the six IEEE divisions and the square root changes no result.
+            target = 1.0f;
           } else {
-            target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
+            const float pilotMagNow = FM_SQRT(s2);
+            const float pilotRatio = pbm / mx;
+            const float pilotCoherence = pilotMagNow / pm;
+            const float pllErrHz = dfs / (2.0f * kPi);
+            const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
+            const float cohQ =
+                fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
+            const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
+            const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
+            float shaped = quality * quality;
+            if (mode == 0) {
+              shaped = FM_SQRT(fmaxf(0.0f, quality));
+            } else if (mode == 2) {
+              shaped = quality * quality * quality;
+            }
+            if (pilotRatio < (kPilotRatioHold * gate) ||
+                pilotCoherence < (kPilotCoherenceHold * gate) || pllErrHz > (kPllLockHoldHz * 1.10f)) {
+              target = 0.0f;
+            } else {
+              target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
+            }
           }
         }
 
