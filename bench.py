@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=10000, help="channels per GPU")
     ap.add_argument("--blocks", type=int, default=2, help="logical blocks per step")
-    ap.add_argument("--groups", type=int, default=4, help="pipeline groups (streams) per GPU")
+    ap.add_argument("--groups", type=int, default=8, help="pipeline groups (streams) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -157,7 +157,9 @@ extern "C" int fmgpu_synth_iq(int device, const fmgpu_synth_params *params_host,
     return FMGPU_ENODEV;
   }
   // four 0A groups carrying PS "CHnnnn  " (nnnn = seed mod 10000)
-  constexpr int kBits = 4 * 104;
+  // The differential encoder state must close around the cycle: the 416-bit pattern is laid
+  // down twice (832 bits), which has even parity whatever the payload.
+  constexpr int kBits = 2 * 4 * 104;
   constexpr int kChips = 2 * kBits;
   std::vector<int8_t> chips(static_cast<size_t>(n_channels) * kChips);
   for (int c = 0; c < n_channels; c++) {
@@ -165,19 +167,21 @@ extern "C" int fmgpu_synth_iq(int device, const fmgpu_synth_params *params_host,
     std::snprintf(ps, sizeof(ps), "CH%04u  ", params_host[c].seed % 10000u);
     int e = 0;
     size_t w = static_cast<size_t>(c) * kChips;
-    for (int seg = 0; seg < 4; seg++) {
-      const uint16_t blocks[4] = {
-          params_host[c].pi,
-          static_cast<uint16_t>((10u << 5) | (1u << 3) | static_cast<unsigned>(seg)), 0xE0CD,
-          static_cast<uint16_t>((static_cast<unsigned char>(ps[2 * seg]) << 8) |
-                                static_cast<unsigned char>(ps[2 * seg + 1]))};
-      const int offIdx[4] = {0, 1, 2, 4};
-      for (int b = 0; b < 4; b++) {
-        const uint32_t word = fmgpu::encodeBlock(blocks[b], offIdx[b]);
-        for (int i = 25; i >= 0; i--) {
-          e ^= static_cast<int>((word >> i) & 1u);
-          chips[w++] = static_cast<int8_t>(e ? 1 : -1);
-          chips[w++] = static_cast<int8_t>(e ? -1 : 1);
+    for (int rep = 0; rep < 2; rep++) {
+      for (int seg = 0; seg < 4; seg++) {
+        const uint16_t blocks[4] = {
+            params_host[c].pi,
+            static_cast<uint16_t>((10u << 5) | (1u << 3) | static_cast<unsigned>(seg)), 0xE0CD,
+            static_cast<uint16_t>((static_cast<unsigned char>(ps[2 * seg]) << 8) |
+                                  static_cast<unsigned char>(ps[2 * seg + 1]))};
+        const int offIdx[4] = {0, 1, 2, 4};
+        for (int b = 0; b < 4; b++) {
+          const uint32_t word = fmgpu::encodeBlock(blocks[b], offIdx[b]);
+          for (int i = 25; i >= 0; i--) {
+            e ^= static_cast<int>((word >> i) & 1u);
+            chips[w++] = static_cast<int8_t>(e ? 1 : -1);
+            chips[w++] = static_cast<int8_t>(e ? -1 : 1);
+          }
         }
       }
     }

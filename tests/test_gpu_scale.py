@@ -1,0 +1,112 @@
+"""BASELINE full-size configurations through size-independent properties (the oracle is far too
+slow to decode them entirely): replica equality, channel-permutation equivariance, determinism,
+plus exact oracle spot checks on a few channels of each configuration."""
+import numpy as np
+import pytest
+
+import fmtuner_sdr_b200 as fm
+from oracle import orc
+from tests.common import groups_equal, rates, run_engine_chunks
+
+pytestmark = pytest.mark.gpu
+
+
+def _distinct(n, nblk, snr_lo=20.0, snr_hi=60.0, seed=0):
+    iq_rate, decim = rates("240k")
+    rng = np.random.default_rng(seed)
+    rows = []
+    for c in range(n):
+        s = orc.config3_signal(500 + c, fs_iq=iq_rate)
+        s.snr_db = float(rng.uniform(snr_lo, snr_hi))
+        rows.append(s.generate(nblk * 8192 * decim))
+    return np.stack(rows)
+
+
+def test_config3_256_channels(orc_fm):
+    """BASELINE config 3: 256 channels batched on one GPU."""
+    C, nblk, nd = 256, 4, 12
+    base = _distinct(nd, nblk)
+    rng = np.random.default_rng(1)
+    which = rng.integers(0, nd, C)
+    which[:nd] = np.arange(nd)
+    iq = base[which]
+    eng = fm.Engine(fm.make_config(max_blocks=2), C, 0)
+    eng.set_pipeline_groups(4)
+    audio, groups, status, _ = run_engine_chunks(eng, iq, nblk, 2)
+    eng.close()
+    # replicas of the same multiplex decode identically wherever they sit in the batch
+    for c in range(C):
+        r = int(which[c])
+        assert np.array_equal(audio[c], audio[r]), c
+        assert groups_equal(groups[c], groups[r]), c
+        assert np.array_equal(status[c], status[r]), c
+    # and the distinct ones equal the oracle exactly
+    for r in range(nd):
+        ref = orc.Channel(orc_fm, orc.make_config()).process(base[r])
+        assert np.array_equal(audio[r][0], ref.left) and np.array_equal(audio[r][1], ref.right), r
+        assert np.array_equal(status[r], ref.status) and groups_equal(groups[r], ref.groups), r
+    # permuting the channels permutes the results (no cross-channel term)
+    perm = rng.permutation(C)
+    eng2 = fm.Engine(fm.make_config(max_blocks=4), C, 0)
+    audio2, groups2, status2, _ = run_engine_chunks(eng2, iq[perm], nblk, 4)
+    eng2.close()
+    for i in range(0, C, 7):
+        assert np.array_equal(audio2[i], audio[perm[i]])
+        assert groups_equal(groups2[i], groups[perm[i]])
+
+
+def test_config5_10000_channels(orc_fm):
+    """BASELINE config 5 at full channel count (one logical block per call, two calls):
+    SNR 10-40 dB, blend mode c % 3, dsp_agc fast."""
+    C, nblk, nd = 10_000, 2, 9
+    base = _distinct(nd, nblk, 10.0, 40.0, seed=5)
+    # replica r uses signal r % nd and blend mode (r % nd) % 3 so replicas share all settings
+    which = np.arange(C) % nd
+    iq = base[which]
+    eng = fm.Engine(fm.make_config(max_blocks=1, dsp_agc=1), C, 0)
+    eng.set_pipeline_groups(8)
+    for c in range(C):
+        if (which[c] % 3) != 1:
+            eng.set_blend_mode(int(which[c] % 3), c)
+    audio, groups, status, _ = run_engine_chunks(eng, iq, nblk, 1)
+    assert eng.launch_count() > 0
+    eng.close()
+    for c in range(nd, C):
+        r = int(which[c])
+        assert np.array_equal(audio[c], audio[r]), c
+        assert np.array_equal(status[c], status[r]), c
+        assert groups_equal(groups[c], groups[r]), c
+    for r in range(nd):
+        ref = orc.Channel(orc_fm, orc.make_config(dsp_agc=1, stereo_blend=r % 3)).process(base[r])
+        assert np.array_equal(audio[r][0], ref.left) and np.array_equal(audio[r][1], ref.right), r
+        assert np.array_equal(status[r], ref.status), r
+
+
+def test_device_synth_decodes_and_is_deterministic():
+    """The on-device generator used by bench.py: deterministic in its seeds, decodes to stereo
+    with the PI it was given."""
+    import torch
+    C, B, calls = 64, 14, 2
+    n_iq = calls * B * 81920
+    stride = 2 * n_iq
+    outs = []
+    for _ in range(2):
+        iq = torch.empty((C, stride), dtype=torch.uint8, device="cuda:0")
+        params = [fm.SynthParams(75000.0, 400.0 + 37.0 * c, 0.8, 700.0 + 53.0 * c, 0.8, 0.10, 0.04,
+                                 0.5, 35.0, c, 0x2000 + c, 0) for c in range(C)]
+        fm.synth_iq(0, params, 2_400_000, n_iq, iq.data_ptr(), stride)
+        torch.cuda.synchronize()
+        outs.append(iq.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    eng = fm.Engine(fm.make_config(max_blocks=B), C, 0)
+    per = B * 81920 * 2
+    pis = [[] for _ in range(C)]
+    for k in range(calls):
+        a, na, g, ng, st = eng.process_host(outs[0][:, k * per:(k + 1) * per], B, group_cap=16)
+        for c in range(C):
+            gg = g[c, :ng[c]]
+            pis[c].extend(int(x) for x in gg["a"][(gg["errors"] >> 6) == 0])
+    eng.close()
+    assert st["stereo"][:, -1].all()
+    for c in range(C):
+        assert len(pis[c]) >= 2 and all(p == 0x2000 + c for p in pis[c]), (c, pis[c])
