@@ -307,6 +307,10 @@ size_t orc_demod_process_split_complex(void *h, const float *iq_cf32, float *mpx
   return static_cast<FMDemod *>(h)->processSplitComplex(reinterpret_cast<const cf32 *>(iq_cf32),
                                                         mpx, mono, n);
 }
+void orc_demod_set_deviation(void *h, double dev) { static_cast<FMDemod *>(h)->setDeviation(dev); }
+size_t orc_demod_downsample(void *h, const float *mpx, float *audio, size_t n) {
+  return static_cast<FMDemod *>(h)->downsampleAudio(mpx, audio, n);
+}
 float orc_demod_clip_ratio(void *h) { return static_cast<FMDemod *>(h)->getClippingRatio(); }
 int orc_demod_is_clipping(void *h) { return static_cast<FMDemod *>(h)->isClipping() ? 1 : 0; }
 

@@ -138,6 +138,10 @@ class OracleLib:
         L.orc_demod_process_split_complex.argtypes = [C.c_void_p, C.POINTER(C.c_float),
                                                       C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                       C.c_size_t]
+        L.orc_demod_set_deviation.argtypes = [C.c_void_p, C.c_double]
+        L.orc_demod_downsample.restype = C.c_size_t
+        L.orc_demod_downsample.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                           C.c_size_t]
         L.orc_demod_clip_ratio.restype = C.c_float
         L.orc_demod_clip_ratio.argtypes = [C.c_void_p]
         L.orc_demod_is_clipping.argtypes = [C.c_void_p]

@@ -95,5 +95,32 @@ int main(int argc, char **argv) {
   std::fclose(fa);
   std::fclose(fs);
   std::fclose(fg);
+
+  // ---- the rest of the public surface, on fresh objects ---------------------------------
+  {
+    FILE *fx = std::fopen((prefix + ".extra.bin").c_str(), "wb");
+    const size_t n = std::min<size_t>(4096, iq.size() / 2 / std::max(1, decim));
+    // ComplexDecimator::execute (re-quantised uint8 output)
+    if (decim > 1) {
+      fm_tuner::dsp::liquid::ComplexDecimator d2;
+      d2.init(f32, (f32 >= 8U) ? 28U : ((f32 >= 4U) ? 20U : 12U), 80.0f);
+      std::vector<uint8_t> q(2 * n);
+      const size_t k = d2.execute(iq.data(), n * decim, q.data(), n);
+      std::fwrite(q.data(), 1, 2 * k, fx);
+    }
+    // FMDemod::process (mono audio), processNoDownsample, downsampleAudio, setDeviation,
+    // setBandwidthMode on raw uint8 IQ at the DSP rate
+    FMDemod d3(INPUT_RATE, OUTPUT_RATE);
+    d3.setBandwidthMode(9);
+    d3.setDeviation(50000.0);
+    std::vector<float> a(n), b(n), c(n);
+    d3.process(iq.data(), a.data(), n);
+    std::fwrite(a.data(), sizeof(float), n * OUTPUT_RATE / INPUT_RATE - 2, fx);
+    d3.processNoDownsample(iq.data() + 2 * n, b.data(), n);
+    std::fwrite(b.data(), sizeof(float), n, fx);
+    const size_t k2 = d3.downsampleAudio(b.data(), c.data(), n);
+    std::fwrite(c.data(), sizeof(float), k2, fx);
+    std::fclose(fx);
+  }
   return 0;
 }

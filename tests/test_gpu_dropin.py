@@ -27,6 +27,42 @@ def harness(tmp_path_factory):
     return out
 
 
+def _check_extra(orc_fm, iq, iq_rate, decim, prefix):
+    """The rest of the public class surface (see the tail of dropin_harness.cpp)."""
+    import ctypes as C
+    L = orc_fm.lib
+    F = C.POINTER(C.c_float)
+    U8 = C.POINTER(C.c_uint8)
+    fs = iq_rate // decim
+    raw = np.fromfile(prefix + ".extra.bin", np.uint8)
+    n = min(4096, iq.size // 2 // max(1, decim))
+    pos = 0
+    if decim > 1:
+        d = L.orc_decim_create(decim, 28 if decim >= 8 else 20, 80.0)
+        q = np.zeros(2 * n, np.uint8)
+        k = L.orc_decim_execute_u8(d, iq.ctypes.data_as(U8), n * decim, q.ctypes.data_as(U8), n)
+        assert k == n and np.array_equal(raw[:2 * n], q)
+        pos = 2 * n
+        L.orc_decim_destroy(d)
+    fl = raw[pos:].view(np.float32)
+    h = L.orc_demod_create(fs, 32000)
+    L.orc_demod_set_bandwidth_mode(h, 9)
+    L.orc_demod_set_deviation(h, 50000.0)
+    a = np.zeros(n, np.float32)
+    mpx = np.zeros(n, np.float32)
+    ka = L.orc_demod_process_split(h, iq.ctypes.data_as(U8), mpx.ctypes.data_as(F), a.ctypes.data_as(F), n)
+    na = n * 32000 // fs - 2
+    assert ka >= na and np.array_equal(fl[:na], a[:na])
+    b = np.zeros(n, np.float32)
+    second = np.ascontiguousarray(iq[2 * n:4 * n])
+    L.orc_demod_process_split(h, second.ctypes.data_as(U8), b.ctypes.data_as(F), None, n)
+    assert np.array_equal(fl[na:na + n], b)
+    c = np.zeros(n, np.float32)
+    kc = L.orc_demod_downsample(h, b.ctypes.data_as(F), c.ctypes.data_as(F), n)
+    assert np.array_equal(fl[na + n:na + n + kc], c[:kc]) and fl.size == na + n + kc
+    L.orc_demod_destroy(h)
+
+
 @pytest.mark.parametrize("rate", ["256k", "direct256k", "240k"])
 def test_reference_style_main_loop(harness, orc_fm, tmp_path, rate):
     iq_rate, decim = rates(rate)
@@ -51,6 +87,7 @@ def test_reference_style_main_loop(harness, orc_fm, tmp_path, rate):
     assert np.array_equal(status[:, 2].astype(int), ref.status["pilot_tenths"])
     assert np.allclose(status[:, 3], ref.status["clip_ratio"], rtol=0, atol=1e-9)
     assert np.array_equal(status[:, 4].astype(int), ref.status["n_groups"])
+    _check_extra(orc_fm, iq, iq_rate, decim, prefix)
     g = np.loadtxt(prefix + ".groups.txt").reshape(-1, 6).astype(np.int64)
     assert len(g) == len(ref.groups)
     for row, r in zip(g, ref.groups):
