@@ -82,6 +82,8 @@ struct fmgpu_engine {
   fmgpu_block_status *dStatus = nullptr;
   uint32_t *dNAudio = nullptr, *dNGroups = nullptr;
   uint8_t *dBits = nullptr;
+  unsigned long long *dWords = nullptr;
+  uint32_t *dBitEnd = nullptr;
   size_t x2Pitch = 0, yPitch = 0, mpxPitch = 0, lrPitch = 0, lfPitch = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // the RDS branch runs beside the stereo branch
@@ -437,8 +439,11 @@ void stageRds(fmgpu_engine *e, fmgpu_rds_group *groups, uint32_t gcap, fmgpu_blo
               int nblk, int blk_len, int n, int ch0, int nch, cudaStream_t s) {
   Span sp(e, "rds", s);
   launchRds(e->dMpx, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
-            e->dMf, e->dDmf, groups, gcap, e->dBits, static_cast<uint32_t>(e->bitsCap), status, nblk,
-            nblk, blk_len, n, ch0, nch, e->k, s);
+            e->dMf, e->dDmf, e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, nblk, blk_len, n,
+            ch0, nch, e->k, s);
+  launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords, groups,
+                  gcap, status, nblk, nblk, ch0, nch, s);
+  e->launches += 1;
   launchSaveTail(e->dMpx, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, n, ch0, nch, s);
   e->launches += 2;
 }
@@ -832,6 +837,8 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(devAlloc(&e->dNAudio, C));
   CKC(devAlloc(&e->dNGroups, C));
   CKC(devAlloc(&e->dBits, C * e->bitsCap));
+  CKC(devAlloc(&e->dWords, C * e->bitsCap));
+  CKC(devAlloc(&e->dBitEnd, C * static_cast<size_t>(e->maxBlocks)));
   CKC(cudaMemcpy(e->dAudBank, e->audRs.bank.data(), e->audRs.bank.size() * sizeof(float),
                  cudaMemcpyHostToDevice));
   CKC(cudaMemcpy(e->dRdsBank, e->rdsRs.bank.data(), e->rdsRs.bank.size() * sizeof(float),
@@ -892,7 +899,7 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
                   e->dRing,    e->dRdsHist, e->dMonoHist, e->dChanTaps, e->dChanScale, e->dChanLp,
                   e->dAudBank, e->dRdsBank, e->dRdsLpf, e->dMf,     e->dDmf,     e->dParams,
                   e->dDemod,   e->dStereo, e->dAudioSt, e->dRds,    e->dGroups,  e->dStatus,
-                  e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid};
+                  e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd};
   for (void *p : ptrs) {
     if (p) {
       cudaFree(p);

@@ -1157,17 +1157,17 @@ __device__ __forceinline__ bool rdsCouldFollow(int off, uint32_t pos, int ooff, 
          ((uint32_t)rdsBlockNumberDev(ooff) + d / 26) % 4 == (uint32_t)rdsBlockNumberDev(off);
 }
 
-__device__ void rdsPushBit(RdsState &s, bool bit, fmgpu_rds_group *groups, uint32_t gcap,
-                           uint32_t block_index) {
-  s.reg = (s.reg << 1) + (bit ? 1u : 0u);
+// BlockStream::pushBit with the 26-bit window `raw` ending at this bit and its syndrome `syn`
+// already evaluated (k_blocksync phase 1 computes them for every bit offset in parallel).
+__device__ void rdsPushWord(RdsState &s, uint32_t raw, uint32_t syn, fmgpu_rds_group *groups,
+                            uint32_t gcap, uint32_t block_index) {
+  s.reg = (s.reg << 1) + (raw & 1u);
   s.until--;
   s.bitcount++;
   if (s.until != 0) {
     return;
   }
   // findBlockInInputRegister
-  const uint32_t raw = s.reg & 0x3ffffffu;
-  const uint32_t syn = rdsSyndromeDev(raw);
   int off = rdsOffsetForSyndromeDev(syn);
   if (!s.in_sync) {
     s.bits_since_lost++;
@@ -1260,9 +1260,9 @@ __global__ void __launch_bounds__(64)
 k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
       int hist_pitch, RdsState *st, float2 *ring,
       const float *__restrict__ g_bank, const float *__restrict__ g_lpf,
-      const float *__restrict__ g_mf, const float *__restrict__ g_dmf, fmgpu_rds_group *groups,
-      uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap, fmgpu_block_status *status,
-      int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
+      const float *__restrict__ g_mf, const float *__restrict__ g_dmf, uint8_t *bits_out,
+      uint32_t bits_cap, uint32_t *bit_end, int nblk, int blk_len, int n_total, int ch0, int nch,
+      EngineConst k) {
   __shared__ float s_bank[32 * RDS_RS_LEN];
   __shared__ float s_lpf[RDS_LPF_LEN + 1];
   __shared__ float s_mf[32 * SS_LEN];
@@ -1300,8 +1300,7 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
   }
   int sp = 0;  // ring position of the oldest symsync window element
   float2 *ringc = ring + (size_t)c * RDS_RING;
-  fmgpu_rds_group *gout = groups ? groups + (size_t)c * gcap : nullptr;
-  uint8_t *bout = bits_dbg ? bits_dbg + (size_t)c * bits_cap : nullptr;
+  uint8_t *bout = bits_out + (size_t)c * bits_cap;
 
   float2 acc[RDS_NACC];
 #pragma unroll
@@ -1358,7 +1357,6 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
   __syncthreads();
   int blk = 0, in_blk = 0;
   int cur_len = min(blk_len, n_total);
-  uint32_t groups_before = s.n_groups;
 
   for (int ck = 0; ck < nchunks; ck++) {
     const int clen = min(LT, n_total - ck * LT);
@@ -1498,11 +1496,10 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
             if (has) {
               const bool bit = (bval != (s.delta_prev != 0));
               s.delta_prev = bval ? 1 : 0;
-              if (bout && s.n_bits < bits_cap) {
+              if (s.n_bits < bits_cap) {
                 bout[s.n_bits] = bit ? 1 : 0;
               }
               s.n_bits++;
-              rdsPushBit(s, bit, gout, gcap, (uint32_t)blk);
             }
           }
         }
@@ -1516,10 +1513,7 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
       }
       phase -= (1u << 24);
       if (++in_blk == cur_len) {
-        if (status) {
-          status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - groups_before);
-        }
-        groups_before = s.n_groups;
+        bit_end[(size_t)c * nblk + blk] = min(s.n_bits, bits_cap);  // bits demodulated so far
         blk++;
         in_blk = 0;
         cur_len = min(blk_len, n_total - blk * blk_len);
@@ -1540,6 +1534,90 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
     sp = (sp + 1 == SS_LEN) ? 0 : sp + 1;
   }
   st[c] = s;
+}
+
+// ---------------------------------------------------------------------------
+// K7c: RDS block synchroniser (block_sync.cpp:235-313). Phase 1 evaluates the (26,16) syndrome
+// of the 26-bit window ending at EVERY bit offset, in parallel over (channel, bit); phase 2 is
+// the sequential sync / FEC state machine, one lane per channel, consuming those syndromes
+// (every bit while searching for sync, every 26th once locked).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t *__restrict__ bit_end,
+            RdsState *st, unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
+            fmgpu_block_status *status, int status_pitch, int nblk, int ch0, int nch) {
+  __shared__ uint32_t s_reg[32], s_nb[32];
+  const int c0 = ch0 + blockIdx.x * 32;
+  const int nrows = min(32, ch0 + nch - c0);
+  if (threadIdx.x < 32) {
+    const bool valid = (int)threadIdx.x < nrows;
+    s_reg[threadIdx.x] = valid ? st[c0 + threadIdx.x].reg : 0u;
+    s_nb[threadIdx.x] = valid ? min(st[c0 + threadIdx.x].n_bits, bits_cap) : 0u;
+  }
+  __syncthreads();
+  for (int r = 0; r < nrows; r++) {
+    const uint32_t nb = s_nb[r];
+    const uint32_t reg = s_reg[r];
+    const uint8_t *brow = bits + (size_t)(c0 + r) * bits_cap;
+    unsigned long long *wrow = words + (size_t)(c0 + r) * bits_cap;
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int q = 25; q >= 0; q--) {  // bit i-q of the stream; bits before this call sit in reg
+        const int idx = (int)i - q;
+        const uint32_t bit = (idx >= 0) ? (uint32_t)brow[idx] : ((reg >> (-idx - 1)) & 1u);
+        w = (w << 1) | bit;
+      }
+      wrow[i] = (unsigned long long)w | ((unsigned long long)rdsSyndromeDev(w) << 32);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= nrows) {
+    return;
+  }
+  const int c = c0 + threadIdx.x;
+  RdsState s = st[c];
+  const uint32_t nb = s_nb[threadIdx.x];
+  const unsigned long long *wrow = words + (size_t)c * bits_cap;
+  const uint32_t *bend = bit_end + (size_t)c * nblk;
+  fmgpu_rds_group *gout = groups ? groups + (size_t)c * gcap : nullptr;
+  int blk = 0;
+  uint32_t before = s.n_groups;
+  for (uint32_t i = 0; i < nb; i++) {
+    while (blk < nblk - 1 && i >= bend[blk]) {
+      if (status) {
+        status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - before);
+      }
+      before = s.n_groups;
+      blk++;
+    }
+    const unsigned long long w = wrow[i];
+    rdsPushWord(s, (uint32_t)w & 0x3ffffffu, (uint32_t)(w >> 32), gout, gcap, (uint32_t)blk);
+  }
+  if (status) {
+    for (; blk < nblk; blk++) {
+      status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - before);
+      before = s.n_groups;
+    }
+  }
+  // only the block-synchroniser fields changed
+  RdsState *o = &st[c];
+  o->bitcount = s.bitcount;
+  o->until = s.until;
+  o->reg = s.reg;
+  o->bits_since_lost = s.bits_since_lost;
+  o->expected = s.expected;
+  o->in_sync = s.in_sync;
+  o->err_ptr = s.err_ptr;
+  o->err_mask = s.err_mask;
+  for (int q = 0; q < 4; q++) {
+    o->cur_data[q] = s.cur_data[q];
+    o->pulse_pos[q] = s.pulse_pos[q];
+    o->pulse_off[q] = s.pulse_off[q];
+  }
+  o->cur_recv = s.cur_recv;
+  o->cur_err = s.cur_err;
+  o->n_groups = s.n_groups;
 }
 
 // ---------------------------------------------------------------------------
@@ -1715,13 +1793,20 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
 
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
-               fmgpu_rds_group *groups, uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap,
-               fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
-               int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+               uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end, int nblk, int blk_len,
+               int n_total, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
   constexpr size_t smem = 2 * 32 * (LT + RDS_HIST) * sizeof(float);
   k_rds<<<(nch + 31) / 32, 64, smem, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, ring, bank, lpf,
-                                           mf, dmf, groups, gcap, bits_dbg, bits_cap, status,
-                                           status_pitch, nblk, blk_len, n_total, ch0, nch, k);
+                                              mf, dmf, bits_out, bits_cap, bit_end, nblk, blk_len,
+                                              n_total, ch0, nch, k);
+}
+
+void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit_end, RdsState *st,
+                     unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
+                     fmgpu_block_status *status, int status_pitch, int nblk, int ch0, int nch,
+                     cudaStream_t stream) {
+  k_blocksync<<<(nch + 31) / 32, 128, 0, stream>>>(bits, bits_cap, bit_end, st, words, groups, gcap,
+                                                  status, status_pitch, nblk, ch0, nch);
 }
 
 }  // namespace fmgpu

@@ -65,9 +65,12 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
                        cudaStream_t stream);
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
-               fmgpu_rds_group *groups, uint32_t gcap, uint8_t *bits_dbg, uint32_t bits_cap,
-               fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
-               int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+               uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end, int nblk, int blk_len,
+               int n_total, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit_end, RdsState *st,
+                     unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
+                     fmgpu_block_status *status, int status_pitch, int nblk, int ch0, int nch,
+                     cudaStream_t stream);
 
 // synth.cu
 cudaError_t launchSynth(const fmgpu_synth_params *params_dev, const int8_t *chips_dev,
