@@ -1304,6 +1304,64 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
   return FMGPU_OK;
 }
 
+int fmgpu_signal_level_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
+                             int n_blocks, fmgpu_level_sums *sums_dev, void *stream) {
+  if (!e || !iq_dev || !sums_dev || n_blocks < 1) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long spb = static_cast<long>(e->N) * e->M;
+  if (iq_stride_bytes < static_cast<size_t>(n_blocks) * spb * 2) {
+    e->lastError = "signal_level: stride smaller than the bytes per channel";
+    return FMGPU_EINVAL;
+  }
+  CK(cudaMemsetAsync(sums_dev, 0, static_cast<size_t>(e->C) * n_blocks * sizeof(fmgpu_level_sums), s));
+  launchSigLevel(iq_dev, iq_stride_bytes, sums_dev, n_blocks, spb, 0, e->C, s);
+  e->launches += 1;
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    e->lastError = std::string("signal_level: ") + cudaGetErrorString(err);
+    return FMGPU_ENODEV;
+  }
+  return FMGPU_OK;
+}
+
+void fmgpu_signal_level_finish(const fmgpu_level_sums *su, int applied_gain_db,
+                               double gain_comp_factor, double signal_bias_db, double floor_dbfs,
+                               double ceil_dbfs, fmgpu_signal_level *out) {
+  if (!su || !out) {
+    return;
+  }
+  *out = fmgpu_signal_level{0.0f, -120.0, -120.0, 0.0, 0.0};
+  if (su->n_samples == 0) {
+    return;
+  }
+  // sum of (v - 127.5)/127.5 and of its square, from the exact integer sums
+  const double n = static_cast<double>(su->n_samples);
+  const double k = 1.0 / 127.5;
+  const double sI = (static_cast<double>(su->sum_i) - 127.5 * n) * k;
+  const double sQ = (static_cast<double>(su->sum_q) - 127.5 * n) * k;
+  const double sII = (static_cast<double>(su->sum_ii) - 255.0 * static_cast<double>(su->sum_i) +
+                      127.5 * 127.5 * n) * k * k;
+  const double sQQ = (static_cast<double>(su->sum_qq) - 255.0 * static_cast<double>(su->sum_q) +
+                      127.5 * 127.5 * n) * k * k;
+  const double meanI = sI / n, meanQ = sQ / n;
+  const double varI = std::max(0.0, (sII / n) - (meanI * meanI));
+  const double varQ = std::max(0.0, (sQQ / n) - (meanQ * meanQ));
+  const double rms = std::sqrt(std::max(1e-15, 0.5 * (varI + varQ)));
+  out->dbfs = 20.0 * std::log10(rms + 1e-12);
+  out->compensated_dbfs = out->dbfs - (static_cast<double>(applied_gain_db) * gain_comp_factor) +
+                          signal_bias_db;
+  const double safeCeil = std::max(ceil_dbfs, floor_dbfs + 1.0);
+  const double norm = (out->compensated_dbfs - floor_dbfs) / (safeCeil - floor_dbfs);
+  out->level120 = std::clamp(static_cast<float>(norm * 120.0), 0.0f, 120.0f);
+  const double iqValues = 2.0 * n;
+  out->hard_clip_ratio = (2.0 * static_cast<double>(su->hard_clip)) / iqValues;
+  out->near_clip_ratio = (2.0 * static_cast<double>(su->near_clip)) / iqValues;
+}
+
 int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups) {
   if (!e || groups < 1 || groups > fmgpu_engine::kMaxGroups) {
     return FMGPU_EINVAL;

@@ -13,6 +13,8 @@
 // Compiled with -fmad=false: only explicit fmaf() fuses.
 #include "kernels.h"
 
+#include <algorithm>
+
 #include "fm_math.h"
 
 namespace fmgpu {
@@ -1621,6 +1623,78 @@ k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t 
 }
 
 // ---------------------------------------------------------------------------
+// RF level meter (signal_level.cpp:145-178): exact integer sums of the IQ bytes of every
+// logical block. 128-bit loads, per-thread uint32 partials, warp shuffle + one 64-bit atomic
+// per warp. HBM-bound: 2 B per IQ sample in, 48 B per block out.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,
+           long samples_per_block, int slices, int ch0) {
+  const int c = blockIdx.y + ch0;
+  const int b = blockIdx.x / slices;
+  const int sl = blockIdx.x - b * slices;
+  const long per = (samples_per_block + slices - 1) / slices;
+  const long s0 = sl * per;
+  const long s1 = min(samples_per_block, s0 + per);
+  const uint8_t *base = iq + (size_t)c * iq_stride + 2 * (size_t)b * samples_per_block;
+  unsigned long long si = 0, sq = 0, sii = 0, sqq = 0;
+  uint32_t hard = 0, nearc = 0, cnt = 0;
+  // 16-byte chunks (8 IQ pairs); block starts are 16-byte aligned when samples_per_block % 8 == 0
+  const long c0 = (s0 + 7) >> 3, c1 = s1 >> 3;
+  auto one = [&](uint32_t vi, uint32_t vq) {
+    si += vi;
+    sq += vq;
+    sii += vi * vi;
+    sqq += vq * vq;
+    hard += (vi <= 1u || vi >= 254u || vq <= 1u || vq >= 254u) ? 1u : 0u;
+    nearc += (vi <= 8u || vi >= 247u || vq <= 8u || vq >= 247u) ? 1u : 0u;
+    cnt++;
+  };
+  const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
+  if (aligned && c1 > c0) {
+    for (long s = s0 + threadIdx.x; s < (c0 << 3); s += blockDim.x) {  // head
+      one(base[2 * s], base[2 * s + 1]);
+    }
+    for (long ck = c0 + threadIdx.x; ck < c1; ck += blockDim.x) {       // 128-bit body
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(base + 16 * ck));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        one(w[q] & 0xffu, (w[q] >> 8) & 0xffu);
+        one((w[q] >> 16) & 0xffu, w[q] >> 24);
+      }
+    }
+    for (long s = (c1 << 3) + threadIdx.x; s < s1; s += blockDim.x) {   // tail
+      one(base[2 * s], base[2 * s + 1]);
+    }
+  } else {
+    for (long s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+      one(base[2 * s], base[2 * s + 1]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    si += __shfl_down_sync(0xffffffffu, si, o);
+    sq += __shfl_down_sync(0xffffffffu, sq, o);
+    sii += __shfl_down_sync(0xffffffffu, sii, o);
+    sqq += __shfl_down_sync(0xffffffffu, sqq, o);
+    hard += __shfl_down_sync(0xffffffffu, hard, o);
+    nearc += __shfl_down_sync(0xffffffffu, nearc, o);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    fmgpu_level_sums *o = &sums[(size_t)c * nblk + b];
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_i), si);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_q), sq);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_ii), sii);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_qq), sqq);
+    atomicAdd(&o->hard_clip, hard);
+    atomicAdd(&o->near_clip, nearc);
+    atomicAdd(&o->n_samples, cnt);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 #define FMGPU_DECIM_CASE(MM)                                                                     \
@@ -1807,6 +1881,14 @@ void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit
                      cudaStream_t stream) {
   k_blocksync<<<(nch + 31) / 32, 128, 0, stream>>>(bits, bits_cap, bit_end, st, words, groups, gcap,
                                                   status, status_pitch, nblk, ch0, nch);
+}
+
+void launchSigLevel(const uint8_t *iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,
+                    long samples_per_block, int ch0, int nch, cudaStream_t stream) {
+  // enough CTAs to fill the machine even for few channels, ~16K samples per CTA at most
+  int slices = (int)std::min<long>(64, std::max<long>(1, samples_per_block / 16384));
+  dim3 grid(nblk * slices, nch);
+  k_siglevel<<<grid, 256, 0, stream>>>(iq, iq_stride, sums, nblk, samples_per_block, slices, ch0);
 }
 
 }  // namespace fmgpu

@@ -43,6 +43,17 @@ def make_config(iq_rate=2_400_000, decimation=10, output_rate=32000, block_sampl
                   decim_taps_per_phase, decim_atten_db)
 
 
+class LevelSums(C.Structure):
+    _fields_ = [("sum_i", C.c_uint64), ("sum_q", C.c_uint64), ("sum_ii", C.c_uint64),
+                ("sum_qq", C.c_uint64), ("hard_clip", C.c_uint32), ("near_clip", C.c_uint32),
+                ("n_samples", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class SignalLevel(C.Structure):
+    _fields_ = [("level120", C.c_float), ("dbfs", C.c_double), ("compensated_dbfs", C.c_double),
+                ("hard_clip_ratio", C.c_double), ("near_clip_ratio", C.c_double)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("deviation_hz", C.c_float), ("tone_l_hz", C.c_float), ("tone_l_amp", C.c_float),
                 ("tone_r_hz", C.c_float), ("tone_r_amp", C.c_float), ("pilot_amp", C.c_float),
@@ -111,6 +122,10 @@ def load_library(build: bool = True):
     L.fmgpu_launch_count.argtypes = [vp]
     L.fmgpu_enable_stage_timing.argtypes = [vp, i32]
     L.fmgpu_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]
+    L.fmgpu_signal_level_batch.argtypes = [vp, u8p, sz, i32, vp, vp]
+    L.fmgpu_signal_level_finish.restype = None
+    L.fmgpu_signal_level_finish.argtypes = [C.POINTER(LevelSums), i32, C.c_double, C.c_double,
+                                            C.c_double, C.c_double, C.POINTER(SignalLevel)]
     L.fmgpu_synth_iq.argtypes = [i32, C.POINTER(SynthParams), i32, C.c_double, sz, u8p, sz, vp]
     _lib = L
     return L
@@ -252,6 +267,17 @@ class Engine:
         self._check(self.L.fmgpu_process_batch(self.h, iq_dev_ptr, stride, n_blocks, audio_ptr, acap,
                                                n_audio_ptr, groups_ptr, gcap, n_groups_ptr,
                                                status_ptr, stream), "process_batch")
+
+    def signal_level_batch(self, iq_dev_ptr, stride, n_blocks, sums_dev_ptr, stream=None):
+        self._check(self.L.fmgpu_signal_level_batch(self.h, iq_dev_ptr, stride, n_blocks,
+                                                    sums_dev_ptr, stream), "signal_level_batch")
+
+    def signal_level_finish(self, sums: "LevelSums", gain_db=0, comp=0.0, bias=0.0, floor=-70.0,
+                            ceil=-5.0) -> "SignalLevel":
+        out = SignalLevel()
+        self.L.fmgpu_signal_level_finish(C.byref(sums), gain_db, comp, bias, floor, ceil,
+                                         C.byref(out))
+        return out
 
     # ---- stage-level (reference method names) --------------------------------
     def executeComplex(self, iq: np.ndarray, out_capacity: int, channel=0) -> np.ndarray:

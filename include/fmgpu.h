@@ -127,6 +127,32 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
                        fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
                        fmgpu_block_status *status_host);
 
+/* ---- RF signal level: the per-block meter main.cpp computes from the raw
+ * IQ bytes (computeSignalLevel, src/signal_level.cpp:145-203, called at main.cpp:1167).
+ * The device pass reduces each logical block of each channel to EXACT integer sums; the host
+ * helper finishes them in double precision the way the reference does. */
+typedef struct fmgpu_level_sums {
+  uint64_t sum_i, sum_q;   /* sum of the I / Q bytes */
+  uint64_t sum_ii, sum_qq; /* sum of their squares */
+  uint32_t hard_clip;      /* samples with a byte <= 1 or >= 254 (signal_level.cpp:169-171) */
+  uint32_t near_clip;      /* samples with a byte <= 8 or >= 247 (signal_level.cpp:172-174) */
+  uint32_t n_samples;      /* IQ pairs reduced */
+  uint32_t pad;
+} fmgpu_level_sums;
+
+typedef struct fmgpu_signal_level { /* SignalLevelResult, include/signal_level.h:7-13 */
+  float level120;
+  double dbfs, compensated_dbfs, hard_clip_ratio, near_clip_ratio;
+} fmgpu_signal_level;
+
+/* sums_dev [C][n_blocks]; iq layout as fmgpu_process_batch. Asynchronous on `stream`. */
+int fmgpu_signal_level_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
+                             int n_blocks, fmgpu_level_sums *sums_dev, void *stream);
+/* Host only: dBFS / 0..120 meter / clip ratios from one block's sums (signal_level.cpp:180-203). */
+void fmgpu_signal_level_finish(const fmgpu_level_sums *sums, int applied_gain_db,
+                               double gain_comp_factor, double signal_bias_db, double floor_dbfs,
+                               double ceil_dbfs, fmgpu_signal_level *out);
+
 /* Split the channels into `groups` (1..8) ranges that run the pipeline on separate streams:
  * one range's serial (one-lane-per-channel) kernels then overlap another range's FIR kernels
  * and, in fmgpu_process_host, its host<->device copies. Results do not depend on it. */

@@ -30,7 +30,8 @@ def build(force: bool = False) -> None:
     need = force or stale("liboracle_libm.so", oracle_deps) or stale("liboracle_fm.so", oracle_deps) \
         or stale("libsiggen.so", ("siggen.cpp", "Makefile"))
     have_ref_src = os.path.isdir("/root/reference/src/redsea_port")
-    ref_missing = have_ref_src and not os.path.exists(os.path.join(HERE, "_ref", "libredsea_ref.so"))
+    ref_missing = have_ref_src and not all(
+        os.path.exists(os.path.join(HERE, "_ref", f)) for f in ("libredsea_ref.so", "libsiglevel_ref.so"))
     if need or ref_missing:
         subprocess.run(["make", "-C", HERE, "--no-print-directory"], check=True,
                        stdout=subprocess.DEVNULL)
@@ -424,3 +425,36 @@ def ref_blockstream(bits: np.ndarray):
     out = np.zeros(max(4, bits.size // 26 + 4), GROUP_DTYPE)
     n = lib.ref_blockstream_run(_p(bits, C.c_uint8), bits.size, out.ctypes.data, out.size)
     return out[:n]
+
+
+def signal_level(iq: np.ndarray, gain_db=0, comp=0.0, bias=0.0, floor=-70.0, ceil=-5.0):
+    """RF level of one block of IQ bytes: the REFERENCE's computeSignalLevel when oracle/_ref was
+    built, else a numpy restatement of src/signal_level.cpp:145-203 (sequential double sums).
+    Returns (level120, dbfs, compensated_dbfs, hard_clip_ratio, near_clip_ratio, source)."""
+    iq = np.ascontiguousarray(iq, np.uint8).reshape(-1)
+    n = iq.size // 2
+    path = os.path.join(HERE, "_ref", "libsiglevel_ref.so")
+    if os.path.exists(path):
+        lib = C.CDLL(path)
+        lib.ref_compute_signal_level.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_double,
+                                                 C.c_double, C.c_double, C.c_double,
+                                                 C.POINTER(C.c_double)]
+        out = (C.c_double * 5)()
+        lib.ref_compute_signal_level(_p(iq, C.c_uint8), n, gain_db, comp, bias, floor, ceil, out)
+        return (float(np.float32(out[0])), out[1], out[2], out[3], out[4], "reference")
+    i = (iq[0::2].astype(np.float64) - 127.5) * (1.0 / 127.5)
+    q = (iq[1::2].astype(np.float64) - 127.5) * (1.0 / 127.5)
+    s_i, s_q = np.cumsum(i)[-1], np.cumsum(q)[-1]
+    s_ii, s_qq = np.cumsum(i * i)[-1], np.cumsum(q * q)[-1]
+    ib, qb = iq[0::2], iq[1::2]
+    hard = 2 * int(((ib <= 1) | (ib >= 254) | (qb <= 1) | (qb >= 254)).sum())
+    near = 2 * int(((ib <= 8) | (ib >= 247) | (qb <= 8) | (qb >= 247)).sum())
+    mi, mq = s_i / n, s_q / n
+    var_i = max(0.0, s_ii / n - mi * mi)
+    var_q = max(0.0, s_qq / n - mq * mq)
+    rms = np.sqrt(max(1e-15, 0.5 * (var_i + var_q)))
+    dbfs = 20.0 * np.log10(rms + 1e-12)
+    cdb = dbfs - gain_db * comp + bias
+    norm = (cdb - floor) / (max(ceil, floor + 1.0) - floor)
+    lvl = float(np.clip(np.float32(norm * 120.0), np.float32(0), np.float32(120)))
+    return (lvl, dbfs, cdb, hard / (2.0 * n), near / (2.0 * n), "restated")
