@@ -1362,6 +1362,20 @@ void fmgpu_signal_level_finish(const fmgpu_level_sums *su, int applied_gain_db,
   out->near_clip_ratio = (2.0 * static_cast<double>(su->near_clip)) / iqValues;
 }
 
+int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
+                     const uint32_t *n_audio_dev, float volume_scale, int16_t *pcm_dev,
+                     void *stream) {
+  if (!e || !audio_dev || !n_audio_dev || !pcm_dev || audio_cap == 0) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  launchPackPcm16(audio_dev, audio_cap, n_audio_dev, volume_scale, pcm_dev, e->C,
+                  static_cast<int>(std::min(audio_cap, e->acap)), static_cast<cudaStream_t>(stream));
+  e->launches += 1;
+  return cudaGetLastError() == cudaSuccess ? FMGPU_OK : FMGPU_ENODEV;
+}
+
 int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups) {
   if (!e || groups < 1 || groups > fmgpu_engine::kMaxGroups) {
     return FMGPU_EINVAL;

@@ -1695,6 +1695,25 @@ k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *s
 }
 
 // ---------------------------------------------------------------------------
+// K8: float audio -> interleaved int16 PCM (audio_output.cpp:1386-1391,1458-1459). Streaming,
+// HBM-bound: 8 B in, 4 B out per frame.
+// ---------------------------------------------------------------------------
+__global__ void k_pack_pcm16(const float *__restrict__ audio, size_t acap,
+                             const uint32_t *__restrict__ n_audio, float volume,
+                             short2 *__restrict__ pcm, int C) {
+  const int c = blockIdx.y;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || i >= n_audio[c] || i >= acap) {
+    return;
+  }
+  const float l = audio[((size_t)c * 2 + 0) * acap + i] * volume;
+  const float r = audio[((size_t)c * 2 + 1) * acap + i] * volume;
+  const float lc = fmaxf(-1.0f, fminf(1.0f, l));
+  const float rc = fmaxf(-1.0f, fminf(1.0f, r));
+  pcm[(size_t)c * acap + i] = make_short2((short)(lc * 32767.0f), (short)(rc * 32767.0f));
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 #define FMGPU_DECIM_CASE(MM)                                                                     \
@@ -1889,6 +1908,13 @@ void launchSigLevel(const uint8_t *iq, size_t iq_stride, fmgpu_level_sums *sums,
   int slices = (int)std::min<long>(64, std::max<long>(1, samples_per_block / 16384));
   dim3 grid(nblk * slices, nch);
   k_siglevel<<<grid, 256, 0, stream>>>(iq, iq_stride, sums, nblk, samples_per_block, slices, ch0);
+}
+
+void launchPackPcm16(const float *audio, size_t acap, const uint32_t *n_audio, float volume,
+                     int16_t *pcm, int C, int max_frames, cudaStream_t stream) {
+  dim3 grid((max_frames + 255) / 256, C);
+  k_pack_pcm16<<<grid, 256, 0, stream>>>(audio, acap, n_audio, volume,
+                                         reinterpret_cast<short2 *>(pcm), C);
 }
 
 }  // namespace fmgpu

@@ -75,6 +75,9 @@ void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit
 void launchSigLevel(const uint8_t *iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,
                     long samples_per_block, int ch0, int nch, cudaStream_t stream);
 
+void launchPackPcm16(const float *audio, size_t acap, const uint32_t *n_audio, float volume,
+                     int16_t *pcm, int C, int max_frames, cudaStream_t stream);
+
 // synth.cu
 cudaError_t launchSynth(const fmgpu_synth_params *params_dev, const int8_t *chips_dev,
                         int chips_per_channel, int n_channels, double fs_iq, size_t n_samples,

@@ -126,6 +126,7 @@ def load_library(build: bool = True):
     L.fmgpu_signal_level_finish.restype = None
     L.fmgpu_signal_level_finish.argtypes = [C.POINTER(LevelSums), i32, C.c_double, C.c_double,
                                             C.c_double, C.c_double, C.POINTER(SignalLevel)]
+    L.fmgpu_pack_pcm16.argtypes = [vp, f32p, sz, vp, C.c_float, vp, vp]
     L.fmgpu_synth_iq.argtypes = [i32, C.POINTER(SynthParams), i32, C.c_double, sz, u8p, sz, vp]
     _lib = L
     return L
@@ -267,6 +268,10 @@ class Engine:
         self._check(self.L.fmgpu_process_batch(self.h, iq_dev_ptr, stride, n_blocks, audio_ptr, acap,
                                                n_audio_ptr, groups_ptr, gcap, n_groups_ptr,
                                                status_ptr, stream), "process_batch")
+
+    def pack_pcm16(self, audio_ptr, acap, n_audio_ptr, volume_scale, pcm_ptr, stream=None):
+        self._check(self.L.fmgpu_pack_pcm16(self.h, audio_ptr, acap, n_audio_ptr, volume_scale,
+                                            pcm_ptr, stream), "pack_pcm16")
 
     def signal_level_batch(self, iq_dev_ptr, stride, n_blocks, sums_dev_ptr, stream=None):
         self._check(self.L.fmgpu_signal_level_batch(self.h, iq_dev_ptr, stride, n_blocks,

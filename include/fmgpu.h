@@ -153,6 +153,15 @@ void fmgpu_signal_level_finish(const fmgpu_level_sums *sums, int applied_gain_db
                                double gain_comp_factor, double signal_bias_db, double floor_dbfs,
                                double ceil_dbfs, fmgpu_signal_level *out);
 
+/* ---- output formatting: what AudioOutput::write / writeWAVData do to the
+ * clamped float audio before it reaches a WAV file (src/audio_output.cpp:1445-1464,1386-1391):
+ * multiply by the volume scale (0.85 * volume% / 100), clamp to +-1, scale by 32767 and truncate
+ * toward zero, left/right interleaved. audio_dev / n_audio_dev as written by
+ * fmgpu_process_batch; pcm_dev is [C][2*audio_cap] int16. Asynchronous on `stream`. */
+int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
+                     const uint32_t *n_audio_dev, float volume_scale, int16_t *pcm_dev,
+                     void *stream);
+
 /* Split the channels into `groups` (1..8) ranges that run the pipeline on separate streams:
  * one range's serial (one-lane-per-channel) kernels then overlap another range's FIR kernels
  * and, in fmgpu_process_host, its host<->device copies. Results do not depend on it. */

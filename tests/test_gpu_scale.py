@@ -110,3 +110,30 @@ def test_device_synth_decodes_and_is_deterministic():
     assert st["stereo"][:, -1].all()
     for c in range(C):
         assert len(pis[c]) >= 2 and all(p == 0x2000 + c for p in pis[c]), (c, pis[c])
+
+
+def test_pcm16_packing_matches_reference_formula():
+    """audio_output.cpp:1458-1459 (volume scale) + :1386-1391 (clamp, x32767, truncation)."""
+    import torch
+    C, B = 5, 2
+    iq_rate, decim = rates("240k")
+    iq = np.stack([orc.config3_signal(40 + c, fs_iq=iq_rate).generate(B * 8192 * decim) for c in range(C)])
+    eng = fm.Engine(fm.make_config(max_blocks=B), C, 0)
+    d_iq = torch.from_numpy(iq).cuda()
+    acap = eng.audio_capacity(B)
+    audio = torch.zeros((C, 2, acap), dtype=torch.float32, device="cuda")
+    n_audio = torch.zeros(C, dtype=torch.int32, device="cuda")
+    pcm = torch.zeros((C, acap, 2), dtype=torch.int16, device="cuda")
+    eng.process_batch(d_iq.data_ptr(), iq.shape[1], B, audio.data_ptr(), acap, n_audio.data_ptr())
+    # make the packer see values beyond +-1 too
+    audio *= 3.0
+    for vol in (0.85, 0.85 * 0.37):
+        eng.pack_pcm16(audio.data_ptr(), acap, n_audio.data_ptr(), vol, pcm.data_ptr())
+        torch.cuda.synchronize()
+        a = audio.cpu().numpy()
+        n = int(n_audio[0].item())
+        want = np.trunc(np.clip(a[:, :, :n] * np.float32(vol), -1.0, 1.0).astype(np.float32)
+                        * np.float32(32767.0)).astype(np.int16)
+        got = pcm.cpu().numpy()[:, :n, :]
+        assert np.array_equal(got[:, :, 0], want[:, 0]) and np.array_equal(got[:, :, 1], want[:, 1])
+    eng.close()
