@@ -684,26 +684,38 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
 
 // ---------------------------------------------------------------------------
 // S4: 19 kHz pilot PLL, quality metrics, blend, L-R matrix, per-block lock logic
-// (stereo_decoder.cpp:92-286). One lane per channel.
+// (stereo_decoder.cpp:92-286). One lane per channel, the per-sample work split over a
+// three-warp software pipeline (each warp owns an SM sub-partition, so the stages run
+// concurrently, one tile apart):
+//   warp 0  tile mover   global <-> shared (cp.async in, 128-bit stores out)
+//   warp 1  PLL          pilot -> phase error -> NCO update -> sin/cos of the new phase
+//                        (the only truly serial chain: ~60 dependent instructions per sample)
+//   warp 2  everything fed by it: envelopes, coherent pilot I/Q, blend target and recursion,
+//           L-R matrix, and the per-block stereo-lock logic
+// Arithmetic and its order are exactly those of the single-lane loop (and of the CPU oracle).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(96)
 k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ pilot,
          size_t pilot_pitch, float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
          StereoState *st, const ChanParams *cp, fmgpu_block_status *status, int status_pitch,
          int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
-  constexpr int TP = LT + 8;  // 16-byte aligned rows; the delayed tile needs up to 3 extra
+  constexpr int ST = 16;       // samples per tile row
+  constexpr int TP = ST + 8;   // 16-byte aligned rows; the delayed-MPX tile needs up to 3 extra
+  constexpr int TS = 32 * TP;  // floats per tile
   extern __shared__ float sm_st[];
-  float *t_mpx[2] = {sm_st, sm_st + 32 * TP};
-  float *t_pil[2] = {sm_st + 2 * 32 * TP, sm_st + 3 * 32 * TP};
-  float *t_dly[2] = {sm_st + 4 * 32 * TP, sm_st + 5 * 32 * TP};
-  float *t_l[2] = {sm_st + 6 * 32 * TP, sm_st + 7 * 32 * TP};
-  float *t_r[2] = {sm_st + 8 * 32 * TP, sm_st + 9 * 32 * TP};
-  // warp 0 moves tiles (global <-> shared), warp 1 runs the loop: one lane per channel
+  float *t_pil = sm_st;             // ring of 3: chunk j in slot j % 3
+  float *t_mpx = t_pil + 3 * TS;    // ring of 2
+  float *t_dly = t_mpx + 2 * TS;    // ring of 2
+  float *t_sin = t_dly + 2 * TS;    // ring of 2: sin / cos of the phase AFTER each sample
+  float *t_cos = t_sin + 2 * TS;
+  float *t_frq = t_cos + 2 * TS;    // ring of 2: clamped phase increment (m_pllFreq)
+  float *t_l = t_frq + 2 * TS;      // ring of 2
+  float *t_r = t_l + 2 * TS;
   const int lane = threadIdx.x & 31;
-  const bool io = threadIdx.x < 32;
+  const int role = threadIdx.x >> 5;  // 0 mover, 1 PLL, 2 metrics + matrix
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
-  const bool active = !io && lane < nrows;
+  const bool active = role != 0 && lane < nrows;
   const int c = c0 + min(lane, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   constexpr float kMatrixScale = 0.5f;
@@ -724,25 +736,20 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   const float cohDen = fmaxf(kPilotCoherenceAcquire - kPilotCoherenceHold, 1e-4f);
   const float pllDen = fmaxf(kPllLockHoldHz - kPllLockAcquireHz, 1e-3f);
 
+  // both compute warps start from the NCO phase carried in the state
   uint32_t theta = s.theta, dtheta = s.dtheta;
-  float pbm = s.pbm, mm = s.mm, pilotI = s.pilot_i, pilotQ = s.pilot_q, blend = s.blend;
-  float pllFreq = s.pll_freq;
   float phaseNow = ncoPhaseDev(theta);
   float vcoQ, vcoI;
   fm_sincosf(phaseNow, &vcoQ, &vcoI);
+  float pbm = s.pbm, mm = s.mm, pilotI = s.pilot_i, pilotQ = s.pilot_q, blend = s.blend;
+  float pllFreq = s.pll_freq;
 
-  const int nchunks = (n_total + LT - 1) / LT;
+  const int nchunks = (n_total + ST - 1) / ST;
   const int delay4 = (k.delay + 3) & ~3;  // aligned start of the delayed-MPX tile
   const int dskew = delay4 - k.delay;
-  auto prefetch = [&](int ck) {
-    const int n0 = ck * LT;
-    const int len = min(LT, n_total - n0);
-    tileLoadAsync<TP>(t_mpx[ck & 1], mpx, mpx_pitch, c0, nrows, H_MPX + n0, len, lane);
-    tileLoadAsync<TP>(t_pil[ck & 1], pilot, pilot_pitch, c0, nrows, n0, len, lane);
-    tileLoadAsync<TP>(t_dly[ck & 1], mpx, mpx_pitch, c0, nrows, H_MPX + n0 - delay4, len + 4, lane);
-  };
-  if (io) {
-    prefetch(0);
+  auto clen = [&](int ck) { return min(ST, n_total - ck * ST); };
+  if (role == 0) {
+    tileLoadAsync<TP>(t_pil, pilot, pilot_pitch, c0, nrows, 0, clen(0), lane);
     cpAsyncCommit();
     cpAsyncWait<0>();
   }
@@ -750,68 +757,103 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   int b = 0, in_blk = 0;
   int cur_len = min(blk_len, n_total);
   bool stereoDetected = s.stereo != 0;
-  for (int ck = 0; ck < nchunks; ck++) {
-    const int n0 = ck * LT;
-    const int len = min(LT, n_total - n0);
-    if (io) {
-      if (ck + 1 < nchunks) {
-        prefetch(ck + 1);
-        cpAsyncCommit();
+
+  // step kk: PLL on chunk kk, metrics/matrix on chunk kk-1, mover loads pilot[kk+1], mpx[kk],
+  // delayed mpx[kk] and stores L/R of chunk kk-2
+  for (int kk = 0; kk <= nchunks; kk++) {
+    if (role == 0) {
+      if (kk + 1 < nchunks) {
+        tileLoadAsync<TP>(t_pil + ((kk + 1) % 3) * TS, pilot, pilot_pitch, c0, nrows,
+                          (long)(kk + 1) * ST, clen(kk + 1), lane);
       }
-      if (ck > 0) {
-        tileStore<TP>(t_l[(ck - 1) & 1], lraw, lr_pitch, c0, nrows, H_LR + n0 - LT, LT, lane);
-        tileStore<TP>(t_r[(ck - 1) & 1], rraw, lr_pitch, c0, nrows, H_LR + n0 - LT, LT, lane);
+      if (kk < nchunks) {
+        tileLoadAsync<TP>(t_mpx + (kk & 1) * TS, mpx, mpx_pitch, c0, nrows, H_MPX + (long)kk * ST,
+                          clen(kk), lane);
+        tileLoadAsync<TP>(t_dly + (kk & 1) * TS, mpx, mpx_pitch, c0, nrows,
+                          H_MPX + (long)kk * ST - delay4, clen(kk) + 4, lane);
+      }
+      cpAsyncCommit();
+      if (kk >= 2) {
+        const int j = kk - 2;
+        tileStore<TP>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+        tileStore<TP>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
       }
       cpAsyncWait<0>();
-    } else if (active) {
-      const float *tm = t_mpx[ck & 1] + lane * TP;
-      const float *tp = t_pil[ck & 1] + lane * TP;
-      const float *td = t_dly[ck & 1] + lane * TP + dskew;
-      float *tl = t_l[ck & 1] + lane * TP;
-      float *tr = t_r[ck & 1] + lane * TP;
-      int i = 0;
-      while (i < len) {
-      const int run = min(len - i, cur_len - in_blk);
+    } else if (role == 1) {
+      if (active && kk < nchunks) {
+        const int len = clen(kk);
+        const float *tp = t_pil + (kk % 3) * TS + lane * TP;
+        float *ts = t_sin + (kk & 1) * TS + lane * TP;
+        float *tc = t_cos + (kk & 1) * TS + lane * TP;
+        float *tf = t_frq + (kk & 1) * TS + lane * TP;
 #pragma unroll 2
-      for (int j = 0; j < run; j++, i++) {
-        const float x = tm[i];
-        const float pil = tp[i];
-        const float dm = td[i];
-        pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
-        mm = (mm * kSmooth) + (fabsf(x) * kInject);
-        const float error = pil * vcoQ;
-        dtheta += ncoConstrainDev(error * k.pll_alpha);
-        theta += ncoConstrainDev(error * k.pll_beta);
-        theta += dtheta;
-        const float phaseNext = ncoPhaseDev(theta);
-        float dphi = phaseNext - phaseNow;
-        if (dphi > kPi) {
-          dphi -= 2.0f * kPi;
-        } else if (dphi < -kPi) {
-          dphi += 2.0f * kPi;
+        for (int i = 0; i < len; i++) {
+          const float error = tp[i] * vcoQ;
+          dtheta += ncoConstrainDev(error * k.pll_alpha);
+          theta += ncoConstrainDev(error * k.pll_beta);
+          theta += dtheta;
+          const float phaseNext = ncoPhaseDev(theta);
+          float dphi = phaseNext - phaseNow;
+          if (dphi > kPi) {
+            dphi -= 2.0f * kPi;
+          } else if (dphi < -kPi) {
+            dphi += 2.0f * kPi;
+          }
+          tf[i] = fm_clampf(dphi, k.pll_min, k.pll_max);
+          float sn, cs;
+          fm_sincosf(phaseNext, &sn, &cs);
+          ts[i] = sn;
+          tc[i] = cs;
+          phaseNow = phaseNext;
+          vcoQ = sn;
         }
-        pllFreq = fm_clampf(dphi, k.pll_min, k.pll_max);
-        pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
-        pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
+      }
+    } else {
+      if (active && kk >= 1) {
+        const int j = kk - 1;
+        const int len = clen(j);
+        const float *tm = t_mpx + (j & 1) * TS + lane * TP;
+        const float *tp = t_pil + (j % 3) * TS + lane * TP;
+        const float *td = t_dly + (j & 1) * TS + lane * TP + dskew;
+        const float *ts = t_sin + (j & 1) * TS + lane * TP;
+        const float *tc = t_cos + (j & 1) * TS + lane * TP;
+        const float *tf = t_frq + (j & 1) * TS + lane * TP;
+        float *tl = t_l + (j & 1) * TS + lane * TP;
+        float *tr = t_r + (j & 1) * TS + lane * TP;
+        int i = 0;
+        while (i < len) {
+          const int run = min(len - i, cur_len - in_blk);
+#pragma unroll 2
+          for (int q = 0; q < run; q++, i++) {
+            const float x = tm[i];
+            const float pil = tp[i];
+            const float dm = td[i];
+            const float pllIm = ts[i];
+            const float pllRe = tc[i];
+            pllFreq = tf[i];
+            pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
+            mm = (mm * kSmooth) + (fabsf(x) * kInject);
+            pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
+            pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
 
-        float target = 0.0f;
-        if (p.force_mono) {
-          target = 0.0f;
-        } else if (p.force_stereo) {
-          target = 1.0f;
-        } else if (stereoDetected) {
-          const float mx = fmaxf(mm, 1e-3f);
-          const float pm = fmaxf(pbm, 1e-4f);
-          const float s2 = (pilotI * pilotI) + (pilotQ * pilotQ);
-          const float dfs = fabsf(pllFreq - k.nominal_pll) * k.fsf;
-          const float tB = 0.1803f * pm;
-          if (pbm >= 0.0402f * mx && s2 >= tB * tB && dfs <= 1130.0f) {
-            // Clean pilot: with ratio >= 0.0402, coherence >= 0.1803 and |f error| <= 179.9 Hz each
-            // of the three quality terms below clamps to exactly 1 (margins of >= 1e-4 against
-            // rounding errors of ~1e-7) and no gate trips, so target == 1.0f in every blend mode.
-            // Skipping the six IEEE divisions and the square root changes no result.
-            target = 1.0f;
-          } else {
+            float target = 0.0f;
+            if (p.force_mono) {
+              target = 0.0f;
+            } else if (p.force_stereo) {
+              target = 1.0f;
+            } else if (stereoDetected) {
+              const float mx = fmaxf(mm, 1e-3f);
+              const float pm = fmaxf(pbm, 1e-4f);
+              const float s2 = (pilotI * pilotI) + (pilotQ * pilotQ);
+              const float dfs = fabsf(pllFreq - k.nominal_pll) * k.fsf;
+              const float tB = 0.1803f * pm;
+              if (pbm >= 0.0402f * mx && s2 >= tB * tB && dfs <= 1130.0f) {
+                // Clean pilot: with ratio >= 0.0402, coherence >= 0.1803 and |f error| <= 179.9 Hz
+                // each of the three quality terms below clamps to exactly 1 (margins >= 1e-4
+                // against rounding errors of ~1e-7) and no gate trips, so target == 1.0f in every
+                // blend mode. Skipping the six IEEE divisions and the square root changes nothing.
+                target = 1.0f;
+              } else {
             const float pilotMagNow = FM_SQRT(s2);
             const float pilotRatio = pbm / mx;
             const float pilotCoherence = pilotMagNow / pm;
@@ -834,89 +876,91 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
               target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
             }
           }
-        }
-
-        float pllIm, pllRe;
-        fm_sincosf(phaseNext, &pllIm, &pllRe);
-        const float monoNorm = dm * kMatrixScale;
-        const float cos2 = (pllRe * pllRe) - (pllIm * pllIm);
-        const float lr = 2.0f * dm * cos2;
-        const float stereoLeft = (dm + lr) * kMatrixScale;
-        const float stereoRight = (dm - lr) * kMatrixScale;
-        const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
-        blend += (target - blend) * blendAlpha;
-        tl[i] = monoNorm + ((stereoLeft - monoNorm) * blend);
-        tr[i] = monoNorm + ((stereoRight - monoNorm) * blend);
-
-        phaseNow = phaseNext;
-        vcoQ = pllIm;
-        vcoI = pllRe;
-      }
-      in_blk += run;
-        if (in_blk == cur_len) {
-          // per-block tail (stereo_decoder.cpp:243-286)
-          const float pilotMag = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
-          s.pilot_mag = (s.pilot_mag * 0.9f) + (pilotMag * 0.1f);
-          const bool det = s.stereo != 0;
-          const float mpxThreshold = det ? kMpxMinHold : kMpxMinAcquire;
-          const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
-          const float pilotCoherence = s.pilot_mag / fmaxf(pbm, 1e-4f);
-          const float ratioThreshold = det ? kPilotRatioHold : kPilotRatioAcquire;
-          const float coherenceThreshold = det ? kPilotCoherenceHold : kPilotCoherenceAcquire;
-          const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
-          const float pllThreshold = det ? kPllLockHoldHz : kPllLockAcquireHz;
-          const bool pilotPresent = (mm > mpxThreshold) && (pilotRatio > ratioThreshold) &&
-                                    (pilotCoherence > coherenceThreshold) && (pllErrHz < pllThreshold);
-          if (!p.force_stereo) {
-            if (!det) {
-              if (pilotPresent) {
-                s.pilot_count++;
-                s.loss_count = 0;
-                if (s.pilot_count >= 6) {
-                  s.stereo = 1;
-                }
-              } else {
-                s.pilot_count = 0;
-              }
-            } else if (pilotPresent) {
-              s.loss_count = 0;
-            } else if (++s.loss_count >= 24) {
-              s.stereo = 0;
-              s.pilot_count = 0;
-              s.loss_count = 0;
             }
+
+            const float monoNorm = dm * kMatrixScale;
+            const float cos2 = (pllRe * pllRe) - (pllIm * pllIm);
+            const float lr = 2.0f * dm * cos2;
+            const float stereoLeft = (dm + lr) * kMatrixScale;
+            const float stereoRight = (dm - lr) * kMatrixScale;
+            const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
+            blend += (target - blend) * blendAlpha;
+            tl[i] = monoNorm + ((stereoLeft - monoNorm) * blend);
+            tr[i] = monoNorm + ((stereoRight - monoNorm) * blend);
+            vcoQ = pllIm;
+            vcoI = pllRe;
           }
-          const float calibrated = s.pilot_mag * 8.0f;
-          s.pilot_tenths = min(750, max(0, (int)fm_roundf(calibrated * 750.0f)));
-          if (status) {
-            fmgpu_block_status *o = &status[(size_t)c * status_pitch + b];
-            o->stereo = s.stereo;
-            o->pilot_tenths = s.pilot_tenths;
+          in_blk += run;
+          if (in_blk == cur_len) {
+            // per-block tail (stereo_decoder.cpp:243-286)
+            const float pilotMag = FM_SQRT((pilotI * pilotI) + (pilotQ * pilotQ));
+            s.pilot_mag = (s.pilot_mag * 0.9f) + (pilotMag * 0.1f);
+            const bool det = s.stereo != 0;
+            const float mpxThreshold = det ? kMpxMinHold : kMpxMinAcquire;
+            const float pilotRatio = pbm / fmaxf(mm, 1e-3f);
+            const float pilotCoherence = s.pilot_mag / fmaxf(pbm, 1e-4f);
+            const float ratioThreshold = det ? kPilotRatioHold : kPilotRatioAcquire;
+            const float coherenceThreshold = det ? kPilotCoherenceHold : kPilotCoherenceAcquire;
+            const float pllErrHz = fabsf(pllFreq - k.nominal_pll) * k.fsf / (2.0f * kPi);
+            const float pllThreshold = det ? kPllLockHoldHz : kPllLockAcquireHz;
+            const bool pilotPresent = (mm > mpxThreshold) && (pilotRatio > ratioThreshold) &&
+                                      (pilotCoherence > coherenceThreshold) && (pllErrHz < pllThreshold);
+            if (!p.force_stereo) {
+              if (!det) {
+                if (pilotPresent) {
+                  s.pilot_count++;
+                  s.loss_count = 0;
+                  if (s.pilot_count >= 6) {
+                    s.stereo = 1;
+                  }
+                } else {
+                  s.pilot_count = 0;
+                }
+              } else if (pilotPresent) {
+                s.loss_count = 0;
+              } else if (++s.loss_count >= 24) {
+                s.stereo = 0;
+                s.pilot_count = 0;
+                s.loss_count = 0;
+              }
+            }
+            const float calibrated = s.pilot_mag * 8.0f;
+            s.pilot_tenths = min(750, max(0, (int)fm_roundf(calibrated * 750.0f)));
+            if (status) {
+              fmgpu_block_status *o = &status[(size_t)c * status_pitch + b];
+              o->stereo = s.stereo;
+              o->pilot_tenths = s.pilot_tenths;
+            }
+            b++;
+            in_blk = 0;
+            cur_len = min(blk_len, n_total - b * blk_len);
+            stereoDetected = s.stereo != 0;
           }
-          b++;
-          in_blk = 0;
-          cur_len = min(blk_len, n_total - b * blk_len);
-          stereoDetected = s.stereo != 0;
         }
       }
     }
     __syncthreads();
   }
-  if (io) {
-    const int n0 = (nchunks - 1) * LT;
-    tileStore<TP>(t_l[(nchunks - 1) & 1], lraw, lr_pitch, c0, nrows, H_LR + n0, n_total - n0, lane);
-    tileStore<TP>(t_r[(nchunks - 1) & 1], rraw, lr_pitch, c0, nrows, H_LR + n0, n_total - n0, lane);
-  }
-  s.theta = theta;
-  s.dtheta = dtheta;
-  s.pbm = pbm;
-  s.mm = mm;
-  s.pilot_i = pilotI;
-  s.pilot_q = pilotQ;
-  s.blend = blend;
-  s.pll_freq = pllFreq;
-  if (active) {
-    st[c] = s;
+  if (role == 0) {
+    const int j = nchunks - 1;
+    tileStore<TP>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+    tileStore<TP>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+  } else if (active && role == 1) {
+    st[c].theta = theta;
+    st[c].dtheta = dtheta;
+  } else if (active) {
+    StereoState *o = &st[c];
+    o->pbm = pbm;
+    o->mm = mm;
+    o->pilot_i = pilotI;
+    o->pilot_q = pilotQ;
+    o->blend = blend;
+    o->pll_freq = pllFreq;
+    o->pilot_mag = s.pilot_mag;
+    o->stereo = s.stereo;
+    o->pilot_count = s.pilot_count;
+    o->loss_count = s.loss_count;
+    o->pilot_tenths = s.pilot_tenths;
   }
 }
 
@@ -1829,15 +1873,15 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  constexpr size_t smem = 10 * 32 * (LT + 8) * sizeof(float);
+  constexpr size_t smem = 17 * 32 * (16 + 8) * sizeof(float);  // 17 tiles of [32][16 + 8]
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_stereo<<<(nch + 31) / 32, 64, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
-                                              lr_pitch, st, cp, status, status_pitch, nblk, blk_len,
-                                              n_total, ch0, nch, k);
+  k_stereo<<<(nch + 31) / 32, 96, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
+                                                 lr_pitch, st, cp, status, status_pitch, nblk,
+                                                 blk_len, n_total, ch0, nch, k);
 }
 
 void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
