@@ -295,7 +295,13 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     decoded = {"stereo_channels": int(st_host["stereo"][:, -1].sum()),
                "groups_last_step": int(n_groups.sum().item())}
 
-    # ---- per-stage device times (a separate timed pass; events per stage) -----------------
+    # ---- per-stage device times: a separate timed pass with ONE pipeline group, so that the
+    # CUDA events around each stage bracket that stage's kernels only (with several groups the
+    # stages of different groups interleave on the device and the spans include queueing) -------
+    eng.set_pipeline_groups(1)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
     eng.enable_stage_timing(True)
     acc = {}
     reps = 3
@@ -305,10 +311,22 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         for k, v in eng.stage_times().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.enable_stage_timing(False)
+    eng.set_pipeline_groups(args.groups)
     stage_ms = {k: round(v, 4) for k, v in acc.items()}
-    dominant = max(acc, key=acc.get)
+    serial_sum = sum(v for k, v in acc.items() if k != "rds")      # rds runs on its own stream
+    dominant = max((k for k in acc if k != "rds"), key=acc.get)
     roofline = kernel_roofline(dominant, acc[dominant], C, B, clocks)
-    roofline["step_share"] = acc[dominant] / sum(acc.values())
+    roofline["step_share"] = acc[dominant] / serial_sum
+    # the dominant roofline-bound (tile) kernel and the dominant latency-bound (lane) kernel,
+    # whichever of the two `dominant` is (lane kernels are reported as
+    # lane-steps/s, not as a roofline fraction)
+    tile = max((k for k in acc if k in TILE_STAGES), key=acc.get)
+    lane = max((k for k in acc if k in LANE_STAGES), key=acc.get)
+    roofline["dominant_tile_kernel"] = kernel_roofline(tile, acc[tile], C, B, clocks)
+    roofline["dominant_lane_kernel"] = {
+        "kernel": lane, "launch_ms": acc[lane], "class": "latency-bound serial recursion, one lane "
+        "per channel", "lanes": C, "lane_steps_per_s": C * B * BLOCK / (acc[lane] * 1e-3),
+        "realtime_factor": (B * BLOCK / 240000.0) / (acc[lane] * 1e-3)}
     step_alg_bytes = samples_per_step_rank * BYTES_PER_IQ_SAMPLE_ALG
     roofline["whole_step"] = {
         "achieved": step_alg_bytes / (ms / args.steps * 1e-3) / 1e9, "unit": "GB/s",
@@ -376,6 +394,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         }
         print(json.dumps(line), flush=True)
     eng.close()
+
+
+TILE_STAGES = ("decimate", "chanfir", "freqdem", "pilot_fir", "audio_lpf", "afpost")
+LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds")
 
 
 def kernel_roofline(stage: str, stage_ms: float, C: int, B: int, clocks: dict) -> dict:
