@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--channels", type=int, default=10000, help="channels per GPU")
     ap.add_argument("--blocks", type=int, default=2, help="logical blocks per step")
     ap.add_argument("--groups", type=int, default=8, help="pipeline groups (streams) per GPU")
+    ap.add_argument("--sync-steps", action="store_true",
+                    help="join every step on the caller's stream (fmgpu_process_batch) instead of "
+                         "streaming the steps (fmgpu_process_batch_async + one fmgpu_join)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -201,6 +204,8 @@ def workload_config(args, channels_this_arm: int) -> dict:
                     "SNR 10-40 dB, blend soft/normal/aggressive by c%3, dsp_agc fast, stereo + RDS",
         "channels_per_gpu": args.channels, "blocks_per_step": args.blocks,
         "pipeline_groups": args.groups,
+        "step_submission": "joined per step" if args.sync_steps else
+                           "streamed (async steps, one join before the closing event)",
         "block_samples": BLOCK, "iq_rate": IQ_RATE, "decimation": DECIM,
         "channels_in_this_arm": channels_this_arm,
         "l2_policy": "inputs larger than L2 (no flush): "
@@ -258,9 +263,19 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 
+    # Steps are streamed the way the reference's main loop runs block after block
+    # (main.cpp:992): every pipeline group orders itself after its own previous step, so one
+    # step's serial kernels overlap the next step's FIR kernels; fmgpu_join puts all of it back
+    # on the caller's stream before the closing event. --sync-steps joins after every step.
     def step():
-        eng.process_batch(iq_dev.data_ptr(), stride, B, audio.data_ptr(), acap, n_audio.data_ptr(),
-                          groups.data_ptr(), gcap, n_groups.data_ptr(), status.data_ptr(), stream)
+        if args.sync_steps:
+            eng.process_batch(iq_dev.data_ptr(), stride, B, audio.data_ptr(), acap,
+                              n_audio.data_ptr(), groups.data_ptr(), gcap, n_groups.data_ptr(),
+                              status.data_ptr(), stream)
+        else:
+            eng.process_batch_async(iq_dev.data_ptr(), stride, B, audio.data_ptr(), acap,
+                                    n_audio.data_ptr(), groups.data_ptr(), gcap,
+                                    n_groups.data_ptr(), status.data_ptr(), stream)
 
     def barrier():
         if world > 1:
@@ -269,6 +284,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
 
     for _ in range(max(3, args.warmup)):
         step()
+    eng.join(stream)
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -281,6 +297,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     ev0.record()
     for _ in range(args.steps):
         step()
+    eng.join(stream)
     ev1.record()
     barrier()
     w1 = time.time()
@@ -299,14 +316,19 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # CUDA events around each stage bracket that stage's kernels only (with several groups the
     # stages of different groups interleave on the device and the spans include queueing) -------
     eng.set_pipeline_groups(1)
+
+    def sstep():
+        eng.process_batch(iq_dev.data_ptr(), stride, B, audio.data_ptr(), acap, n_audio.data_ptr(),
+                          groups.data_ptr(), gcap, n_groups.data_ptr(), status.data_ptr(), stream)
+
     for _ in range(2):
-        step()
+        sstep()
     torch.cuda.synchronize()
     eng.enable_stage_timing(True)
     acc = {}
     reps = 3
     for _ in range(reps):
-        step()
+        sstep()
         torch.cuda.synchronize()
         for k, v in eng.stage_times().items():
             acc[k] = acc.get(k, 0.0) + v / reps
@@ -338,23 +360,40 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if not args.no_e2e:
         iq_host = torch.empty((C, stride), dtype=torch.uint8).pin_memory()
         iq_host.copy_(iq_dev)
-        a_host = torch.empty((C, 2, acap), dtype=torch.float32).pin_memory()
-        na_host = torch.zeros(C, dtype=torch.int32).pin_memory()
-        g_host = torch.zeros((C, gcap, 16), dtype=torch.uint8).pin_memory()
-        ng_host = torch.zeros(C, dtype=torch.int32).pin_memory()
-        st_h = torch.zeros((C, B, 20), dtype=torch.uint8).pin_memory()
+        # two sets of host output buffers: step k+1 is submitted before step k is waited for
+        outs = []
+        for _ in range(2):
+            outs.append((torch.empty((C, 2, acap), dtype=torch.float32).pin_memory(),
+                         torch.zeros(C, dtype=torch.int32).pin_memory(),
+                         torch.zeros((C, gcap, 16), dtype=torch.uint8).pin_memory(),
+                         torch.zeros(C, dtype=torch.int32).pin_memory(),
+                         torch.zeros((C, B, 20), dtype=torch.uint8).pin_memory()))
+        na_host = outs[0][1]
 
-        def estep():
-            eng.process_host_raw(iq_host.data_ptr(), stride, B, a_host.data_ptr(), acap,
-                                 na_host.data_ptr(), g_host.data_ptr(), gcap, ng_host.data_ptr(),
-                                 st_h.data_ptr())
+        def esubmit(k):
+            a_h, na_h, g_h, ng_h, st_h = outs[k & 1]
+            return eng.submit_host_raw(iq_host.data_ptr(), stride, B, a_h.data_ptr(), acap,
+                                       na_h.data_ptr(), g_h.data_ptr(), gcap, ng_h.data_ptr(),
+                                       st_h.data_ptr())
 
-        for _ in range(max(2, min(args.warmup, 3))):
-            estep()
+        def erun(nsteps):
+            # every step: H2D of its IQ from pinned memory, the pipeline, D2H of audio / groups /
+            # status; at most two steps in flight (fmgpu_submit_host / fmgpu_wait_host)
+            if args.sync_steps:
+                for k in range(nsteps):
+                    eng.wait_host(esubmit(k))
+                return
+            pending = esubmit(0)
+            for k in range(1, nsteps):
+                nxt = esubmit(k)
+                eng.wait_host(pending)
+                pending = nxt
+            eng.wait_host(pending)
+
+        erun(max(2, min(args.warmup, 3)))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            estep()
+        erun(args.steps)
         torch.cuda.synchronize()
         dt = shard.max_over_ranks(time.perf_counter() - t0, dev)
         frames = int(na_host.max().item())

@@ -92,11 +92,20 @@ struct fmgpu_engine {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   // optional channel groups: each group runs the whole pipeline on its own pair of streams so
   // that one group's lane kernels overlap another group's FIR kernels and host copies
-  static constexpr int kMaxGroups = 8;
+  static constexpr int kMaxGroups = 16;
   int nGroups = 1;
   cudaStream_t gStream[kMaxGroups] = {}, gStream2[kMaxGroups] = {}, gLane[kMaxGroups] = {};
   cudaEvent_t gFork[kMaxGroups] = {}, gJoin[kMaxGroups] = {}, gDone[kMaxGroups] = {}, gHop[kMaxGroups] = {};
   cudaEvent_t evStart = nullptr;
+  // streaming host path: two tickets in flight (submit k+1 before waiting for k)
+  cudaEvent_t gHostDone[2][kMaxGroups] = {};
+  struct HostTicket {
+    bool pending = false;
+    uint32_t *nGroupsHost = nullptr;
+    size_t groupCap = 0;
+    bool clampGroups = false;
+  } tickets[2];
+  int nextTicket = 0;
 
   int lastN = 0;  // DSP-rate samples of the last call (debug reads)
   uint64_t launches = 0;
@@ -104,6 +113,9 @@ struct fmgpu_engine {
 
   bool timing = false;
   std::vector<std::tuple<const char *, cudaEvent_t, cudaEvent_t>> spans;
+  std::vector<int> spanGroup;   // pipeline group of each span
+  int curGroup = 0;
+  bool timeline = false;        // keep the raw spans (fmgpu_debug_timeline) instead of merging
   std::vector<std::pair<const char *, float>> lastTimes;
 };
 
@@ -273,6 +285,7 @@ struct Span {
       cudaEventCreate(&b);
       cudaEventRecord(a, s);
       e->spans.emplace_back(name, a, b);
+      e->spanGroup.push_back(e->curGroup);
     }
   }
   ~Span() {
@@ -471,6 +484,7 @@ void collectTimes(fmgpu_engine *e) {
     cudaEventDestroy(std::get<2>(sp));
   }
   e->spans.clear();
+  e->spanGroup.clear();
 }
 
 // the per-block body of main.cpp:1232-1308 for channels [ch0, ch0+nch) on stream s (RDS on s2)
@@ -548,7 +562,8 @@ int checkBatchArgs(fmgpu_engine *e, const void *iq, size_t stride, int n_blocks,
 
 int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks, float *audio_dev,
              size_t audio_cap, uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
-             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, cudaStream_t s) {
+             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, cudaStream_t s,
+             bool join = true) {
   int rc = checkBatchArgs(e, iq_dev, stride, n_blocks, true, audio_dev, audio_cap);
   if (rc != FMGPU_OK) {
     return rc;
@@ -581,10 +596,13 @@ int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks
         continue;
       }
       cudaStreamWaitEvent(e->gStream[g], e->evStart, 0);
+      e->curGroup = g;
       runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, ch0, nch,
                e->gStream[g], e->gStream2[g], e->gFork[g], e->gJoin[g], e->gLane[g], e->gHop[g]);
       cudaEventRecord(e->gDone[g], e->gStream[g]);
-      cudaStreamWaitEvent(s, e->gDone[g], 0);
+      if (join) {
+        cudaStreamWaitEvent(s, e->gDone[g], 0);
+      }
     }
   }
   e->dAudio = audioSaved;
@@ -801,6 +819,8 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
     CKC(cudaEventCreateWithFlags(&e->gFork[g], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->gJoin[g], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&e->gDone[g], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->gHostDone[0][g], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&e->gHostDone[1][g], cudaEventDisableTiming));
   }
   CKC(initRdsTables());
   CKC(devAlloc(&e->dIq, C * e->iqPitch));
@@ -941,7 +961,8 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
       cudaStreamSynchronize(e->gLane[g]);
       cudaStreamDestroy(e->gLane[g]);
     }
-    for (cudaEvent_t ev : {e->gFork[g], e->gJoin[g], e->gDone[g], e->gHop[g]}) {
+    for (cudaEvent_t ev : {e->gFork[g], e->gJoin[g], e->gDone[g], e->gHop[g], e->gHostDone[0][g],
+                           e->gHostDone[1][g]}) {
       if (ev) {
         cudaEventDestroy(ev);
       }
@@ -1217,10 +1238,85 @@ int fmgpu_process_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride
   return rc;
 }
 
+int fmgpu_process_batch_async(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
+                              int n_blocks, float *audio_dev, size_t audio_cap,
+                              uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
+                              uint32_t *n_groups_dev, fmgpu_block_status *status_dev, void *stream) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  return runBatch(e, iq_dev, iq_stride_bytes, n_blocks, audio_dev, audio_cap, n_audio_dev, groups_dev,
+                  group_cap, n_groups_dev, status_dev, static_cast<cudaStream_t>(stream), false);
+}
+
+int fmgpu_join(fmgpu_engine *e, void *stream) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
+    // gDone[g] holds the last batch this group ran (an event never recorded is complete)
+    CK(cudaStreamWaitEvent(s, e->gDone[g], 0));
+  }
+  return FMGPU_OK;
+}
+
+static int waitHostTicket(fmgpu_engine *e, int ticket) {
+  fmgpu_engine::HostTicket &t = e->tickets[ticket];
+  if (!t.pending) {
+    return FMGPU_OK;
+  }
+  t.pending = false;
+  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
+    CK(cudaEventSynchronize(e->gHostDone[ticket][g]));
+  }
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    e->lastError = std::string("process_host: ") + cudaGetErrorString(err);
+    return FMGPU_ENODEV;
+  }
+  if (t.clampGroups) {
+    for (int c = 0; c < e->C; c++) {
+      t.nGroupsHost[c] = std::min<uint32_t>(t.nGroupsHost[c], static_cast<uint32_t>(t.groupCap));
+    }
+  }
+  return FMGPU_OK;
+}
+
+int fmgpu_wait_host(fmgpu_engine *e, int ticket) {
+  if (!e || ticket < 0 || ticket > 1) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  const int rc = waitHostTicket(e, ticket);
+  if (rc == FMGPU_OK && !e->tickets[0].pending && !e->tickets[1].pending) {
+    collectTimes(e);
+  }
+  return rc;
+}
+
 int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_bytes,
                        int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
                        fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
                        fmgpu_block_status *status_host) {
+  const int ticket = fmgpu_submit_host(e, iq_host, iq_stride_bytes, n_blocks, audio_host, audio_cap,
+                                       n_audio_host, groups_host, group_cap, n_groups_host,
+                                       status_host);
+  if (ticket < 0) {
+    return ticket;
+  }
+  return fmgpu_wait_host(e, ticket);
+}
+
+int fmgpu_submit_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_bytes,
+                      int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
+                      fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
+                      fmgpu_block_status *status_host) {
   if (!e) {
     return FMGPU_EINVAL;
   }
@@ -1239,8 +1335,15 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
   const size_t frames = std::min(e->acap, static_cast<size_t>((static_cast<double>(n) * 16777216.0) /
                                                                e->k.aud_step) + 2);
   const int G = std::max(1, e->nGroups);
+  const int ticket = e->nextTicket;
+  rc = waitHostTicket(e, ticket);  // at most two submissions in flight
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
+  e->nextTicket ^= 1;
   // every group: host->device copy of its rows, the pipeline, device->host copy of its results,
-  // all on the group's own stream, so copies of one group overlap kernels of the others
+  // all on the group's own stream, so copies of one group overlap kernels of the others (and,
+  // with a second submission queued behind, the next call's copies overlap this call's tail)
   for (int g = 0; g < G; g++) {
     int ch0 = 0, nch = e->C;
     cudaStream_t s = e->stream, s2 = e->stream2, sl = e->laneStream;
@@ -1285,9 +1388,7 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
       CK(cudaMemcpyAsync(status_host + c0 * n_blocks, e->dStatus + c0 * n_blocks,
                          cn * n_blocks * sizeof(fmgpu_block_status), cudaMemcpyDeviceToHost, s));
     }
-  }
-  for (int g = 0; g < G; g++) {
-    CK(cudaStreamSynchronize(G > 1 ? e->gStream[g] : e->stream));
+    CK(cudaEventRecord(e->gHostDone[ticket][g], s));
   }
   e->lastN = static_cast<int>(n);
   const cudaError_t err = cudaGetLastError();
@@ -1295,13 +1396,12 @@ int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride
     e->lastError = std::string("process_host: ") + cudaGetErrorString(err);
     return FMGPU_ENODEV;
   }
-  if (n_groups_host && groups_host) {
-    for (int c = 0; c < e->C; c++) {
-      n_groups_host[c] = std::min<uint32_t>(n_groups_host[c], static_cast<uint32_t>(group_cap));
-    }
-  }
-  collectTimes(e);
-  return FMGPU_OK;
+  fmgpu_engine::HostTicket &t = e->tickets[ticket];
+  t.pending = true;
+  t.nGroupsHost = n_groups_host;
+  t.groupCap = group_cap;
+  t.clampGroups = n_groups_host && groups_host;
+  return ticket;
 }
 
 int fmgpu_signal_level_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
@@ -1687,6 +1787,41 @@ int fmgpu_enable_stage_timing(fmgpu_engine *e, int on) {
   }
   e->timing = on != 0;
   return FMGPU_OK;
+}
+
+// Debug: with stage timing on, the raw spans (one per stage launch sequence) of every batch
+// queued since the last call, as start/end milliseconds after the earliest span. Synchronises.
+int fmgpu_debug_timeline(fmgpu_engine *e, const char **names, int *groups, float *t0_ms,
+                         float *t1_ms, int cap) {
+  if (!e) {
+    return 0;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  const int n = static_cast<int>(e->spans.size());
+  // the earliest start: spans were recorded in launch order, but on different streams
+  int first = 0;
+  for (int i = 1; i < n; i++) {
+    float d = 0.0f;
+    if (cudaEventElapsedTime(&d, std::get<1>(e->spans[first]), std::get<1>(e->spans[i])) ==
+            cudaSuccess && d < 0.0f) {
+      first = i;
+    }
+  }
+  for (int i = 0; i < n && i < cap; i++) {
+    names[i] = std::get<0>(e->spans[i]);
+    groups[i] = e->spanGroup[i];
+    cudaEventElapsedTime(&t0_ms[i], std::get<1>(e->spans[first]), std::get<1>(e->spans[i]));
+    cudaEventElapsedTime(&t1_ms[i], std::get<1>(e->spans[first]), std::get<2>(e->spans[i]));
+  }
+  for (auto &sp : e->spans) {
+    cudaEventDestroy(std::get<1>(sp));
+    cudaEventDestroy(std::get<2>(sp));
+  }
+  e->spans.clear();
+  e->spanGroup.clear();
+  return n;
 }
 
 int fmgpu_get_stage_times(fmgpu_engine *e, const char **names, float *ms, int cap) {

@@ -14,6 +14,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "fm_math.h"
 
@@ -103,6 +104,26 @@ __device__ __forceinline__ float unwrapDev(float p) {
     return p + k2Pi;
   }
   return p;
+}
+
+// Packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): acc.x = fma(h, x.x, acc.x) and
+// acc.y = fma(h, x.y, acc.y) in ONE instruction, each half an IEEE round-to-nearest fma, so the
+// result is bit-identical to two fmaf() calls. ptxas folds the {h, h} pair into a scalar
+// (uniform-register) operand. The FIR kernels are issue-bound (ncu r01: 83 % of issue slots,
+// FMA pipe 50 %): halving the FMA instruction count frees the slots for the LDS / LDCU traffic.
+template <bool PACK>
+__device__ __forceinline__ float2 fma2(float h, float2 x, float2 acc) {
+  if (PACK) {
+    unsigned long long hh, xx, aa, r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(h));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(hh), "l"(xx), "l"(aa));
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+  }
+  return make_float2(fmaf(h, x.x, acc.x), fmaf(h, x.y, acc.y));
 }
 
 // ---------------------------------------------------------------------------
@@ -217,7 +238,7 @@ __global__ void k_save_tail(const float *src, size_t src_pitch, int src_off, flo
 // Input bytes are fetched as 128-bit words from the 16-byte aligned virtual stream
 // hist ++ input.
 // ---------------------------------------------------------------------------
-template <int M>
+template <int M, bool PACK>
 __global__ void __launch_bounds__(128)
 k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
         const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
@@ -295,8 +316,7 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
         const float h = taps.h[(pp + ps) * M + r];
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          acc[j].x = fmaf(h, seg[(j + ps) & 3][r].x, acc[j].x);
-          acc[j].y = fmaf(h, seg[(j + ps) & 3][r].y, acc[j].y);
+          acc[j] = fma2<PACK>(h, seg[(j + ps) & 3][r], acc[j]);
         }
       }
     }
@@ -307,6 +327,122 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
     const int n = n0 + R * t + j;
     if (n < n_out) {
       out[n] = make_float2(acc[j].x * scale, acc[j].y * scale);
+    }
+  }
+}
+
+// K1, second form: the I and the Q component of a tile go to separate shared-memory planes and
+// to separate halves of the CTA (threads 0..63 -> I, 64..127 -> Q), each thread keeping R = 8
+// consecutive outputs of ONE component. A sample read from shared memory (one 32-bit LDS) now
+// feeds 8 FFMAs instead of 4, which halves the shared-memory bytes per FFMA: the first form
+// needs 128 B/clk/SM of LDS bandwidth at full FMA rate (ncu: FMA pipe 50 % busy, r01), this
+// one half of that. Same taps, same order (oldest sample first, one accumulator per output).
+template <int M, int R>
+__global__ void __launch_bounds__(128)
+k_decim_split(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
+              const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch,
+              int n_out, int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
+  constexpr int T = 64 * R;
+  constexpr int RM = R * M;
+  extern __shared__ float xpl[];
+  const int c = blockIdx.y + ch0;
+  const int n0 = blockIdx.x * T;
+  const int t = threadIdx.x;
+  const long o = (long)(n0 - Pp) * M + 1;  // stream index of tile element 0
+  const int tile_len = (T + Pp - 1) * M;
+  const int plane = tile_len + tile_len / RM + 2;
+  float *xi = xpl;
+  float *xq = xpl + plane;
+  const long v0 = o + H_IQ;                // virtual index (history first)
+  const long ck0 = v0 >> 3;
+  const long ck1 = (v0 + tile_len - 1) >> 3;
+  const long n_in = (long)n_out * M;
+  const uint8_t *in_c = iq + (size_t)c * iq_stride;
+  const uint8_t *hist_c = hist + (size_t)c * (2 * H_IQ);
+  const long v_first_valid = H_IQ - hist_valid[c];
+  constexpr float kScale = 1.0f / 127.5f;
+
+  for (long ck = ck0 + t; ck <= ck1; ck += 128) {
+    const long v = ck << 3;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (v < H_IQ) {
+      raw = *reinterpret_cast<const uint4 *>(hist_c + 2 * v);
+    } else if (v - H_IQ < n_in) {
+      raw = __ldg(reinterpret_cast<const uint4 *>(in_c + 2 * (v - H_IQ)));
+    }
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const long a = v + e - v0;
+      if (a >= 0 && a < tile_len) {
+        const uint32_t word = w[e >> 1] >> ((e & 1) * 16);
+        float fi = ((float)(word & 0xffu) - 127.5f) * kScale;
+        float fq = ((float)((word >> 8) & 0xffu) - 127.5f) * kScale;
+        if (v + e < v_first_valid) {
+          fi = 0.0f;
+          fq = 0.0f;
+        }
+        const int ai = (int)a;
+        const int idx = ai + ai / RM;
+        xi[idx] = fi;
+        xq[idx] = fq;
+      }
+    }
+  }
+  __syncthreads();
+
+  const int comp = t >> 6;
+  const int tt = t & 63;
+  const float *xp = comp ? xq : xi;
+  float acc[R];
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    acc[j] = 0.0f;
+  }
+  float seg[R][M];
+  const int tbase = tt * (RM + 1);
+#pragma unroll
+  for (int u = 0; u < R - 1; u++) {
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+      seg[u][r] = xp[tbase + u * M + r];  // u < R: no skew word yet
+    }
+  }
+  // one tap phase: the newest segment comes in, then M taps x R outputs
+#define FMGPU_DECIM_PHASE(PP, PS)                                  \
+  {                                                                \
+    const int u = (PP) + (PS) + R - 1;                             \
+    const int sb = tbase + u * M + u / R;                          \
+    _Pragma("unroll") for (int r = 0; r < M; r++) {                \
+      seg[((PS) + R - 1) % R][r] = xp[sb + r];                     \
+    }                                                              \
+    _Pragma("unroll") for (int r = 0; r < M; r++) {                \
+      const float h = taps.h[((PP) + (PS)) * M + r];               \
+      _Pragma("unroll") for (int j = 0; j < R; j++) {              \
+        acc[j] = fmaf(h, seg[(j + (PS)) % R][r], acc[j]);          \
+      }                                                            \
+    }                                                              \
+  }
+  int pp = 0;
+  for (; pp + R <= Pp; pp += R) {
+#pragma unroll
+    for (int ps = 0; ps < R; ps++) {
+      FMGPU_DECIM_PHASE(pp, ps)
+    }
+  }
+  if (pp < Pp) {  // Pp is a multiple of 4: at most one half round left (pp % R == 0 here)
+#pragma unroll
+    for (int ps = 0; ps < 4; ps++) {
+      FMGPU_DECIM_PHASE(pp, ps)
+    }
+  }
+#undef FMGPU_DECIM_PHASE
+  float *out = reinterpret_cast<float *>(x1 + (size_t)c * x1_pitch) + comp;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int n = n0 + R * tt + j;
+    if (n < n_out) {
+      out[2 * n] = acc[j] * scale;
     }
   }
 }
@@ -476,6 +612,7 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
 // K2: channel filter (firfilt_crcf, 81/121 real taps on complex data, per-channel
 // bandwidth). 128 threads x 8 consecutive complex outputs, sliding register window.
 // ---------------------------------------------------------------------------
+template <bool PACK>
 __global__ void __launch_bounds__(128)
 k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ ybuf,
           size_t y_pitch, const float *__restrict__ chan_taps, const int *__restrict__ chan_lp,
@@ -515,8 +652,7 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
       const float h = hs[i + u];
 #pragma unroll
       for (int j = 0; j < R; j++) {
-        acc[j].x = fmaf(h, win[(j + u) & (R - 1)].x, acc[j].x);
-        acc[j].y = fmaf(h, win[(j + u) & (R - 1)].y, acc[j].y);
+        acc[j] = fma2<PACK>(h, win[(j + u) & (R - 1)], acc[j]);
       }
       const int a = t * R + i + u + R;
       win[u] = xs[a + (a >> 3)];
@@ -635,22 +771,23 @@ __global__ void k_freqdem(const float2 *__restrict__ ybuf, size_t y_pitch, float
 // K3 / K5: real FIR with taps in the kernel-parameter constant bank
 // (pilot band-pass 305/325 taps; 2 x 121-tap 15 kHz low-pass via gridDim.z = 2)
 // ---------------------------------------------------------------------------
+template <int R>
 __global__ void __launch_bounds__(128)
 k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
-  constexpr int R = 8;
   constexpr int T = 128 * R;
+  constexpr int SH = (R == 16) ? 4 : 3;  // one skew word per R samples: odd per-thread stride
   extern __shared__ float fs_x[];
   const int c = blockIdx.y + job.ch0;
   const int z = blockIdx.z;
   const int n0 = blockIdx.x * T;
   const int t = threadIdx.x;
-  const int Lp = job.Lp;
+  const int Lp = job.Lp;  // multiple of 8
   const float *row = job.in[z] + (size_t)c * job.in_pitch + job.in_off;
   const int b0 = n0 - (Lp - 1);
   const int tile_len = T + Lp - 1 + R;
   for (int a = t; a < tile_len; a += 128) {
     const int s = b0 + a;
-    fs_x[a + (a >> 3)] = (s < job.n_total) ? row[s] : 0.0f;
+    fs_x[a + (a >> SH)] = (s < job.n_total) ? row[s] : 0.0f;
   }
   __syncthreads();
   float acc[R], win[R];
@@ -658,9 +795,10 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
   for (int j = 0; j < R; j++) {
     acc[j] = 0.0f;
     const int a = t * R + j;
-    win[j] = fs_x[a + (a >> 3)];
+    win[j] = fs_x[a + (a >> SH)];
   }
-  for (int i = 0; i < Lp; i += R) {
+  int i = 0;
+  for (; i + R <= Lp; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
       const float h = taps.h[i + u];
@@ -669,7 +807,19 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
         acc[j] = fmaf(h, win[(j + u) & (R - 1)], acc[j]);
       }
       const int a = t * R + i + u + R;
-      win[u] = fs_x[a + (a >> 3)];
+      win[u] = fs_x[a + (a >> SH)];
+    }
+  }
+  if (R == 16 && i < Lp) {  // Lp is a multiple of 8: one half round left
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const float h = taps.h[i + u];
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        acc[j] = fmaf(h, win[(j + u) & (R - 1)], acc[j]);
+      }
+      const int a = t * R + i + u + R;
+      win[u] = fs_x[a + (a >> SH)];
     }
   }
   float *out = job.out[z] + (size_t)c * job.out_pitch + job.out_off;
@@ -1760,6 +1910,16 @@ __global__ void k_pack_pcm16(const float *__restrict__ audio, size_t acap,
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
+// FMGPU_FFMA2=0 falls back to scalar FFMA in the FIR kernels (same results, for A/B timing)
+static bool usePackedFma() {
+  static int v = -1;
+  if (v < 0) {
+    const char *s = getenv("FMGPU_FFMA2");
+    v = (s && atoi(s) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 #define FMGPU_DECIM_CASE(MM)                                                                     \
   case MM: {                                                                                     \
     constexpr int T = 512;                                                                       \
@@ -1767,18 +1927,65 @@ __global__ void k_pack_pcm16(const float *__restrict__ audio, size_t acap,
     const size_t smem = (size_t)(tile_len + tile_len / (4 * MM) + 2) * sizeof(float2);           \
     static bool attr_done = false;                                                               \
     if (!attr_done) {                                                                            \
-      cudaFuncSetAttribute(k_decim<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
+      cudaFuncSetAttribute(k_decim<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                           160 * 1024);                                                          \
+      cudaFuncSetAttribute(k_decim<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           160 * 1024);                                                          \
       attr_done = true;                                                                          \
     }                                                                                            \
     dim3 grid((n_out + T - 1) / T, nch);                                                         \
-    k_decim<MM><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1, x1_pitch, n_out, \
-                                             ch0, Pp, scale, taps);                              \
+    if (usePackedFma()) {                                                                        \
+      k_decim<MM, true><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,        \
+                                                     x1_pitch, n_out, ch0, Pp, scale, taps);     \
+    } else {                                                                                     \
+      k_decim<MM, false><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,       \
+                                                      x1_pitch, n_out, ch0, Pp, scale, taps);    \
+    }                                                                                            \
     break;                                                                                       \
   }
+
+// split-component form, R = 8 outputs per thread (register ring of 8 x M samples)
+#define FMGPU_DECIM_SPLIT_CASE(MM)                                                               \
+  case MM: {                                                                                     \
+    constexpr int R = 8;                                                                         \
+    constexpr int T = 64 * R;                                                                    \
+    const int tile_len = (T + Pp - 1) * MM;                                                      \
+    const size_t smem = (size_t)2 * (tile_len + tile_len / (R * MM) + 2) * sizeof(float);        \
+    static bool attr_done = false;                                                               \
+    if (!attr_done) {                                                                            \
+      cudaFuncSetAttribute(k_decim_split<MM, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                           160 * 1024);                                                          \
+      attr_done = true;                                                                          \
+    }                                                                                            \
+    dim3 grid((n_out + T - 1) / T, nch);                                                         \
+    k_decim_split<MM, R><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,       \
+                                                      x1_pitch, n_out, ch0, Pp, scale, taps);    \
+    break;                                                                                       \
+  }
+
+int g_decim_variant = -1;  // FMGPU_DECIM_VARIANT=1 selects the split-component (R = 8) form
 
 void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
                  const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
                  const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream) {
+  if (g_decim_variant < 0) {
+    const char *v = getenv("FMGPU_DECIM_VARIANT");
+    g_decim_variant = v ? atoi(v) : 0;
+  }
+  if (g_decim_variant == 1) {
+    switch (M) {
+      FMGPU_DECIM_SPLIT_CASE(2)
+      FMGPU_DECIM_SPLIT_CASE(4)
+      FMGPU_DECIM_SPLIT_CASE(5)
+      FMGPU_DECIM_SPLIT_CASE(8)
+      FMGPU_DECIM_SPLIT_CASE(10)
+    default:
+      break;  // M = 16 and others: the forms below
+    }
+    if (M == 2 || M == 4 || M == 5 || M == 8 || M == 10) {
+      return;
+    }
+  }
   switch (M) {
     FMGPU_DECIM_CASE(2)
     FMGPU_DECIM_CASE(4)
@@ -1839,8 +2046,13 @@ void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pit
   const int tile_len = T + CHAN_TAPS_PITCH - 1 + 8;
   const size_t smem = (size_t)(tile_len + (tile_len >> 3) + 2) * sizeof(float2);
   dim3 grid((n_total + T - 1) / T, nch);
-  k_chanfir<<<grid, 128, smem, stream>>>(x2, x2_pitch, ybuf, y_pitch, chan_taps, chan_lp,
-                                         chan_scale, cp, n_total, ch0);
+  if (usePackedFma()) {
+    k_chanfir<true><<<grid, 128, smem, stream>>>(x2, x2_pitch, ybuf, y_pitch, chan_taps, chan_lp,
+                                                 chan_scale, cp, n_total, ch0);
+  } else {
+    k_chanfir<false><<<grid, 128, smem, stream>>>(x2, x2_pitch, ybuf, y_pitch, chan_taps, chan_lp,
+                                                  chan_scale, cp, n_total, ch0);
+  }
 }
 
 void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total,
@@ -1860,13 +2072,101 @@ void launchFreqDem(const float2 *ybuf, size_t y_pitch, float *mpx, size_t mpx_pi
   k_freqdem<<<grid, 256, 0, stream>>>(ybuf, y_pitch, mpx, mpx_pitch, n_total, ch0, ref);
 }
 
+// K3 / K5, packed form: two real signals that share the taps ride in the two halves of FFMA2 —
+// the L and R rows of one channel (15 kHz low-pass), or the same row of two neighbouring
+// channels (pilot band-pass). The tile is interleaved into float2 {a, b} in shared memory; the
+// inner loop is the complex FIR's (8 outputs x 2 signals per thread, one LDS.64 and 8 FFMA2 per
+// tap, taps as uniform-register scalars). Each half is the same oldest-first fmaf chain as
+// k_fir_real: results are bit-identical.
+__global__ void __launch_bounds__(128)
+k_fir_pair(FirRealJob job, int pair_channels, int nch, const __grid_constant__ TapsParam taps) {
+  constexpr int R = 8;
+  constexpr int T = 128 * R;
+  extern __shared__ float2 fp_x[];
+  const int n0 = blockIdx.x * T;
+  const int t = threadIdx.x;
+  const int Lp = job.Lp;
+  // rows a and b of this CTA
+  const int ca = job.ch0 + (pair_channels ? 2 * blockIdx.y : blockIdx.y);
+  const bool has_b = pair_channels ? (2 * (int)blockIdx.y + 1 < nch) : true;
+  const int cb = pair_channels ? (has_b ? ca + 1 : ca) : ca;
+  const float *rowa = job.in[0] + (size_t)ca * job.in_pitch + job.in_off;
+  const float *rowb = (pair_channels ? job.in[0] : job.in[1]) + (size_t)cb * job.in_pitch + job.in_off;
+  const int b0 = n0 - (Lp - 1);
+  const int tile_len = T + Lp - 1 + R;
+  for (int a = t; a < tile_len; a += 128) {
+    const int s = b0 + a;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (s < job.n_total) {
+      v = make_float2(rowa[s], rowb[s]);
+    }
+    fp_x[a + (a >> 3)] = v;
+  }
+  __syncthreads();
+  float2 acc[R], win[R];
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    acc[j] = make_float2(0.0f, 0.0f);
+    const int a = t * R + j;
+    win[j] = fp_x[a + (a >> 3)];
+  }
+  for (int i = 0; i < Lp; i += R) {
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+      const float h = taps.h[i + u];
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        acc[j] = fma2<true>(h, win[(j + u) & (R - 1)], acc[j]);
+      }
+      const int a = t * R + i + u + R;
+      win[u] = fp_x[a + (a >> 3)];
+    }
+  }
+  float *outa = job.out[0] + (size_t)ca * job.out_pitch + job.out_off;
+  float *outb = (pair_channels ? job.out[0] : job.out[1]) + (size_t)cb * job.out_pitch + job.out_off;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int n = n0 + t * R + j;
+    if (n < job.n_total) {
+      outa[n] = acc[j].x * job.scale;
+      if (has_b) {
+        outb[n] = acc[j].y * job.scale;
+      }
+    }
+  }
+}
+
+int g_fir_r = -1;  // FMGPU_FIR_R=16 selects 16 outputs per thread (default 8; measured no faster)
+
 void launchFirReal(const FirRealJob &job, int nsig, int nch, const TapsParam &taps,
                    cudaStream_t stream) {
+  if (g_fir_r < 0) {
+    const char *v = getenv("FMGPU_FIR_R");
+    g_fir_r = (v && atoi(v) == 16) ? 16 : 8;
+  }
+  if (usePackedFma() && (nsig == 2 || nch >= 2)) {
+    constexpr int T = 1024;
+    const int tile_len = T + job.Lp - 1 + 8;
+    const size_t smem = (size_t)(tile_len + (tile_len >> 3) + 2) * sizeof(float2);
+    const int pair_channels = (nsig == 2) ? 0 : 1;
+    dim3 grid((job.n_total + T - 1) / T, pair_channels ? (nch + 1) / 2 : nch);
+    k_fir_pair<<<grid, 128, smem, stream>>>(job, pair_channels, nch, taps);
+    return;
+  }
+  // short inputs gain nothing from the wider tile
+  if (g_fir_r == 16 && job.n_total >= 2048) {
+    constexpr int T = 128 * 16;
+    const int tile_len = T + job.Lp - 1 + 16;
+    const size_t smem = (size_t)(tile_len + (tile_len >> 4) + 2) * sizeof(float);
+    dim3 grid((job.n_total + T - 1) / T, nch, nsig);
+    k_fir_real<16><<<grid, 128, smem, stream>>>(job, taps);
+    return;
+  }
   constexpr int T = 1024;
   const int tile_len = T + job.Lp - 1 + 8;
   const size_t smem = (size_t)(tile_len + (tile_len >> 3) + 2) * sizeof(float);
   dim3 grid((job.n_total + T - 1) / T, nch, nsig);
-  k_fir_real<<<grid, 128, smem, stream>>>(job, taps);
+  k_fir_real<8><<<grid, 128, smem, stream>>>(job, taps);
 }
 
 void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t pilot_pitch,

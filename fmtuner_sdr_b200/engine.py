@@ -97,6 +97,10 @@ def load_library(build: bool = True):
     L.fmgpu_is_clipping.argtypes = [vp, i32]
     L.fmgpu_process_batch.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp, vp]
     L.fmgpu_process_host.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp]
+    L.fmgpu_process_batch_async.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp, vp]
+    L.fmgpu_join.argtypes = [vp, vp]
+    L.fmgpu_submit_host.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp]
+    L.fmgpu_wait_host.argtypes = [vp, i32]
     L.fmgpu_decimate.restype = sz
     L.fmgpu_decimate.argtypes = [vp, i32, u8p, sz, f32p, sz]
     L.fmgpu_demod_u8.restype = sz
@@ -121,6 +125,8 @@ def load_library(build: bool = True):
     L.fmgpu_launch_count.restype = C.c_uint64
     L.fmgpu_launch_count.argtypes = [vp]
     L.fmgpu_enable_stage_timing.argtypes = [vp, i32]
+    L.fmgpu_debug_timeline.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), i32]
     L.fmgpu_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]
     L.fmgpu_signal_level_batch.argtypes = [vp, u8p, sz, i32, vp, vp]
     L.fmgpu_signal_level_finish.restype = None
@@ -268,6 +274,39 @@ class Engine:
         self._check(self.L.fmgpu_process_batch(self.h, iq_dev_ptr, stride, n_blocks, audio_ptr, acap,
                                                n_audio_ptr, groups_ptr, gcap, n_groups_ptr,
                                                status_ptr, stream), "process_batch")
+
+    def process_batch_async(self, iq_dev_ptr, stride, n_blocks, audio_ptr=None, acap=0,
+                            n_audio_ptr=None, groups_ptr=None, gcap=0, n_groups_ptr=None,
+                            status_ptr=None, stream=None):
+        """Streaming form: `stream` does not wait for the batch; call join(stream) for that."""
+        self._check(self.L.fmgpu_process_batch_async(self.h, iq_dev_ptr, stride, n_blocks, audio_ptr,
+                                                     acap, n_audio_ptr, groups_ptr, gcap,
+                                                     n_groups_ptr, status_ptr, stream),
+                    "process_batch_async")
+
+    def join(self, stream=None):
+        self._check(self.L.fmgpu_join(self.h, stream), "join")
+
+    def submit_host_raw(self, iq_ptr, stride, n_blocks, audio_ptr, acap, n_audio_ptr, groups_ptr,
+                        gcap, n_groups_ptr, status_ptr) -> int:
+        """Queue one host-buffer batch without waiting; returns the ticket for wait_host()."""
+        t = self.L.fmgpu_submit_host(self.h, iq_ptr, stride, n_blocks, audio_ptr, acap, n_audio_ptr,
+                                     groups_ptr, gcap, n_groups_ptr, status_ptr)
+        if t < 0:
+            self._check(t, "submit_host")
+        return t
+
+    def wait_host(self, ticket: int):
+        self._check(self.L.fmgpu_wait_host(self.h, ticket), "wait_host")
+
+    def debug_timeline(self, cap: int = 8192):
+        """[(stage, group, t0_ms, t1_ms)] of the spans recorded since the last call."""
+        names = (C.c_char_p * cap)()
+        groups = (C.c_int32 * cap)()
+        t0 = (C.c_float * cap)()
+        t1 = (C.c_float * cap)()
+        n = min(cap, self.L.fmgpu_debug_timeline(self.h, names, groups, t0, t1, cap))
+        return [(names[i].decode(), groups[i], t0[i], t1[i]) for i in range(n)]
 
     def pack_pcm16(self, audio_ptr, acap, n_audio_ptr, volume_scale, pcm_ptr, stream=None):
         self._check(self.L.fmgpu_pack_pcm16(self.h, audio_ptr, acap, n_audio_ptr, volume_scale,

@@ -120,12 +120,37 @@ int fmgpu_process_batch(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride
                         fmgpu_rds_group *groups_dev, size_t group_cap, uint32_t *n_groups_dev,
                         fmgpu_block_status *status_dev, void *stream);
 
+/* Streaming form of fmgpu_process_batch for back-to-back calls (the reference's main loop runs one
+ * block after another, main.cpp:992): the pipeline groups start after the work already queued on
+ * `stream` (so the IQ must be ready in stream order), but `stream` does NOT wait for them; each
+ * group orders itself after its own previous batch, so one call's serial (lane) kernels overlap
+ * the next call's FIR kernels. Outputs are complete once fmgpu_join(e, stream) has been queued and
+ * `stream` has reached it; give consecutive calls different output buffers if each call's
+ * results are needed. */
+int fmgpu_process_batch_async(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_stride_bytes,
+                              int n_blocks, float *audio_dev, size_t audio_cap,
+                              uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
+                              uint32_t *n_groups_dev, fmgpu_block_status *status_dev, void *stream);
+/* Make `stream` wait for every batch queued so far by fmgpu_process_batch_async. */
+int fmgpu_join(fmgpu_engine *e, void *stream);
+
 /* Same work with HOST buffers: copies the IQ bytes host->device, runs the batch,
  * copies audio / groups / status back and synchronises. Layouts as above. */
 int fmgpu_process_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_bytes,
                        int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
                        fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
                        fmgpu_block_status *status_host);
+/* Streaming form: fmgpu_submit_host queues the copies and the batch and returns a ticket (0 or 1,
+ * negative = error) without waiting; fmgpu_wait_host(ticket) blocks until that submission's
+ * outputs are in the host buffers. Two submissions may be in flight, so a caller that submits
+ * block k+1 before waiting for block k keeps the PCIe copies and the kernels of consecutive
+ * blocks overlapped. The host buffers of a submission must stay valid (and pinned, for the copies
+ * to be asynchronous) until its ticket has been waited for. fmgpu_process_host = submit + wait. */
+int fmgpu_submit_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_bytes,
+                      int n_blocks, float *audio_host, size_t audio_cap, uint32_t *n_audio_host,
+                      fmgpu_rds_group *groups_host, size_t group_cap, uint32_t *n_groups_host,
+                      fmgpu_block_status *status_host);
+int fmgpu_wait_host(fmgpu_engine *e, int ticket);
 
 /* ---- RF signal level: the per-block meter main.cpp computes from the raw
  * IQ bytes (computeSignalLevel, src/signal_level.cpp:145-203, called at main.cpp:1167).
@@ -162,7 +187,7 @@ int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
                      const uint32_t *n_audio_dev, float volume_scale, int16_t *pcm_dev,
                      void *stream);
 
-/* Split the channels into `groups` (1..8) ranges that run the pipeline on separate streams:
+/* Split the channels into `groups` (1..16) ranges that run the pipeline on separate streams:
  * one range's serial (one-lane-per-channel) kernels then overlap another range's FIR kernels
  * and, in fmgpu_process_host, its host<->device copies. Results do not depend on it. */
 int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups);
@@ -212,6 +237,11 @@ size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, siz
 size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t cap);
 /* Number of kernels this engine has launched so far. */
 uint64_t fmgpu_launch_count(const fmgpu_engine *e);
+/* With stage timing enabled and batches queued by fmgpu_process_batch_async: every stage span
+ * recorded since the last call (name, pipeline group, start and end in ms after the earliest
+ * span). Synchronises the device. Returns the number of spans. */
+int fmgpu_debug_timeline(fmgpu_engine *e, const char **names, int *groups, float *t0_ms,
+                         float *t1_ms, int cap);
 /* Device time (ms) spent per pipeline stage during the last fmgpu_process_batch when
  * stage timing was enabled with fmgpu_enable_stage_timing; names[i] are static strings. */
 int fmgpu_enable_stage_timing(fmgpu_engine *e, int on);
