@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=10000, help="channels per GPU")
     ap.add_argument("--blocks", type=int, default=2, help="logical blocks per step")
-    ap.add_argument("--groups", type=int, default=8, help="pipeline groups (streams) per GPU")
+    ap.add_argument("--groups", type=int, default=1, help="channel ranges with their own set of stage streams (1 or 2)")
     ap.add_argument("--sync-steps", action="store_true",
                     help="join every step on the caller's stream (fmgpu_process_batch) instead of "
                          "streaming the steps (fmgpu_process_batch_async + one fmgpu_join)")

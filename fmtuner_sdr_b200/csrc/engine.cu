@@ -68,6 +68,8 @@ struct fmgpu_engine {
   uint8_t *dIq = nullptr, *dHistIq = nullptr;
   int *dHistValid = nullptr;
   float2 *dX1 = nullptr, *dX2 = nullptr, *dY = nullptr, *dRing = nullptr;
+  float *dR171 = nullptr;  // MPX resampled to 171 kHz (RDS branch), one call at a time
+  size_t r171Pitch = 0;
   float *dMpx = nullptr, *dPilot = nullptr, *dLraw = nullptr, *dRraw = nullptr, *dLf = nullptr,
         *dRf = nullptr, *dAudio = nullptr, *dRdsHist = nullptr, *dMonoHist = nullptr;
   float *dChanTaps = nullptr, *dChanScale = nullptr, *dAudBank = nullptr, *dRdsBank = nullptr,
@@ -85,20 +87,41 @@ struct fmgpu_engine {
   unsigned long long *dWords = nullptr;
   uint32_t *dBitEnd = nullptr;
   size_t x2Pitch = 0, yPitch = 0, mpxPitch = 0, lrPitch = 0, lfPitch = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // the RDS branch runs beside the stereo branch
-  cudaStream_t laneStream = nullptr;  // high priority: lane kernels jump ahead of queued FIR CTAs
-  cudaEvent_t evHop = nullptr;
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
-  // optional channel groups: each group runs the whole pipeline on its own pair of streams so
-  // that one group's lane kernels overlap another group's FIR kernels and host copies
-  static constexpr int kMaxGroups = 16;
+  cudaStream_t stream = nullptr;  // stage-level (single-channel) entry points, resets, reads
+
+  // ---- block pipeline ---------------------------------------------------------------------
+  // The batched path runs ONE LOGICAL BLOCK AT A TIME through per-stage streams: every stage
+  // (decimate, DC block, channel FIR, AGC, discriminator, pilot FIR, PLL/matrix, low-pass,
+  // resample/de-emphasis, RDS) owns a stream and handles block after block in order (its
+  // carried state demands that order anyway), and an event per (stage, block) releases the
+  // consumer stage. Stage s of block q therefore runs beside stage s+1 of block q-1: the serial
+  // one-lane-per-channel kernels of successive blocks overlap each other and the FIR kernels, and
+  // the latency of a block is the slowest stage, not the sum of the stages.
+  // Scratch buffers are rings of K = max(2, max_blocks) block slots laid out contiguously in
+  // time behind the halo, [H | slot 0 | slot 1 | ...]: block q lives in slot q % K, its FIR halo
+  // is simply the tail of the previous slot, and only slot 0 needs the tail of slot K-1 copied
+  // in front of it. A producer about to overwrite slot q % K first waits for the consumers of
+  // block q - K.
+  enum Stage {
+    ST_H2D = 0, ST_DECIM, ST_DC, ST_CHAN, ST_AGC, ST_FD, ST_PILOT, ST_STEREO, ST_LPF, ST_AF, ST_RDS,
+    ST_D2H, ST_COUNT
+  };
+  struct Pipe {
+    cudaStream_t st[ST_COUNT] = {};
+    std::vector<cudaEvent_t> done[ST_COUNT];  // ring of ER events per stage
+    cudaEvent_t callDone = nullptr;           // everything of the last batch call of this pipe
+    cudaEvent_t hostDone[2] = {};             // per host ticket: results are in the host buffers
+  };
+  static constexpr int kMaxGroups = 2;        // channel ranges with their own pipe (streams)
   int nGroups = 1;
-  cudaStream_t gStream[kMaxGroups] = {}, gStream2[kMaxGroups] = {}, gLane[kMaxGroups] = {};
-  cudaEvent_t gFork[kMaxGroups] = {}, gJoin[kMaxGroups] = {}, gDone[kMaxGroups] = {}, gHop[kMaxGroups] = {};
+  Pipe pipes[kMaxGroups];
+  int K = 2;             // ring slots
+  int ER = 3;            // events per stage (> K)
+  uint64_t seq = 0;      // logical blocks queued so far (slot = seq % K)
+  bool headFresh = true; // the halo in front of slot 0 is already in place (start, reset, realign)
+  bool asyncPending = false;
   cudaEvent_t evStart = nullptr;
   // streaming host path: two tickets in flight (submit k+1 before waiting for k)
-  cudaEvent_t gHostDone[2][kMaxGroups] = {};
   struct HostTicket {
     bool pending = false;
     uint32_t *nGroupsHost = nullptr;
@@ -106,6 +129,13 @@ struct fmgpu_engine {
     bool clampGroups = false;
   } tickets[2];
   int nextTicket = 0;
+  // second set of device result buffers: consecutive host submissions alternate between the sets
+  float *dAudio2 = nullptr;
+  fmgpu_rds_group *dGroups2 = nullptr;
+  fmgpu_block_status *dStatus2 = nullptr;
+  uint32_t *dNAudio2 = nullptr, *dNGroups2 = nullptr;
+  uint64_t lastSeq0 = 0;  // first block of the last batch call (debug reads)
+  int lastBlocks = 0;
 
   int lastN = 0;  // DSP-rate samples of the last call (debug reads)
   uint64_t launches = 0;
@@ -235,10 +265,13 @@ int filterSlot(fmgpu_engine *e, unsigned len, float cutoff, float atten) {
   return slot;
 }
 
+void syncPipes(fmgpu_engine *e);
+
 int uploadParams(fmgpu_engine *e) {
   if (!e->paramsDirty) {
     return FMGPU_OK;
   }
+  syncPipes(e);  // blocks already queued keep the parameters they were queued with
   CK(cudaMemcpyAsync(e->dParams, e->hParams.data(), e->hParams.size() * sizeof(ChanParams),
                      cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -448,14 +481,20 @@ void stageMono(fmgpu_engine *e, int n, int clamp, int dup, int ch0, int nch, cud
   e->launches += 3;
 }
 
+// upper bound of the 171 kHz samples n DSP-rate inputs produce (any resampler phase)
+int max171(const fmgpu_engine *e, int n) {
+  return static_cast<int>((static_cast<unsigned long long>(n) << 24) / e->k.rds_step) + 2;
+}
+
 void stageRds(fmgpu_engine *e, fmgpu_rds_group *groups, uint32_t gcap, fmgpu_block_status *status,
               int nblk, int blk_len, int n, int ch0, int nch, cudaStream_t s) {
   Span sp(e, "rds", s);
+  (void)blk_len;
   launchRds(e->dMpx, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
-            e->dMf, e->dDmf, e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, nblk, blk_len, n,
-            ch0, nch, e->k, s);
+            e->dMf, e->dDmf, e->dR171, e->r171Pitch, max171(e, n), e->dBits,
+            static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, s);
   launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords, groups,
-                  gcap, status, nblk, nblk, ch0, nch, s);
+                  gcap, status, nblk, nblk, 0, ch0, nch, s);
   e->launches += 1;
   launchSaveTail(e->dMpx, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, n, ch0, nch, s);
   e->launches += 2;
@@ -487,54 +526,288 @@ void collectTimes(fmgpu_engine *e) {
   e->spanGroup.clear();
 }
 
-// the per-block body of main.cpp:1232-1308 for channels [ch0, ch0+nch) on stream s (RDS on s2)
-void runRange(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks,
-              uint32_t *n_audio, fmgpu_rds_group *groups, uint32_t gcap, uint32_t *n_groups,
-              fmgpu_block_status *status, int ch0, int nch, cudaStream_t s, cudaStream_t s2,
-              cudaEvent_t evFork, cudaEvent_t evJoin, cudaStream_t lane, cudaEvent_t evHop) {
-  const int n = n_blocks * e->N;
-  const bool stereo = e->cfg.stereo != 0;
-  {
-    Span sp(e, "prepare", s);
-    launchPrepare(e->dAudioSt, e->dRds, status, n_blocks, n_blocks, e->N, n, ch0, nch,
-                  e->k.aud_step, e->k.rds_step, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
-    e->launches += 1;
-  }
-  if (e->M > 1) {
-    stageDecimate(e, iq_dev, stride, n, ch0, nch, s);
-    stageDemod(e, nullptr, 0, status, n_blocks, e->N, n, ch0, nch, s, lane, evHop);
-  } else {
-    stageDemod(e, iq_dev, stride, status, n_blocks, e->N, n, ch0, nch, s, lane, evHop);
-  }
-  // MPX is complete: the RDS branch (reads MPX data + its own window) runs on a second
-  // stream beside the stereo/audio branch; both only read the MPX data region.
-  cudaEventRecord(evFork, s);
-  cudaStreamWaitEvent(s2, evFork, 0);
-  stageRds(e, groups, gcap, status, n_blocks, e->N, n, ch0, nch, s2);
-  cudaEventRecord(evJoin, s2);
-  if (stereo) {
-    stageStereo(e, status, n_blocks, e->N, n, ch0, nch, s, lane, evHop);
-    stageAfPost(e, n, 1, ch0, nch, s);
-  } else {
-    stageMono(e, n, 1, 1, ch0, nch, s);
-    launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, ch0, nch, s);
-    e->launches += 1;
-  }
-  cudaStreamWaitEvent(s, evJoin, 0);
-  {
-    Span sp(e, "commit", s);
-    launchStoreCounts(e->dAudioSt, e->dRds, n_audio, n_groups, ch0, nch, stereo ? 0 : 1,
-                      static_cast<uint32_t>(e->acap), gcap, s);
-    launchCommit(e->dAudioSt, e->dRds, ch0, nch, stereo ? 1 : 0, stereo ? 0 : 1, 1, s);
-    e->launches += 2;
-  }
-}
+// ---------------------------------------------------------------------------
+// block pipeline (see fmgpu_engine::Pipe)
+// ---------------------------------------------------------------------------
+struct BatchOut {
+  float *audio = nullptr;  // [C][2][acap]
+  size_t acap = 0;
+  uint32_t *nAudio = nullptr;
+  fmgpu_rds_group *groups = nullptr;
+  uint32_t gcap = 0;
+  uint32_t *nGroups = nullptr;
+  fmgpu_block_status *status = nullptr;  // [C][n_blocks]
+};
 
 // channel range of pipeline group g (multiples of 32 channels: one warp of lane kernels)
 void groupRange(const fmgpu_engine *e, int g, int *ch0, int *nch) {
   const int per = static_cast<int>(roundUp((e->C + e->nGroups - 1) / e->nGroups, 32));
   *ch0 = std::min(e->C, g * per);
   *nch = std::min(e->C, (g + 1) * per) - *ch0;
+}
+
+void syncPipes(fmgpu_engine *e) {
+  if (!e->asyncPending) {
+    return;
+  }
+  for (auto &P : e->pipes) {
+    for (cudaStream_t st : P.st) {
+      if (st) {
+        cudaStreamSynchronize(st);
+      }
+    }
+  }
+  e->asyncPending = false;
+}
+
+// Put every FIR halo back in front of slot 0 and restart the block counter at a multiple of K:
+// the stage-level entry points and reset() work at buffer offset 0 with in-place carries.
+void realign(fmgpu_engine *e) {
+  syncPipes(e);
+  e->lastBlocks = 0;
+  const int slot = static_cast<int>(e->seq % static_cast<uint64_t>(e->K));
+  if (slot == 0 && e->headFresh) {
+    return;
+  }
+  const size_t pos = static_cast<size_t>(slot == 0 ? e->K : slot) * e->N;  // end of the last block
+  cudaStream_t s = e->stream;
+  launchCarryF2(e->dX2, e->x2Pitch, H_X2, pos, 0, e->C, s);
+  launchCarryF2(e->dY, e->yPitch, Y_OFF, pos, 0, e->C, s);
+  launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, pos, 0, e->C, s);
+  launchCarryF32(e->dLraw, e->lrPitch, H_LR, pos, 0, e->C, s);
+  launchCarryF32(e->dRraw, e->lrPitch, H_LR, pos, 0, e->C, s);
+  launchCarryF32(e->dLf, e->lfPitch, H_LF, pos, 0, e->C, s);
+  launchCarryF32(e->dRf, e->lfPitch, H_LF, pos, 0, e->C, s);
+  cudaStreamSynchronize(s);
+  e->launches += 7;
+  e->seq = roundUp(e->seq, e->K);
+  e->headFresh = true;
+}
+
+// One logical block (global number q, block b of a call of nb blocks) of channels
+// [ch0, ch0 + nch) through the stage streams of pipe P. iq / stride: this block's bytes.
+void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint64_t q, int b, int nb,
+                 const uint8_t *iq, size_t stride, bool waitH2D, const BatchOut &out) {
+  using E = fmgpu_engine;
+  const int K = e->K, N = e->N;
+  const int slot = static_cast<int>(q % static_cast<uint64_t>(K));
+  const size_t t0 = static_cast<size_t>(slot) * N;  // the block's offset in every ring buffer
+  const size_t ringEnd = static_cast<size_t>(K) * N;
+  const bool carry = (slot == 0) && !e->headFresh;  // bring the tail of slot K-1 in front of slot 0
+  const bool stereo = e->cfg.stereo != 0;
+  const bool first = (b == 0), last = (b == nb - 1);
+  fmgpu_block_status *status = out.status ? out.status + b : nullptr;
+  auto ev = [&](int st, uint64_t qq) { return P.done[st][qq % static_cast<uint64_t>(e->ER)]; };
+  // producers: stages of THIS block whose output the stage reads; overwritten: consumer stages
+  // of the buffers it writes, which must have finished block q - K (same ring slot)
+  auto need = [&](int st, std::initializer_list<int> producers, std::initializer_list<int> readers) {
+    for (int p : producers) {
+      cudaStreamWaitEvent(P.st[st], ev(p, q), 0);
+    }
+    if (q >= static_cast<uint64_t>(K)) {
+      for (int r : readers) {
+        cudaStreamWaitEvent(P.st[st], ev(r, q - K), 0);
+      }
+    }
+  };
+  auto done = [&](int st) { cudaEventRecord(ev(st, q), P.st[st]); };
+
+  if (e->M > 1) {
+    cudaStream_t s = P.st[E::ST_DECIM];
+    if (waitH2D) {
+      need(E::ST_DECIM, {E::ST_H2D}, {E::ST_DC});
+    } else {
+      need(E::ST_DECIM, {}, {E::ST_DC});
+    }
+    {
+      Span sp(e, "decimate", s);
+      launchDecim(e->M, iq, stride, e->dHistIq, e->dHistValid, e->dX1 + t0, e->pitch, N, ch0, nch,
+                  e->decPp, e->decL, e->decScale, e->decParam, e->decParamRaw, s);
+      launchCarryIq(e->dHistIq, e->dHistValid, iq, stride, static_cast<long>(N) * e->M, ch0, nch, s);
+      e->launches += 2;
+    }
+    done(E::ST_DECIM);
+  }
+  {
+    cudaStream_t s = P.st[E::ST_DC];
+    if (e->M > 1) {
+      need(E::ST_DC, {E::ST_DECIM}, {E::ST_CHAN});
+    } else if (waitH2D) {
+      need(E::ST_DC, {E::ST_H2D}, {E::ST_CHAN});
+    } else {
+      need(E::ST_DC, {}, {E::ST_CHAN});
+    }
+    Span sp(e, "dcblock", s);
+    if (carry) {
+      launchCarryF2(e->dX2, e->x2Pitch, H_X2, ringEnd, ch0, nch, s);
+      e->launches += 1;
+    }
+    launchDcBlock(e->M > 1 ? e->dX1 + t0 : nullptr, e->pitch, e->M > 1 ? nullptr : iq, stride,
+                  e->dX2 + t0, e->x2Pitch, e->dDemod, status, nb, 1, N, N, ch0, nch, e->k.dc_a1_iq, s);
+    e->launches += 1;
+  }
+  done(E::ST_DC);
+  {
+    cudaStream_t s = P.st[E::ST_CHAN];
+    need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD});
+    Span sp(e, "chanfir", s);
+    launchChanFir(e->dX2 + t0, e->x2Pitch, e->dY + t0, e->yPitch, e->dChanTaps, e->dChanLp,
+                  e->dChanScale, e->dParams, N, ch0, nch, s);
+    e->launches += 1;
+  }
+  done(E::ST_CHAN);
+  {
+    cudaStream_t s = P.st[E::ST_AGC];
+    need(E::ST_AGC, {E::ST_CHAN}, {E::ST_FD});
+    bool anyAgc = false;
+    for (int c = ch0; c < ch0 + nch && !anyAgc; c++) {
+      anyAgc = e->hParams[c].agc_mode != 0;
+    }
+    if (anyAgc) {
+      Span sp(e, "agc", s);
+      launchAgc(e->dY + t0, e->yPitch, e->dDemod, e->dParams, N, ch0, nch, s);
+      e->launches += 1;
+    }
+  }
+  done(E::ST_AGC);
+  {
+    cudaStream_t s = P.st[E::ST_FD];
+    if (stereo) {
+      need(E::ST_FD, {E::ST_AGC}, {E::ST_PILOT, E::ST_STEREO, E::ST_RDS});
+    } else {
+      need(E::ST_FD, {E::ST_AGC}, {E::ST_RDS, E::ST_AF /* the mono chain reads MPX */});
+    }
+    Span sp(e, "freqdem", s);
+    if (carry) {
+      launchCarryF2(e->dY, e->yPitch, Y_OFF, ringEnd, ch0, nch, s);  // slot Y_OFF-1 <- last output
+      launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, ringEnd, ch0, nch, s);
+      e->launches += 2;
+    }
+    launchFreqDem(e->dY + t0, e->yPitch, e->dMpx + t0, e->mpxPitch, N, ch0, nch, e->k.fd_ref, s);
+    e->launches += 1;
+  }
+  done(E::ST_FD);
+  // ---- RDS branch --------------------------------------------------------------------------
+  {
+    cudaStream_t s = P.st[E::ST_RDS];
+    need(E::ST_RDS, {E::ST_FD}, {});
+    Span sp(e, "rds", s);
+    launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
+                  0, 0, 1, first ? 1 : 0, s);
+    launchRds(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
+              e->dMf, e->dDmf, e->dR171, e->r171Pitch, max171(e, N), e->dBits,
+              static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, s);
+    e->launches += 1;
+    launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords,
+                    out.groups, out.gcap, status, nb, 1, b, ch0, nch, s);
+    launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
+    launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, s);
+    e->launches += 5;
+  }
+  done(E::ST_RDS);
+  // ---- audio branch ------------------------------------------------------------------------
+  cudaStream_t sAf = P.st[E::ST_AF];
+  if (stereo) {
+    {
+      cudaStream_t s = P.st[E::ST_PILOT];
+      need(E::ST_PILOT, {E::ST_FD}, {E::ST_STEREO});
+      Span sp(e, "pilot_fir", s);
+      FirRealJob j{};
+      j.in[0] = e->dMpx + t0;
+      j.out[0] = e->dPilot + t0;
+      j.in_pitch = e->mpxPitch;
+      j.out_pitch = e->pitch;
+      j.in_off = H_MPX;
+      j.out_off = 0;
+      j.n_total = N;
+      j.Lp = e->pilLp;
+      j.scale = 1.0f;
+      j.ch0 = ch0;
+      launchFirReal(j, 1, nch, e->pilParam, s);
+      e->launches += 1;
+    }
+    done(E::ST_PILOT);
+    {
+      cudaStream_t s = P.st[E::ST_STEREO];
+      need(E::ST_STEREO, {E::ST_PILOT}, {E::ST_LPF});
+      Span sp(e, "stereo_pll", s);
+      if (carry) {
+        launchCarryF32(e->dLraw, e->lrPitch, H_LR, ringEnd, ch0, nch, s);
+        launchCarryF32(e->dRraw, e->lrPitch, H_LR, ringEnd, ch0, nch, s);
+        e->launches += 2;
+      }
+      launchStereo(e->dMpx + t0, e->mpxPitch, e->dPilot + t0, e->pitch, e->dLraw + t0, e->dRraw + t0,
+                   e->lrPitch, e->dStereo, e->dParams, status, nb, 1, N, N, ch0, nch, e->k, s);
+      e->launches += 1;
+    }
+    done(E::ST_STEREO);
+    {
+      cudaStream_t s = P.st[E::ST_LPF];
+      need(E::ST_LPF, {E::ST_STEREO}, {E::ST_AF});
+      Span sp(e, "audio_lpf", s);
+      if (carry) {
+        launchCarryF32(e->dLf, e->lfPitch, H_LF, ringEnd, ch0, nch, s);
+        launchCarryF32(e->dRf, e->lfPitch, H_LF, ringEnd, ch0, nch, s);
+        e->launches += 2;
+      }
+      FirRealJob j{};
+      j.in[0] = e->dLraw + t0;
+      j.in[1] = e->dRraw + t0;
+      j.out[0] = e->dLf + t0;
+      j.out[1] = e->dRf + t0;
+      j.in_pitch = e->lrPitch;
+      j.out_pitch = e->lfPitch;
+      j.in_off = H_LR;
+      j.out_off = H_LF;
+      j.n_total = N;
+      j.Lp = e->audLp;
+      j.scale = e->k.aud_scale;
+      j.ch0 = ch0;
+      launchFirReal(j, 2, nch, e->audParam, s);
+      e->launches += 1;
+    }
+    done(E::ST_LPF);
+    {
+      need(E::ST_AF, {E::ST_LPF}, {});
+      Span sp(e, "afpost", sAf);
+      launchPrepare(e->dAudioSt, e->dRds, status, nb, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
+                    1, 0, 0, first ? 1 : 0, sAf);
+      const int maxOut = static_cast<int>(std::min<size_t>(
+          out.acap, static_cast<size_t>((static_cast<double>(N) * 16777216.0) / e->k.aud_step) + 2));
+      launchResample(e->dLf + t0, e->dRf + t0, e->lfPitch, H_LF, nullptr, 0, out.audio, out.acap,
+                     e->dAudBank, AUD_RS_LEN, e->k.aud_step, e->dAudioSt, 0, maxOut, ch0, nch, sAf);
+      launchAudioIir(out.audio, out.acap, e->dAudioSt, e->dParams, ch0, nch, e->k.dc_a1_af, 0, 1, 0,
+                     sAf);
+      launchCommit(e->dAudioSt, e->dRds, ch0, nch, 1, 0, 0, sAf);
+      e->launches += 4;
+    }
+  } else {
+    // FMDemod mono chain (main.cpp:1267-1279): MPX -> resample -> de-emphasis -> DC block, x0.5 to
+    // both rows
+    need(E::ST_AF, {E::ST_FD}, {});
+    Span sp(e, "mono", sAf);
+    launchPrepare(e->dAudioSt, e->dRds, status, nb, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
+                  0, 1, 0, first ? 1 : 0, sAf);
+    const int maxOut = static_cast<int>(std::min<size_t>(
+        out.acap, static_cast<size_t>((static_cast<double>(N) * 16777216.0) / e->k.aud_step) + 2));
+    launchResample(e->dMpx + t0, nullptr, e->mpxPitch, H_MPX, e->dMonoHist, 32, out.audio, out.acap,
+                   e->dAudBank, AUD_RS_LEN, e->k.aud_step, e->dAudioSt, 1, maxOut, ch0, nch, sAf);
+    launchAudioIir(out.audio, out.acap, e->dAudioSt, e->dParams, ch0, nch, e->k.mono_dc_a1, 1, 1, 1,
+                   sAf);
+    launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dMonoHist, 32, AUD_RS_LEN - 1, N, ch0, nch,
+                   sAf);
+    launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 1, 0, sAf);
+    e->launches += 5;
+  }
+  if (last) {
+    // the call's counts, once both branches have finished its last block
+    cudaStreamWaitEvent(sAf, ev(E::ST_RDS, q), 0);
+    Span sp(e, "commit", sAf);
+    launchStoreCounts(e->dAudioSt, e->dRds, out.nAudio, out.nGroups, ch0, nch, stereo ? 0 : 1,
+                      static_cast<uint32_t>(out.acap), out.gcap, sAf);
+    e->launches += 1;
+  }
+  done(E::ST_AF);
 }
 
 int checkBatchArgs(fmgpu_engine *e, const void *iq, size_t stride, int n_blocks, bool device,
@@ -560,6 +833,88 @@ int checkBatchArgs(fmgpu_engine *e, const void *iq, size_t stride, int n_blocks,
   return FMGPU_OK;
 }
 
+// Queue n_blocks logical blocks of every channel. hostIq != nullptr: the bytes come from host
+// memory through the H2D stage (block by block into the device ring); else iq_dev is read in place.
+int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, size_t stride,
+                int n_blocks, const BatchOut &out, cudaStream_t caller, bool callerWaits) {
+  using E = fmgpu_engine;
+  const size_t blockBytes = static_cast<size_t>(e->N) * e->M * 2;
+  const int G = std::max(1, e->nGroups);
+  if (!iq_host) {
+    cudaEventRecord(e->evStart, caller);  // the IQ (and the output buffers) are ready in stream order
+  }
+  for (int g = 0; g < G; g++) {
+    E::Pipe &P = e->pipes[g];
+    int ch0, nch;
+    groupRange(e, g, &ch0, &nch);
+    if (nch <= 0) {
+      continue;
+    }
+    if (!iq_host) {
+      cudaStreamWaitEvent(P.st[e->M > 1 ? E::ST_DECIM : E::ST_DC], e->evStart, 0);
+    }
+  }
+  for (int b = 0; b < n_blocks; b++) {
+    const uint64_t q = e->seq + static_cast<uint64_t>(b);
+    const int slot = static_cast<int>(q % static_cast<uint64_t>(e->K));
+    for (int g = 0; g < G; g++) {
+      E::Pipe &P = e->pipes[g];
+      int ch0, nch;
+      groupRange(e, g, &ch0, &nch);
+      if (nch <= 0) {
+        continue;
+      }
+      e->curGroup = g;
+      const uint8_t *iq = nullptr;
+      size_t st = stride;
+      if (iq_host) {
+        // H2D stage: this block's rows into ring slot `slot` of the device staging buffer, once
+        // the first compute stage has finished with block q - K
+        cudaStream_t s = P.st[E::ST_H2D];
+        if (q >= static_cast<uint64_t>(e->K)) {
+          cudaStreamWaitEvent(
+              s, P.done[e->M > 1 ? E::ST_DECIM : E::ST_DC][(q - e->K) % static_cast<uint64_t>(e->ER)], 0);
+        }
+        uint8_t *dst = e->dIq + static_cast<size_t>(ch0) * e->iqPitch + slot * blockBytes;
+        cudaMemcpy2DAsync(dst, e->iqPitch, iq_host + static_cast<size_t>(ch0) * stride + b * blockBytes,
+                          stride, blockBytes, static_cast<size_t>(nch), cudaMemcpyHostToDevice, s);
+        cudaEventRecord(P.done[E::ST_H2D][q % static_cast<uint64_t>(e->ER)], s);
+        iq = e->dIq + slot * blockBytes;
+        st = e->iqPitch;
+      } else {
+        iq = iq_dev + b * blockBytes;
+      }
+      launchBlock(e, P, ch0, nch, q, b, n_blocks, iq, st, iq_host != nullptr, out);
+    }
+    if (slot == 0) {
+      e->headFresh = false;
+    }
+  }
+  for (int g = 0; g < G; g++) {
+    E::Pipe &P = e->pipes[g];
+    int ch0, nch;
+    groupRange(e, g, &ch0, &nch);
+    if (nch <= 0) {
+      continue;
+    }
+    cudaEventRecord(P.callDone, P.st[E::ST_AF]);
+    if (callerWaits) {
+      cudaStreamWaitEvent(caller, P.callDone, 0);
+    }
+  }
+  e->lastSeq0 = e->seq;
+  e->lastBlocks = n_blocks;
+  e->seq += static_cast<uint64_t>(n_blocks);
+  e->asyncPending = true;
+  e->lastN = n_blocks * e->N;
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    e->lastError = std::string("kernel launch: ") + cudaGetErrorString(err);
+    return FMGPU_ENODEV;
+  }
+  return FMGPU_OK;
+}
+
 int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks, float *audio_dev,
              size_t audio_cap, uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
              uint32_t *n_groups_dev, fmgpu_block_status *status_dev, cudaStream_t s,
@@ -572,48 +927,16 @@ int runBatch(fmgpu_engine *e, const uint8_t *iq_dev, size_t stride, int n_blocks
   if (rc != FMGPU_OK) {
     return rc;
   }
-  fmgpu_block_status *status = status_dev ? status_dev : e->dStatus;
-  fmgpu_rds_group *groups = groups_dev ? groups_dev : e->dGroups;
-  const uint32_t gcap = static_cast<uint32_t>(groups_dev ? group_cap : e->gcap);
-  uint32_t *n_audio = n_audio_dev ? n_audio_dev : e->dNAudio;
-  uint32_t *n_groups = n_groups_dev ? n_groups_dev : e->dNGroups;
+  BatchOut out;
+  out.status = status_dev ? status_dev : e->dStatus;
+  out.groups = groups_dev ? groups_dev : e->dGroups;
+  out.gcap = static_cast<uint32_t>(groups_dev ? group_cap : e->gcap);
+  out.nAudio = n_audio_dev ? n_audio_dev : e->dNAudio;
+  out.nGroups = n_groups_dev ? n_groups_dev : e->dNGroups;
   // audio is produced straight into the caller's buffer when one is given
-  float *audioSaved = e->dAudio;
-  const size_t acapSaved = e->acap;
-  if (audio_dev) {
-    e->dAudio = audio_dev;
-    e->acap = audio_cap;
-  }
-  if (e->nGroups <= 1) {
-    runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, 0, e->C, s,
-             e->stream2, e->evFork, e->evJoin, e->laneStream, e->evHop);
-  } else {
-    cudaEventRecord(e->evStart, s);
-    for (int g = 0; g < e->nGroups; g++) {
-      int ch0, nch;
-      groupRange(e, g, &ch0, &nch);
-      if (nch <= 0) {
-        continue;
-      }
-      cudaStreamWaitEvent(e->gStream[g], e->evStart, 0);
-      e->curGroup = g;
-      runRange(e, iq_dev, stride, n_blocks, n_audio, groups, gcap, n_groups, status, ch0, nch,
-               e->gStream[g], e->gStream2[g], e->gFork[g], e->gJoin[g], e->gLane[g], e->gHop[g]);
-      cudaEventRecord(e->gDone[g], e->gStream[g]);
-      if (join) {
-        cudaStreamWaitEvent(s, e->gDone[g], 0);
-      }
-    }
-  }
-  e->dAudio = audioSaved;
-  e->acap = acapSaved;
-  e->lastN = n_blocks * e->N;
-  const cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) {
-    e->lastError = std::string("kernel launch: ") + cudaGetErrorString(err);
-    return FMGPU_ENODEV;
-  }
-  return FMGPU_OK;
+  out.audio = audio_dev ? audio_dev : e->dAudio;
+  out.acap = audio_dev ? audio_cap : e->acap;
+  return queueBlocks(e, iq_dev, nullptr, stride, n_blocks, out, s, join);
 }
 
 // All design-time work of the reference constructors; touches no CUDA state.
@@ -782,13 +1105,23 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   e->N = cfg->block_samples;
   e->maxBlocks = cfg->max_blocks;
   e->nmax = static_cast<size_t>(e->N) * e->maxBlocks;
-  e->pitch = roundUp(e->nmax, 32);
+  // ring of K block slots per scratch buffer (see fmgpu_engine::Pipe); slots must start on
+  // 16-byte boundaries for the cp.async tile loads, else every block goes through slot 0
+  e->K = (e->N % 32 == 0) ? std::max(2, e->maxBlocks) : 1;
+  if (e->K == 1 && e->maxBlocks > 1) {
+    e->lastError = "fmgpu_engine_create: max_blocks > 1 needs block_samples to be a multiple of 32";
+    g_create_error = e->lastError;
+    delete e;
+    return FMGPU_EINVAL;
+  }
+  e->ER = e->K + 1;
+  e->pitch = roundUp(static_cast<size_t>(e->K) * e->N, 32);
   e->x2Pitch = H_X2 + e->pitch;
   e->yPitch = 32 + e->pitch;
   e->mpxPitch = H_MPX + e->pitch;
   e->lrPitch = H_LR + e->pitch;
   e->lfPitch = H_LF + e->pitch;
-  e->iqPitch = roundUp(e->nmax * e->M * 2, 16);
+  e->iqPitch = roundUp(static_cast<size_t>(e->K) * e->N * e->M * 2, 16);
   CKC(cudaSetDevice(device));
 
   {
@@ -805,22 +1138,38 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   int prLo = 0, prHi = 0;
   CKC(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));  // prHi = numerically smallest = highest
-  CKC(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, prHi));
-  CKC(cudaStreamCreateWithPriority(&e->laneStream, cudaStreamNonBlocking, prHi));
-  CKC(cudaEventCreateWithFlags(&e->evHop, cudaEventDisableTiming));
-  CKC(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
-  CKC(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->evStart, cudaEventDisableTiming));
-  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
-    CKC(cudaStreamCreateWithFlags(&e->gStream[g], cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithPriority(&e->gStream2[g], cudaStreamNonBlocking, prHi));
-    CKC(cudaStreamCreateWithPriority(&e->gLane[g], cudaStreamNonBlocking, prHi));
-    CKC(cudaEventCreateWithFlags(&e->gHop[g], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&e->gFork[g], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&e->gJoin[g], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&e->gDone[g], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&e->gHostDone[0][g], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&e->gHostDone[1][g], cudaEventDisableTiming));
+  for (auto &P : e->pipes) {
+    for (int st = 0; st < fmgpu_engine::ST_COUNT; st++) {
+      // Priorities grow downstream. The serial one-lane-per-channel stages are the slowest per
+      // block, so they get the top priority (their few CTAs are scheduled ahead of the thousands
+      // of queued FIR CTAs), and among the FIR stages the one nearest the output wins: a
+      // decimator running two blocks ahead must not take SMs from the pilot filter the PLL of
+      // the current block is waiting for (r3 timeline: pilot_fir 7.7 ms beside a 10.6 ms decimate).
+      int rank = 0;
+      switch (st) {
+      case fmgpu_engine::ST_DECIM: rank = 0; break;
+      case fmgpu_engine::ST_CHAN: rank = 1; break;
+      case fmgpu_engine::ST_FD: rank = 2; break;
+      case fmgpu_engine::ST_PILOT: rank = 3; break;
+      case fmgpu_engine::ST_LPF: rank = 4; break;
+      case fmgpu_engine::ST_DC:
+      case fmgpu_engine::ST_AGC:
+      case fmgpu_engine::ST_STEREO:
+      case fmgpu_engine::ST_RDS:
+      case fmgpu_engine::ST_AF: rank = 5; break;
+      default: rank = 0; break;  // copies
+      }
+      const int prio = prLo - std::min(rank, prLo - prHi);
+      CKC(cudaStreamCreateWithPriority(&P.st[st], cudaStreamNonBlocking, prio));
+      P.done[st].resize(static_cast<size_t>(e->ER));
+      for (auto &ev : P.done[st]) {
+        CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      }
+    }
+    CKC(cudaEventCreateWithFlags(&P.callDone, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&P.hostDone[0], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&P.hostDone[1], cudaEventDisableTiming));
   }
   CKC(initRdsTables());
   CKC(devAlloc(&e->dIq, C * e->iqPitch));
@@ -836,6 +1185,8 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(devAlloc(&e->dLf, C * e->lfPitch));
   CKC(devAlloc(&e->dRf, C * e->lfPitch));
   CKC(devAlloc(&e->dAudio, C * 2 * e->acap));
+  e->r171Pitch = roundUp(static_cast<size_t>(max171(e, static_cast<int>(e->nmax))) + 32, 32);
+  CKC(devAlloc(&e->dR171, C * e->r171Pitch));
   CKC(devAlloc(&e->dRing, C * RDS_RING));
   CKC(devAlloc(&e->dRdsHist, C * 32));
   CKC(devAlloc(&e->dMonoHist, C * 32));
@@ -856,6 +1207,11 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(devAlloc(&e->dStatus, C * static_cast<size_t>(e->maxBlocks)));
   CKC(devAlloc(&e->dNAudio, C));
   CKC(devAlloc(&e->dNGroups, C));
+  CKC(devAlloc(&e->dAudio2, C * 2 * e->acap));
+  CKC(devAlloc(&e->dGroups2, C * e->gcap));
+  CKC(devAlloc(&e->dStatus2, C * static_cast<size_t>(e->maxBlocks)));
+  CKC(devAlloc(&e->dNAudio2, C));
+  CKC(devAlloc(&e->dNGroups2, C));
   CKC(devAlloc(&e->dBits, C * e->bitsCap));
   CKC(devAlloc(&e->dWords, C * e->bitsCap));
   CKC(devAlloc(&e->dBitEnd, C * static_cast<size_t>(e->maxBlocks)));
@@ -911,15 +1267,14 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
     return;
   }
   cudaSetDevice(e->device);
-  if (e->stream) {
-    cudaStreamSynchronize(e->stream);
-  }
+  cudaDeviceSynchronize();
   void *ptrs[] = {e->dIq,      e->dHistIq, e->dX1,     e->dX2,      e->dY,       e->dMpx,
                   e->dPilot,   e->dLraw,   e->dRraw,   e->dLf,      e->dRf,      e->dAudio,
                   e->dRing,    e->dRdsHist, e->dMonoHist, e->dChanTaps, e->dChanScale, e->dChanLp,
                   e->dAudBank, e->dRdsBank, e->dRdsLpf, e->dMf,     e->dDmf,     e->dParams,
                   e->dDemod,   e->dStereo, e->dAudioSt, e->dRds,    e->dGroups,  e->dStatus,
-                  e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd};
+                  e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd,
+                  e->dAudio2,  e->dGroups2, e->dStatus2, e->dNAudio2, e->dNGroups2, e->dR171};
   for (void *p : ptrs) {
     if (p) {
       cudaFree(p);
@@ -928,41 +1283,21 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
   if (e->stream) {
     cudaStreamDestroy(e->stream);
   }
-  if (e->stream2) {
-    cudaStreamSynchronize(e->stream2);
-    cudaStreamDestroy(e->stream2);
-  }
-  if (e->evFork) {
-    cudaEventDestroy(e->evFork);
-  }
-  if (e->evJoin) {
-    cudaEventDestroy(e->evJoin);
-  }
   if (e->evStart) {
     cudaEventDestroy(e->evStart);
   }
-  if (e->laneStream) {
-    cudaStreamSynchronize(e->laneStream);
-    cudaStreamDestroy(e->laneStream);
-  }
-  if (e->evHop) {
-    cudaEventDestroy(e->evHop);
-  }
-  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
-    if (e->gStream[g]) {
-      cudaStreamSynchronize(e->gStream[g]);
-      cudaStreamDestroy(e->gStream[g]);
+  for (auto &P : e->pipes) {
+    for (int st = 0; st < fmgpu_engine::ST_COUNT; st++) {
+      if (P.st[st]) {
+        cudaStreamDestroy(P.st[st]);
+      }
+      for (cudaEvent_t ev : P.done[st]) {
+        if (ev) {
+          cudaEventDestroy(ev);
+        }
+      }
     }
-    if (e->gStream2[g]) {
-      cudaStreamSynchronize(e->gStream2[g]);
-      cudaStreamDestroy(e->gStream2[g]);
-    }
-    if (e->gLane[g]) {
-      cudaStreamSynchronize(e->gLane[g]);
-      cudaStreamDestroy(e->gLane[g]);
-    }
-    for (cudaEvent_t ev : {e->gFork[g], e->gJoin[g], e->gDone[g], e->gHop[g], e->gHostDone[0][g],
-                           e->gHostDone[1][g]}) {
+    for (cudaEvent_t ev : {P.callDone, P.hostDone[0], P.hostDone[1]}) {
       if (ev) {
         cudaEventDestroy(ev);
       }
@@ -1006,6 +1341,7 @@ int fmgpu_set_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
     p.filt = slot;
     e->paramsDirty = true;
     // the FIR is re-created with an empty window (fm_demod.cpp:134); r_prev is kept
+    realign(e);  // queued blocks finish; the window (halo) sits in front of ring slot 0
     zeroPrefix(e->dX2, e->x2Pitch, H_X2, c, c + 1, e->stream);
     cudaStreamSynchronize(e->stream);
     return FMGPU_OK;
@@ -1069,6 +1405,7 @@ int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz) {
   // freqdem is re-created: new reference gain, r_prev cleared (fm_demod.cpp:64-71)
   const float kf = static_cast<float>(deviation_hz / static_cast<double>(e->fs));
   e->k.fd_ref = static_cast<float>(1.0 / (2.0 * M_PI * static_cast<double>(kf)));
+  realign(e);
   zeroPrefix(e->dY, e->yPitch, Y_OFF, 0, e->C, e->stream);
   CK(cudaStreamSynchronize(e->stream));
   return FMGPU_OK;
@@ -1111,6 +1448,7 @@ int fmgpu_reset(fmgpu_engine *e, int channel, unsigned what) {
   const int hi = (channel < 0) ? e->C : channel + 1;
   const size_t cnt = static_cast<size_t>(hi - lo);
   cudaStream_t s = e->stream;
+  realign(e);  // queued blocks finish; every halo sits in front of slot 0 again
   CK(cudaStreamSynchronize(s));
   if (what & FMGPU_RESET_DECIM) {
     if (e->M > 1) {
@@ -1187,6 +1525,7 @@ static int readStereo(fmgpu_engine *e, int channel, StereoState *out) {
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
+  syncPipes(e);
   CK(cudaMemcpyAsync(out, e->dStereo + channel, sizeof(StereoState), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return FMGPU_OK;
@@ -1197,6 +1536,7 @@ static int readDemod(fmgpu_engine *e, int channel, DemodState *out) {
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
+  syncPipes(e);
   CK(cudaMemcpyAsync(out, e->dDemod + channel, sizeof(DemodState), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return FMGPU_OK;
@@ -1258,9 +1598,9 @@ int fmgpu_join(fmgpu_engine *e, void *stream) {
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
-    // gDone[g] holds the last batch this group ran (an event never recorded is complete)
-    CK(cudaStreamWaitEvent(s, e->gDone[g], 0));
+  for (auto &P : e->pipes) {
+    // callDone holds the last batch this pipe ran (an event never recorded is complete)
+    CK(cudaStreamWaitEvent(s, P.callDone, 0));
   }
   return FMGPU_OK;
 }
@@ -1271,8 +1611,8 @@ static int waitHostTicket(fmgpu_engine *e, int ticket) {
     return FMGPU_OK;
   }
   t.pending = false;
-  for (int g = 0; g < fmgpu_engine::kMaxGroups; g++) {
-    CK(cudaEventSynchronize(e->gHostDone[ticket][g]));
+  for (auto &P : e->pipes) {
+    CK(cudaEventSynchronize(P.hostDone[ticket]));
   }
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -1330,7 +1670,6 @@ int fmgpu_submit_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_
   if (rc != FMGPU_OK) {
     return rc;
   }
-  const size_t bytes = static_cast<size_t>(n_blocks) * e->N * e->M * 2;
   const size_t n = static_cast<size_t>(n_blocks) * e->N;
   const size_t frames = std::min(e->acap, static_cast<size_t>((static_cast<double>(n) * 16777216.0) /
                                                                e->k.aud_step) + 2);
@@ -1341,56 +1680,64 @@ int fmgpu_submit_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_
     return rc;
   }
   e->nextTicket ^= 1;
-  // every group: host->device copy of its rows, the pipeline, device->host copy of its results,
-  // all on the group's own stream, so copies of one group overlap kernels of the others (and,
-  // with a second submission queued behind, the next call's copies overlap this call's tail)
+  // H2D stage: block after block into the device ring, each block's kernels released by its own
+  // copy; results go back on the D2H stage once the call's last block is done. With a second
+  // submission queued behind, its copies overlap this call's kernels.
+  // device-side result buffers alternate with the ticket, so the next submission's kernels never
+  // wait for this one's device-to-host copies
+  float *dAud = ticket ? e->dAudio2 : e->dAudio;
+  fmgpu_rds_group *dGrp = ticket ? e->dGroups2 : e->dGroups;
+  fmgpu_block_status *dSt = ticket ? e->dStatus2 : e->dStatus;
+  uint32_t *dNA = ticket ? e->dNAudio2 : e->dNAudio;
+  uint32_t *dNG = ticket ? e->dNGroups2 : e->dNGroups;
+  BatchOut out;
+  out.audio = dAud;
+  out.acap = e->acap;
+  out.nAudio = dNA;
+  out.groups = dGrp;
+  out.gcap = static_cast<uint32_t>(e->gcap);
+  out.nGroups = dNG;
+  out.status = dSt;
+  rc = queueBlocks(e, nullptr, iq_host, iq_stride_bytes, n_blocks, out, nullptr, false);
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
   for (int g = 0; g < G; g++) {
     int ch0 = 0, nch = e->C;
-    cudaStream_t s = e->stream, s2 = e->stream2, sl = e->laneStream;
-    cudaEvent_t evF = e->evFork, evJ = e->evJoin, evH = e->evHop;
-    if (G > 1) {
-      groupRange(e, g, &ch0, &nch);
-      if (nch <= 0) {
-        continue;
-      }
-      s = e->gStream[g];
-      s2 = e->gStream2[g];
-      evF = e->gFork[g];
-      evJ = e->gJoin[g];
-      sl = e->gLane[g];
-      evH = e->gHop[g];
+    groupRange(e, g, &ch0, &nch);
+    if (nch <= 0) {
+      continue;
     }
+    fmgpu_engine::Pipe &P = e->pipes[g];
+    cudaStream_t s = P.st[fmgpu_engine::ST_D2H];
+    CK(cudaStreamWaitEvent(s, P.callDone, 0));
     const size_t c0 = static_cast<size_t>(ch0), cn = static_cast<size_t>(nch);
-    CK(cudaMemcpy2DAsync(e->dIq + c0 * e->iqPitch, e->iqPitch, iq_host + c0 * iq_stride_bytes,
-                         iq_stride_bytes, bytes, cn, cudaMemcpyHostToDevice, s));
-    runRange(e, e->dIq, e->iqPitch, n_blocks, e->dNAudio, e->dGroups, static_cast<uint32_t>(e->gcap),
-             e->dNGroups, e->dStatus, ch0, nch, s, s2, evF, evJ, sl, evH);
     if (audio_host) {
       CK(cudaMemcpy2DAsync(audio_host + c0 * 2 * audio_cap, audio_cap * sizeof(float),
-                           e->dAudio + c0 * 2 * e->acap, e->acap * sizeof(float),
-                           frames * sizeof(float), cn * 2, cudaMemcpyDeviceToHost, s));
+                           dAud + c0 * 2 * e->acap, e->acap * sizeof(float), frames * sizeof(float),
+                           cn * 2, cudaMemcpyDeviceToHost, s));
     }
     if (n_audio_host) {
-      CK(cudaMemcpyAsync(n_audio_host + c0, e->dNAudio + c0, cn * sizeof(uint32_t),
-                         cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(n_audio_host + c0, dNA + c0, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                         s));
     }
     if (groups_host) {
       const size_t gw = std::min(group_cap, e->gcap);
       CK(cudaMemcpy2DAsync(groups_host + c0 * group_cap, group_cap * sizeof(fmgpu_rds_group),
-                           e->dGroups + c0 * e->gcap, e->gcap * sizeof(fmgpu_rds_group),
+                           dGrp + c0 * e->gcap, e->gcap * sizeof(fmgpu_rds_group),
                            gw * sizeof(fmgpu_rds_group), cn, cudaMemcpyDeviceToHost, s));
     }
     if (n_groups_host) {
-      CK(cudaMemcpyAsync(n_groups_host + c0, e->dNGroups + c0, cn * sizeof(uint32_t),
-                         cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(n_groups_host + c0, dNG + c0, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                         s));
     }
     if (status_host) {
-      CK(cudaMemcpyAsync(status_host + c0 * n_blocks, e->dStatus + c0 * n_blocks,
+      // the status rows of this call are [C][n_blocks] (pitch = n_blocks)
+      CK(cudaMemcpyAsync(status_host + c0 * n_blocks, dSt + c0 * n_blocks,
                          cn * n_blocks * sizeof(fmgpu_block_status), cudaMemcpyDeviceToHost, s));
     }
-    CK(cudaEventRecord(e->gHostDone[ticket][g], s));
+    CK(cudaEventRecord(P.hostDone[ticket], s));
   }
-  e->lastN = static_cast<int>(n);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     e->lastError = std::string("process_host: ") + cudaGetErrorString(err);
@@ -1477,11 +1824,15 @@ int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
 }
 
 int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups) {
-  if (!e || groups < 1 || groups > fmgpu_engine::kMaxGroups) {
+  if (!e || groups < 1 || groups > 16) {
     return FMGPU_EINVAL;
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
-  e->nGroups = groups;
+  CK(cudaSetDevice(e->device));
+  syncPipes(e);
+  // every group owns a full set of stage streams; more than two sets buy nothing (the block
+  // pipeline already overlaps the stages) and would exceed the device's hardware queues
+  e->nGroups = std::min(groups, fmgpu_engine::kMaxGroups);
   return FMGPU_OK;
 }
 
@@ -1494,6 +1845,7 @@ int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups) {
   if (cudaSetDevice(e->device) != cudaSuccess || uploadParams(e) != FMGPU_OK) { \
     return 0;                                                                   \
   }                                                                             \
+  realign(e); /* the stage-level calls work at ring offset 0, halos in place */ \
   cudaStream_t s = e->stream;
 
 static bool stageFail(fmgpu_engine *e, const char *what) {
@@ -1542,7 +1894,7 @@ static size_t demodCommon(fmgpu_engine *e, int channel, const uint8_t *iq_u8, co
   }
   if (mono_out) {
     launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                  e->k.rds_step, 0, 1, 0, s);
+                  e->k.rds_step, 0, 1, 0, 1, s);
   }
   stageDemod(e, iq_u8 ? e->dIq : nullptr, e->iqPitch, nullptr, 1, ni, ni, channel, 1, s);
   if (mpx_out) {
@@ -1588,7 +1940,7 @@ size_t fmgpu_downsample_mono(fmgpu_engine *e, int channel, const float *mpx, flo
   cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
                   n * sizeof(float), cudaMemcpyHostToDevice, s);
   launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                e->k.rds_step, 0, 1, 0, s);
+                e->k.rds_step, 0, 1, 0, 1, s);
   stageMono(e, ni, 0, 0, channel, 1, s);
   launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, s);
   e->launches += 2;
@@ -1655,7 +2007,7 @@ size_t fmgpu_afpost(fmgpu_engine *e, int channel, const float *in_left, const fl
   cudaMemcpyAsync(e->dRf + static_cast<size_t>(channel) * e->lfPitch + H_LF, in_right,
                   n_eff * sizeof(float), cudaMemcpyHostToDevice, s);
   launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                e->k.rds_step, 1, 0, 0, s);
+                e->k.rds_step, 1, 0, 0, 1, s);
   stageAfPost(e, ni, 0, channel, 1, s);
   launchCommit(e->dAudioSt, e->dRds, channel, 1, 1, 0, 0, s);
   cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
@@ -1681,7 +2033,7 @@ size_t fmgpu_rds(fmgpu_engine *e, int channel, const float *mpx, size_t n, fmgpu
   cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
                   n * sizeof(float), cudaMemcpyHostToDevice, s);
   launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                e->k.rds_step, 0, 0, 1, s);
+                e->k.rds_step, 0, 0, 1, 1, s);
   stageRds(e, e->dGroups, static_cast<uint32_t>(e->gcap), nullptr, 1, ni, ni, channel, 1, s);
   launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 0, 1, s);
   e->launches += 2;
@@ -1742,23 +2094,35 @@ size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, siz
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   cudaSetDevice(e->device);
+  syncPipes(e);
   const size_t c = static_cast<size_t>(channel);
-  const size_t n = static_cast<size_t>(e->lastN);
-  const float *src = nullptr;
-  size_t count = n;
+  const float *base = nullptr;
+  size_t per = 1;  // floats per sample
   switch (which) {
-  case 0: src = reinterpret_cast<const float *>(e->dX1 + c * e->pitch); count = 2 * n; break;
-  case 1: src = e->dMpx + c * e->mpxPitch + H_MPX; break;
-  case 2: src = e->dLf + c * e->lfPitch + H_LF; break;
-  case 3: src = e->dRf + c * e->lfPitch + H_LF; break;
-  case 4: src = e->dPilot + c * e->pitch; break;
+  case 0: base = reinterpret_cast<const float *>(e->dX1 + c * e->pitch); per = 2; break;
+  case 1: base = e->dMpx + c * e->mpxPitch + H_MPX; break;
+  case 2: base = e->dLf + c * e->lfPitch + H_LF; break;
+  case 3: base = e->dRf + c * e->lfPitch + H_LF; break;
+  case 4: base = e->dPilot + c * e->pitch; break;
   default: return 0;
   }
-  // NOTE: mpx / lf / rf halos have already been carried; the data region is intact.
-  count = std::min(count, cap);
-  cudaMemcpyAsync(out, src, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  size_t written = 0;
+  if (e->lastBlocks > 0) {
+    // a batch call: its blocks sit in ring slots (seq0 + b) % K
+    for (int b = 0; b < e->lastBlocks && written < cap; b++) {
+      const size_t slot = static_cast<size_t>((e->lastSeq0 + b) % static_cast<uint64_t>(e->K));
+      const size_t cnt = std::min(cap - written, per * static_cast<size_t>(e->N));
+      cudaMemcpyAsync(out + written, base + per * slot * e->N, cnt * sizeof(float),
+                      cudaMemcpyDeviceToHost, e->stream);
+      written += cnt;
+    }
+  } else {
+    // a stage-level call: offset 0 (the halos have been carried; the data region is intact)
+    written = std::min(per * static_cast<size_t>(e->lastN), cap);
+    cudaMemcpyAsync(out, base, written * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  }
   cudaStreamSynchronize(e->stream);
-  return count;
+  return written;
 }
 
 size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t cap) {
@@ -1767,6 +2131,7 @@ size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t c
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   cudaSetDevice(e->device);
+  syncPipes(e);
   RdsState r{};
   cudaMemcpyAsync(&r, e->dRds + channel, sizeof(r), cudaMemcpyDeviceToHost, e->stream);
   cudaStreamSynchronize(e->stream);

@@ -77,7 +77,8 @@ struct StereoState {  // StereoDecoder carried state (stereo_decoder.h:29-54)
 struct AudioState {   // AFPostProcessor (af_post_processor.h:27-32) + FMDemod mono chain
   float de_v1[2], dc_v1[2];
   uint32_t rs_phase, rs_phase_next;
-  uint32_t n_out;     // outputs of the current call
+  uint32_t n_out;     // outputs of the current logical block
+  uint32_t out_base;  // frames written by the earlier blocks of the current call
   float mono_de_v1, mono_dc_v1;
   uint32_t mono_phase, mono_phase_next, mono_n_out;
 };
@@ -109,6 +110,7 @@ struct RdsState {     // redsea SubcarrierSet + BlockStream (subcarrier.hh:38-90
   int pulse_off[4];
   uint32_t n_groups;  // groups emitted in the current call
   uint32_t n_bits;    // bits demodulated in the current call
+  uint32_t bits_done; // of those, already consumed by the block synchroniser
 };
 
 // Engine-wide constants (by value in kernel parameters).

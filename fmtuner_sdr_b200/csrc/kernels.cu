@@ -331,118 +331,173 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
   }
 }
 
-// K1, second form: the I and the Q component of a tile go to separate shared-memory planes and
-// to separate halves of the CTA (threads 0..63 -> I, 64..127 -> Q), each thread keeping R = 8
-// consecutive outputs of ONE component. A sample read from shared memory (one 32-bit LDS) now
-// feeds 8 FFMAs instead of 4, which halves the shared-memory bytes per FFMA: the first form
-// needs 128 B/clk/SM of LDS bandwidth at full FMA rate (ncu: FMA pipe 50 % busy, r01), this
-// one half of that. Same taps, same order (oldest sample first, one accumulator per output).
-template <int M, int R>
-__global__ void __launch_bounds__(128)
-k_decim_split(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
-              const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch,
-              int n_out, int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
-  constexpr int T = 64 * R;
+// K1, register-ring form (the one the engine launches when M and the phase count have an
+// instantiation). What ncu showed on the first form (r01): 83 % of the issue slots used with the
+// FMA pipe only 50 % busy, the LSU data pipe 75 % busy, and 5.8 shared-memory wavefronts per tile
+// store. Three changes:
+//  * a thread keeps R = 8 outputs and walks the input segment by segment (M samples each): a
+//    sample read from shared memory (one LDS.64 of {I, Q}) feeds all 8 outputs = 8 FFMA2, twice the
+//    reuse of the first form, so the LSU pipe is half as busy per FMA;
+//  * what rotates through registers is the TAPS (the last 8 phases, 8 x M floats, refilled with
+//    128-bit broadcast LDS), not the samples; FFMA2 takes the tap as a scalar operand;
+//  * the tile is staged as raw bytes with 16-byte cp.async, then converted with 32-bit index
+//    arithmetic, consecutive lanes on consecutive samples: conflict-free LDS.U16 / STS.64.
+// Output j of a thread uses segment u with tap phase p = u - j: every accumulator still receives
+// its products oldest sample first, phase by phase — the same fmaf chain as the first form and
+// as the CPU oracle.
+template <int M, int PP>
+__global__ void __launch_bounds__(64)
+k_decim_ring(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
+             const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
+             int ch0, float scale, const __grid_constant__ TapsParam taps) {
+  constexpr int R = 8;
+  constexpr int NT = 64;
+  constexpr int T = NT * R;                 // outputs per CTA
   constexpr int RM = R * M;
-  extern __shared__ float xpl[];
+  constexpr int TILE = (T + PP - 1) * M;    // samples per tile
+  constexpr int TQ = (M + 3) / 4;           // float4 per tap phase in shared memory
+  constexpr int PRE = 7 + ((PP - 7) % 8);   // unrolled lead-in: the main loop then runs whole rounds
+  static_assert(PP >= 15, "phase count too small for the register ring");
+  extern __shared__ __align__(16) unsigned char dr_smem[];
+  float4 *sh4 = reinterpret_cast<float4 *>(dr_smem);                       // [PP][TQ] taps
+  float2 *xs = reinterpret_cast<float2 *>(dr_smem + PP * TQ * 16);         // skewed float2 tile
+  constexpr int XS = (TILE + TILE / RM + 3) & ~1;  // even: the byte stage behind it stays 16-byte aligned
+  unsigned char *raw = dr_smem + PP * TQ * 16 + XS * 8;                    // staged bytes
   const int c = blockIdx.y + ch0;
   const int n0 = blockIdx.x * T;
   const int t = threadIdx.x;
-  const long o = (long)(n0 - Pp) * M + 1;  // stream index of tile element 0
-  const int tile_len = (T + Pp - 1) * M;
-  const int plane = tile_len + tile_len / RM + 2;
-  float *xi = xpl;
-  float *xq = xpl + plane;
-  const long v0 = o + H_IQ;                // virtual index (history first)
-  const long ck0 = v0 >> 3;
-  const long ck1 = (v0 + tile_len - 1) >> 3;
-  const long n_in = (long)n_out * M;
+  // tile element a <-> stream sample o + a; virtual index (history first) v = o + a + H_IQ
+  const int v0 = (n0 - PP) * M + 1 + H_IQ;
+  const int ck0 = v0 >> 3;                  // v0 >= 1 + H_IQ - PP*M > 0
+  const int nck = ((v0 + TILE - 1) >> 3) - ck0 + 1;
+  const int n_in = n_out * M;
   const uint8_t *in_c = iq + (size_t)c * iq_stride;
   const uint8_t *hist_c = hist + (size_t)c * (2 * H_IQ);
-  const long v_first_valid = H_IQ - hist_valid[c];
-  constexpr float kScale = 1.0f / 127.5f;
 
-  for (long ck = ck0 + t; ck <= ck1; ck += 128) {
-    const long v = ck << 3;
-    uint4 raw = make_uint4(0, 0, 0, 0);
+  for (int j = t; j < nck; j += NT) {
+    const int v = (ck0 + j) << 3;
+    unsigned char *dst = raw + 16 * j;
     if (v < H_IQ) {
-      raw = *reinterpret_cast<const uint4 *>(hist_c + 2 * v);
+      cpAsync16(dst, hist_c + 2 * v);
     } else if (v - H_IQ < n_in) {
-      raw = __ldg(reinterpret_cast<const uint4 *>(in_c + 2 * (v - H_IQ)));
+      cpAsync16(dst, in_c + 2 * (v - H_IQ));
+    } else {
+      *reinterpret_cast<uint4 *>(dst) = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
     }
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-      const long a = v + e - v0;
-      if (a >= 0 && a < tile_len) {
-        const uint32_t word = w[e >> 1] >> ((e & 1) * 16);
-        float fi = ((float)(word & 0xffu) - 127.5f) * kScale;
-        float fq = ((float)((word >> 8) & 0xffu) - 127.5f) * kScale;
-        if (v + e < v_first_valid) {
-          fi = 0.0f;
-          fq = 0.0f;
-        }
-        const int ai = (int)a;
-        const int idx = ai + ai / RM;
-        xi[idx] = fi;
-        xq[idx] = fq;
+  }
+  cpAsyncCommit();
+  // taps: PP phases of M, padded to TQ float4 each
+  for (int i = t; i < PP * TQ * 4; i += NT) {
+    const int p = i / (TQ * 4), r = i - p * (TQ * 4);
+    reinterpret_cast<float *>(sh4)[i] = (r < M) ? taps.h[p * M + r] : 0.0f;
+  }
+  cpAsyncWait<0>();
+  __syncthreads();
+  {
+    constexpr float kScale = 1.0f / 127.5f;
+    const unsigned short *raw16 = reinterpret_cast<const unsigned short *>(raw) + (v0 - (ck0 << 3));
+    // samples older than the valid history are the zero window of a fresh firdecim
+    const int first_valid = (H_IQ - hist_valid[c]) - v0;
+#pragma unroll 4
+    for (int a = t; a < TILE; a += NT) {
+      const unsigned w = raw16[a];
+      float fi = ((float)(w & 0xffu) - 127.5f) * kScale;
+      float fq = ((float)(w >> 8) - 127.5f) * kScale;
+      if (a < first_valid) {
+        fi = 0.0f;
+        fq = 0.0f;
       }
+      xs[a + a / RM] = make_float2(fi, fq);
     }
   }
   __syncthreads();
 
-  const int comp = t >> 6;
-  const int tt = t & 63;
-  const float *xp = comp ? xq : xi;
-  float acc[R];
+  float2 acc[R];
 #pragma unroll
   for (int j = 0; j < R; j++) {
-    acc[j] = 0.0f;
+    acc[j] = make_float2(0.0f, 0.0f);
   }
-  float seg[R][M];
-  const int tbase = tt * (RM + 1);
+  float tr[8][TQ * 4];   // the last 8 tap phases; slot = phase % 8
+  const float2 *xb = xs + t * (RM + 1);
+  // segment u of this thread: samples t*RM + u*M + r at xb[u*M + r + u/8]
+#define FMGPU_RING_LOAD_TAPS(U, SLOT)                                   \
+  _Pragma("unroll") for (int qd = 0; qd < TQ; qd++) {                   \
+    const float4 tv = sh4[(U) * TQ + qd];                               \
+    tr[SLOT][4 * qd + 0] = tv.x;                                        \
+    tr[SLOT][4 * qd + 1] = tv.y;                                        \
+    tr[SLOT][4 * qd + 2] = tv.z;                                        \
+    tr[SLOT][4 * qd + 3] = tv.w;                                        \
+  }
+  // lead-in: phases 0 .. PRE-1 (outputs j <= u only while u < 7)
 #pragma unroll
-  for (int u = 0; u < R - 1; u++) {
+  for (int u = 0; u < PRE; u++) {
+    FMGPU_RING_LOAD_TAPS(u, u % 8)
+    const float2 *xp = xb + u * M + u / 8;
+    float2 x[M];
 #pragma unroll
     for (int r = 0; r < M; r++) {
-      seg[u][r] = xp[tbase + u * M + r];  // u < R: no skew word yet
+      x[r] = xp[r];
     }
-  }
-  // one tap phase: the newest segment comes in, then M taps x R outputs
-#define FMGPU_DECIM_PHASE(PP, PS)                                  \
-  {                                                                \
-    const int u = (PP) + (PS) + R - 1;                             \
-    const int sb = tbase + u * M + u / R;                          \
-    _Pragma("unroll") for (int r = 0; r < M; r++) {                \
-      seg[((PS) + R - 1) % R][r] = xp[sb + r];                     \
-    }                                                              \
-    _Pragma("unroll") for (int r = 0; r < M; r++) {                \
-      const float h = taps.h[((PP) + (PS)) * M + r];               \
-      _Pragma("unroll") for (int j = 0; j < R; j++) {              \
-        acc[j] = fmaf(h, seg[(j + (PS)) % R][r], acc[j]);          \
-      }                                                            \
-    }                                                              \
-  }
-  int pp = 0;
-  for (; pp + R <= Pp; pp += R) {
 #pragma unroll
-    for (int ps = 0; ps < R; ps++) {
-      FMGPU_DECIM_PHASE(pp, ps)
-    }
-  }
-  if (pp < Pp) {  // Pp is a multiple of 4: at most one half round left (pp % R == 0 here)
+    for (int j = 0; j < R; j++) {
+      if (u - j >= 0) {
 #pragma unroll
-    for (int ps = 0; ps < 4; ps++) {
-      FMGPU_DECIM_PHASE(pp, ps)
+        for (int r = 0; r < M; r++) {
+          acc[j] = fma2<true>(tr[(u - j) % 8][r], x[r], acc[j]);
+        }
+      }
     }
   }
-#undef FMGPU_DECIM_PHASE
-  float *out = reinterpret_cast<float *>(x1 + (size_t)c * x1_pitch) + comp;
+  // whole rounds of 8 segments: every output active, ring slots static within the round
+  for (int u0 = PRE; u0 < PP; u0 += 8) {
+#pragma unroll
+    for (int sgm = 0; sgm < 8; sgm++) {
+      const int u = u0 + sgm;
+      FMGPU_RING_LOAD_TAPS(u, (PRE + sgm) % 8)
+      const float2 *xp = xb + u * M + (u >> 3);
+      float2 x[M];
+#pragma unroll
+      for (int r = 0; r < M; r++) {
+        x[r] = xp[r];
+      }
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+          acc[j] = fma2<true>(tr[(PRE + sgm - j + 8) % 8][r], x[r], acc[j]);
+        }
+      }
+    }
+  }
+  // lead-out: segments PP .. PP+6 only reach outputs j > u - PP
+#pragma unroll
+  for (int d = 0; d < 7; d++) {
+    constexpr int kDummy = 0;
+    (void)kDummy;
+    const int u = PP + d;
+    const float2 *xp = xb + u * M + u / 8;
+    float2 x[M];
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+      x[r] = xp[r];
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      if (j > d) {
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+          acc[j] = fma2<true>(tr[(PP + d - j) % 8][r], x[r], acc[j]);
+        }
+      }
+    }
+  }
+#undef FMGPU_RING_LOAD_TAPS
+  float2 *out = x1 + (size_t)c * x1_pitch;
 #pragma unroll
   for (int j = 0; j < R; j++) {
-    const int n = n0 + R * tt + j;
+    const int n = n0 + R * t + j;
     if (n < n_out) {
-      out[2 * n] = acc[j] * scale;
+      out[n] = make_float2(acc[j].x * scale, acc[j].y * scale);
     }
   }
 }
@@ -602,9 +657,11 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
                   2 * (n_total - n0), lane);
   }
   if (active) {
-    s.dc_i = vi;
-    s.dc_q = vq;
-    st[c] = s;
+    // only this stage's fields: the AGC stage of the previous block may be running beside it
+    st[c].dc_i = vi;
+    st[c].dc_q = vq;
+    st[c].clipping = s.clipping;
+    st[c].clip_ratio = s.clip_ratio;
   }
 }
 
@@ -1132,7 +1189,7 @@ __device__ __forceinline__ uint32_t resampCount(uint32_t phase0, uint32_t step, 
 __global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *status,
                           int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch,
                           uint32_t aud_step, uint32_t rds_step, int do_audio, int do_mono,
-                          int do_rds) {
+                          int do_rds, int first) {
   const int lane = blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= nch) {
     return;
@@ -1143,6 +1200,9 @@ __global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *sta
     uint32_t nx;
     const uint32_t p0 = do_mono ? a->mono_phase : a->rs_phase;
     const uint32_t total = resampCount(p0, aud_step, n_total, &nx);
+    if (first) {
+      a->out_base = 0;  // first logical block of a call: frames are appended from the row start
+    }
     if (do_mono) {
       a->mono_n_out = total;
       a->mono_phase_next = nx;
@@ -1166,8 +1226,11 @@ __global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *sta
     uint32_t nx;
     r->n171 = resampCount(r->rs_phase, rds_step, n_total, &nx);
     r->rs_phase_next = nx;
-    r->n_groups = 0;
-    r->n_bits = 0;
+    if (first) {
+      r->n_groups = 0;  // groups and bits accumulate over the logical blocks of one call
+      r->n_bits = 0;
+      r->bits_done = 0;
+    }
   }
 }
 
@@ -1180,9 +1243,11 @@ __global__ void k_commit(AudioState *au, RdsState *rds, int ch0, int nch, int do
   const int c = ch0 + lane;
   if (do_audio) {
     au[c].rs_phase = au[c].rs_phase_next;
+    au[c].out_base += au[c].n_out;
   }
   if (do_mono) {
     au[c].mono_phase = au[c].mono_phase_next;
+    au[c].out_base += au[c].mono_n_out;
   }
   if (do_rds) {
     rds[c].rs_phase = rds[c].rs_phase_next;
@@ -1205,7 +1270,8 @@ __global__ void k_resample(const float *__restrict__ in0, const float *__restric
   const int c = blockIdx.y + ch0;
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_out = mono ? au[c].mono_n_out : au[c].n_out;
-  if (j >= n_out || j >= acap) {
+  const uint32_t ob = au[c].out_base;  // frames already written by earlier blocks of this call
+  if (j >= n_out || ob + j >= acap) {
     return;
   }
   const uint32_t phase0 = mono ? au[c].mono_phase : au[c].rs_phase;
@@ -1229,14 +1295,14 @@ __global__ void k_resample(const float *__restrict__ in0, const float *__restric
       acc0 = fmaf(h[q], a[q], acc0);
     }
   }
-  out[((size_t)c * 2 + 0) * acap + j] = acc0;
+  out[((size_t)c * 2 + 0) * acap + ob + j] = acc0;
   if (in1) {
     const float *b = in1 + (size_t)c * in_pitch + in_off + i - (sub_len - 1);
     float acc1 = 0.0f;
     for (int q = 0; q < sub_len; q++) {
       acc1 = fmaf(h[q], b[q], acc1);
     }
-    out[((size_t)c * 2 + 1) * acap + j] = acc1;
+    out[((size_t)c * 2 + 1) * acap + ob + j] = acc1;
   }
 }
 
@@ -1257,9 +1323,10 @@ __global__ void k_audio_iir(float *audio, size_t acap, AudioState *au, const Cha
   const int side = mono ? 0 : (lane & 1);
   AudioState *a = &au[c];
   const ChanParams p = cp[c];
-  const uint32_t n = min((uint32_t)acap, mono ? a->mono_n_out : a->n_out);
-  float *row = audio + ((size_t)c * 2 + side) * acap;
-  float *row2 = audio + ((size_t)c * 2 + 1) * acap;
+  const uint32_t ob = min((uint32_t)acap, a->out_base);
+  const uint32_t n = min((uint32_t)acap - ob, mono ? a->mono_n_out : a->n_out);
+  float *row = audio + ((size_t)c * 2 + side) * acap + ob;
+  float *row2 = audio + ((size_t)c * 2 + 1) * acap + ob;
   const bool de = mono ? (p.mono_deemph_on != 0) : (p.deemph_on != 0);
   const float b0 = mono ? p.mono_de_b0 : p.de_b0;
   const float a1 = mono ? p.mono_de_a1 : p.de_a1;
@@ -1304,7 +1371,7 @@ __global__ void k_store_counts(const AudioState *au, const RdsState *rds, uint32
   }
   const int c = ch0 + lane;
   if (n_audio) {
-    n_audio[c] = min(acap, mono ? au[c].mono_n_out : au[c].n_out);
+    n_audio[c] = min(acap, au[c].out_base);  // runs after k_commit of the call's last block
   }
   if (n_groups) {
     n_groups[c] = min(gcap, rds[c].n_groups);
@@ -1452,25 +1519,63 @@ __device__ void rdsPushWord(RdsState &s, uint32_t raw, uint32_t syn, fmgpu_rds_g
   s.until = s.in_sync ? 26 : 1;
 }
 
-__global__ void __launch_bounds__(64)
-k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
-      int hist_pitch, RdsState *st, float2 *ring,
-      const float *__restrict__ g_bank, const float *__restrict__ g_lpf,
-      const float *__restrict__ g_mf, const float *__restrict__ g_dmf, uint8_t *bits_out,
-      uint32_t bits_cap, uint32_t *bit_end, int nblk, int blk_len, int n_total, int ch0, int nch,
-      EngineConst k) {
+// S7a: MPX -> 171 kHz (resamp_rrrf, m = 13, 32 branches; subcarrier.cpp:117-147). The resampler
+// has no feedback, so it runs as a tile kernel, one thread per 171 kHz output: output k of a
+// channel sits at fixed-point position P = phase + k * step, reads the 26 inputs ending at
+// P >> 24 through branch (P >> 19) & 31 — the same dot product, oldest input first, that the
+// serial loop of the reference evaluates. Inputs before this call come from the RDS resampler's
+// own window (it is not reset with the stereo path).
+__global__ void __launch_bounds__(128)
+k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
+               int hist_pitch, const RdsState *__restrict__ st, const float *__restrict__ g_bank,
+               float *__restrict__ r171, size_t r_pitch, uint32_t step, int ch0) {
   __shared__ float s_bank[32 * RDS_RS_LEN];
+  for (int i = threadIdx.x; i < 32 * RDS_RS_LEN; i += blockDim.x) {
+    s_bank[i] = g_bank[i];
+  }
+  __syncthreads();
+  const int c = blockIdx.y + ch0;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st[c].n171) {
+    return;
+  }
+  const unsigned long long P = (unsigned long long)st[c].rs_phase + (unsigned long long)k * step;
+  const long i = (long)(P >> 24);
+  const int br = (int)((P & 0xffffffull) >> 19);
+  const float *h = s_bank + br * RDS_RS_LEN;
+  const float *a = mpx + (size_t)c * mpx_pitch + H_MPX + i - (RDS_RS_LEN - 1);
+  const float *hc = hist + (size_t)c * hist_pitch + RDS_HIST;
+  float smp = 0.0f;
+  if (i < RDS_RS_LEN - 1) {
+#pragma unroll
+    for (int q = 0; q < RDS_RS_LEN; q++) {
+      const long si = i - (RDS_RS_LEN - 1) + q;
+      smp = fmaf(h[q], (si >= 0) ? a[q] : hc[si], smp);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < RDS_RS_LEN; q++) {
+      smp = fmaf(h[q], a[q], smp);
+    }
+  }
+  r171[(size_t)c * r_pitch + k] = smp;
+}
+
+// S7b: the serial part, one lane per channel, fed by the 171 kHz stream of k_rds_resample.
+__global__ void __launch_bounds__(64)
+k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring,
+      const float *__restrict__ g_lpf, const float *__restrict__ g_mf,
+      const float *__restrict__ g_dmf, uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end,
+      int ch0, int nch, EngineConst k) {
   __shared__ float s_lpf[RDS_LPF_LEN + 1];
   __shared__ float s_mf[32 * SS_LEN];
   __shared__ float s_dmf[32 * SS_LEN];
   __shared__ float2 s_wmf[SS_LEN][32];
   __shared__ float2 s_wdmf[SS_LEN][32];
-  // warp 0 streams MPX tiles into shared memory, warp 1 runs the demodulator (lane = channel)
+  __shared__ uint32_t s_nmax;
+  // warp 0 streams 171 kHz tiles into shared memory, warp 1 runs the demodulator (lane = channel)
   const int tl = threadIdx.x & 31;
   const bool io = threadIdx.x < 32;
-  for (int i = threadIdx.x; i < 32 * RDS_RS_LEN; i += 64) {
-    s_bank[i] = g_bank[i];
-  }
   for (int i = threadIdx.x; i < RDS_LPF_LEN; i += 64) {
     s_lpf[i] = g_lpf[i];
   }
@@ -1478,8 +1583,7 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
     s_mf[i] = g_mf[i];
     s_dmf[i] = g_dmf[i];
   }
-  __syncthreads();
-  constexpr int TPR = LT + RDS_HIST;  // tile element q <-> MPX sample n0 - RDS_HIST + q
+  constexpr int TPR = LT + 4;  // 16-byte aligned rows
   extern __shared__ float sm_rds[];
   float *t_in[2] = {sm_rds, sm_rds + 32 * TPR};
   const int c0 = ch0 + blockIdx.x * 32;
@@ -1488,6 +1592,14 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
   const int c = c0 + min(tl, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   RdsState s = st[c];
+  {
+    const uint32_t mine = (tl < nrows) ? s.n171 : 0u;
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, mine);
+    if (threadIdx.x == 0) {
+      s_nmax = mx;
+    }
+  }
+  __syncthreads();
   if (!io) {
     for (int q = 0; q < SS_LEN; q++) {
       s_wmf[q][tl] = s.wmf[q];
@@ -1525,37 +1637,27 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
     s.realign = 0;
   }
 
-  uint32_t phase = s.rs_phase;
   uint32_t produced = 0;
-  const uint32_t n171 = s.n171;
-  const int nchunks = (n_total + LT - 1) / LT;
-  // tile element k of chunk ck <-> MPX sample ck*LT - 25 + k; samples before this call come
-  // from the RDS resampler's own window (it is not reset with the stereo path)
+  const uint32_t n171 = active ? s.n171 : 0u;
+  const int nchunks = (int)((s_nmax + LT - 1) / LT);
+  // tile element ii of chunk ck <-> 171 kHz sample ck*LT + ii (rows are padded to whole tiles)
   auto prefetch = [&](int ck) {
-    const int n0 = ck * LT;
-    const int cpr = (min(LT, n_total - n0) + RDS_HIST + 3) >> 2;
+    constexpr int cpr = LT / 4;
     const int total = nrows * cpr;
     for (int idx = tl; idx < total; idx += 32) {
       const int r = idx / cpr;
       const int q4 = 4 * (idx - r * cpr);
-      const int si = n0 - RDS_HIST + q4;  // multiple of 4: a chunk never straddles sample 0
-      const float *src = (si >= 0)
-                             ? mpx + (size_t)(c0 + r) * mpx_pitch + H_MPX + si
-                             : hist + (size_t)(c0 + r) * hist_pitch + RDS_HIST + si;
-      cpAsync16(t_in[ck & 1] + r * TPR + q4, src);
+      cpAsync16(t_in[ck & 1] + r * TPR + q4, r171 + (size_t)(c0 + r) * r_pitch + (size_t)ck * LT + q4);
     }
   };
-  if (io) {
+  if (io && nchunks > 0) {
     prefetch(0);
     cpAsyncCommit();
     cpAsyncWait<0>();
   }
   __syncthreads();
-  int blk = 0, in_blk = 0;
-  int cur_len = min(blk_len, n_total);
 
   for (int ck = 0; ck < nchunks; ck++) {
-    const int clen = min(LT, n_total - ck * LT);
     if (io) {
       if (ck + 1 < nchunks) {
         prefetch(ck + 1);
@@ -1564,17 +1666,9 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
       cpAsyncWait<0>();
     }
     const float *trow = t_in[ck & 1] + tl * TPR;
-    for (int ii = 0; active && ii < clen; ii++) {
-      while (phase < (1u << 24)) {
-        const int br = (int)(phase >> 19);
-        const float *h = s_bank + br * RDS_RS_LEN;
-        const float *w = trow + ii + (RDS_HIST - (RDS_RS_LEN - 1));
-        float smp = 0.0f;
-#pragma unroll
-        for (int q = 0; q < RDS_RS_LEN; q++) {
-          smp = fmaf(h[q], w[q], smp);
-        }
-        phase += k.rds_step;
+    for (int ii = 0; ii < LT; ii++) {
+      if ((uint32_t)(ck * LT + ii) < n171) {
+        const float smp = trow[ii];
         // ---- one 171 kHz sample -------------------------------------------------
         float sn, cs;
         fm_sincosf(-s.phase0, &sn, &cs);
@@ -1707,19 +1801,13 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
         s.phase0 = unwrapDev(s.phase0 + ((delta * 57000.f) / 57000.f));
         s.since_reset++;
       }
-      phase -= (1u << 24);
-      if (++in_blk == cur_len) {
-        bit_end[(size_t)c * nblk + blk] = min(s.n_bits, bits_cap);  // bits demodulated so far
-        blk++;
-        in_blk = 0;
-        cur_len = min(blk_len, n_total - blk * blk_len);
-      }
     }
     __syncthreads();
   }
   if (!active) {
     return;
   }
+  bit_end[c] = min(s.n_bits, bits_cap);  // bits demodulated so far in this call
 #pragma unroll
   for (int j = 0; j < RDS_NACC; j++) {
     s.acc[j] = acc[j];
@@ -1741,27 +1829,31 @@ k_rds(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__
 __global__ void __launch_bounds__(128)
 k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t *__restrict__ bit_end,
             RdsState *st, unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
-            fmgpu_block_status *status, int status_pitch, int nblk, int ch0, int nch) {
-  __shared__ uint32_t s_reg[32], s_nb[32];
+            fmgpu_block_status *status, int status_pitch, int nblk, int blk0, int ch0, int nch) {
+  __shared__ uint32_t s_reg[32], s_nb[32], s_b0[32];
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
   if (threadIdx.x < 32) {
     const bool valid = (int)threadIdx.x < nrows;
     s_reg[threadIdx.x] = valid ? st[c0 + threadIdx.x].reg : 0u;
     s_nb[threadIdx.x] = valid ? min(st[c0 + threadIdx.x].n_bits, bits_cap) : 0u;
+    // bits [0, b0) of this call went through the synchroniser with the earlier logical blocks
+    s_b0[threadIdx.x] = valid ? min(st[c0 + threadIdx.x].bits_done, s_nb[threadIdx.x]) : 0u;
   }
   __syncthreads();
   for (int r = 0; r < nrows; r++) {
     const uint32_t nb = s_nb[r];
-    const uint32_t reg = s_reg[r];
+    const uint32_t b0 = s_b0[r];
+    const uint32_t reg = s_reg[r];  // the 26-bit register after bit b0 - 1
     const uint8_t *brow = bits + (size_t)(c0 + r) * bits_cap;
     unsigned long long *wrow = words + (size_t)(c0 + r) * bits_cap;
-    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+    for (uint32_t i = b0 + threadIdx.x; i < nb; i += blockDim.x) {
       uint32_t w = 0;
 #pragma unroll
-      for (int q = 25; q >= 0; q--) {  // bit i-q of the stream; bits before this call sit in reg
+      for (int q = 25; q >= 0; q--) {  // bit i-q of the stream; bits before b0 sit in reg
         const int idx = (int)i - q;
-        const uint32_t bit = (idx >= 0) ? (uint32_t)brow[idx] : ((reg >> (-idx - 1)) & 1u);
+        const uint32_t bit = (idx >= (int)b0) ? (uint32_t)brow[idx]
+                                              : ((reg >> ((int)b0 - 1 - idx)) & 1u);
         w = (w << 1) | bit;
       }
       wrow[i] = (unsigned long long)w | ((unsigned long long)rdsSyndromeDev(w) << 32);
@@ -1774,12 +1866,13 @@ k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t 
   const int c = c0 + threadIdx.x;
   RdsState s = st[c];
   const uint32_t nb = s_nb[threadIdx.x];
+  const uint32_t bit0 = s_b0[threadIdx.x];
   const unsigned long long *wrow = words + (size_t)c * bits_cap;
   const uint32_t *bend = bit_end + (size_t)c * nblk;
   fmgpu_rds_group *gout = groups ? groups + (size_t)c * gcap : nullptr;
   int blk = 0;
   uint32_t before = s.n_groups;
-  for (uint32_t i = 0; i < nb; i++) {
+  for (uint32_t i = bit0; i < nb; i++) {
     while (blk < nblk - 1 && i >= bend[blk]) {
       if (status) {
         status[(size_t)c * status_pitch + blk].n_groups = (int)(s.n_groups - before);
@@ -1788,7 +1881,8 @@ k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t 
       blk++;
     }
     const unsigned long long w = wrow[i];
-    rdsPushWord(s, (uint32_t)w & 0x3ffffffu, (uint32_t)(w >> 32), gout, gcap, (uint32_t)blk);
+    rdsPushWord(s, (uint32_t)w & 0x3ffffffu, (uint32_t)(w >> 32), gout, gcap,
+                (uint32_t)(blk0 + blk));
   }
   if (status) {
     for (; blk < nblk; blk++) {
@@ -1814,6 +1908,7 @@ k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t 
   o->cur_recv = s.cur_recv;
   o->cur_err = s.cur_err;
   o->n_groups = s.n_groups;
+  o->bits_done = nb;
 }
 
 // ---------------------------------------------------------------------------
@@ -1944,47 +2039,44 @@ static bool usePackedFma() {
     break;                                                                                       \
   }
 
-// split-component form, R = 8 outputs per thread (register ring of 8 x M samples)
-#define FMGPU_DECIM_SPLIT_CASE(MM)                                                               \
-  case MM: {                                                                                     \
-    constexpr int R = 8;                                                                         \
-    constexpr int T = 64 * R;                                                                    \
-    const int tile_len = (T + Pp - 1) * MM;                                                      \
-    const size_t smem = (size_t)2 * (tile_len + tile_len / (R * MM) + 2) * sizeof(float);        \
-    static bool attr_done = false;                                                               \
-    if (!attr_done) {                                                                            \
-      cudaFuncSetAttribute(k_decim_split<MM, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                           160 * 1024);                                                          \
-      attr_done = true;                                                                          \
-    }                                                                                            \
-    dim3 grid((n_out + T - 1) / T, nch);                                                         \
-    k_decim_split<MM, R><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,       \
-                                                      x1_pitch, n_out, ch0, Pp, scale, taps);    \
-    break;                                                                                       \
+template <int M, int PP>
+static void launchDecimRing(const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
+                            const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0,
+                            int nch, float scale, const TapsParam &taps, cudaStream_t stream) {
+  constexpr int T = 512;
+  constexpr int TILE = (T + PP - 1) * M;
+  constexpr int TQ = (M + 3) / 4;
+  constexpr size_t smem = (size_t)PP * TQ * 16 + (size_t)((TILE + TILE / (8 * M) + 3) & ~1) * 8 +
+                          (size_t)(2 * TILE + 48 + 15) / 16 * 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_decim_ring<M, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
   }
-
-int g_decim_variant = -1;  // FMGPU_DECIM_VARIANT=1 selects the split-component (R = 8) form
+  dim3 grid((n_out + T - 1) / T, nch);
+  k_decim_ring<M, PP><<<grid, 64, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1, x1_pitch,
+                                                  n_out, ch0, scale, taps);
+}
 
 void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
                  const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
                  const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream) {
-  if (g_decim_variant < 0) {
-    const char *v = getenv("FMGPU_DECIM_VARIANT");
-    g_decim_variant = v ? atoi(v) : 0;
+  static int ring = -1;  // FMGPU_DECIM_RING=1 selects the register-ring form (A/B timing)
+  if (ring < 0) {
+    const char *v = getenv("FMGPU_DECIM_RING");
+    ring = (v && atoi(v) == 1) ? 1 : 0;
   }
-  if (g_decim_variant == 1) {
-    switch (M) {
-      FMGPU_DECIM_SPLIT_CASE(2)
-      FMGPU_DECIM_SPLIT_CASE(4)
-      FMGPU_DECIM_SPLIT_CASE(5)
-      FMGPU_DECIM_SPLIT_CASE(8)
-      FMGPU_DECIM_SPLIT_CASE(10)
-    default:
-      break;  // M = 16 and others: the forms below
-    }
-    if (M == 2 || M == 4 || M == 5 || M == 8 || M == 10) {
-      return;
-    }
+  if (ring && usePackedFma()) {
+#define FMGPU_RING_CASE(MM, PPP)                                                                  \
+  if (M == MM && Pp == PPP) {                                                                     \
+    launchDecimRing<MM, PPP>(iq, iq_stride, hist, hist_valid, x1, x1_pitch, n_out, ch0, nch, scale, \
+                             taps, stream);                                                       \
+    return;                                                                                       \
+  }
+    FMGPU_RING_CASE(10, 28)  // 2.4 MS/s / 10, 280 taps
+    FMGPU_RING_CASE(8, 28)   // 2.048 MS/s / 8, 224 taps (main.cpp:672-674)
+    FMGPU_RING_CASE(4, 20)   // 1.024 MS/s / 4, 80 taps
+#undef FMGPU_RING_CASE
   }
   switch (M) {
     FMGPU_DECIM_CASE(2)
@@ -2186,10 +2278,11 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
 
 void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
                    int nblk, int blk_len, int n_total, int ch0, int nch, uint32_t aud_step,
-                   uint32_t rds_step, int do_audio, int do_mono, int do_rds, cudaStream_t stream) {
+                   uint32_t rds_step, int do_audio, int do_mono, int do_rds, int first,
+                   cudaStream_t stream) {
   k_prepare<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, status, status_pitch, nblk, blk_len,
                                                   n_total, ch0, nch, aud_step, rds_step, do_audio,
-                                                  do_mono, do_rds);
+                                                  do_mono, do_rds, first);
 }
 
 void launchCommit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
@@ -2230,20 +2323,22 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
 
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
-               uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end, int nblk, int blk_len,
-               int n_total, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  constexpr size_t smem = 2 * 32 * (LT + RDS_HIST) * sizeof(float);
-  k_rds<<<(nch + 31) / 32, 64, smem, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, ring, bank, lpf,
-                                              mf, dmf, bits_out, bits_cap, bit_end, nblk, blk_len,
-                                              n_total, ch0, nch, k);
+               float *r171, size_t r_pitch, int max_171, uint8_t *bits_out, uint32_t bits_cap,
+               uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+  dim3 grid((max_171 + 127) / 128, nch);
+  k_rds_resample<<<grid, 128, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch,
+                                           k.rds_step, ch0);
+  constexpr size_t smem = 2 * 32 * (LT + 4) * sizeof(float);
+  k_rds<<<(nch + 31) / 32, 64, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
+                                              bits_cap, bit_end, ch0, nch, k);
 }
 
 void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit_end, RdsState *st,
                      unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
-                     fmgpu_block_status *status, int status_pitch, int nblk, int ch0, int nch,
-                     cudaStream_t stream) {
+                     fmgpu_block_status *status, int status_pitch, int nblk, int blk0, int ch0,
+                     int nch, cudaStream_t stream) {
   k_blocksync<<<(nch + 31) / 32, 128, 0, stream>>>(bits, bits_cap, bit_end, st, words, groups, gcap,
-                                                  status, status_pitch, nblk, ch0, nch);
+                                                  status, status_pitch, nblk, blk0, ch0, nch);
 }
 
 void launchSigLevel(const uint8_t *iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,

@@ -51,7 +51,8 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream);
 void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
                    int nblk, int blk_len, int n_total, int ch0, int nch, uint32_t aud_step,
-                   uint32_t rds_step, int do_audio, int do_mono, int do_rds, cudaStream_t stream);
+                   uint32_t rds_step, int do_audio, int do_mono, int do_rds, int first,
+                   cudaStream_t stream);
 void launchCommit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
                   int do_rds, cudaStream_t stream);
 void launchResample(const float *in0, const float *in1, size_t in_pitch, int in_off,
@@ -63,14 +64,16 @@ void launchAudioIir(float *audio, size_t acap, AudioState *au, const ChanParams 
 void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,
                        uint32_t *n_groups, int ch0, int nch, int mono, uint32_t acap, uint32_t gcap,
                        cudaStream_t stream);
+// MPX -> 171 kHz (tile kernel) -> serial demodulator (lane kernel); max_171 >= every channel's
+// n171 of this call, r171 rows padded to whole 32-sample tiles
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
-               uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end, int nblk, int blk_len,
-               int n_total, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+               float *r171, size_t r_pitch, int max_171, uint8_t *bits_out, uint32_t bits_cap,
+               uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
 void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit_end, RdsState *st,
                      unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
-                     fmgpu_block_status *status, int status_pitch, int nblk, int ch0, int nch,
-                     cudaStream_t stream);
+                     fmgpu_block_status *status, int status_pitch, int nblk, int blk0, int ch0,
+                     int nch, cudaStream_t stream);
 
 void launchSigLevel(const uint8_t *iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,
                     long samples_per_block, int ch0, int nch, cudaStream_t stream);

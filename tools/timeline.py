@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--channels", type=int, default=10000)
     ap.add_argument("--blocks", type=int, default=2)
-    ap.add_argument("--groups", type=int, default=8)
+    ap.add_argument("--groups", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--sync-steps", action="store_true")
     args = ap.parse_args()
