@@ -312,10 +312,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     decoded = {"stereo_channels": int(st_host["stereo"][:, -1].sum()),
                "groups_last_step": int(n_groups.sum().item())}
 
-    # ---- per-stage device times: a separate timed pass with ONE pipeline group, so that the
-    # CUDA events around each stage bracket that stage's kernels only (with several groups the
-    # stages of different groups interleave on the device and the spans include queueing) -------
-    eng.set_pipeline_groups(1)
+    # ---- per-stage device times: a separate timed pass with the stages of the block pipeline
+    # queued on ONE stream (fmgpu_set_stage_overlap(0)), so that the CUDA events around each stage
+    # bracket that stage's kernels running alone (in the timed steps above the stages of successive
+    # blocks overlap on the device) --------------------------------------------------------------
+    eng.set_stage_overlap(False)
 
     def sstep():
         eng.process_batch(iq_dev.data_ptr(), stride, B, audio.data_ptr(), acap, n_audio.data_ptr(),
@@ -333,10 +334,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         for k, v in eng.stage_times().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.enable_stage_timing(False)
-    eng.set_pipeline_groups(args.groups)
+    eng.set_stage_overlap(True)
     stage_ms = {k: round(v, 4) for k, v in acc.items()}
-    serial_sum = sum(v for k, v in acc.items() if k != "rds")      # rds runs on its own stream
-    dominant = max((k for k in acc if k != "rds"), key=acc.get)
+    serial_sum = sum(acc.values())
+    dominant = max(acc, key=acc.get)
     roofline = kernel_roofline(dominant, acc[dominant], C, B, clocks)
     roofline["step_share"] = acc[dominant] / serial_sum
     # the dominant roofline-bound (tile) kernel and the dominant latency-bound (lane) kernel,

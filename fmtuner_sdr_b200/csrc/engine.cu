@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -107,7 +108,8 @@ struct fmgpu_engine {
     ST_D2H, ST_COUNT
   };
   struct Pipe {
-    cudaStream_t st[ST_COUNT] = {};
+    cudaStream_t st[ST_COUNT] = {};   // the streams as created
+    cudaStream_t run[ST_COUNT] = {};  // the streams in use (all the same one when serialStages)
     std::vector<cudaEvent_t> done[ST_COUNT];  // ring of ER events per stage
     cudaEvent_t callDone = nullptr;           // everything of the last batch call of this pipe
     cudaEvent_t hostDone[2] = {};             // per host ticket: results are in the host buffers
@@ -120,6 +122,7 @@ struct fmgpu_engine {
   uint64_t seq = 0;      // logical blocks queued so far (slot = seq % K)
   bool headFresh = true; // the halo in front of slot 0 is already in place (start, reset, realign)
   bool asyncPending = false;
+  bool serialStages = false;  // measurement aid: every stage on ONE stream, no overlap
   cudaEvent_t evStart = nullptr;
   // streaming host path: two tickets in flight (submit k+1 before waiting for k)
   struct HostTicket {
@@ -602,18 +605,18 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   // of the buffers it writes, which must have finished block q - K (same ring slot)
   auto need = [&](int st, std::initializer_list<int> producers, std::initializer_list<int> readers) {
     for (int p : producers) {
-      cudaStreamWaitEvent(P.st[st], ev(p, q), 0);
+      cudaStreamWaitEvent(P.run[st], ev(p, q), 0);
     }
     if (q >= static_cast<uint64_t>(K)) {
       for (int r : readers) {
-        cudaStreamWaitEvent(P.st[st], ev(r, q - K), 0);
+        cudaStreamWaitEvent(P.run[st], ev(r, q - K), 0);
       }
     }
   };
-  auto done = [&](int st) { cudaEventRecord(ev(st, q), P.st[st]); };
+  auto done = [&](int st) { cudaEventRecord(ev(st, q), P.run[st]); };
 
   if (e->M > 1) {
-    cudaStream_t s = P.st[E::ST_DECIM];
+    cudaStream_t s = P.run[E::ST_DECIM];
     if (waitH2D) {
       need(E::ST_DECIM, {E::ST_H2D}, {E::ST_DC});
     } else {
@@ -629,7 +632,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     done(E::ST_DECIM);
   }
   {
-    cudaStream_t s = P.st[E::ST_DC];
+    cudaStream_t s = P.run[E::ST_DC];
     if (e->M > 1) {
       need(E::ST_DC, {E::ST_DECIM}, {E::ST_CHAN});
     } else if (waitH2D) {
@@ -648,7 +651,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   }
   done(E::ST_DC);
   {
-    cudaStream_t s = P.st[E::ST_CHAN];
+    cudaStream_t s = P.run[E::ST_CHAN];
     need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD});
     Span sp(e, "chanfir", s);
     launchChanFir(e->dX2 + t0, e->x2Pitch, e->dY + t0, e->yPitch, e->dChanTaps, e->dChanLp,
@@ -657,7 +660,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   }
   done(E::ST_CHAN);
   {
-    cudaStream_t s = P.st[E::ST_AGC];
+    cudaStream_t s = P.run[E::ST_AGC];
     need(E::ST_AGC, {E::ST_CHAN}, {E::ST_FD});
     bool anyAgc = false;
     for (int c = ch0; c < ch0 + nch && !anyAgc; c++) {
@@ -671,7 +674,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   }
   done(E::ST_AGC);
   {
-    cudaStream_t s = P.st[E::ST_FD];
+    cudaStream_t s = P.run[E::ST_FD];
     if (stereo) {
       need(E::ST_FD, {E::ST_AGC}, {E::ST_PILOT, E::ST_STEREO, E::ST_RDS});
     } else {
@@ -689,7 +692,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   done(E::ST_FD);
   // ---- RDS branch --------------------------------------------------------------------------
   {
-    cudaStream_t s = P.st[E::ST_RDS];
+    cudaStream_t s = P.run[E::ST_RDS];
     need(E::ST_RDS, {E::ST_FD}, {});
     Span sp(e, "rds", s);
     launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
@@ -706,10 +709,10 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   }
   done(E::ST_RDS);
   // ---- audio branch ------------------------------------------------------------------------
-  cudaStream_t sAf = P.st[E::ST_AF];
+  cudaStream_t sAf = P.run[E::ST_AF];
   if (stereo) {
     {
-      cudaStream_t s = P.st[E::ST_PILOT];
+      cudaStream_t s = P.run[E::ST_PILOT];
       need(E::ST_PILOT, {E::ST_FD}, {E::ST_STEREO});
       Span sp(e, "pilot_fir", s);
       FirRealJob j{};
@@ -728,7 +731,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     }
     done(E::ST_PILOT);
     {
-      cudaStream_t s = P.st[E::ST_STEREO];
+      cudaStream_t s = P.run[E::ST_STEREO];
       need(E::ST_STEREO, {E::ST_PILOT}, {E::ST_LPF});
       Span sp(e, "stereo_pll", s);
       if (carry) {
@@ -742,7 +745,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     }
     done(E::ST_STEREO);
     {
-      cudaStream_t s = P.st[E::ST_LPF];
+      cudaStream_t s = P.run[E::ST_LPF];
       need(E::ST_LPF, {E::ST_STEREO}, {E::ST_AF});
       Span sp(e, "audio_lpf", s);
       if (carry) {
@@ -851,7 +854,7 @@ int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, 
       continue;
     }
     if (!iq_host) {
-      cudaStreamWaitEvent(P.st[e->M > 1 ? E::ST_DECIM : E::ST_DC], e->evStart, 0);
+      cudaStreamWaitEvent(P.run[e->M > 1 ? E::ST_DECIM : E::ST_DC], e->evStart, 0);
     }
   }
   for (int b = 0; b < n_blocks; b++) {
@@ -870,7 +873,7 @@ int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, 
       if (iq_host) {
         // H2D stage: this block's rows into ring slot `slot` of the device staging buffer, once
         // the first compute stage has finished with block q - K
-        cudaStream_t s = P.st[E::ST_H2D];
+        cudaStream_t s = P.run[E::ST_H2D];
         if (q >= static_cast<uint64_t>(e->K)) {
           cudaStreamWaitEvent(
               s, P.done[e->M > 1 ? E::ST_DECIM : E::ST_DC][(q - e->K) % static_cast<uint64_t>(e->ER)], 0);
@@ -897,7 +900,7 @@ int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, 
     if (nch <= 0) {
       continue;
     }
-    cudaEventRecord(P.callDone, P.st[E::ST_AF]);
+    cudaEventRecord(P.callDone, P.run[E::ST_AF]);
     if (callerWaits) {
       cudaStreamWaitEvent(caller, P.callDone, 0);
     }
@@ -1108,6 +1111,11 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   // ring of K block slots per scratch buffer (see fmgpu_engine::Pipe); slots must start on
   // 16-byte boundaries for the cp.async tile loads, else every block goes through slot 0
   e->K = (e->N % 32 == 0) ? std::max(2, e->maxBlocks) : 1;
+  if (const char *rk = getenv("FMGPU_RING_K")) {  // deeper ring: stages may run further ahead
+    if (e->K > 1) {
+      e->K = std::max(e->K, std::min(16, atoi(rk)));
+    }
+  }
   if (e->K == 1 && e->maxBlocks > 1) {
     e->lastError = "fmgpu_engine_create: max_blocks > 1 needs block_samples to be a multiple of 32";
     g_create_error = e->lastError;
@@ -1162,6 +1170,7 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
       }
       const int prio = prLo - std::min(rank, prLo - prHi);
       CKC(cudaStreamCreateWithPriority(&P.st[st], cudaStreamNonBlocking, prio));
+      P.run[st] = P.st[st];
       P.done[st].resize(static_cast<size_t>(e->ER));
       for (auto &ev : P.done[st]) {
         CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1709,7 +1718,7 @@ int fmgpu_submit_host(fmgpu_engine *e, const uint8_t *iq_host, size_t iq_stride_
       continue;
     }
     fmgpu_engine::Pipe &P = e->pipes[g];
-    cudaStream_t s = P.st[fmgpu_engine::ST_D2H];
+    cudaStream_t s = P.run[fmgpu_engine::ST_D2H];
     CK(cudaStreamWaitEvent(s, P.callDone, 0));
     const size_t c0 = static_cast<size_t>(ch0), cn = static_cast<size_t>(nch);
     if (audio_host) {
@@ -1821,6 +1830,22 @@ int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
                   static_cast<int>(std::min(audio_cap, e->acap)), static_cast<cudaStream_t>(stream));
   e->launches += 1;
   return cudaGetLastError() == cudaSuccess ? FMGPU_OK : FMGPU_ENODEV;
+}
+
+int fmgpu_set_stage_overlap(fmgpu_engine *e, int on) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  syncPipes(e);
+  e->serialStages = (on == 0);
+  for (auto &P : e->pipes) {
+    for (int st = 0; st < fmgpu_engine::ST_COUNT; st++) {
+      P.run[st] = e->serialStages ? P.st[fmgpu_engine::ST_DECIM] : P.st[st];
+    }
+  }
+  return FMGPU_OK;
 }
 
 int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups) {

@@ -136,7 +136,17 @@ __device__ __forceinline__ float2 fma2(float h, float2 x, float2 acc) {
 // memory. Row pitches are multiples of 4 floats so rows move as 16-byte transfers; the
 // 4-way bank conflict that costs a lane kernel is noise next to its dependent-issue latency.
 // ---------------------------------------------------------------------------
-constexpr int LT = 32;  // samples per tile row (small tiles keep >= 4 lane CTAs resident per SM)
+#ifndef FMGPU_LT
+#define FMGPU_LT 32
+#endif
+#ifndef FMGPU_ST
+#define FMGPU_ST 16
+#endif
+// samples per tile row of the lane kernels. The tiles of every lane kernel of a block sit in
+// shared memory for milliseconds while FIR CTAs of other blocks want the same SMs: small tiles
+// leave the shared memory to them.
+constexpr int LT = FMGPU_LT;
+constexpr int STEREO_ST = FMGPU_ST;
 
 __device__ __forceinline__ void cpAsync16(void *smem, const void *gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
@@ -238,13 +248,18 @@ __global__ void k_save_tail(const float *src, size_t src_pitch, int src_off, flo
 // Input bytes are fetched as 128-bit words from the 16-byte aligned virtual stream
 // hist ++ input.
 // ---------------------------------------------------------------------------
+#ifndef FMGPU_DECIM_NT
+#define FMGPU_DECIM_NT 128
+#endif
+constexpr int DECIM_NT = FMGPU_DECIM_NT;  // threads per decimator CTA (4 outputs each)
+
 template <int M, bool PACK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DECIM_NT)
 k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
         const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
         int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
   constexpr int R = 4;
-  constexpr int T = 128 * R;
+  constexpr int T = DECIM_NT * R;
   constexpr int RM = R * M;
   extern __shared__ float2 xs[];
   const int c = blockIdx.y + ch0;
@@ -261,7 +276,7 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
   const long v_first_valid = H_IQ - hist_valid[c];
   constexpr float kScale = 1.0f / 127.5f;
 
-  for (long ck = ck0 + t; ck <= ck1; ck += 128) {
+  for (long ck = ck0 + t; ck <= ck1; ck += DECIM_NT) {
     const long v = ck << 3;
     uint4 raw = make_uint4(0, 0, 0, 0);
     if (v < H_IQ) {
@@ -321,177 +336,6 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
       }
     }
   }
-  float2 *out = x1 + (size_t)c * x1_pitch;
-#pragma unroll
-  for (int j = 0; j < R; j++) {
-    const int n = n0 + R * t + j;
-    if (n < n_out) {
-      out[n] = make_float2(acc[j].x * scale, acc[j].y * scale);
-    }
-  }
-}
-
-// K1, register-ring form (the one the engine launches when M and the phase count have an
-// instantiation). What ncu showed on the first form (r01): 83 % of the issue slots used with the
-// FMA pipe only 50 % busy, the LSU data pipe 75 % busy, and 5.8 shared-memory wavefronts per tile
-// store. Three changes:
-//  * a thread keeps R = 8 outputs and walks the input segment by segment (M samples each): a
-//    sample read from shared memory (one LDS.64 of {I, Q}) feeds all 8 outputs = 8 FFMA2, twice the
-//    reuse of the first form, so the LSU pipe is half as busy per FMA;
-//  * what rotates through registers is the TAPS (the last 8 phases, 8 x M floats, refilled with
-//    128-bit broadcast LDS), not the samples; FFMA2 takes the tap as a scalar operand;
-//  * the tile is staged as raw bytes with 16-byte cp.async, then converted with 32-bit index
-//    arithmetic, consecutive lanes on consecutive samples: conflict-free LDS.U16 / STS.64.
-// Output j of a thread uses segment u with tap phase p = u - j: every accumulator still receives
-// its products oldest sample first, phase by phase — the same fmaf chain as the first form and
-// as the CPU oracle.
-template <int M, int PP>
-__global__ void __launch_bounds__(64)
-k_decim_ring(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
-             const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
-             int ch0, float scale, const __grid_constant__ TapsParam taps) {
-  constexpr int R = 8;
-  constexpr int NT = 64;
-  constexpr int T = NT * R;                 // outputs per CTA
-  constexpr int RM = R * M;
-  constexpr int TILE = (T + PP - 1) * M;    // samples per tile
-  constexpr int TQ = (M + 3) / 4;           // float4 per tap phase in shared memory
-  constexpr int PRE = 7 + ((PP - 7) % 8);   // unrolled lead-in: the main loop then runs whole rounds
-  static_assert(PP >= 15, "phase count too small for the register ring");
-  extern __shared__ __align__(16) unsigned char dr_smem[];
-  float4 *sh4 = reinterpret_cast<float4 *>(dr_smem);                       // [PP][TQ] taps
-  float2 *xs = reinterpret_cast<float2 *>(dr_smem + PP * TQ * 16);         // skewed float2 tile
-  constexpr int XS = (TILE + TILE / RM + 3) & ~1;  // even: the byte stage behind it stays 16-byte aligned
-  unsigned char *raw = dr_smem + PP * TQ * 16 + XS * 8;                    // staged bytes
-  const int c = blockIdx.y + ch0;
-  const int n0 = blockIdx.x * T;
-  const int t = threadIdx.x;
-  // tile element a <-> stream sample o + a; virtual index (history first) v = o + a + H_IQ
-  const int v0 = (n0 - PP) * M + 1 + H_IQ;
-  const int ck0 = v0 >> 3;                  // v0 >= 1 + H_IQ - PP*M > 0
-  const int nck = ((v0 + TILE - 1) >> 3) - ck0 + 1;
-  const int n_in = n_out * M;
-  const uint8_t *in_c = iq + (size_t)c * iq_stride;
-  const uint8_t *hist_c = hist + (size_t)c * (2 * H_IQ);
-
-  for (int j = t; j < nck; j += NT) {
-    const int v = (ck0 + j) << 3;
-    unsigned char *dst = raw + 16 * j;
-    if (v < H_IQ) {
-      cpAsync16(dst, hist_c + 2 * v);
-    } else if (v - H_IQ < n_in) {
-      cpAsync16(dst, in_c + 2 * (v - H_IQ));
-    } else {
-      *reinterpret_cast<uint4 *>(dst) = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-    }
-  }
-  cpAsyncCommit();
-  // taps: PP phases of M, padded to TQ float4 each
-  for (int i = t; i < PP * TQ * 4; i += NT) {
-    const int p = i / (TQ * 4), r = i - p * (TQ * 4);
-    reinterpret_cast<float *>(sh4)[i] = (r < M) ? taps.h[p * M + r] : 0.0f;
-  }
-  cpAsyncWait<0>();
-  __syncthreads();
-  {
-    constexpr float kScale = 1.0f / 127.5f;
-    const unsigned short *raw16 = reinterpret_cast<const unsigned short *>(raw) + (v0 - (ck0 << 3));
-    // samples older than the valid history are the zero window of a fresh firdecim
-    const int first_valid = (H_IQ - hist_valid[c]) - v0;
-#pragma unroll 4
-    for (int a = t; a < TILE; a += NT) {
-      const unsigned w = raw16[a];
-      float fi = ((float)(w & 0xffu) - 127.5f) * kScale;
-      float fq = ((float)(w >> 8) - 127.5f) * kScale;
-      if (a < first_valid) {
-        fi = 0.0f;
-        fq = 0.0f;
-      }
-      xs[a + a / RM] = make_float2(fi, fq);
-    }
-  }
-  __syncthreads();
-
-  float2 acc[R];
-#pragma unroll
-  for (int j = 0; j < R; j++) {
-    acc[j] = make_float2(0.0f, 0.0f);
-  }
-  float tr[8][TQ * 4];   // the last 8 tap phases; slot = phase % 8
-  const float2 *xb = xs + t * (RM + 1);
-  // segment u of this thread: samples t*RM + u*M + r at xb[u*M + r + u/8]
-#define FMGPU_RING_LOAD_TAPS(U, SLOT)                                   \
-  _Pragma("unroll") for (int qd = 0; qd < TQ; qd++) {                   \
-    const float4 tv = sh4[(U) * TQ + qd];                               \
-    tr[SLOT][4 * qd + 0] = tv.x;                                        \
-    tr[SLOT][4 * qd + 1] = tv.y;                                        \
-    tr[SLOT][4 * qd + 2] = tv.z;                                        \
-    tr[SLOT][4 * qd + 3] = tv.w;                                        \
-  }
-  // lead-in: phases 0 .. PRE-1 (outputs j <= u only while u < 7)
-#pragma unroll
-  for (int u = 0; u < PRE; u++) {
-    FMGPU_RING_LOAD_TAPS(u, u % 8)
-    const float2 *xp = xb + u * M + u / 8;
-    float2 x[M];
-#pragma unroll
-    for (int r = 0; r < M; r++) {
-      x[r] = xp[r];
-    }
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      if (u - j >= 0) {
-#pragma unroll
-        for (int r = 0; r < M; r++) {
-          acc[j] = fma2<true>(tr[(u - j) % 8][r], x[r], acc[j]);
-        }
-      }
-    }
-  }
-  // whole rounds of 8 segments: every output active, ring slots static within the round
-  for (int u0 = PRE; u0 < PP; u0 += 8) {
-#pragma unroll
-    for (int sgm = 0; sgm < 8; sgm++) {
-      const int u = u0 + sgm;
-      FMGPU_RING_LOAD_TAPS(u, (PRE + sgm) % 8)
-      const float2 *xp = xb + u * M + (u >> 3);
-      float2 x[M];
-#pragma unroll
-      for (int r = 0; r < M; r++) {
-        x[r] = xp[r];
-      }
-#pragma unroll
-      for (int j = 0; j < R; j++) {
-#pragma unroll
-        for (int r = 0; r < M; r++) {
-          acc[j] = fma2<true>(tr[(PRE + sgm - j + 8) % 8][r], x[r], acc[j]);
-        }
-      }
-    }
-  }
-  // lead-out: segments PP .. PP+6 only reach outputs j > u - PP
-#pragma unroll
-  for (int d = 0; d < 7; d++) {
-    constexpr int kDummy = 0;
-    (void)kDummy;
-    const int u = PP + d;
-    const float2 *xp = xb + u * M + u / 8;
-    float2 x[M];
-#pragma unroll
-    for (int r = 0; r < M; r++) {
-      x[r] = xp[r];
-    }
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      if (j > d) {
-#pragma unroll
-        for (int r = 0; r < M; r++) {
-          acc[j] = fma2<true>(tr[(PP + d - j) % 8][r], x[r], acc[j]);
-        }
-      }
-    }
-  }
-#undef FMGPU_RING_LOAD_TAPS
   float2 *out = x1 + (size_t)c * x1_pitch;
 #pragma unroll
   for (int j = 0; j < R; j++) {
@@ -906,7 +750,7 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
          size_t pilot_pitch, float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
          StereoState *st, const ChanParams *cp, fmgpu_block_status *status, int status_pitch,
          int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
-  constexpr int ST = 16;       // samples per tile row
+  constexpr int ST = STEREO_ST;  // samples per tile row
   constexpr int TP = ST + 8;   // 16-byte aligned rows; the delayed-MPX tile needs up to 3 extra
   constexpr int TS = 32 * TP;  // floats per tile
   extern __shared__ float sm_st[];
@@ -2017,7 +1861,7 @@ static bool usePackedFma() {
 
 #define FMGPU_DECIM_CASE(MM)                                                                     \
   case MM: {                                                                                     \
-    constexpr int T = 512;                                                                       \
+    constexpr int T = 4 * DECIM_NT;                                                                     \
     const int tile_len = (T + Pp - 1) * MM;                                                      \
     const size_t smem = (size_t)(tile_len + tile_len / (4 * MM) + 2) * sizeof(float2);           \
     static bool attr_done = false;                                                               \
@@ -2030,54 +1874,18 @@ static bool usePackedFma() {
     }                                                                                            \
     dim3 grid((n_out + T - 1) / T, nch);                                                         \
     if (usePackedFma()) {                                                                        \
-      k_decim<MM, true><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,        \
+      k_decim<MM, true><<<grid, DECIM_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,        \
                                                      x1_pitch, n_out, ch0, Pp, scale, taps);     \
     } else {                                                                                     \
-      k_decim<MM, false><<<grid, 128, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,       \
+      k_decim<MM, false><<<grid, DECIM_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,       \
                                                       x1_pitch, n_out, ch0, Pp, scale, taps);    \
     }                                                                                            \
     break;                                                                                       \
   }
 
-template <int M, int PP>
-static void launchDecimRing(const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
-                            const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0,
-                            int nch, float scale, const TapsParam &taps, cudaStream_t stream) {
-  constexpr int T = 512;
-  constexpr int TILE = (T + PP - 1) * M;
-  constexpr int TQ = (M + 3) / 4;
-  constexpr size_t smem = (size_t)PP * TQ * 16 + (size_t)((TILE + TILE / (8 * M) + 3) & ~1) * 8 +
-                          (size_t)(2 * TILE + 48 + 15) / 16 * 16;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_decim_ring<M, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  dim3 grid((n_out + T - 1) / T, nch);
-  k_decim_ring<M, PP><<<grid, 64, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1, x1_pitch,
-                                                  n_out, ch0, scale, taps);
-}
-
 void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
                  const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
                  const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream) {
-  static int ring = -1;  // FMGPU_DECIM_RING=1 selects the register-ring form (A/B timing)
-  if (ring < 0) {
-    const char *v = getenv("FMGPU_DECIM_RING");
-    ring = (v && atoi(v) == 1) ? 1 : 0;
-  }
-  if (ring && usePackedFma()) {
-#define FMGPU_RING_CASE(MM, PPP)                                                                  \
-  if (M == MM && Pp == PPP) {                                                                     \
-    launchDecimRing<MM, PPP>(iq, iq_stride, hist, hist_valid, x1, x1_pitch, n_out, ch0, nch, scale, \
-                             taps, stream);                                                       \
-    return;                                                                                       \
-  }
-    FMGPU_RING_CASE(10, 28)  // 2.4 MS/s / 10, 280 taps
-    FMGPU_RING_CASE(8, 28)   // 2.048 MS/s / 8, 224 taps (main.cpp:672-674)
-    FMGPU_RING_CASE(4, 20)   // 1.024 MS/s / 4, 80 taps
-#undef FMGPU_RING_CASE
-  }
   switch (M) {
     FMGPU_DECIM_CASE(2)
     FMGPU_DECIM_CASE(4)
@@ -2265,7 +2073,7 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  constexpr size_t smem = 17 * 32 * (16 + 8) * sizeof(float);  // 17 tiles of [32][16 + 8]
+  constexpr size_t smem = 17 * 32 * (STEREO_ST + 8) * sizeof(float);  // 17 tiles of [32][ST + 8]
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

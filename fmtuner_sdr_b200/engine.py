@@ -77,7 +77,8 @@ def load_library(build: bool = True):
         _build.build_lib()
     if not os.path.exists(_build.LIB):
         raise EngineError(f"{_build.LIB} is missing: run __graft_entry__.build() (no CPU fallback)")
-    L = C.CDLL(_build.LIB)
+    # FMGPU_LIB: an alternative build of the same library (A/B timing of compile-time variants)
+    L = C.CDLL(os.environ.get("FMGPU_LIB") or _build.LIB)
     vp, i32, sz, u8p, f32p = C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p
     L.fmgpu_engine_create.argtypes = [C.POINTER(Config), i32, i32, C.POINTER(vp)]
     L.fmgpu_engine_destroy.argtypes = [vp]
@@ -90,6 +91,7 @@ def load_library(build: bool = True):
         getattr(L, f"fmgpu_{name}").argtypes = [vp, i32, i32]
     L.fmgpu_reset.argtypes = [vp, i32, C.c_uint]
     L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
+    L.fmgpu_set_stage_overlap.argtypes = [vp, i32]
     L.fmgpu_is_stereo.argtypes = [vp, i32]
     L.fmgpu_pilot_tenths.argtypes = [vp, i32]
     L.fmgpu_clip_ratio.argtypes = [vp, i32]
@@ -217,6 +219,9 @@ class Engine:
 
     def set_pipeline_groups(self, groups: int):
         self._check(self.L.fmgpu_set_pipeline_groups(self.h, groups), "set_pipeline_groups")
+
+    def set_stage_overlap(self, on: bool):
+        self._check(self.L.fmgpu_set_stage_overlap(self.h, int(on)), "set_stage_overlap")
 
     def reset(self, what=RESET_ALL, channel=-1):
         self._check(self.L.fmgpu_reset(self.h, channel, what), "reset")

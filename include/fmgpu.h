@@ -237,6 +237,10 @@ size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, siz
 size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t cap);
 /* Number of kernels this engine has launched so far. */
 uint64_t fmgpu_launch_count(const fmgpu_engine *e);
+/* Measurement aid: with on = 0 every stage of the block pipeline is queued on ONE stream, so no two
+ * stages overlap and the per-stage times of fmgpu_get_stage_times are those of the kernels running
+ * alone. Results do not depend on it. Default: on (stages overlap). */
+int fmgpu_set_stage_overlap(fmgpu_engine *e, int on);
 /* With stage timing enabled and batches queued by fmgpu_process_batch_async: every stage span
  * recorded since the last call (name, pipeline group, start and end in ms after the earliest
  * span). Synchronises the device. Returns the number of spans. */
