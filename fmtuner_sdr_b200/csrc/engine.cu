@@ -590,7 +590,8 @@ void realign(fmgpu_engine *e) {
 // One logical block (global number q, block b of a call of nb blocks) of channels
 // [ch0, ch0 + nch) through the stage streams of pipe P. iq / stride: this block's bytes.
 void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint64_t q, int b, int nb,
-                 const uint8_t *iq, size_t stride, bool waitH2D, const BatchOut &out) {
+                 const uint8_t *iq, size_t stride, bool waitH2D, const BatchOut &out,
+                 const float2 *xcf = nullptr, size_t xcfStride = 0) {
   using E = fmgpu_engine;
   const int K = e->K, N = e->N;
   const int slot = static_cast<int>(q % static_cast<uint64_t>(K));
@@ -615,7 +616,8 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   };
   auto done = [&](int st) { cudaEventRecord(ev(st, q), P.run[st]); };
 
-  if (e->M > 1) {
+  const bool decim = (e->M > 1) && !xcf;
+  if (decim) {
     cudaStream_t s = P.run[E::ST_DECIM];
     if (waitH2D) {
       need(E::ST_DECIM, {E::ST_H2D}, {E::ST_DC});
@@ -633,7 +635,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   }
   {
     cudaStream_t s = P.run[E::ST_DC];
-    if (e->M > 1) {
+    if (decim) {
       need(E::ST_DC, {E::ST_DECIM}, {E::ST_CHAN});
     } else if (waitH2D) {
       need(E::ST_DC, {E::ST_H2D}, {E::ST_CHAN});
@@ -645,8 +647,15 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       launchCarryF2(e->dX2, e->x2Pitch, H_X2, ringEnd, ch0, nch, s);
       e->launches += 1;
     }
-    launchDcBlock(e->M > 1 ? e->dX1 + t0 : nullptr, e->pitch, e->M > 1 ? nullptr : iq, stride,
-                  e->dX2 + t0, e->x2Pitch, e->dDemod, status, nb, 1, N, N, ch0, nch, e->k.dc_a1_iq, s);
+    if (xcf) {
+      // complex-float input at the DSP rate (FMDemod::processSplitComplex): read in place
+      launchDcBlock(xcf, xcfStride, nullptr, 0, e->dX2 + t0, e->x2Pitch, e->dDemod, status, nb, 1, N,
+                    N, ch0, nch, e->k.dc_a1_iq, s);
+    } else {
+      launchDcBlock(decim ? e->dX1 + t0 : nullptr, e->pitch, decim ? nullptr : iq, stride,
+                    e->dX2 + t0, e->x2Pitch, e->dDemod, status, nb, 1, N, N, ch0, nch,
+                    e->k.dc_a1_iq, s);
+    }
     e->launches += 1;
   }
   done(E::ST_DC);
@@ -839,7 +848,8 @@ int checkBatchArgs(fmgpu_engine *e, const void *iq, size_t stride, int n_blocks,
 // Queue n_blocks logical blocks of every channel. hostIq != nullptr: the bytes come from host
 // memory through the H2D stage (block by block into the device ring); else iq_dev is read in place.
 int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, size_t stride,
-                int n_blocks, const BatchOut &out, cudaStream_t caller, bool callerWaits) {
+                int n_blocks, const BatchOut &out, cudaStream_t caller, bool callerWaits,
+                const float2 *xcf = nullptr, size_t xcfStride = 0) {
   using E = fmgpu_engine;
   const size_t blockBytes = static_cast<size_t>(e->N) * e->M * 2;
   const int G = std::max(1, e->nGroups);
@@ -854,7 +864,7 @@ int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, 
       continue;
     }
     if (!iq_host) {
-      cudaStreamWaitEvent(P.run[e->M > 1 ? E::ST_DECIM : E::ST_DC], e->evStart, 0);
+      cudaStreamWaitEvent(P.run[(e->M > 1 && !xcf) ? E::ST_DECIM : E::ST_DC], e->evStart, 0);
     }
   }
   for (int b = 0; b < n_blocks; b++) {
@@ -884,10 +894,11 @@ int queueBlocks(fmgpu_engine *e, const uint8_t *iq_dev, const uint8_t *iq_host, 
         cudaEventRecord(P.done[E::ST_H2D][q % static_cast<uint64_t>(e->ER)], s);
         iq = e->dIq + slot * blockBytes;
         st = e->iqPitch;
-      } else {
+      } else if (iq_dev) {
         iq = iq_dev + b * blockBytes;
       }
-      launchBlock(e, P, ch0, nch, q, b, n_blocks, iq, st, iq_host != nullptr, out);
+      launchBlock(e, P, ch0, nch, q, b, n_blocks, iq, st, iq_host != nullptr, out,
+                  xcf ? xcf + static_cast<size_t>(b) * e->N : nullptr, xcfStride);
     }
     if (slot == 0) {
       e->headFresh = false;
@@ -1598,6 +1609,52 @@ int fmgpu_process_batch_async(fmgpu_engine *e, const uint8_t *iq_dev, size_t iq_
   CK(cudaSetDevice(e->device));
   return runBatch(e, iq_dev, iq_stride_bytes, n_blocks, audio_dev, audio_cap, n_audio_dev, groups_dev,
                   group_cap, n_groups_dev, status_dev, static_cast<cudaStream_t>(stream), false);
+}
+
+int fmgpu_process_batch_cf32(fmgpu_engine *e, const float *x_cf32_dev, size_t stride_samples,
+                             int n_blocks, float *audio_dev, size_t audio_cap,
+                             uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
+                             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, void *stream) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  if (e->M != 1) {
+    e->lastError = "process_batch_cf32: the engine must be created with decimation = 1";
+    return FMGPU_EINVAL;
+  }
+  if (!x_cf32_dev || n_blocks < 1 || n_blocks > e->maxBlocks ||
+      (reinterpret_cast<uintptr_t>(x_cf32_dev) & 15u) || (stride_samples & 1u) ||
+      stride_samples < static_cast<size_t>(n_blocks) * e->N) {
+    e->lastError = "process_batch_cf32: bad input pointer, alignment, stride or block count";
+    return FMGPU_EINVAL;
+  }
+  const size_t n = static_cast<size_t>(n_blocks) * e->N;
+  const size_t needAudio = static_cast<size_t>((static_cast<double>(n) * 16777216.0) / e->k.aud_step) + 2;
+  if (audio_dev && audio_cap < needAudio) {
+    e->lastError = "process: audio capacity too small";
+    return FMGPU_ERANGE;
+  }
+  int rc = uploadParams(e);
+  if (rc != FMGPU_OK) {
+    return rc;
+  }
+  BatchOut out;
+  out.status = status_dev ? status_dev : e->dStatus;
+  out.groups = groups_dev ? groups_dev : e->dGroups;
+  out.gcap = static_cast<uint32_t>(groups_dev ? group_cap : e->gcap);
+  out.nAudio = n_audio_dev ? n_audio_dev : e->dNAudio;
+  out.nGroups = n_groups_dev ? n_groups_dev : e->dNGroups;
+  out.audio = audio_dev ? audio_dev : e->dAudio;
+  out.acap = audio_dev ? audio_cap : e->acap;
+  rc = queueBlocks(e, nullptr, nullptr, 0, n_blocks, out, static_cast<cudaStream_t>(stream), true,
+                   reinterpret_cast<const float2 *>(x_cf32_dev), stride_samples);
+  if (rc == FMGPU_OK && e->timing) {
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    collectTimes(e);
+  }
+  return rc;
 }
 
 int fmgpu_join(fmgpu_engine *e, void *stream) {

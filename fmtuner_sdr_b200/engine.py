@@ -101,6 +101,15 @@ def load_library(build: bool = True):
     L.fmgpu_process_host.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp]
     L.fmgpu_process_batch_async.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp, vp]
     L.fmgpu_join.argtypes = [vp, vp]
+    L.fmgpu_process_batch_cf32.argtypes = [vp, f32p, sz, i32, f32p, sz, vp, vp, sz, vp, vp, vp]
+    L.fmgpu_channelizer_create.argtypes = [i32, i32, i32, i32, C.c_double, C.c_double, i32,
+                                           C.c_double, C.c_float, C.POINTER(vp)]
+    L.fmgpu_channelizer_destroy.argtypes = [vp]
+    L.fmgpu_channelizer_destroy.restype = None
+    L.fmgpu_channelizer_output_rate.argtypes = [vp]
+    L.fmgpu_channelizer_taps.argtypes = [vp, f32p, sz]
+    L.fmgpu_channelizer_taps.restype = sz
+    L.fmgpu_channelizer_process.argtypes = [vp, u8p, sz, i32, i32, f32p, sz, vp]
     L.fmgpu_submit_host.argtypes = [vp, u8p, sz, i32, f32p, sz, vp, vp, sz, vp, vp]
     L.fmgpu_wait_host.argtypes = [vp, i32]
     L.fmgpu_decimate.restype = sz
@@ -289,6 +298,15 @@ class Engine:
                                                      n_groups_ptr, status_ptr, stream),
                     "process_batch_async")
 
+    def process_batch_cf32(self, x_dev_ptr, stride_samples, n_blocks, audio_ptr=None, acap=0,
+                           n_audio_ptr=None, groups_ptr=None, gcap=0, n_groups_ptr=None,
+                           status_ptr=None, stream=None):
+        """Complex-float input at the DSP rate (engine created with decimation=1)."""
+        self._check(self.L.fmgpu_process_batch_cf32(self.h, x_dev_ptr, stride_samples, n_blocks,
+                                                    audio_ptr, acap, n_audio_ptr, groups_ptr, gcap,
+                                                    n_groups_ptr, status_ptr, stream),
+                    "process_batch_cf32")
+
     def join(self, stream=None):
         self._check(self.L.fmgpu_join(self.h, stream), "join")
 
@@ -411,3 +429,51 @@ class Engine:
         ms = (C.c_float * 32)()
         n = self.L.fmgpu_get_stage_times(self.h, names, ms, 32)
         return {names[i].decode(): float(ms[i]) for i in range(min(n, 32))}
+
+
+class Channelizer:
+    """Wideband front end for BASELINE config 4 (include/fmgpu.h: fmgpu_channelizer_*): one uint8
+    IQ capture -> n_channels complex-float streams at wide_rate / decimation."""
+
+    def __init__(self, wide_rate=24_000_000, decimation=100, n_channels=100,
+                 first_center_hz=-9_900_000.0, spacing_hz=200_000.0, taps_per_phase=16,
+                 cutoff_hz=100_000.0, atten_db=60.0, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.fmgpu_channelizer_create(device, wide_rate, decimation, n_channels,
+                                             first_center_hz, spacing_hz, taps_per_phase, cutoff_hz,
+                                             atten_db, C.byref(h))
+        if rc != 0:
+            raise EngineError(f"fmgpu_channelizer_create failed ({rc}); no CPU fallback")
+        self.h = h
+        self.wide_rate, self.decimation, self.n_channels = wide_rate, decimation, n_channels
+        self.first_center_hz, self.spacing_hz = first_center_hz, spacing_hz
+
+    @property
+    def output_rate(self) -> int:
+        return self.L.fmgpu_channelizer_output_rate(self.h)
+
+    def taps(self) -> np.ndarray:
+        n = self.L.fmgpu_channelizer_taps(self.h, None, 0)
+        out = np.zeros(n, np.float32)
+        self.L.fmgpu_channelizer_taps(self.h, _ptr(out), n)
+        return out
+
+    def process(self, iq_dev_ptr, n_in, out_dev_ptr, out_stride_samples, ch_first=0, ch_count=None,
+                stream=None):
+        ch_count = self.n_channels - ch_first if ch_count is None else ch_count
+        rc = self.L.fmgpu_channelizer_process(self.h, iq_dev_ptr, n_in, ch_first, ch_count,
+                                              out_dev_ptr, out_stride_samples, stream)
+        if rc != 0:
+            raise EngineError(f"fmgpu_channelizer_process failed ({rc})")
+
+    def close(self):
+        if self.h:
+            self.L.fmgpu_channelizer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -187,6 +187,39 @@ int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
                      const uint32_t *n_audio_dev, float volume_scale, int16_t *pcm_dev,
                      void *stream);
 
+/* ---- wideband channelizer (BASELINE config 4) --------------------
+ * NO reference counterpart: the reference tunes one carrier in the RTL-SDR hardware. One uint8 IQ
+ * capture at wide_rate holds n_channels carriers, channel k centred first_center_hz +
+ * k * spacing_hz away from the capture centre; each is mixed to baseband, low-pass filtered by a
+ * Kaiser-windowed sinc of decimation * taps_per_phase taps (cut-off cutoff_hz, atten_db) and
+ * decimated to wide_rate / decimation — complex float at the engine's DSP rate, the input of
+ * fmgpu_process_batch_cf32 (the FMDemod::processSplitComplex path, fm_demod.cpp:258-274).
+ * Definition (what tests/test_gpu_channelizer.py evaluates in float64):
+ *   y_k[m] = sum_n h[n] x[m*D - n] exp(-j 2 pi f_k (m*D - n) / wide_rate),  x = (u8 - 127.5)/127.5,
+ * m counted from creation, input before the first call = 0. */
+typedef struct fmgpu_channelizer fmgpu_channelizer;
+int fmgpu_channelizer_create(int device, int wide_rate, int decimation, int n_channels,
+                             double first_center_hz, double spacing_hz, int taps_per_phase,
+                             double cutoff_hz, float atten_db, fmgpu_channelizer **out);
+void fmgpu_channelizer_destroy(fmgpu_channelizer *z);
+int fmgpu_channelizer_output_rate(const fmgpu_channelizer *z);
+size_t fmgpu_channelizer_taps(const fmgpu_channelizer *z, float *out, size_t cap);
+/* iq_dev: n_in uint8 I,Q pairs (n_in a multiple of the decimation) continuing the stream of the
+ * previous call; out_cf32_dev [ch_count][out_stride_samples] complex float for channels
+ * ch_first .. ch_first + ch_count - 1 (a rank of a sharded job extracts only its own channels from
+ * the capture every rank reads). Asynchronous on `stream`. */
+int fmgpu_channelizer_process(fmgpu_channelizer *z, const uint8_t *iq_dev, size_t n_in,
+                              int ch_first, int ch_count, float *out_cf32_dev,
+                              size_t out_stride_samples, void *stream);
+
+/* fmgpu_process_batch with complex-float input at the DSP rate (engine created with
+ * decimation = 1): x_cf32_dev [C][stride_samples] interleaved re,im; base and stride 16-byte
+ * aligned. FMDemod::processSplitComplex for every channel (clip flag: |I| or |Q| >= 0.995). */
+int fmgpu_process_batch_cf32(fmgpu_engine *e, const float *x_cf32_dev, size_t stride_samples,
+                             int n_blocks, float *audio_dev, size_t audio_cap,
+                             uint32_t *n_audio_dev, fmgpu_rds_group *groups_dev, size_t group_cap,
+                             uint32_t *n_groups_dev, fmgpu_block_status *status_dev, void *stream);
+
 /* Split the channels into `groups` (1..16) ranges that run the pipeline on separate streams:
  * one range's serial (one-lane-per-channel) kernels then overlap another range's FIR kernels
  * and, in fmgpu_process_host, its host<->device copies. Results do not depend on it. */
