@@ -347,9 +347,14 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     lane = max((k for k in acc if k in LANE_STAGES), key=acc.get)
     roofline["dominant_tile_kernel"] = kernel_roofline(tile, acc[tile], C, B, clocks)
     roofline["dominant_lane_kernel"] = {
-        "kernel": lane, "launch_ms": acc[lane], "class": "latency-bound serial recursion, one lane "
-        "per channel", "lanes": C, "lane_steps_per_s": C * B * BLOCK / (acc[lane] * 1e-3),
+        "kernel": lane, "launch_ms": acc[lane] / B, "class": "latency-bound serial recursion, one "
+        "lane per channel", "lanes": C, "lane_steps_per_s": C * B * BLOCK / (acc[lane] * 1e-3),
         "realtime_factor": (B * BLOCK / 240000.0) / (acc[lane] * 1e-3)}
+    roofline["stage_sum_ms"] = serial_sum
+    roofline["overlap_factor"] = serial_sum / (ms / args.steps)
+    roofline["overlap_note"] = ("stage_ms are the stages run one after the other (fmgpu_set_stage_"
+                                "overlap(0)); in the timed steps the block pipeline overlaps them: "
+                                "overlap_factor = their sum / the measured step")
     step_alg_bytes = samples_per_step_rank * BYTES_PER_IQ_SAMPLE_ALG
     roofline["whole_step"] = {
         "achieved": step_alg_bytes / (ms / args.steps * 1e-3) / 1e9, "unit": "GB/s",
@@ -440,10 +445,23 @@ TILE_STAGES = ("decimate", "chanfir", "freqdem", "pilot_fir", "audio_lpf", "afpo
 LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds")
 
 
+# DRAM bytes per DSP-rate sample (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of
+# each stage, from the ncu --set full capture of this command committed as
+# profiles/r01_top_kernels_ncu.csv (1250 channels x 8192 samples per launch; writes that were still
+# in L2 when the kernel ended are not in the figure).
+NCU_TRAFFIC_BYTES_PER_SAMPLE = {
+    "decimate": 25.9, "chanfir": 11.8, "pilot_fir": 4.4, "audio_lpf": 11.6, "stereo_pll": 12.7,
+    "dcblock": 12.2, "agc": 10.7, "freqdem": 9.7, "rds": 7.1, "afpost": 9.6,
+}
+
+
 def kernel_roofline(stage: str, stage_ms: float, C: int, B: int, clocks: dict) -> dict:
-    """Algorithmic bytes / flops of one launch of the dominant stage."""
-    n = C * B * BLOCK            # DSP-rate samples per launch
+    """Algorithmic bytes / flops of ONE LAUNCH of the stage (one logical block of all C channels;
+    DESIGN.md section 4) over its average launch duration (stage_ms is the sum over the B blocks of a
+    step, measured with the stages serialised)."""
+    n = C * BLOCK                # DSP-rate samples per launch
     n_iq = n * DECIM
+    launch_ms = stage_ms / B
     alg = {   # stage: (bytes, flops) per launch
         "decimate": (2.0 * n_iq + 8.0 * n, 2.0 * 2 * 280 * n),
         "chanfir": (8.0 * n + 8.0 * n, 2.0 * 2 * 81 * n),
@@ -462,12 +480,16 @@ def kernel_roofline(stage: str, stage_ms: float, C: int, B: int, clocks: dict) -
             peak_hbm, how = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
-    t = stage_ms * 1e-3
+    t = launch_ms * 1e-3
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    traffic = NCU_TRAFFIC_BYTES_PER_SAMPLE.get(stage)
     return {"kernel": stage, "bound": "hbm", "achieved": alg[0] / t / 1e9, "peak": peak_hbm,
-            "peak_source": how, "unit": "GB/s", "frac": alg[0] / t / 1e9 / peak_hbm, "traffic": None,
-            "launch_ms": stage_ms,
+            "peak_source": how, "unit": "GB/s", "frac": alg[0] / t / 1e9 / peak_hbm,
+            "traffic": (traffic * n) if traffic is not None else None,
+            "traffic_source": "ncu dram bytes per sample (profiles/r01_top_kernels_ncu.csv) x the "
+                              "samples of one launch",
+            "algorithmic_bytes": alg[0], "launch_ms": launch_ms, "launches_per_step": B,
             "fp32": {"achieved_tflops": alg[1] / t / 1e12, "peak_tflops": fp32_peak,
                      "peak_source": "148 SM x 128 FMA/clk x 2 at the SM clock sampled under load",
                      "frac": alg[1] / t / 1e12 / fp32_peak},

@@ -751,7 +751,9 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
          StereoState *st, const ChanParams *cp, fmgpu_block_status *status, int status_pitch,
          int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
   constexpr int ST = STEREO_ST;  // samples per tile row
-  constexpr int TP = ST + 8;   // 16-byte aligned rows; the delayed-MPX tile needs up to 3 extra
+  // 16-byte aligned rows; the delayed-MPX tile needs up to 3 extra samples + alignment. With
+  // ST = 16 the pitch of 20 floats spreads the 32 lanes over 8 banks (a pitch of 24 only over 4).
+  constexpr int TP = ST + 4;
   constexpr int TS = 32 * TP;  // floats per tile
   extern __shared__ float sm_st[];
   float *t_pil = sm_st;             // ring of 3: chunk j in slot j % 3
@@ -2073,7 +2075,7 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  constexpr size_t smem = 17 * 32 * (STEREO_ST + 8) * sizeof(float);  // 17 tiles of [32][ST + 8]
+  constexpr size_t smem = 17 * 32 * (STEREO_ST + 4) * sizeof(float);  // 17 tiles of [32][ST + 4]
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
