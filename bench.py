@@ -355,6 +355,31 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     roofline["overlap_note"] = ("stage_ms are the stages run one after the other (fmgpu_set_stage_"
                                 "overlap(0)); in the timed steps the block pipeline overlaps them: "
                                 "overlap_factor = their sum / the measured step")
+    # the HBM-bound (streaming) kernels of the path against the measured copy bandwidth: the
+    # discriminator (8 B in + 4 B out per DSP-rate sample) from the stage pass above, and the RF
+    # level meter (2 B in per IQ sample), timed here on its own
+    streaming = []
+    if "freqdem" in acc:
+        fd_bytes = 12.0 * C * BLOCK
+        fd_gbs = fd_bytes / (acc["freqdem"] / B * 1e-3) / 1e9
+        streaming.append({"kernel": "freqdem", "bytes_per_launch": fd_bytes,
+                          "launch_ms": acc["freqdem"] / B, "achieved": fd_gbs, "unit": "GB/s",
+                          "frac": fd_gbs / roofline["peak"]})
+    sums = torch.zeros((C, B, 48), dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        eng.signal_level_batch(iq_dev.data_ptr(), stride, B, sums.data_ptr(), stream)
+    sl0, sl1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    sl0.record()
+    for _ in range(5):
+        eng.signal_level_batch(iq_dev.data_ptr(), stride, B, sums.data_ptr(), stream)
+    sl1.record()
+    torch.cuda.synchronize()
+    sl_ms = sl0.elapsed_time(sl1) / 5
+    sl_gbs = 2.0 * C * n_iq / (sl_ms * 1e-3) / 1e9
+    streaming.append({"kernel": "signal_level", "bytes_per_launch": 2.0 * C * n_iq, "launch_ms": sl_ms,
+                      "achieved": sl_gbs, "unit": "GB/s", "frac": sl_gbs / roofline["peak"]})
+    roofline["streaming_kernels"] = streaming
     step_alg_bytes = samples_per_step_rank * BYTES_PER_IQ_SAMPLE_ALG
     roofline["whole_step"] = {
         "achieved": step_alg_bytes / (ms / args.steps * 1e-3) / 1e9, "unit": "GB/s",

@@ -4,5 +4,5 @@ Python is plumbing only: `Engine` is a ctypes view of the C ABI in include/fmgpu
 (libfmgpu.so, hand-written sm_100a CUDA). There is no CPU fallback; creating an
 engine without a CUDA device raises.
 """
-from .engine import (Channelizer, Engine, EngineError, LevelSums, SignalLevel, SynthParams, GROUP_DTYPE, STATUS_DTYPE, lib_path,  # noqa: F401
+from .engine import (Channelizer, Engine, EngineError, LevelSums, SignalLevel, SynthParams, GROUP_DTYPE, STATUS_DTYPE, XdrRdsFormatter, lib_path,  # noqa: F401
                      load_library, make_config, synth_iq)

@@ -652,20 +652,36 @@ k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_
   }
 }
 
-// K2b: quadrature discriminator, arg(conj(y[n-1]) * y[n]) / (2 pi kf)   (freqdem)
-__global__ void k_freqdem(const float2 *__restrict__ ybuf, size_t y_pitch, float *__restrict__ mpx,
-                          size_t mpx_pitch, int n_total, int ch0, float ref) {
+// K2b: quadrature discriminator, arg(conj(y[n-1]) * y[n]) / (2 pi kf)   (freqdem). A streaming
+// kernel (12 B per sample): four samples per thread, 128-bit loads and stores (the data region of
+// a y row starts 16-byte aligned at Y_OFF, the MPX data region at H_MPX).
+__global__ void __launch_bounds__(256)
+k_freqdem(const float2 *__restrict__ ybuf, size_t y_pitch, float *__restrict__ mpx,
+          size_t mpx_pitch, int n_total, int ch0, float ref) {
   const int c = blockIdx.y + ch0;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (n >= n_total) {
     return;
   }
-  const float2 *y = ybuf + (size_t)c * y_pitch + (Y_OFF - 1);
-  const float2 p = y[n];
-  const float2 r = y[n + 1];
-  const float re = (p.x * r.x) + (p.y * r.y);
-  const float im = (p.x * r.y) - (p.y * r.x);
-  mpx[(size_t)c * mpx_pitch + H_MPX + n] = fm_atan2f(im, re) * ref;
+  const float2 *y = ybuf + (size_t)c * y_pitch + Y_OFF;  // y[-1] = r_prev
+  float *out = mpx + (size_t)c * mpx_pitch + H_MPX;
+  auto one = [&](float2 p, float2 r) {
+    const float re = (p.x * r.x) + (p.y * r.y);
+    const float im = (p.x * r.y) - (p.y * r.x);
+    return fm_atan2f(im, re) * ref;
+  };
+  if (n + 4 <= n_total) {
+    const float2 p = y[n - 1];
+    const float4 a = *reinterpret_cast<const float4 *>(y + n);      // y[n], y[n+1]
+    const float4 b = *reinterpret_cast<const float4 *>(y + n + 2);  // y[n+2], y[n+3]
+    const float2 y0 = make_float2(a.x, a.y), y1 = make_float2(a.z, a.w);
+    const float2 y2 = make_float2(b.x, b.y), y3 = make_float2(b.z, b.w);
+    *reinterpret_cast<float4 *>(out + n) = make_float4(one(p, y0), one(y0, y1), one(y1, y2), one(y2, y3));
+  } else {
+    for (int i = n; i < n_total; i++) {
+      out[i] = one(y[i - 1], y[i]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1970,7 +1986,7 @@ void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *c
 
 void launchFreqDem(const float2 *ybuf, size_t y_pitch, float *mpx, size_t mpx_pitch, int n_total,
                    int ch0, int nch, float ref, cudaStream_t stream) {
-  dim3 grid((n_total + 255) / 256, nch);
+  dim3 grid((n_total + 1023) / 1024, nch);  // 256 threads x 4 samples
   k_freqdem<<<grid, 256, 0, stream>>>(ybuf, y_pitch, mpx, mpx_pitch, n_total, ch0, ref);
 }
 

@@ -431,6 +431,34 @@ class Engine:
         return {names[i].decode(): float(ms[i]) for i in range(min(n, 32))}
 
 
+class XdrRdsState(C.Structure):
+    _fields_ = [("pi_buffer", C.c_uint16 * 64), ("pi_error", C.c_uint8 * 8), ("pi_fill", C.c_uint8),
+                ("pi_pos", C.c_uint8), ("pi_last_state", C.c_uint8), ("pad", C.c_uint8),
+                ("pi_last_value", C.c_uint16)]
+
+
+class XdrRdsFormatter:
+    """Per-channel XDR / FM-DX view of an RDS stream (fmgpu_xdr_rds_*: XDRServer::updateRDS)."""
+
+    def __init__(self):
+        self.L = load_library()
+        self.L.fmgpu_xdr_rds_init.argtypes = [C.POINTER(XdrRdsState)]
+        self.L.fmgpu_xdr_rds_init.restype = None
+        self.L.fmgpu_xdr_rds_lines.argtypes = [C.POINTER(XdrRdsState), C.c_void_p, C.c_char_p]
+        self.state = XdrRdsState()
+        self.reset()
+
+    def reset(self):
+        self.L.fmgpu_xdr_rds_init(C.byref(self.state))
+
+    def lines(self, group) -> list:
+        """group: one element of a GROUP_DTYPE array -> the text lines it produces."""
+        one = np.array([group], GROUP_DTYPE)
+        buf = C.create_string_buffer(64)
+        n = self.L.fmgpu_xdr_rds_lines(C.byref(self.state), one.ctypes.data, buf)
+        return [buf.raw[32 * i:32 * i + 32].split(b"\0")[0].decode() for i in range(n)]
+
+
 class Channelizer:
     """Wideband front end for BASELINE config 4 (include/fmgpu.h: fmgpu_channelizer_*): one uint8
     IQ capture -> n_channels complex-float streams at wide_rate / decimation."""

@@ -187,6 +187,22 @@ int fmgpu_pack_pcm16(fmgpu_engine *e, const float *audio_dev, size_t audio_cap,
                      const uint32_t *n_audio_dev, float volume_scale, int16_t *pcm_dev,
                      void *stream);
 
+/* ---- XDR / FM-DX view of the RDS stream -------------------------
+ * XDRServer::updateRDS (src/xdr_server.cpp:403-457) with its PI debounce (evaluatePiState,
+ * :189-215), one state per channel, for hosts that serve many channels: every group gives up to
+ * two text lines, "P<PI>" followed by one '?' per error level of block A once the PI is
+ * debounced, and "R<B><C><D><errors>" when block B was received clean. Host-side; no device work. */
+typedef struct fmgpu_xdr_rds_state {
+  uint16_t pi_buffer[64];
+  uint8_t pi_error[8];
+  uint8_t pi_fill, pi_pos, pi_last_state, pad;
+  uint16_t pi_last_value;
+} fmgpu_xdr_rds_state;
+/* the state of a constructed server and after every start / retune (xdr_server.cpp:257-266,461-470) */
+void fmgpu_xdr_rds_init(fmgpu_xdr_rds_state *s);
+/* returns the number of lines written (0..2), each NUL-terminated */
+int fmgpu_xdr_rds_lines(fmgpu_xdr_rds_state *s, const fmgpu_rds_group *g, char lines[2][32]);
+
 /* ---- wideband channelizer (BASELINE config 4) --------------------
  * NO reference counterpart: the reference tunes one carrier in the RTL-SDR hardware. One uint8 IQ
  * capture at wide_rate holds n_channels carriers, channel k centred first_center_hz +

@@ -31,7 +31,8 @@ def build(force: bool = False) -> None:
         or stale("libsiggen.so", ("siggen.cpp", "Makefile"))
     have_ref_src = os.path.isdir("/root/reference/src/redsea_port")
     ref_missing = have_ref_src and not all(
-        os.path.exists(os.path.join(HERE, "_ref", f)) for f in ("libredsea_ref.so", "libsiglevel_ref.so"))
+        os.path.exists(os.path.join(HERE, "_ref", f))
+        for f in ("libredsea_ref.so", "libsiglevel_ref.so", "libxdr_ref.so"))
     if need or ref_missing:
         subprocess.run(["make", "-C", HERE, "--no-print-directory"], check=True,
                        stdout=subprocess.DEVNULL)
