@@ -13,6 +13,8 @@
 // Compiled with -fmad=false: only explicit fmaf() fuses.
 #include "kernels.h"
 
+#include <type_traits>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -124,6 +126,29 @@ __device__ __forceinline__ float2 fma2(float h, float2 x, float2 acc) {
     return o;
   }
   return make_float2(fmaf(h, x.x, acc.x), fmaf(h, x.y, acc.y));
+}
+
+// One uint8 IQ pair (I in byte 0, Q in byte 1) -> ((float)byte - 127.5f) * (1 / 127.5f), the
+// conversion of ComplexDecimator::executeComplex (liquid_primitives.cpp:480-484), without the
+// int->float converter: PRMT builds the bits 0x47000000 | byte << 8 = 32768 + byte exactly, one
+// exact subtraction of 32895.5 leaves byte - 127.5 (a 9-bit number), and the single rounding is the
+// final multiplication, as in the scalar formula. Both halves go through the packed f32x2 ALU ops.
+__device__ __forceinline__ float2 iqBytesToFloat(uint32_t w) {
+  const float vi = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404));
+  const float vq = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7414));
+  constexpr float kScale = 1.0f / 127.5f;
+  unsigned long long v, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(vi), "f"(vq));
+  asm("{\n\t.reg .b64 c, k;\n\t"
+      "mov.b64 c, {%2, %2};\n\t"
+      "mov.b64 k, {%3, %3};\n\t"
+      "add.rn.f32x2 %0, %1, c;\n\t"
+      "mul.rn.f32x2 %0, %0, k;\n\t}"
+      : "=l"(r)
+      : "l"(v), "f"(-32895.5f), "f"(kScale));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
 }
 
 // ---------------------------------------------------------------------------
@@ -268,37 +293,52 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
   const long o = (long)(n0 - Pp) * M + 1;  // stream index of tile element 0
   const int tile_len = (T + Pp - 1) * M;
   const long v0 = o + H_IQ;                // virtual index (history first)
-  const long ck0 = v0 >> 3;
-  const long ck1 = (v0 + tile_len - 1) >> 3;
   const long n_in = (long)n_out * M;
-  const uint8_t *in_c = iq + (size_t)c * iq_stride;
-  const uint8_t *hist_c = hist + (size_t)c * (2 * H_IQ);
+  const unsigned short *in_c = reinterpret_cast<const unsigned short *>(iq + (size_t)c * iq_stride);
+  const unsigned short *hist_c = reinterpret_cast<const unsigned short *>(hist) + (size_t)c * H_IQ;
   const long v_first_valid = H_IQ - hist_valid[c];
   constexpr float kScale = 1.0f / 127.5f;
 
-  for (long ck = ck0 + t; ck <= ck1; ck += DECIM_NT) {
-    const long v = ck << 3;
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (v < H_IQ) {
-      raw = *reinterpret_cast<const uint4 *>(hist_c + 2 * v);
-    } else if (v - H_IQ < n_in) {
-      raw = __ldg(reinterpret_cast<const uint4 *>(in_c + 2 * (v - H_IQ)));
-    }
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-      const long a = v + e - v0;
-      if (a >= 0 && a < tile_len) {
-        const uint32_t word = w[e >> 1] >> ((e & 1) * 16);
-        float fi = ((float)(word & 0xffu) - 127.5f) * kScale;
-        float fq = ((float)((word >> 8) & 0xffu) - 127.5f) * kScale;
-        if (v + e < v_first_valid) {
-          fi = 0.0f;
-          fq = 0.0f;
+  // Tile fill: the lanes of a warp take CONSECUTIVE samples (one 16-bit load each), so every
+  // 64-bit store of the converted pair is bank-conflict free and the index arithmetic is three
+  // adds per sample. (The earlier form converted the 8 samples of one 128-bit load per thread:
+  // lane stride 64 B = 8-way conflicts on the stores — ncu r01: 13.7 M of the 20.6 M store
+  // wavefronts were conflicts — and ~30 instructions per sample of bounds logic; the fill then
+  // cost as many issue slots as the FMA loop.) Samples older than `valid` are the zero window of a
+  // fresh firdecim; samples past the end of the input only feed outputs that are never stored.
+  {
+    // tile-relative bounds, so the loop itself is 32-bit: [a_lo, a_hi) holds real samples, elements
+    // below a_hist come from the history buffer
+    const int a_lo = (int)max(0L, min((long)tile_len, v_first_valid - v0));
+    const int a_hi = (int)max(0L, min((long)tile_len, n_in + H_IQ - v0));
+    const int a_hist = (int)max(0L, min((long)tile_len, (long)H_IQ - v0));
+    const unsigned short *p_hist = hist_c + v0;
+    const unsigned short *p_in = in_c + (v0 - H_IQ);
+    auto fill = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;  // whole tile inside the input row
+#pragma unroll 7
+      for (unsigned a = t; a < (unsigned)tile_len; a += DECIM_NT) {
+        uint32_t w = 0;
+        bool ok = true;
+        if (FAST) {
+          w = __ldg(p_in + a);
+        } else {
+          ok = ((int)a >= a_lo) && ((int)a < a_hi);
+          if (ok) {
+            w = __ldg((((int)a < a_hist) ? p_hist : p_in) + a);
+          }
         }
-        const int ai = (int)a;
-        xs[ai + ai / RM] = make_float2(fi, fq);
+        float2 f = iqBytesToFloat(w);
+        if (!FAST && !ok) {
+          f = make_float2(0.0f, 0.0f);
+        }
+        xs[a + a / RM] = f;
       }
+    };
+    if (a_lo == 0 && a_hist == 0 && a_hi == tile_len) {
+      fill(std::true_type{});
+    } else {
+      fill(std::false_type{});
     }
   }
   __syncthreads();
@@ -1775,9 +1815,13 @@ k_blocksync(const uint8_t *__restrict__ bits, uint32_t bits_cap, const uint32_t 
 
 // ---------------------------------------------------------------------------
 // RF level meter (signal_level.cpp:145-178): exact integer sums of the IQ bytes of every
-// logical block. 128-bit loads, per-thread uint32 partials, warp shuffle + one 64-bit atomic
-// per warp. HBM-bound: 2 B per IQ sample in, 48 B per block out.
-// ---------------------------------------------------------------------------
+// logical block. HBM-bound by design (2 B per IQ sample in, 48 B per block out), so the per-sample
+// instruction count is what has to stay small: 128-bit loads; the four sums through dp4a (two
+// samples per instruction: I0*m0 + Q0*m1 + I1*m2 + Q1*m3 with byte masks or the word itself as the
+// second operand); the two clip counters behind a branch-free any-byte test per word — a byte is
+// near clip (<= 8 or >= 247) iff (byte + 9) mod 256 < 18 — so the per-sample comparisons only run
+// for the rare words that hold such a byte (hard clip, <= 1 or >= 254, is a subset of near clip).
+// uint32 partials per thread (a thread sees a few hundred samples), one 64-bit atomic per warp.
 __global__ void __launch_bounds__(256)
 k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,
            long samples_per_block, int slices, int ch0) {
@@ -1788,10 +1832,8 @@ k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *s
   const long s0 = sl * per;
   const long s1 = min(samples_per_block, s0 + per);
   const uint8_t *base = iq + (size_t)c * iq_stride + 2 * (size_t)b * samples_per_block;
-  unsigned long long si = 0, sq = 0, sii = 0, sqq = 0;
+  uint32_t si = 0, sq = 0, sii = 0, sqq = 0;
   uint32_t hard = 0, nearc = 0, cnt = 0;
-  // 16-byte chunks (8 IQ pairs); block starts are 16-byte aligned when samples_per_block % 8 == 0
-  const long c0 = (s0 + 7) >> 3, c1 = s1 >> 3;
   auto one = [&](uint32_t vi, uint32_t vq) {
     si += vi;
     sq += vq;
@@ -1801,6 +1843,24 @@ k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *s
     nearc += (vi <= 8u || vi >= 247u || vq <= 8u || vq >= 247u) ? 1u : 0u;
     cnt++;
   };
+  auto word = [&](uint32_t w) {  // two samples: bytes I0, Q0, I1, Q1
+    si = __dp4a(w, 0x00010001u, si);
+    sq = __dp4a(w, 0x01000100u, sq);
+    sii = __dp4a(w, w & 0x00ff00ffu, sii);
+    sqq = __dp4a(w, w & 0xff00ff00u, sqq);
+    // byte + 9 (mod 256) in every lane of the word, then "any byte < 18"
+    const uint32_t t = ((w & 0x7f7f7f7fu) + 0x09090909u) ^ (w & 0x80808080u);
+    if ((t - 0x12121212u) & ~t & 0x80808080u) {
+      const uint32_t i0 = w & 0xffu, q0 = (w >> 8) & 0xffu, i1 = (w >> 16) & 0xffu, q1 = w >> 24;
+      hard += (i0 <= 1u || i0 >= 254u || q0 <= 1u || q0 >= 254u) ? 1u : 0u;
+      hard += (i1 <= 1u || i1 >= 254u || q1 <= 1u || q1 >= 254u) ? 1u : 0u;
+      nearc += (i0 <= 8u || i0 >= 247u || q0 <= 8u || q0 >= 247u) ? 1u : 0u;
+      nearc += (i1 <= 8u || i1 >= 247u || q1 <= 8u || q1 >= 247u) ? 1u : 0u;
+    }
+    cnt += 2;
+  };
+  // 16-byte chunks (8 IQ pairs); block starts are 16-byte aligned when samples_per_block % 8 == 0
+  const long c0 = (s0 + 7) >> 3, c1 = s1 >> 3;
   const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
   if (aligned && c1 > c0) {
     for (long s = s0 + threadIdx.x; s < (c0 << 3); s += blockDim.x) {  // head
@@ -1808,12 +1868,10 @@ k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *s
     }
     for (long ck = c0 + threadIdx.x; ck < c1; ck += blockDim.x) {       // 128-bit body
       const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(base + 16 * ck));
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        one(w[q] & 0xffu, (w[q] >> 8) & 0xffu);
-        one((w[q] >> 16) & 0xffu, w[q] >> 24);
-      }
+      word(raw.x);
+      word(raw.y);
+      word(raw.z);
+      word(raw.w);
     }
     for (long s = (c1 << 3) + threadIdx.x; s < s1; s += blockDim.x) {   // tail
       one(base[2 * s], base[2 * s + 1]);
@@ -1823,22 +1881,23 @@ k_siglevel(const uint8_t *__restrict__ iq, size_t iq_stride, fmgpu_level_sums *s
       one(base[2 * s], base[2 * s + 1]);
     }
   }
+  unsigned long long wi = si, wq = sq, wii = sii, wqq = sqq;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    si += __shfl_down_sync(0xffffffffu, si, o);
-    sq += __shfl_down_sync(0xffffffffu, sq, o);
-    sii += __shfl_down_sync(0xffffffffu, sii, o);
-    sqq += __shfl_down_sync(0xffffffffu, sqq, o);
+    wi += __shfl_down_sync(0xffffffffu, wi, o);
+    wq += __shfl_down_sync(0xffffffffu, wq, o);
+    wii += __shfl_down_sync(0xffffffffu, wii, o);
+    wqq += __shfl_down_sync(0xffffffffu, wqq, o);
     hard += __shfl_down_sync(0xffffffffu, hard, o);
     nearc += __shfl_down_sync(0xffffffffu, nearc, o);
     cnt += __shfl_down_sync(0xffffffffu, cnt, o);
   }
   if ((threadIdx.x & 31) == 0) {
     fmgpu_level_sums *o = &sums[(size_t)c * nblk + b];
-    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_i), si);
-    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_q), sq);
-    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_ii), sii);
-    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_qq), sqq);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_i), wi);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_q), wq);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_ii), wii);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_qq), wqq);
     atomicAdd(&o->hard_clip, hard);
     atomicAdd(&o->near_clip, nearc);
     atomicAdd(&o->n_samples, cnt);
@@ -2170,9 +2229,11 @@ void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit
 void launchSigLevel(const uint8_t *iq, size_t iq_stride, fmgpu_level_sums *sums, int nblk,
                     long samples_per_block, int ch0, int nch, cudaStream_t stream) {
   // enough CTAs to fill the machine even for few channels, ~16K samples per CTA at most
-  int slices = (int)std::min<long>(64, std::max<long>(1, samples_per_block / 16384));
-  dim3 grid(nblk * slices, nch);
-  k_siglevel<<<grid, 256, 0, stream>>>(iq, iq_stride, sums, nblk, samples_per_block, slices, ch0);
+  long slices = std::min<long>(64, std::max<long>(1, samples_per_block / 16384));
+  // the kernel's per-thread uint32 partials hold 255^2 * 32768 samples: never give a thread more
+  slices = std::max<long>(slices, (samples_per_block + 256L * 32768 - 1) / (256L * 32768));
+  dim3 grid((unsigned)(nblk * slices), nch);
+  k_siglevel<<<grid, 256, 0, stream>>>(iq, iq_stride, sums, nblk, samples_per_block, (int)slices, ch0);
 }
 
 void launchPackPcm16(const float *audio, size_t acap, const uint32_t *n_audio, float volume,
