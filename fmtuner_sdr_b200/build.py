@@ -41,6 +41,18 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Build build/libfmgpu_<name>.so with extra -D macros (measurement variants; load it through
+    the FMGPU_LIB environment variable)."""
+    out_dir = os.path.join(HERE, "..", "build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.abspath(os.path.join(out_dir, f"libfmgpu_{name}.so"))
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + srcs
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return out
+
+
 def build_dropin(force: bool = False) -> str:
     """C++ wrapper classes with the reference's names/signatures over the C ABI."""
     src = os.path.join(HERE, "dropin", "dropin.cpp")

@@ -165,11 +165,20 @@ __device__ __forceinline__ float2 iqBytesToFloat(uint32_t w) {
 #define FMGPU_LT 32
 #endif
 #ifndef FMGPU_ST
-#define FMGPU_ST 16
+#define FMGPU_ST 8
 #endif
 // samples per tile row of the lane kernels. The tiles of every lane kernel of a block sit in
 // shared memory for milliseconds while FIR CTAs of other blocks want the same SMs: small tiles
 // leave the shared memory to them.
+// Timing experiments only (tools/gpu_exp_bounds.sh; results are WRONG with either set): the lane
+// kernels walk 1/FMGPU_EXP_LANE_DIV of their samples, the FIR kernels 1/FMGPU_EXP_FIR_DIV of their
+// taps. They bound what the step could gain from faster lane kernels or faster FIR kernels.
+#ifndef FMGPU_EXP_LANE_DIV
+#define FMGPU_EXP_LANE_DIV 1
+#endif
+#ifndef FMGPU_EXP_FIR_DIV
+#define FMGPU_EXP_FIR_DIV 1
+#endif
 constexpr int LT = FMGPU_LT;
 constexpr int STEREO_ST = FMGPU_ST;
 
@@ -196,6 +205,28 @@ __device__ __forceinline__ void tileLoadAsync(float *tile, const float *base, si
     const int r = idx / cpr;
     const int q = idx - r * cpr;
     cpAsync16(tile + r * TP + 4 * q, base + (size_t)(c0 + r) * pitch + start + 4 * q);
+  }
+}
+
+__device__ __forceinline__ void cpAsync4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem)),
+               "l"(gmem)
+               : "memory");
+}
+
+// same tile, element by element (4-byte cp.async): for a global start that is not 16-byte aligned
+// (the delayed MPX of the stereo matrix), so that the tile still lands aligned in shared memory
+template <int TP, int LEN>
+__device__ __forceinline__ void tileLoadAsync4(float *tile, const float *base, size_t pitch, int c0,
+                                               int nrows, long start, int len, int lane) {
+  const int total = nrows * LEN;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / LEN;
+    const int q = idx - r * LEN;
+    if (q < len) {
+      cpAsync4(tile + r * TP + q, base + (size_t)(c0 + r) * pitch + start + q);
+    }
   }
 }
 
@@ -297,7 +328,6 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
   const unsigned short *in_c = reinterpret_cast<const unsigned short *>(iq + (size_t)c * iq_stride);
   const unsigned short *hist_c = reinterpret_cast<const unsigned short *>(hist) + (size_t)c * H_IQ;
   const long v_first_valid = H_IQ - hist_valid[c];
-  constexpr float kScale = 1.0f / 127.5f;
 
   // Tile fill: the lanes of a warp take CONSECUTIVE samples (one 16-bit load each), so every
   // 64-bit store of the converted pair is bank-conflict free and the index arithmetic is three
@@ -357,7 +387,7 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
       seg[u][r] = xs[tbase + u * M + r];  // u < 4: no skew word yet
     }
   }
-  for (int pp = 0; pp < Pp; pp += 4) {
+  for (int pp = 0; pp < Pp / FMGPU_EXP_FIR_DIV; pp += 4) {
 #pragma unroll
     for (int ps = 0; ps < 4; ps++) {
       const int u = pp + ps + 3;
@@ -382,6 +412,140 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
     const int n = n0 + R * t + j;
     if (n < n_out) {
       out[n] = make_float2(acc[j].x * scale, acc[j].y * scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1, eight outputs per thread. k_decim above is bound by shared-memory bandwidth: with 4 outputs
+// per thread one LDS.64 feeds 4 FFMA2, which needs the full 128 B/clk/SM at the full FMA rate (ncu
+// r01: LSU data pipe 81 %, FMA pipe 55 %). Holding 8 outputs' worth of sample segments in registers
+// (8 x M complex) does not fit. Instead the second set of four outputs runs FOUR TAP SEGMENTS
+// BEHIND the first: at step tau outputs 0..3 apply tap segment tau to sample segments tau..tau+3,
+// and outputs 4..7 apply tap segment tau-4 to segments (tau-4)+4.. = the SAME four segments. Every
+// segment read from shared memory now feeds 8 FFMA2 with the same 4-segment register ring, and each
+// output still sees its taps in ascending order (oldest sample first): bit-identical results.
+// ---------------------------------------------------------------------------
+#ifndef FMGPU_DECIM8_NT
+#define FMGPU_DECIM8_NT 64
+#endif
+constexpr int DECIM8_NT = FMGPU_DECIM8_NT;
+
+template <int M, bool PACK>
+__global__ void __launch_bounds__(DECIM8_NT)
+k_decim8(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
+         const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
+         int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
+  constexpr int R = 8;
+  constexpr int T = DECIM8_NT * R;
+  constexpr int RM = R * M;
+  extern __shared__ float2 xs[];
+  const int c = blockIdx.y + ch0;
+  const int n0 = blockIdx.x * T;
+  const int t = threadIdx.x;
+  const long o = (long)(n0 - Pp) * M + 1;  // stream index of tile element 0
+  const int tile_len = (T + Pp - 1) * M;
+  const long v0 = o + H_IQ;                // virtual index (history first)
+  const long n_in = (long)n_out * M;
+  const unsigned short *in_c = reinterpret_cast<const unsigned short *>(iq + (size_t)c * iq_stride);
+  const unsigned short *hist_c = reinterpret_cast<const unsigned short *>(hist) + (size_t)c * H_IQ;
+  const long v_first_valid = H_IQ - hist_valid[c];
+  {  // tile fill, as in k_decim (one skew element per RM samples: odd per-thread stride)
+    const int a_lo = (int)max(0L, min((long)tile_len, v_first_valid - v0));
+    const int a_hi = (int)max(0L, min((long)tile_len, n_in + H_IQ - v0));
+    const int a_hist = (int)max(0L, min((long)tile_len, (long)H_IQ - v0));
+    const unsigned short *p_hist = hist_c + v0;
+    const unsigned short *p_in = in_c + (v0 - H_IQ);
+    auto fill = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+#pragma unroll 6
+      for (unsigned a = t; a < (unsigned)tile_len; a += DECIM8_NT) {
+        uint32_t w = 0;
+        bool ok = true;
+        if (FAST) {
+          w = __ldg(p_in + a);
+        } else {
+          ok = ((int)a >= a_lo) && ((int)a < a_hi);
+          if (ok) {
+            w = __ldg((((int)a < a_hist) ? p_hist : p_in) + a);
+          }
+        }
+        float2 f = iqBytesToFloat(w);
+        if (!FAST && !ok) {
+          f = make_float2(0.0f, 0.0f);
+        }
+        xs[a + a / RM] = f;
+      }
+    };
+    if (a_lo == 0 && a_hist == 0 && a_hi == tile_len) {
+      fill(std::true_type{});
+    } else {
+      fill(std::false_type{});
+    }
+  }
+  __syncthreads();
+
+  float2 accA[4], accB[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    accA[j] = make_float2(0.0f, 0.0f);
+    accB[j] = make_float2(0.0f, 0.0f);
+  }
+  float2 seg[4][M];
+  const int tbase = t * (RM + 1);
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+      seg[u][r] = xs[tbase + u * M + r];  // u < 8: no skew element yet
+    }
+  }
+  // groups of four steps (ring slots are compile-time). Outputs 0..3 run tap segments 0..Pp-1 at
+  // steps 0..Pp-1, outputs 4..7 the same segments at steps 4..Pp+3; both branches are uniform.
+  const int PpE = Pp / FMGPU_EXP_FIR_DIV;
+  for (int tau0 = 0; tau0 <= PpE; tau0 += 4) {
+    const bool a_on = tau0 < PpE;
+    const bool b_on = tau0 >= 4;
+#pragma unroll
+    for (int ps = 0; ps < 4; ps++) {
+      const int u = tau0 + ps + 3;
+      const int sb = tbase + u * M + (u >> 3);
+#pragma unroll
+      for (int r = 0; r < M; r++) {
+        seg[(ps + 3) & 3][r] = xs[sb + r];
+      }
+      if (a_on) {
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+          const float h = taps.h[(tau0 + ps) * M + r];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            accA[j] = fma2<PACK>(h, seg[(j + ps) & 3][r], accA[j]);
+          }
+        }
+      }
+      if (b_on) {
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+          const float h = taps.h[(tau0 + ps - 4) * M + r];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            accB[j] = fma2<PACK>(h, seg[(j + ps) & 3][r], accB[j]);
+          }
+        }
+      }
+    }
+  }
+
+  float2 *out = x1 + (size_t)c * x1_pitch;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int n = n0 + R * t + j;
+    if (n < n_out) {
+      out[n] = make_float2(accA[j].x * scale, accA[j].y * scale);
+    }
+    if (n + 4 < n_out) {
+      out[n + 4] = make_float2(accB[j].x * scale, accB[j].y * scale);
     }
   }
 }
@@ -434,21 +598,24 @@ __global__ void k_convert_u8(const uint8_t *__restrict__ iq, size_t iq_stride,
 // S1: I/Q DC blockers (iirfilt dc_blocker, alpha = 0.0005) + clip statistics.
 // One lane per channel; fm_demod.cpp:150-208.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
 k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restrict__ iq_u8,
           size_t iq_stride, float2 *__restrict__ x2, size_t x2_pitch, DemodState *st,
           fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total, int ch0,
           int nch, float a1) {
-  // warp 0 moves tiles (global <-> shared), warp 1 runs the recursions: one lane per channel
+  n_total /= FMGPU_EXP_LANE_DIV;
+  // ONE warp per 32 channels, one lane per channel: the warp prefetches its next input tile
+  // (cp.async), runs the recursions on the current one and writes the finished tile back itself.
+  // (A separate mover warp doubles the registers and warp slots this kernel keeps from the FIR
+  // kernels for as long as it runs.)
   constexpr int TP = 2 * LT + 4;  // interleaved re,im; 16-byte aligned rows
   extern __shared__ float sm_dc[];
-  float *tin[2] = {sm_dc, sm_dc + 32 * TP};
-  float *tout[2] = {sm_dc + 2 * 32 * TP, sm_dc + 3 * 32 * TP};
-  const int lane = threadIdx.x & 31;
-  const bool io = threadIdx.x < 32;
+  auto tin = [&](int k2) { return sm_dc + (k2 & 1) * (32 * TP); };
+  float *tout = sm_dc + 2 * 32 * TP;
+  const int lane = threadIdx.x;
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
-  const bool active = !io && lane < nrows;
+  const bool active = lane < nrows;
   const int c = c0 + min(lane, nrows - 1);
   DemodState s{};
   if (active) {
@@ -460,31 +627,25 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
   const float *x1f = reinterpret_cast<const float *>(x1);
   float *x2f = reinterpret_cast<float *>(x2);
   const int nchunks = (n_total + LT - 1) / LT;
-  if (io && !iq_u8) {
-    tileLoadAsync<TP>(tin[0], x1f, 2 * x1_pitch, c0, nrows, 0, 2 * min(LT, n_total), lane);
+  if (!iq_u8 && nchunks > 0) {
+    tileLoadAsync<TP>(tin(0), x1f, 2 * x1_pitch, c0, nrows, 0, 2 * min(LT, n_total), lane);
     cpAsyncCommit();
-    cpAsyncWait<0>();
   }
-  __syncthreads();
   int b = 0, in_blk = 0, clip = 0;
   int cur_len = min(blk_len, n_total);
   for (int ck = 0; ck < nchunks; ck++) {
     const int n0 = ck * LT;
     const int len = min(LT, n_total - n0);
-    if (io) {
-      if (!iq_u8 && ck + 1 < nchunks) {
-        tileLoadAsync<TP>(tin[(ck + 1) & 1], x1f, 2 * x1_pitch, c0, nrows, 2L * (n0 + LT),
-                          2 * min(LT, n_total - n0 - LT), lane);
-        cpAsyncCommit();
-      }
-      if (ck > 0) {
-        tileStore<TP>(tout[(ck - 1) & 1], x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0 - LT),
-                      2 * LT, lane);
-      }
-      cpAsyncWait<0>();
-    } else if (active) {
-      const float *ti = tin[ck & 1] + lane * TP;
-      float *to = tout[ck & 1] + lane * TP;
+    cpAsyncWait<0>();  // tile ck has landed ...
+    __syncwarp();      // ... for every lane; every lane is done with tile ck - 1 and its output
+    if (!iq_u8 && ck + 1 < nchunks) {
+      tileLoadAsync<TP>(tin(ck + 1), x1f, 2 * x1_pitch, c0, nrows, 2L * (n0 + LT),
+                        2 * min(LT, n_total - n0 - LT), lane);
+      cpAsyncCommit();
+    }
+    if (active) {
+      const float *ti = tin(ck) + lane * TP;
+      float *to = tout + lane * TP;
       int i = 0;
       while (i < len) {
         const int run = min(len - i, cur_len - in_blk);
@@ -504,19 +665,32 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
             vq = v0q;
           }
         } else {
-#pragma unroll 4
-          for (int j = 0; j < run; j++, i++) {
-            const float ir = ti[2 * i];
-            const float qr = ti[2 * i + 1];
+          auto sample = [&](float ir, float qr, float &o_i, float &o_q) {
             if (fabsf(ir) >= 0.995f || fabsf(qr) >= 0.995f) {
               clip++;
             }
             const float v0i = ir - (a1 * vi);
-            to[2 * i] = v0i - vi;
+            o_i = v0i - vi;
             vi = v0i;
             const float v0q = qr - (a1 * vq);
-            to[2 * i + 1] = v0q - vq;
+            o_q = v0q - vq;
             vq = v0q;
+          };
+          int j = 0;
+          if ((i & 1) == 0) {
+            // two complex samples per 128-bit shared-memory access (conflict-free; the 32-bit
+            // form hits 8 banks)
+#pragma unroll 2
+            for (; j + 2 <= run; j += 2, i += 2) {
+              const float4 v = *reinterpret_cast<const float4 *>(ti + 2 * i);
+              float4 o;
+              sample(v.x, v.y, o.x, o.y);
+              sample(v.z, v.w, o.z, o.w);
+              *reinterpret_cast<float4 *>(to + 2 * i) = o;
+            }
+          }
+          for (; j < run; j++, i++) {
+            sample(ti[2 * i], ti[2 * i + 1], to[2 * i], to[2 * i + 1]);
           }
         }
         in_blk += run;
@@ -533,12 +707,8 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
         }
       }
     }
-    __syncthreads();
-  }
-  if (io) {
-    const int n0 = (nchunks - 1) * LT;
-    tileStore<TP>(tout[(nchunks - 1) & 1], x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0),
-                  2 * (n_total - n0), lane);
+    __syncwarp();  // the output tile is complete: write it back, 128 contiguous bytes per row
+    tileStore<TP>(tout, x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0), 2 * len, lane);
   }
   if (active) {
     // only this stage's fields: the AGC stage of the previous block may be running beside it
@@ -587,7 +757,7 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
     const int a = t * R + j;
     win[j] = xs[a + (a >> 3)];
   }
-  for (int i = 0; i < Lp; i += R) {
+  for (int i = 0; i < Lp / FMGPU_EXP_FIR_DIV; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
       const float h = hs[i + u];
@@ -610,62 +780,51 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
 }
 
 // S2: pre-discriminator AGC (agc_crcf; fm_demod.cpp:170-172,196-198), in place, lanes with AGC on
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
 k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total, int ch0,
       int nch) {
-  // warp 0 moves tiles, warp 1 runs the AGC recursion in place on the tile (3 rotating tiles:
-  // one loading, one computing, one storing)
+  n_total /= FMGPU_EXP_LANE_DIV;
+  // ONE warp per 32 channels (see k_dcblock): prefetch the next tile, run the AGC recursion in
+  // place on the current one, write it back. Two tiles.
   constexpr int TP = 2 * LT + 4;
   extern __shared__ float sm_agc[];
-  float *tb[3] = {sm_agc, sm_agc + 32 * TP, sm_agc + 2 * 32 * TP};
-  __shared__ int any_agc;
-  const int lane = threadIdx.x & 31;
-  const bool io = threadIdx.x < 32;
+  auto tb = [&](int k2) { return sm_agc + (k2 & 1) * (32 * TP); };
+  const int lane = threadIdx.x;
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
   const int c = c0 + min(lane, nrows - 1);
   const bool has_agc = lane < nrows && cp[c].agc_mode != 0;
-  if (io) {
-    const unsigned m = __ballot_sync(0xffffffffu, has_agc);
-    if (lane == 0) {
-      any_agc = (m != 0u) ? 1 : 0;
-    }
-  }
-  __syncthreads();
-  if (!any_agc) {
+  if (__ballot_sync(0xffffffffu, has_agc) == 0u) {
     return;  // no channel of this block runs an AGC
   }
-  const bool active = !io && has_agc;
+  const bool active = has_agc;
   const float alpha = active ? cp[c].agc_alpha : 0.0f;
-  float g = active ? st[c].agc_g : 1.0f;
-  float y2 = active ? st[c].agc_y2 : 1.0f;
+  float g = 1.0f, y2 = 1.0f;
+  if (active) {
+    g = st[c].agc_g;
+    y2 = st[c].agc_y2;
+  }
   float *yf = reinterpret_cast<float *>(ybuf);
   const int nchunks = (n_total + LT - 1) / LT;
-  if (io) {
-    tileLoadAsync<TP>(tb[0], yf, 2 * y_pitch, c0, nrows, 2 * Y_OFF, 2 * min(LT, n_total), lane);
+  if (nchunks > 0) {
+    tileLoadAsync<TP>(tb(0), yf, 2 * y_pitch, c0, nrows, 2L * Y_OFF, 2 * min(LT, n_total), lane);
     cpAsyncCommit();
-    cpAsyncWait<0>();
   }
-  __syncthreads();
   for (int ck = 0; ck < nchunks; ck++) {
     const int n0 = ck * LT;
     const int len = min(LT, n_total - n0);
-    if (io) {
-      if (ck + 1 < nchunks) {
-        tileLoadAsync<TP>(tb[(ck + 1) % 3], yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 + LT),
-                          2 * min(LT, n_total - n0 - LT), lane);
-        cpAsyncCommit();
-      }
-      if (ck > 0) {
-        tileStore<TP>(tb[(ck - 1) % 3], yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 - LT), 2 * LT,
-                      lane);
-      }
-      cpAsyncWait<0>();
-    } else if (active) {
-      float *t = tb[ck % 3] + lane * TP;
-      for (int i = 0; i < len; i++) {
-        const float ox = t[2 * i] * g;
-        const float oy = t[2 * i + 1] * g;
+    cpAsyncWait<0>();
+    __syncwarp();  // tile ck visible to every lane; tile ck - 1 has been written back by every lane
+    if (ck + 1 < nchunks) {
+      tileLoadAsync<TP>(tb(ck + 1), yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 + LT),
+                        2 * min(LT, n_total - n0 - LT), lane);
+      cpAsyncCommit();
+    }
+    if (active) {
+      float *t = tb(ck) + lane * TP;
+      auto sample = [&](float &x, float &y) {
+        const float ox = x * g;
+        const float oy = y * g;
         const float e = (ox * ox) + (oy * oy);
         y2 = ((1.0f - alpha) * y2) + (alpha * e);
         if (y2 > 1e-6f) {
@@ -674,17 +833,23 @@ k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_
         if (g > 1e6f) {
           g = 1e6f;
         }
-        t[2 * i] = ox;
-        t[2 * i + 1] = oy;
+        x = ox;
+        y = oy;
+      };
+      int i = 0;
+      for (; i + 2 <= len; i += 2) {  // two complex samples per 128-bit access (conflict-free)
+        float4 v = *reinterpret_cast<float4 *>(t + 2 * i);
+        sample(v.x, v.y);
+        sample(v.z, v.w);
+        *reinterpret_cast<float4 *>(t + 2 * i) = v;
+      }
+      for (; i < len; i++) {
+        sample(t[2 * i], t[2 * i + 1]);
       }
     }
-    __syncthreads();
-  }
-  if (io) {
-    const int n0 = (nchunks - 1) * LT;
+    __syncwarp();
     // rows without an AGC are written back unchanged
-    tileStore<TP>(tb[(nchunks - 1) % 3], yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0),
-                  2 * (n_total - n0), lane);
+    tileStore<TP>(tb(ck), yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0), 2 * len, lane);
   }
   if (active) {
     st[c].agc_g = g;
@@ -792,39 +957,55 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
 // ---------------------------------------------------------------------------
 // S4: 19 kHz pilot PLL, quality metrics, blend, L-R matrix, per-block lock logic
 // (stereo_decoder.cpp:92-286). One lane per channel, the per-sample work split over a
-// three-warp software pipeline (each warp owns an SM sub-partition, so the stages run
-// concurrently, one tile apart):
-//   warp 0  tile mover   global <-> shared (cp.async in, 128-bit stores out)
-//   warp 1  PLL          pilot -> phase error -> NCO update -> sin/cos of the new phase
-//                        (the only truly serial chain: ~60 dependent instructions per sample)
-//   warp 2  everything fed by it: envelopes, coherent pilot I/Q, blend target and recursion,
-//           L-R matrix, and the per-block stereo-lock logic
+// four-warp software pipeline, one tile of STEREO_ST samples apart (each warp on its own SM
+// sub-partition):
+//   warp 0     tile mover  global <-> shared (cp.async in, 128-bit stores out), and behind its
+//              copies the blend recursion and the L-R matrix
+//   warp 1     PLL + envelopes: pilot -> phase error -> NCO update -> sin/cos of the new phase is
+//              the one truly serial chain (~264 cycles per sample on B200, tools/microbench/
+//              lat_bench.cu); the four one-pole envelopes and the per-block stereo-lock logic ride
+//              in its idle issue slots
+//   warps 2,3  blend target from the envelopes (up to six IEEE divisions and two square roots per
+//              sample, but element-wise): each takes half of the tile's samples
+// Round 1 ran everything behind the PLL in ONE warp; with weak signals (no clean-pilot shortcut)
+// that warp, not the PLL chain, set the pace: 720-830 cycles per sample.
 // Arithmetic and its order are exactly those of the single-lane loop (and of the CPU oracle).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(96)
+constexpr int STEREO_TILES = 23;
+constexpr int STEREO_THREADS = 128;
+#ifndef FMGPU_STEREO_MINB
+#define FMGPU_STEREO_MINB 8  // 64 registers per thread
+#endif
+
+__global__ void __launch_bounds__(STEREO_THREADS, FMGPU_STEREO_MINB)
 k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ pilot,
          size_t pilot_pitch, float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
          StereoState *st, const ChanParams *cp, fmgpu_block_status *status, int status_pitch,
          int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
+  n_total /= FMGPU_EXP_LANE_DIV;
   constexpr int ST = STEREO_ST;  // samples per tile row
   // 16-byte aligned rows; the delayed-MPX tile needs up to 3 extra samples + alignment. With
   // ST = 16 the pitch of 20 floats spreads the 32 lanes over 8 banks (a pitch of 24 only over 4).
   constexpr int TP = ST + 4;
   constexpr int TS = 32 * TP;  // floats per tile
   extern __shared__ float sm_st[];
-  float *t_pil = sm_st;             // ring of 3: chunk j in slot j % 3
-  float *t_mpx = t_pil + 3 * TS;    // ring of 2
-  float *t_dly = t_mpx + 2 * TS;    // ring of 2
-  float *t_sin = t_dly + 2 * TS;    // ring of 2: sin / cos of the phase AFTER each sample
-  float *t_cos = t_sin + 2 * TS;
-  float *t_frq = t_cos + 2 * TS;    // ring of 2: clamped phase increment (m_pllFreq)
-  float *t_l = t_frq + 2 * TS;      // ring of 2
-  float *t_r = t_l + 2 * TS;
+  // chunk j of a ring of n sits in slot j % n
+  float *t_pil = sm_st;             // 2: mover -> PLL
+  float *t_mpx = t_pil + 2 * TS;    // 2: mover -> PLL (envelope of |mpx|)
+  float *t_dly = t_mpx + 2 * TS;    // 2: mover -> matrix (delayed MPX)
+  float *t_c2 = t_dly + 2 * TS;     // 3: PLL -> matrix, cos(2 * phase after the sample)
+  float *t_frq = t_c2 + 3 * TS;     // 2: PLL -> target, clamped phase increment (m_pllFreq)
+  float *t_pbm = t_frq + 2 * TS;    // 2: PLL -> target, pilot-band envelope
+  float *t_mm = t_pbm + 2 * TS;     // 2: PLL -> target, MPX envelope
+  float *t_s2 = t_mm + 2 * TS;      // 2: PLL -> target, |coherent pilot|^2, or -1 while mono
+  float *t_tgt = t_s2 + 2 * TS;     // 2: target -> matrix
+  float *t_l = t_tgt + 2 * TS;      // 2: matrix -> mover
+  float *t_r = t_l + 2 * TS;        // 2
   const int lane = threadIdx.x & 31;
-  const int role = threadIdx.x >> 5;  // 0 mover, 1 PLL, 2 metrics + matrix
+  const int role = threadIdx.x >> 5;  // 0 mover + blend + matrix, 1 PLL + envelopes, 2/3 target
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
-  const bool active = role != 0 && lane < nrows;
+  const bool active = lane < nrows;
   const int c = c0 + min(lane, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   constexpr float kMatrixScale = 0.5f;
@@ -845,7 +1026,7 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   const float cohDen = fmaxf(kPilotCoherenceAcquire - kPilotCoherenceHold, 1e-4f);
   const float pllDen = fmaxf(kPllLockHoldHz - kPllLockAcquireHz, 1e-3f);
 
-  // both compute warps start from the NCO phase carried in the state
+  // PLL warp: the NCO phase carried in the state, and the envelopes
   uint32_t theta = s.theta, dtheta = s.dtheta;
   float phaseNow = ncoPhaseDev(theta);
   float vcoQ, vcoI;
@@ -854,11 +1035,10 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   float pllFreq = s.pll_freq;
 
   const int nchunks = (n_total + ST - 1) / ST;
-  const int delay4 = (k.delay + 3) & ~3;  // aligned start of the delayed-MPX tile
-  const int dskew = delay4 - k.delay;
   auto clen = [&](int ck) { return min(ST, n_total - ck * ST); };
-  if (role == 0) {
+  if (role == 0 && nchunks > 0) {
     tileLoadAsync<TP>(t_pil, pilot, pilot_pitch, c0, nrows, 0, clen(0), lane);
+    tileLoadAsync<TP>(t_mpx, mpx, mpx_pitch, c0, nrows, H_MPX, clen(0), lane);
     cpAsyncCommit();
     cpAsyncWait<0>();
   }
@@ -867,37 +1047,85 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   int cur_len = min(blk_len, n_total);
   bool stereoDetected = s.stereo != 0;
 
-  // step kk: PLL on chunk kk, metrics/matrix on chunk kk-1, mover loads pilot[kk+1], mpx[kk],
-  // delayed mpx[kk] and stores L/R of chunk kk-2
-  for (int kk = 0; kk <= nchunks; kk++) {
+  // step kk: PLL + envelopes on chunk kk, target on chunk kk-1, blend + matrix on chunk kk-2; the
+  // mover loads pilot[kk+1], mpx[kk+1], delayed mpx[kk-1] and stores L/R of chunk kk-3
+  for (int kk = 0; kk <= nchunks + 2; kk++) {
     if (role == 0) {
       if (kk + 1 < nchunks) {
-        tileLoadAsync<TP>(t_pil + ((kk + 1) % 3) * TS, pilot, pilot_pitch, c0, nrows,
+        tileLoadAsync<TP>(t_pil + ((kk + 1) & 1) * TS, pilot, pilot_pitch, c0, nrows,
                           (long)(kk + 1) * ST, clen(kk + 1), lane);
+        tileLoadAsync<TP>(t_mpx + ((kk + 1) & 1) * TS, mpx, mpx_pitch, c0, nrows,
+                          H_MPX + (long)(kk + 1) * ST, clen(kk + 1), lane);
       }
-      if (kk < nchunks) {
-        tileLoadAsync<TP>(t_mpx + (kk & 1) * TS, mpx, mpx_pitch, c0, nrows, H_MPX + (long)kk * ST,
-                          clen(kk), lane);
-        tileLoadAsync<TP>(t_dly + (kk & 1) * TS, mpx, mpx_pitch, c0, nrows,
-                          H_MPX + (long)kk * ST - delay4, clen(kk) + 4, lane);
+      if (kk >= 1 && kk - 1 < nchunks) {
+        const int j = kk - 1;
+        tileLoadAsync4<TP, ST>(t_dly + (j & 1) * TS, mpx, mpx_pitch, c0, nrows,
+                               H_MPX + (long)j * ST - k.delay, clen(j), lane);
       }
       cpAsyncCommit();
-      if (kk >= 2) {
-        const int j = kk - 2;
+      if (kk >= 3) {
+        const int j = kk - 3;
         tileStore<TP>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
         tileStore<TP>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+      }
+      // ... and, while its copies are in flight, the blend recursion and the L-R matrix
+      if (active && kk >= 2 && kk - 2 < nchunks) {
+        const int j = kk - 2;
+        const int len = clen(j);
+        const int ro = (j & 1) * TS + lane * TP;
+        const float *td = t_dly + ro;
+        const float *tc2 = t_c2 + (j % 3) * TS + lane * TP;
+        const float *tt = t_tgt + ro;
+        float *tl = t_l + ro;
+        float *tr = t_r + ro;
+        auto matrix = [&](float dm, float cos2, float target, float &o_l, float &o_r) {
+          const float monoNorm = dm * kMatrixScale;
+          const float lr = 2.0f * dm * cos2;
+          const float stereoLeft = (dm + lr) * kMatrixScale;
+          const float stereoRight = (dm - lr) * kMatrixScale;
+          const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
+          blend += (target - blend) * blendAlpha;
+          o_l = monoNorm + ((stereoLeft - monoNorm) * blend);
+          o_r = monoNorm + ((stereoRight - monoNorm) * blend);
+        };
+        int i = 0;
+        for (; i + 4 <= len; i += 4) {
+          const float4 dv = *reinterpret_cast<const float4 *>(td + i);
+          const float4 cv = *reinterpret_cast<const float4 *>(tc2 + i);
+          const float4 tv = *reinterpret_cast<const float4 *>(tt + i);
+          float4 lv, rv;
+          matrix(dv.x, cv.x, tv.x, lv.x, rv.x);
+          matrix(dv.y, cv.y, tv.y, lv.y, rv.y);
+          matrix(dv.z, cv.z, tv.z, lv.z, rv.z);
+          matrix(dv.w, cv.w, tv.w, lv.w, rv.w);
+          *reinterpret_cast<float4 *>(tl + i) = lv;
+          *reinterpret_cast<float4 *>(tr + i) = rv;
+        }
+        for (; i < len; i++) {
+          matrix(td[i], tc2[i], tt[i], tl[i], tr[i]);
+        }
       }
       cpAsyncWait<0>();
     } else if (role == 1) {
       if (active && kk < nchunks) {
         const int len = clen(kk);
-        const float *tp = t_pil + (kk % 3) * TS + lane * TP;
-        float *ts = t_sin + (kk & 1) * TS + lane * TP;
-        float *tc = t_cos + (kk & 1) * TS + lane * TP;
-        float *tf = t_frq + (kk & 1) * TS + lane * TP;
-#pragma unroll 2
-        for (int i = 0; i < len; i++) {
-          const float error = tp[i] * vcoQ;
+        const int ro = (kk & 1) * TS + lane * TP;
+        const float *tp = t_pil + ro;
+        const float *tm = t_mpx + ro;
+        float *tc2 = t_c2 + (kk % 3) * TS + lane * TP;
+        float *tf = t_frq + ro;
+        float *tpb = t_pbm + ro;
+        float *tmm = t_mm + ro;
+        float *ts2 = t_s2 + ro;
+        // one sample: envelopes with the VCO phase BEFORE this sample's update
+        // (stereo_decoder.cpp:176-186), then the PLL step
+        auto sample = [&](float pil, float x, float &o_frq, float &o_pbm, float &o_mm, float &o_s2,
+                          float &o_c2) {
+          pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
+          mm = (mm * kSmooth) + (fabsf(x) * kInject);
+          pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
+          pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
+          const float error = pil * vcoQ;
           dtheta += ncoConstrainDev(error * k.pll_alpha);
           theta += ncoConstrainDev(error * k.pll_beta);
           theta += dtheta;
@@ -908,96 +1136,42 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
           } else if (dphi < -kPi) {
             dphi += 2.0f * kPi;
           }
-          tf[i] = fm_clampf(dphi, k.pll_min, k.pll_max);
+          pllFreq = fm_clampf(dphi, k.pll_min, k.pll_max);
           float sn, cs;
           fm_sincosf(phaseNext, &sn, &cs);
-          ts[i] = sn;
-          tc[i] = cs;
+          o_frq = pllFreq;
+          o_pbm = pbm;
+          o_mm = mm;
+          o_s2 = stereoDetected ? ((pilotI * pilotI) + (pilotQ * pilotQ)) : -1.0f;
+          o_c2 = (cs * cs) - (sn * sn);
           phaseNow = phaseNext;
           vcoQ = sn;
-        }
-      }
-    } else {
-      if (active && kk >= 1) {
-        const int j = kk - 1;
-        const int len = clen(j);
-        const float *tm = t_mpx + (j & 1) * TS + lane * TP;
-        const float *tp = t_pil + (j % 3) * TS + lane * TP;
-        const float *td = t_dly + (j & 1) * TS + lane * TP + dskew;
-        const float *ts = t_sin + (j & 1) * TS + lane * TP;
-        const float *tc = t_cos + (j & 1) * TS + lane * TP;
-        const float *tf = t_frq + (j & 1) * TS + lane * TP;
-        float *tl = t_l + (j & 1) * TS + lane * TP;
-        float *tr = t_r + (j & 1) * TS + lane * TP;
+          vcoI = cs;
+        };
         int i = 0;
         while (i < len) {
           const int run = min(len - i, cur_len - in_blk);
-#pragma unroll 2
-          for (int q = 0; q < run; q++, i++) {
-            const float x = tm[i];
-            const float pil = tp[i];
-            const float dm = td[i];
-            const float pllIm = ts[i];
-            const float pllRe = tc[i];
-            pllFreq = tf[i];
-            pbm = (pbm * kSmooth) + (fabsf(pil) * kInject);
-            mm = (mm * kSmooth) + (fabsf(x) * kInject);
-            pilotI = (pilotI * kSmooth) + ((pil * vcoI) * kInject);
-            pilotQ = (pilotQ * kSmooth) + ((pil * vcoQ) * kInject);
-
-            float target = 0.0f;
-            if (p.force_mono) {
-              target = 0.0f;
-            } else if (p.force_stereo) {
-              target = 1.0f;
-            } else if (stereoDetected) {
-              const float mx = fmaxf(mm, 1e-3f);
-              const float pm = fmaxf(pbm, 1e-4f);
-              const float s2 = (pilotI * pilotI) + (pilotQ * pilotQ);
-              const float dfs = fabsf(pllFreq - k.nominal_pll) * k.fsf;
-              const float tB = 0.1803f * pm;
-              if (pbm >= 0.0402f * mx && s2 >= tB * tB && dfs <= 1130.0f) {
-                // Clean pilot: with ratio >= 0.0402, coherence >= 0.1803 and |f error| <= 179.9 Hz
-                // each of the three quality terms below clamps to exactly 1 (margins >= 1e-4
-                // against rounding errors of ~1e-7) and no gate trips, so target == 1.0f in every
-                // blend mode. Skipping the six IEEE divisions and the square root changes nothing.
-                target = 1.0f;
-              } else {
-            const float pilotMagNow = FM_SQRT(s2);
-            const float pilotRatio = pbm / mx;
-            const float pilotCoherence = pilotMagNow / pm;
-            const float pllErrHz = dfs / (2.0f * kPi);
-            const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
-            const float cohQ =
-                fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
-            const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
-            const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
-            float shaped = quality * quality;
-            if (mode == 0) {
-              shaped = FM_SQRT(fmaxf(0.0f, quality));
-            } else if (mode == 2) {
-              shaped = quality * quality * quality;
-            }
-            if (pilotRatio < (kPilotRatioHold * gate) ||
-                pilotCoherence < (kPilotCoherenceHold * gate) || pllErrHz > (kPllLockHoldHz * 1.10f)) {
-              target = 0.0f;
-            } else {
-              target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
+          int q = 0;
+          if ((i & 3) == 0) {
+            // four samples per 128-bit shared-memory access: a lane's row is 16-byte aligned, so a
+            // warp's access is conflict-free (the 32-bit form hits 8 banks: 4-way conflicts)
+            for (; q + 4 <= run; q += 4, i += 4) {
+              const float4 pv = *reinterpret_cast<const float4 *>(tp + i);
+              const float4 xv = *reinterpret_cast<const float4 *>(tm + i);
+              float4 of, ob, om, os, oc;
+              sample(pv.x, xv.x, of.x, ob.x, om.x, os.x, oc.x);
+              sample(pv.y, xv.y, of.y, ob.y, om.y, os.y, oc.y);
+              sample(pv.z, xv.z, of.z, ob.z, om.z, os.z, oc.z);
+              sample(pv.w, xv.w, of.w, ob.w, om.w, os.w, oc.w);
+              *reinterpret_cast<float4 *>(tf + i) = of;
+              *reinterpret_cast<float4 *>(tpb + i) = ob;
+              *reinterpret_cast<float4 *>(tmm + i) = om;
+              *reinterpret_cast<float4 *>(ts2 + i) = os;
+              *reinterpret_cast<float4 *>(tc2 + i) = oc;
             }
           }
-            }
-
-            const float monoNorm = dm * kMatrixScale;
-            const float cos2 = (pllRe * pllRe) - (pllIm * pllIm);
-            const float lr = 2.0f * dm * cos2;
-            const float stereoLeft = (dm + lr) * kMatrixScale;
-            const float stereoRight = (dm - lr) * kMatrixScale;
-            const float blendAlpha = (target > blend) ? blendAttack : blendRelease;
-            blend += (target - blend) * blendAlpha;
-            tl[i] = monoNorm + ((stereoLeft - monoNorm) * blend);
-            tr[i] = monoNorm + ((stereoRight - monoNorm) * blend);
-            vcoQ = pllIm;
-            vcoI = pllRe;
+          for (; q < run; q++, i++) {  // ragged ends (a logical block ending inside the tile)
+            sample(tp[i], tm[i], tf[i], tpb[i], tmm[i], ts2[i], tc2[i]);
           }
           in_blk += run;
           if (in_blk == cur_len) {
@@ -1047,29 +1221,97 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
           }
         }
       }
+    } else if (role == 2 || role == 3) {
+      if (active && kk >= 1 && kk - 1 < nchunks) {
+        const int j = kk - 1;
+        const int len = clen(j);
+        // each target warp takes half of the tile, in groups of four samples (128-bit accesses;
+        // elements past len are padding: computed, never used)
+        const int half = (((len + 1) >> 1) + 3) & ~3;
+        const int i0 = (role == 2) ? 0 : half;
+        const int i1 = (role == 2) ? min(half, len) : len;
+        const int ro = (j & 1) * TS + lane * TP;
+        const float *tf = t_frq + ro;
+        const float *tpb = t_pbm + ro;
+        const float *tmm = t_mm + ro;
+        const float *ts2 = t_s2 + ro;
+        float *tt = t_tgt + ro;
+        auto targetOf = [&](float s2, float ebm, float emm, float frq) -> float {
+          float target = 0.0f;
+          if (p.force_mono) {
+            target = 0.0f;
+          } else if (p.force_stereo) {
+            target = 1.0f;
+          } else if (!(s2 < 0.0f)) {  // stereo detected (the PLL warp stores -1 while mono)
+            const float mx = fmaxf(emm, 1e-3f);
+            const float pm = fmaxf(ebm, 1e-4f);
+            const float dfs = fabsf(frq - k.nominal_pll) * k.fsf;
+            const float tB = 0.1803f * pm;
+            if (ebm >= 0.0402f * mx && s2 >= tB * tB && dfs <= 1130.0f) {
+              // Clean pilot: with ratio >= 0.0402, coherence >= 0.1803 and |f error| <= 179.9 Hz
+              // each of the three quality terms below clamps to exactly 1 (margins >= 1e-4
+              // against rounding errors of ~1e-7) and no gate trips, so target == 1.0f in every
+              // blend mode. Skipping the six IEEE divisions and the square root changes nothing.
+              target = 1.0f;
+            } else {
+              const float pilotMagNow = FM_SQRT(s2);
+              const float pilotRatio = ebm / mx;
+              const float pilotCoherence = pilotMagNow / pm;
+              const float pllErrHz = dfs / (2.0f * kPi);
+              const float ratioQ = fm_clampf((pilotRatio - kPilotRatioHold) / ratioDen, 0.0f, 1.0f);
+              const float cohQ =
+                  fm_clampf((pilotCoherence - kPilotCoherenceHold) / cohDen, 0.0f, 1.0f);
+              const float pllQ = fm_clampf((kPllLockHoldHz - pllErrHz) / pllDen, 0.0f, 1.0f);
+              const float quality = fminf(ratioQ, fminf(cohQ, pllQ));
+              float shaped = quality * quality;
+              if (mode == 0) {
+                shaped = FM_SQRT(fmaxf(0.0f, quality));
+              } else if (mode == 2) {
+                shaped = quality * quality * quality;
+              }
+              if (pilotRatio < (kPilotRatioHold * gate) ||
+                  pilotCoherence < (kPilotCoherenceHold * gate) ||
+                  pllErrHz > (kPllLockHoldHz * 1.10f)) {
+                target = 0.0f;
+              } else {
+                target = fm_clampf(0.0f + ((1.0f - 0.0f) * shaped), 0.0f, 1.0f);
+              }
+            }
+          }
+          return target;
+        };
+        for (int i = i0; i < i1; i += 4) {
+          const float4 sv = *reinterpret_cast<const float4 *>(ts2 + i);
+          const float4 bv = *reinterpret_cast<const float4 *>(tpb + i);
+          const float4 mv = *reinterpret_cast<const float4 *>(tmm + i);
+          const float4 fv = *reinterpret_cast<const float4 *>(tf + i);
+          float4 tv;
+          tv.x = targetOf(sv.x, bv.x, mv.x, fv.x);
+          tv.y = targetOf(sv.y, bv.y, mv.y, fv.y);
+          tv.z = targetOf(sv.z, bv.z, mv.z, fv.z);
+          tv.w = targetOf(sv.w, bv.w, mv.w, fv.w);
+          *reinterpret_cast<float4 *>(tt + i) = tv;
+        }
+      }
     }
     __syncthreads();
   }
-  if (role == 0) {
-    const int j = nchunks - 1;
-    tileStore<TP>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
-    tileStore<TP>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
-  } else if (active && role == 1) {
-    st[c].theta = theta;
-    st[c].dtheta = dtheta;
-  } else if (active) {
+  if (active && role == 1) {
     StereoState *o = &st[c];
+    o->theta = theta;
+    o->dtheta = dtheta;
     o->pbm = pbm;
     o->mm = mm;
     o->pilot_i = pilotI;
     o->pilot_q = pilotQ;
-    o->blend = blend;
     o->pll_freq = pllFreq;
     o->pilot_mag = s.pilot_mag;
     o->stereo = s.stereo;
     o->pilot_count = s.pilot_count;
     o->loss_count = s.loss_count;
     o->pilot_tenths = s.pilot_tenths;
+  } else if (active && role == 0) {
+    st[c].blend = blend;
   }
 }
 
@@ -1463,8 +1705,12 @@ k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__r
   r171[(size_t)c * r_pitch + k] = smp;
 }
 
-// S7b: the serial part, one lane per channel, fed by the 171 kHz stream of k_rds_resample.
-__global__ void __launch_bounds__(64)
+// S7b: the serial part, one lane per channel, fed by the 171 kHz stream of k_rds_resample. ONE warp
+// per 32 channels: it prefetches its own next tile (cp.async) before walking the current one. A
+// separate mover warp would hold this kernel's 160+ registers per thread a second time for the
+// whole kernel, and what the lane kernels cost the step is the registers and shared memory they
+// keep from the FIR kernels running beside them, not their issue slots.
+__global__ void __launch_bounds__(32)
 k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring,
       const float *__restrict__ g_lpf, const float *__restrict__ g_mf,
       const float *__restrict__ g_dmf, uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end,
@@ -1475,13 +1721,11 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
   __shared__ float2 s_wmf[SS_LEN][32];
   __shared__ float2 s_wdmf[SS_LEN][32];
   __shared__ uint32_t s_nmax;
-  // warp 0 streams 171 kHz tiles into shared memory, warp 1 runs the demodulator (lane = channel)
-  const int tl = threadIdx.x & 31;
-  const bool io = threadIdx.x < 32;
-  for (int i = threadIdx.x; i < RDS_LPF_LEN; i += 64) {
+  const int tl = threadIdx.x;
+  for (int i = threadIdx.x; i < RDS_LPF_LEN; i += 32) {
     s_lpf[i] = g_lpf[i];
   }
-  for (int i = threadIdx.x; i < 32 * SS_LEN; i += 64) {
+  for (int i = threadIdx.x; i < 32 * SS_LEN; i += 32) {
     s_mf[i] = g_mf[i];
     s_dmf[i] = g_dmf[i];
   }
@@ -1490,7 +1734,7 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
   float *t_in[2] = {sm_rds, sm_rds + 32 * TPR};
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
-  const bool active = !io && tl < nrows;
+  const bool active = tl < nrows;
   const int c = c0 + min(tl, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   RdsState s = st[c];
@@ -1502,11 +1746,9 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
     }
   }
   __syncthreads();
-  if (!io) {
-    for (int q = 0; q < SS_LEN; q++) {
-      s_wmf[q][tl] = s.wmf[q];
-      s_wdmf[q][tl] = s.wdmf[q];
-    }
+  for (int q = 0; q < SS_LEN; q++) {
+    s_wmf[q][tl] = s.wmf[q];
+    s_wdmf[q][tl] = s.wdmf[q];
   }
   int sp = 0;  // ring position of the oldest symsync window element
   float2 *ringc = ring + (size_t)c * RDS_RING;
@@ -1541,7 +1783,7 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
 
   uint32_t produced = 0;
   const uint32_t n171 = active ? s.n171 : 0u;
-  const int nchunks = (int)((s_nmax + LT - 1) / LT);
+  const int nchunks = (int)((s_nmax / FMGPU_EXP_LANE_DIV + LT - 1) / LT);
   // tile element ii of chunk ck <-> 171 kHz sample ck*LT + ii (rows are padded to whole tiles)
   auto prefetch = [&](int ck) {
     constexpr int cpr = LT / 4;
@@ -1552,20 +1794,17 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
       cpAsync16(t_in[ck & 1] + r * TPR + q4, r171 + (size_t)(c0 + r) * r_pitch + (size_t)ck * LT + q4);
     }
   };
-  if (io && nchunks > 0) {
+  if (nchunks > 0) {
     prefetch(0);
     cpAsyncCommit();
-    cpAsyncWait<0>();
   }
-  __syncthreads();
 
   for (int ck = 0; ck < nchunks; ck++) {
-    if (io) {
-      if (ck + 1 < nchunks) {
-        prefetch(ck + 1);
-        cpAsyncCommit();
-      }
-      cpAsyncWait<0>();
+    cpAsyncWait<0>();  // tile ck has landed ...
+    __syncwarp();      // ... for every lane, and every lane is done reading tile ck - 1
+    if (ck + 1 < nchunks) {
+      prefetch(ck + 1);
+      cpAsyncCommit();
     }
     const float *trow = t_in[ck & 1] + tl * TPR;
     for (int ii = 0; ii < LT; ii++) {
@@ -1960,9 +2199,53 @@ static bool usePackedFma() {
     break;                                                                                       \
   }
 
+#define FMGPU_DECIM8_CASE(MM)                                                                    \
+  case MM: {                                                                                     \
+    constexpr int T = 8 * DECIM8_NT;                                                             \
+    const int tile_len = (T + Pp - 1) * MM;                                                      \
+    const size_t smem = (size_t)(tile_len + tile_len / (8 * MM) + 2) * sizeof(float2);           \
+    static bool attr_done = false;                                                               \
+    if (!attr_done) {                                                                            \
+      cudaFuncSetAttribute(k_decim8<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           160 * 1024);                                                          \
+      cudaFuncSetAttribute(k_decim8<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                           160 * 1024);                                                          \
+      attr_done = true;                                                                          \
+    }                                                                                            \
+    dim3 grid((n_out + T - 1) / T, nch);                                                         \
+    if (usePackedFma()) {                                                                        \
+      k_decim8<MM, true><<<grid, DECIM8_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1, \
+                                                            x1_pitch, n_out, ch0, Pp, scale,     \
+                                                            taps);                               \
+    } else {                                                                                     \
+      k_decim8<MM, false><<<grid, DECIM8_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid,    \
+                                                             x1, x1_pitch, n_out, ch0, Pp,       \
+                                                             scale, taps);                       \
+    }                                                                                            \
+    return;                                                                                      \
+  }
+
+// FMGPU_DECIM8=1 selects the eight-outputs-per-thread decimator (bit-identical; slower so far:
+// 139 registers leave 10 warps per SM)
+static bool useDecim8() {
+  static const bool v = [] {
+    const char *e = getenv("FMGPU_DECIM8");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
                  const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
                  const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream) {
+  if (useDecim8()) {  // the factors of the BASELINE configurations (2.048 MS/s / 8, 2.4 MS/s / 10)
+    switch (M) {
+      FMGPU_DECIM8_CASE(8)
+      FMGPU_DECIM8_CASE(10)
+    default:
+      break;
+    }
+  }
   switch (M) {
     FMGPU_DECIM_CASE(2)
     FMGPU_DECIM_CASE(4)
@@ -2005,13 +2288,13 @@ void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size
                    float2 *x2, size_t x2_pitch, DemodState *st, fmgpu_block_status *status,
                    int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, float a1,
                    cudaStream_t stream) {
-  constexpr size_t smem = 4 * 32 * (2 * LT + 4) * sizeof(float);
+  constexpr size_t smem = 3 * 32 * (2 * LT + 4) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_dcblock, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_dcblock<<<(nch + 31) / 32, 64, smem, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
+  k_dcblock<<<(nch + 31) / 32, 32, smem, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
                                                status, status_pitch, nblk, blk_len, n_total, ch0,
                                                nch, a1);
 }
@@ -2034,13 +2317,13 @@ void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pit
 
 void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total,
                int ch0, int nch, cudaStream_t stream) {
-  constexpr size_t smem = 3 * 32 * (2 * LT + 4) * sizeof(float);
+  constexpr size_t smem = 2 * 32 * (2 * LT + 4) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_agc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_agc<<<(nch + 31) / 32, 64, smem, stream>>>(ybuf, y_pitch, st, cp, n_total, ch0, nch);
+  k_agc<<<(nch + 31) / 32, 32, smem, stream>>>(ybuf, y_pitch, st, cp, n_total, ch0, nch);
 }
 
 void launchFreqDem(const float2 *ybuf, size_t y_pitch, float *mpx, size_t mpx_pitch, int n_total,
@@ -2087,7 +2370,7 @@ k_fir_pair(FirRealJob job, int pair_channels, int nch, const __grid_constant__ T
     const int a = t * R + j;
     win[j] = fp_x[a + (a >> 3)];
   }
-  for (int i = 0; i < Lp; i += R) {
+  for (int i = 0; i < Lp / FMGPU_EXP_FIR_DIV; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
       const float h = taps.h[i + u];
@@ -2150,13 +2433,13 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  constexpr size_t smem = 17 * 32 * (STEREO_ST + 4) * sizeof(float);  // 17 tiles of [32][ST + 4]
+  constexpr size_t smem = STEREO_TILES * 32 * (STEREO_ST + 4) * sizeof(float);  // tiles of [32][ST + 4]
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_stereo<<<(nch + 31) / 32, 96, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
+  k_stereo<<<(nch + 31) / 32, STEREO_THREADS, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
                                                  lr_pitch, st, cp, status, status_pitch, nblk,
                                                  blk_len, n_total, ch0, nch, k);
 }
@@ -2214,7 +2497,7 @@ void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_p
   k_rds_resample<<<grid, 128, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch,
                                            k.rds_step, ch0);
   constexpr size_t smem = 2 * 32 * (LT + 4) * sizeof(float);
-  k_rds<<<(nch + 31) / 32, 64, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
+  k_rds<<<(nch + 31) / 32, 32, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
                                               bits_cap, bit_end, ch0, nch, k);
 }
 
