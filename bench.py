@@ -466,8 +466,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     eng.close()
 
 
-TILE_STAGES = ("decimate", "chanfir", "freqdem", "pilot_fir", "audio_lpf", "afpost")
-LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds")
+TILE_STAGES = ("decimate", "chanfir", "freqdem", "pilot_fir", "audio_lpf", "afpost", "rds_resample")
+LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds", "rds_sync")
 
 
 # DRAM bytes per DSP-rate sample (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of
@@ -493,7 +493,9 @@ def kernel_roofline(stage: str, stage_ms: float, C: int, B: int, clocks: dict) -
         "pilot_fir": (4.0 * n + 4.0 * n, 2.0 * 305 * n),
         "stereo_pll": (8.0 * n + 8.0 * n, 75.0 * n),
         "audio_lpf": (8.0 * n + 8.0 * n, 2.0 * 2 * 121 * n),
-        "rds": (4.0 * n, 2.0 * (26 + 22 + 20) * n * 171.0 / 240.0),
+        "rds_resample": (4.0 * n + 4.0 * n * 171.0 / 240.0, 2.0 * 26 * n * 171.0 / 240.0),
+        "rds": (4.0 * n * 171.0 / 240.0, 2.0 * (22 + 20) * n * 171.0 / 240.0),
+        "rds_sync": (0.01 * n, 0.1 * n),
         "dcblock": (8.0 * n + 8.0 * n, 6.0 * n),
         "agc": (8.0 * n + 8.0 * n, 40.0 * n),
         "freqdem": (8.0 * n + 4.0 * n, 30.0 * n),

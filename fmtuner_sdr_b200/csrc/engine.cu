@@ -705,17 +705,26 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   {
     cudaStream_t s = P.run[E::ST_RDS];
     need(E::ST_RDS, {E::ST_FD}, {});
-    Span sp(e, "rds", s);
-    launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
-                  0, 0, 1, first ? 1 : 0, s);
-    launchRds(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
-              e->dMf, e->dDmf, e->dR171, e->r171Pitch, max171(e, N), e->dBits,
-              static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, s);
+    {
+      Span sp(e, "rds_resample", s);  // tile kernel: MPX -> 171 kHz
+      launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step,
+                    e->k.rds_step, 0, 0, 1, first ? 1 : 0, s);
+      launchRdsResample(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRdsBank, e->dR171,
+                        e->r171Pitch, max171(e, N), ch0, nch, e->k, s);
+    }
+    {
+      Span sp(e, "rds", s);  // lane kernel: 57 kHz mix ... bits
+      launchRdsDemod(e->dRds, e->dRing, e->dRdsLpf, e->dMf, e->dDmf, e->dR171, e->r171Pitch, e->dBits,
+                     static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, s);
+    }
     e->launches += 1;
-    launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords,
-                    out.groups, out.gcap, status, nb, 1, b, ch0, nch, s);
-    launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
-    launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, s);
+    {
+      Span sp(e, "rds_sync", s);  // syndromes at every bit offset + block sync state machine
+      launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords,
+                      out.groups, out.gcap, status, nb, 1, b, ch0, nch, s);
+      launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
+      launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, s);
+    }
     e->launches += 5;
   }
   done(E::ST_RDS);

@@ -196,9 +196,23 @@ template <int N> __device__ __forceinline__ void cpAsyncWait() {
 // tile[r][k] <- base[(c0 + r) * pitch + start + k],  r < nrows, k < len, as 16-byte
 // cp.async transfers: start, pitch and the row pitch TP are multiples of 4 floats; len is
 // rounded up to 4 (the over-read stays inside the row's padding). One warp.
-template <int TP>
+// FULL > 0: the row length of a full tile, known at compile time (its index arithmetic is shifts;
+// the generic form divides by a run-time row length, ~25 instructions per transfer, which was half
+// of the instructions k_dcblock executed)
+template <int TP, int FULL = 0>
 __device__ __forceinline__ void tileLoadAsync(float *tile, const float *base, size_t pitch, int c0,
                                               int nrows, long start, int len, int lane) {
+  if (FULL > 0 && len == FULL) {
+    constexpr int cpr = (FULL + 3) / 4;
+    const int total = nrows * cpr;
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
+      const int r = idx / cpr;
+      const int q = idx - r * cpr;
+      cpAsync16(tile + r * TP + 4 * q, base + (size_t)(c0 + r) * pitch + start + 4 * q);
+    }
+    return;
+  }
   const int cpr = (len + 3) >> 2;  // 16-byte chunks per row
   const int total = nrows * cpr;
   for (int idx = lane; idx < total; idx += 32) {
@@ -230,9 +244,21 @@ __device__ __forceinline__ void tileLoadAsync4(float *tile, const float *base, s
   }
 }
 
-template <int TP>
+template <int TP, int FULL = 0>
 __device__ __forceinline__ void tileStore(const float *tile, float *base, size_t pitch, int c0,
                                           int nrows, long start, int len, int lane) {
+  if (FULL > 0 && len == FULL) {
+    constexpr int cpr = (FULL + 3) / 4;
+    const int total = nrows * cpr;
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
+      const int r = idx / cpr;
+      const int q = idx - r * cpr;
+      const float4 v = *reinterpret_cast<const float4 *>(tile + r * TP + 4 * q);
+      *reinterpret_cast<float4 *>(base + (size_t)(c0 + r) * pitch + start + 4 * q) = v;
+    }
+    return;
+  }
   const int cpr = (len + 3) >> 2;
   const int total = nrows * cpr;
   for (int idx = lane; idx < total; idx += 32) {
@@ -307,6 +333,11 @@ __global__ void k_save_tail(const float *src, size_t src_pitch, int src_off, flo
 #ifndef FMGPU_DECIM_NT
 #define FMGPU_DECIM_NT 128
 #endif
+// loads in flight per thread while the tile is filled (the fill is global-latency-bound)
+#ifndef FMGPU_DECIM_FILL_UNROLL
+#define FMGPU_DECIM_FILL_UNROLL 7
+#endif
+constexpr int DECIM_FILL_UNROLL = FMGPU_DECIM_FILL_UNROLL;
 constexpr int DECIM_NT = FMGPU_DECIM_NT;  // threads per decimator CTA (4 outputs each)
 
 template <int M, bool PACK>
@@ -346,7 +377,7 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
     const unsigned short *p_in = in_c + (v0 - H_IQ);
     auto fill = [&](auto fast_tag) {
       constexpr bool FAST = decltype(fast_tag)::value;  // whole tile inside the input row
-#pragma unroll 7
+#pragma unroll DECIM_FILL_UNROLL
       for (unsigned a = t; a < (unsigned)tile_len; a += DECIM_NT) {
         uint32_t w = 0;
         bool ok = true;
@@ -628,7 +659,7 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
   float *x2f = reinterpret_cast<float *>(x2);
   const int nchunks = (n_total + LT - 1) / LT;
   if (!iq_u8 && nchunks > 0) {
-    tileLoadAsync<TP>(tin(0), x1f, 2 * x1_pitch, c0, nrows, 0, 2 * min(LT, n_total), lane);
+    tileLoadAsync<TP, 2 * LT>(tin(0), x1f, 2 * x1_pitch, c0, nrows, 0, 2 * min(LT, n_total), lane);
     cpAsyncCommit();
   }
   int b = 0, in_blk = 0, clip = 0;
@@ -639,7 +670,7 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
     cpAsyncWait<0>();  // tile ck has landed ...
     __syncwarp();      // ... for every lane; every lane is done with tile ck - 1 and its output
     if (!iq_u8 && ck + 1 < nchunks) {
-      tileLoadAsync<TP>(tin(ck + 1), x1f, 2 * x1_pitch, c0, nrows, 2L * (n0 + LT),
+      tileLoadAsync<TP, 2 * LT>(tin(ck + 1), x1f, 2 * x1_pitch, c0, nrows, 2L * (n0 + LT),
                         2 * min(LT, n_total - n0 - LT), lane);
       cpAsyncCommit();
     }
@@ -708,7 +739,7 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
       }
     }
     __syncwarp();  // the output tile is complete: write it back, 128 contiguous bytes per row
-    tileStore<TP>(tout, x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0), 2 * len, lane);
+    tileStore<TP, 2 * LT>(tout, x2f, 2 * x2_pitch, c0, nrows, 2L * (H_X2 + n0), 2 * len, lane);
   }
   if (active) {
     // only this stage's fields: the AGC stage of the previous block may be running beside it
@@ -807,7 +838,7 @@ k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_
   float *yf = reinterpret_cast<float *>(ybuf);
   const int nchunks = (n_total + LT - 1) / LT;
   if (nchunks > 0) {
-    tileLoadAsync<TP>(tb(0), yf, 2 * y_pitch, c0, nrows, 2L * Y_OFF, 2 * min(LT, n_total), lane);
+    tileLoadAsync<TP, 2 * LT>(tb(0), yf, 2 * y_pitch, c0, nrows, 2L * Y_OFF, 2 * min(LT, n_total), lane);
     cpAsyncCommit();
   }
   for (int ck = 0; ck < nchunks; ck++) {
@@ -816,7 +847,7 @@ k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_
     cpAsyncWait<0>();
     __syncwarp();  // tile ck visible to every lane; tile ck - 1 has been written back by every lane
     if (ck + 1 < nchunks) {
-      tileLoadAsync<TP>(tb(ck + 1), yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 + LT),
+      tileLoadAsync<TP, 2 * LT>(tb(ck + 1), yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0 + LT),
                         2 * min(LT, n_total - n0 - LT), lane);
       cpAsyncCommit();
     }
@@ -849,7 +880,7 @@ k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_
     }
     __syncwarp();
     // rows without an AGC are written back unchanged
-    tileStore<TP>(tb(ck), yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0), 2 * len, lane);
+    tileStore<TP, 2 * LT>(tb(ck), yf, 2 * y_pitch, c0, nrows, 2L * (Y_OFF + n0), 2 * len, lane);
   }
   if (active) {
     st[c].agc_g = g;
@@ -1037,8 +1068,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   const int nchunks = (n_total + ST - 1) / ST;
   auto clen = [&](int ck) { return min(ST, n_total - ck * ST); };
   if (role == 0 && nchunks > 0) {
-    tileLoadAsync<TP>(t_pil, pilot, pilot_pitch, c0, nrows, 0, clen(0), lane);
-    tileLoadAsync<TP>(t_mpx, mpx, mpx_pitch, c0, nrows, H_MPX, clen(0), lane);
+    tileLoadAsync<TP, ST>(t_pil, pilot, pilot_pitch, c0, nrows, 0, clen(0), lane);
+    tileLoadAsync<TP, ST>(t_mpx, mpx, mpx_pitch, c0, nrows, H_MPX, clen(0), lane);
     cpAsyncCommit();
     cpAsyncWait<0>();
   }
@@ -1052,9 +1083,9 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   for (int kk = 0; kk <= nchunks + 2; kk++) {
     if (role == 0) {
       if (kk + 1 < nchunks) {
-        tileLoadAsync<TP>(t_pil + ((kk + 1) & 1) * TS, pilot, pilot_pitch, c0, nrows,
+        tileLoadAsync<TP, ST>(t_pil + ((kk + 1) & 1) * TS, pilot, pilot_pitch, c0, nrows,
                           (long)(kk + 1) * ST, clen(kk + 1), lane);
-        tileLoadAsync<TP>(t_mpx + ((kk + 1) & 1) * TS, mpx, mpx_pitch, c0, nrows,
+        tileLoadAsync<TP, ST>(t_mpx + ((kk + 1) & 1) * TS, mpx, mpx_pitch, c0, nrows,
                           H_MPX + (long)(kk + 1) * ST, clen(kk + 1), lane);
       }
       if (kk >= 1 && kk - 1 < nchunks) {
@@ -1065,8 +1096,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
       cpAsyncCommit();
       if (kk >= 3) {
         const int j = kk - 3;
-        tileStore<TP>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
-        tileStore<TP>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+        tileStore<TP, ST>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+        tileStore<TP, ST>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
       }
       // ... and, while its copies are in flight, the blend recursion and the L-R matrix
       if (active && kk >= 2 && kk - 2 < nchunks) {
@@ -1669,40 +1700,88 @@ __device__ void rdsPushWord(RdsState &s, uint32_t raw, uint32_t syn, fmgpu_rds_g
 // P >> 24 through branch (P >> 19) & 31 — the same dot product, oldest input first, that the
 // serial loop of the reference evaluates. Inputs before this call come from the RDS resampler's
 // own window (it is not reset with the stereo path).
+constexpr int RDS_RS_OUT = 512;                    // outputs per CTA (4 per thread)
+constexpr int RDS_RS_ROW = (RDS_RS_LEN + 3) & ~3;  // branch rows padded to 16 bytes
+// inputs one CTA can touch: its outputs advance by step / 2^24 < 2 inputs each
+constexpr int RDS_RS_SPAN = 2 * RDS_RS_OUT + RDS_RS_LEN + 8;
+
 __global__ void __launch_bounds__(128)
 k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
                int hist_pitch, const RdsState *__restrict__ st, const float *__restrict__ g_bank,
                float *__restrict__ r171, size_t r_pitch, uint32_t step, int ch0) {
-  __shared__ float s_bank[32 * RDS_RS_LEN];
-  for (int i = threadIdx.x; i < 32 * RDS_RS_LEN; i += blockDim.x) {
-    s_bank[i] = g_bank[i];
-  }
-  __syncthreads();
+  // Both operands of the 26-tap dot products come from shared memory: the 32 branch rows (128-bit
+  // reads) and the input window of the CTA's 512 outputs, filled once with coalesced loads. (The
+  // first form read its 26 inputs per output straight from global memory and copied the whole bank
+  // per 128 outputs: 215 instructions per output.)
+  __shared__ __align__(16) float s_bank[32 * RDS_RS_ROW];
+  __shared__ float s_x[RDS_RS_SPAN];
   const int c = blockIdx.y + ch0;
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= st[c].n171) {
+  const uint32_t n171 = st[c].n171;
+  const uint32_t k0 = blockIdx.x * RDS_RS_OUT;
+  if (k0 >= n171) {
     return;
   }
-  const unsigned long long P = (unsigned long long)st[c].rs_phase + (unsigned long long)k * step;
-  const long i = (long)(P >> 24);
-  const int br = (int)((P & 0xffffffull) >> 19);
-  const float *h = s_bank + br * RDS_RS_LEN;
-  const float *a = mpx + (size_t)c * mpx_pitch + H_MPX + i - (RDS_RS_LEN - 1);
-  const float *hc = hist + (size_t)c * hist_pitch + RDS_HIST;
-  float smp = 0.0f;
-  if (i < RDS_RS_LEN - 1) {
-#pragma unroll
-    for (int q = 0; q < RDS_RS_LEN; q++) {
-      const long si = i - (RDS_RS_LEN - 1) + q;
-      smp = fmaf(h[q], (si >= 0) ? a[q] : hc[si], smp);
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < RDS_RS_LEN; q++) {
-      smp = fmaf(h[q], a[q], smp);
+  for (int i = threadIdx.x; i < 32 * RDS_RS_ROW; i += blockDim.x) {
+    const int br = i / RDS_RS_ROW;
+    const int q = i - br * RDS_RS_ROW;
+    s_bank[i] = (q < RDS_RS_LEN) ? g_bank[br * RDS_RS_LEN + q] : 0.0f;
+  }
+  const unsigned long long phase = st[c].rs_phase;
+  const uint32_t k_last = min(n171, k0 + RDS_RS_OUT) - 1;
+  const long i_lo = (long)((phase + (unsigned long long)k0 * step) >> 24) - (RDS_RS_LEN - 1);
+  const long i_hi = (long)((phase + (unsigned long long)k_last * step) >> 24);
+  const long span = i_hi - i_lo + 1;
+  const float *row = mpx + (size_t)c * mpx_pitch + H_MPX;
+  const float *hc = hist + (size_t)c * hist_pitch + RDS_HIST;  // hc[-1] is the newest old input
+  // DSP rates above 2 x 171 kHz advance more than 2 inputs per output: the window does not fit,
+  // read the inputs from global memory then (same arithmetic)
+  const bool staged = span <= RDS_RS_SPAN;
+  if (staged) {
+    for (int a = threadIdx.x; a < (int)span; a += blockDim.x) {
+      const long si = i_lo + a;
+      s_x[a] = (si >= 0) ? row[si] : hc[si];
     }
   }
-  r171[(size_t)c * r_pitch + k] = smp;
+  __syncthreads();
+  if (!staged) {
+    for (uint32_t k = k0 + threadIdx.x; k <= k_last; k += blockDim.x) {
+      const unsigned long long P = phase + (unsigned long long)k * step;
+      const long i = (long)(P >> 24);
+      const float *h = s_bank + (int)((P & 0xffffffull) >> 19) * RDS_RS_ROW;
+      float smp = 0.0f;
+      for (int q = 0; q < RDS_RS_LEN; q++) {
+        const long si = i - (RDS_RS_LEN - 1) + q;
+        smp = fmaf(h[q], (si >= 0) ? row[si] : hc[si], smp);
+      }
+      r171[(size_t)c * r_pitch + k] = smp;
+    }
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < RDS_RS_OUT / 128; u++) {
+    const uint32_t k = k0 + u * 128 + threadIdx.x;
+    if (k < n171) {
+      const unsigned long long P = phase + (unsigned long long)k * step;
+      const int br = (int)((P & 0xffffffull) >> 19);
+      const float *h = s_bank + br * RDS_RS_ROW;
+      const float *x = s_x + ((long)(P >> 24) - (RDS_RS_LEN - 1) - i_lo);
+      float hq[RDS_RS_ROW];
+#pragma unroll
+      for (int q = 0; q < RDS_RS_ROW; q += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(h + q);
+        hq[q] = v.x;
+        hq[q + 1] = v.y;
+        hq[q + 2] = v.z;
+        hq[q + 3] = v.w;
+      }
+      float smp = 0.0f;
+#pragma unroll
+      for (int q = 0; q < RDS_RS_LEN; q++) {  // oldest input first, as resamp_rrrf's dot product
+        smp = fmaf(hq[q], x[q], smp);
+      }
+      r171[(size_t)c * r_pitch + k] = smp;
+    }
+  }
 }
 
 // S7b: the serial part, one lane per channel, fed by the 171 kHz stream of k_rds_resample. ONE warp
@@ -1807,140 +1886,184 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
       cpAsyncCommit();
     }
     const float *trow = t_in[ck & 1] + tl * TPR;
-    for (int ii = 0; ii < LT; ii++) {
-      if ((uint32_t)(ck * LT + ii) < n171) {
-        const float smp = trow[ii];
-        // ---- one 171 kHz sample -------------------------------------------------
-        float sn, cs;
-        fm_sincosf(-s.phase0, &sn, &cs);
-        const float2 bb = make_float2(smp * cs, smp * sn);
-        if (n171 - produced <= (uint32_t)RDS_RING) {
-          ringc[s.ring_pos & (RDS_RING - 1)] = bb;
-        }
-        s.ring_pos++;
-        produced++;
-        const uint32_t ph = s.since_reset % 24u;
-        const int d0 = (ph == 0) ? 0 : (int)(24u - ph);
+    // Samples of this lane in the tile. They are walked in groups of up to 8 that end at the lane's
+    // next /24 decimation instant (or the end of the tile): inside a group nothing feeds back into
+    // the NCO, so the 8 NCO steps, the 8 IEEE divisions and the 8 sincos are independent
+    // instruction streams instead of one dependent chain per sample, and the symbol-rate block runs
+    // once per group boundary for the whole warp, whatever the lanes' /24 phases are. Per value,
+    // operations and their order are those of the per-sample loop (subcarrier.cpp:117-235).
+    const uint32_t t0 = (uint32_t)ck * LT;
+    const int nvalid = (n171 > t0) ? (int)min((uint32_t)LT, n171 - t0) : 0;
+    int ii = 0;
+    while (__any_sync(0xffffffffu, ii < nvalid)) {
+      const uint32_t ph = s.since_reset % 24u;
+      const int d0 = (ph == 0) ? 0 : (int)(24u - ph);  // offset of the next decimation instant
+      const int m = (ii < nvalid) ? min(8, min(d0 + 1, nvalid - ii)) : 0;
+      const bool heavy_last = (m > 0) && (m == d0 + 1);
+      // ---- NCO::step for the first m - 1 samples (liquid_wrappers.cpp:125-139) ----
+      float pn[8], ph0[8];
+      ph0[0] = s.phase0;
+      pn[0] = s.prev_f0_phase;
 #pragma unroll
-        for (int j = 0; j < RDS_NACC; j++) {
-          const int idx = 254 - d0 - 24 * j;
-          if (idx >= 0) {
-            const float hh = s_lpf[idx];
-            acc[j].x = fmaf(hh, bb.x, acc[j].x);
-            acc[j].y = fmaf(hh, bb.y, acc[j].y);
+      for (int q = 1; q < 8; q++) {
+        pn[q] = ncoPhaseDev(s.theta + (uint32_t)q * s.dtheta);
+      }
+#pragma unroll
+      for (int q = 1; q < 8; q++) {
+        const float delta = unwrapDev(pn[q] - pn[q - 1]);
+        const float x = (delta * 57000.f) / 57000.f;
+        ph0[q] = x;
+      }
+#pragma unroll
+      for (int q = 1; q < 8; q++) {
+        ph0[q] = unwrapDev(ph0[q - 1] + ph0[q]);
+      }
+#pragma unroll
+      for (int q = 1; q < 8; q++) {
+        if (q < m) {
+          s.theta += s.dtheta;
+          s.prev_f0_phase = pn[q];
+          s.phase0 = ph0[q];
+        }
+      }
+      // ---- mix down, 57 kHz low-pass sums ----
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (q < m) {
+          const float smp = trow[ii + q];
+          float sn, cs;
+          fm_sincosf(-ph0[q], &sn, &cs);
+          const float2 bb = make_float2(smp * cs, smp * sn);
+          if (n171 - produced <= (uint32_t)RDS_RING) {
+            ringc[s.ring_pos & (RDS_RING - 1)] = bb;
+          }
+          s.ring_pos++;
+          produced++;
+          const int base = 254 - (d0 - q);  // window index of this sample in the next output
+#pragma unroll
+          for (int j = 0; j < RDS_NACC; j++) {
+            // base - 24 j >= 0 for every j < 10 (base >= 231)
+            if (j < 10 || base >= 24 * j) {
+              const float hh = s_lpf[base - 24 * j];
+              acc[j].x = fmaf(hh, bb.x, acc[j].x);
+              acc[j].y = fmaf(hh, bb.y, acc[j].y);
+            }
           }
         }
-        if (ph == 0) {
-          const float2 lo = make_float2(acc[0].x * k.rds_lpf_scale, acc[0].y * k.rds_lpf_scale);
+      }
+      if (heavy_last) {
+        const float2 lo = make_float2(acc[0].x * k.rds_lpf_scale, acc[0].y * k.rds_lpf_scale);
 #pragma unroll
-          for (int j = 0; j < RDS_NACC - 1; j++) {
-            acc[j] = acc[j + 1];
+        for (int j = 0; j < RDS_NACC - 1; j++) {
+          acc[j] = acc[j + 1];
+        }
+        acc[RDS_NACC - 1] = make_float2(0.0f, 0.0f);
+        // agc_crcf
+        const float2 y = make_float2(lo.x * s.agc_g, lo.y * s.agc_g);
+        const float e = (y.x * y.x) + (y.y * y.y);
+        s.agc_y2 = ((1.0f - k.rds_agc_alpha) * s.agc_y2) + (k.rds_agc_alpha * e);
+        if (s.agc_y2 > 1e-6f) {
+          s.agc_g = s.agc_g * fm_expf((-0.5f * k.rds_agc_alpha) * fm_logf(s.agc_y2));
+        }
+        if (s.agc_g > 1e6f) {
+          s.agc_g = 1e6f;
+        }
+        // symsync_crcf step
+        s_wmf[sp][tl] = y;
+        s_wdmf[sp][tl] = y;
+        sp = (sp + 1 == SS_LEN) ? 0 : sp + 1;
+        int n_out = 0;
+        float2 sym = make_float2(0.0f, 0.0f);
+        while (s.b < 32) {
+          float mr = 0.0f, mi = 0.0f;
+          const float *hm = s_mf + s.b * SS_LEN;
+          int wp = sp;
+          for (int q = 0; q < SS_LEN; q++) {
+            const float2 wv = s_wmf[wp][tl];
+            mr = fmaf(hm[q], wv.x, mr);
+            mi = fmaf(hm[q], wv.y, mi);
+            wp = (wp + 1 == SS_LEN) ? 0 : wp + 1;
           }
-          acc[RDS_NACC - 1] = make_float2(0.0f, 0.0f);
-          // agc_crcf
-          const float2 y = make_float2(lo.x * s.agc_g, lo.y * s.agc_g);
-          const float e = (y.x * y.x) + (y.y * y.y);
-          s.agc_y2 = ((1.0f - k.rds_agc_alpha) * s.agc_y2) + (k.rds_agc_alpha * e);
-          if (s.agc_y2 > 1e-6f) {
-            s.agc_g = s.agc_g * fm_expf((-0.5f * k.rds_agc_alpha) * fm_logf(s.agc_y2));
+          if (n_out == 0) {
+            sym = make_float2(mr / 3.0f, mi / 3.0f);
           }
-          if (s.agc_g > 1e6f) {
-            s.agc_g = 1e6f;
-          }
-          // symsync_crcf step
-          s_wmf[sp][tl] = y;
-          s_wdmf[sp][tl] = y;
-          sp = (sp + 1 == SS_LEN) ? 0 : sp + 1;
-          int n_out = 0;
-          float2 sym = make_float2(0.0f, 0.0f);
-          while (s.b < 32) {
-            float mr = 0.0f, mi = 0.0f;
-            const float *hm = s_mf + s.b * SS_LEN;
-            int wp = sp;
+          if (s.decim_counter == 1u) {
+            s.decim_counter = 0;
+            float dr = 0.0f, di = 0.0f;
+            const float *hd = s_dmf + s.b * SS_LEN;
+            wp = sp;
             for (int q = 0; q < SS_LEN; q++) {
-              const float2 wv = s_wmf[wp][tl];
-              mr = fmaf(hm[q], wv.x, mr);
-              mi = fmaf(hm[q], wv.y, mi);
+              const float2 wv = s_wdmf[wp][tl];
+              dr = fmaf(hd[q], wv.x, dr);
+              di = fmaf(hd[q], wv.y, di);
               wp = (wp + 1 == SS_LEN) ? 0 : wp + 1;
             }
-            if (n_out == 0) {
-              sym = make_float2(mr / 3.0f, mi / 3.0f);
+            float qe = (mr * dr) + (mi * di);
+            if (qe > 1.0f) {
+              qe = 1.0f;
+            } else if (qe < -1.0f) {
+              qe = -1.0f;
             }
-            if (s.decim_counter == 1u) {
-              s.decim_counter = 0;
-              float dr = 0.0f, di = 0.0f;
-              const float *hd = s_dmf + s.b * SS_LEN;
-              wp = sp;
-              for (int q = 0; q < SS_LEN; q++) {
-                const float2 wv = s_wdmf[wp][tl];
-                dr = fmaf(hd[q], wv.x, dr);
-                di = fmaf(hd[q], wv.y, di);
-                wp = (wp + 1 == SS_LEN) ? 0 : wp + 1;
-              }
-              float qe = (mr * dr) + (mi * di);
-              if (qe > 1.0f) {
-                qe = 1.0f;
-              } else if (qe < -1.0f) {
-                qe = -1.0f;
-              }
-              const float v0 = qe - (k.ss_a1 * s.sos_v1);
-              s.q_hat = k.ss_b0 * v0;
-              s.sos_v1 = v0;
-              s.rate = s.rate + (k.ss_rate_adj * s.q_hat);
-              s.del = s.rate + s.q_hat;
-            }
-            s.decim_counter++;
-            s.tau = s.tau + s.del;
-            const float bf = s.tau * 32.0f;
-            s.b = (int)fm_roundf(bf);
-            n_out++;
+            const float v0 = qe - (k.ss_a1 * s.sos_v1);
+            s.q_hat = k.ss_b0 * v0;
+            s.sos_v1 = v0;
+            s.rate = s.rate + (k.ss_rate_adj * s.q_hat);
+            s.del = s.rate + s.q_hat;
           }
-          s.tau = s.tau - 1.0f;
-          s.b -= 32;
-          if (n_out == 1) {
-            const float pe_raw = (sym.x > 0.0f) ? sym.y : -sym.y;
-            const float pe = fm_clampf(pe_raw, -kPi, kPi);
-            const float dphi = pe * 12.0f;
-            s.dtheta += ncoConstrainDev(dphi * k.rds_pll_alpha);
-            s.theta += ncoConstrainDev(dphi * k.rds_pll_beta);
-            // biphase
-            const float bre = (sym.x - s.bi_prev_re) * 0.5f;
-            const bool bval = bre >= 0.0f;
-            const bool has = ((s.bi_clock & 1u) == s.bi_polarity);
-            s.bi_prev_re = sym.x;
-            if (s.bi_clock & 1u) {
-              s.bi_odd += fabsf(bre);
-            } else {
-              s.bi_even += fabsf(bre);
+          s.decim_counter++;
+          s.tau = s.tau + s.del;
+          const float bf = s.tau * 32.0f;
+          s.b = (int)fm_roundf(bf);
+          n_out++;
+        }
+        s.tau = s.tau - 1.0f;
+        s.b -= 32;
+        if (n_out == 1) {
+          const float pe_raw = (sym.x > 0.0f) ? sym.y : -sym.y;
+          const float pe = fm_clampf(pe_raw, -kPi, kPi);
+          const float dphi = pe * 12.0f;
+          s.dtheta += ncoConstrainDev(dphi * k.rds_pll_alpha);
+          s.theta += ncoConstrainDev(dphi * k.rds_pll_beta);
+          // biphase
+          const float bre = (sym.x - s.bi_prev_re) * 0.5f;
+          const bool bval = bre >= 0.0f;
+          const bool has = ((s.bi_clock & 1u) == s.bi_polarity);
+          s.bi_prev_re = sym.x;
+          if (s.bi_clock & 1u) {
+            s.bi_odd += fabsf(bre);
+          } else {
+            s.bi_even += fabsf(bre);
+          }
+          s.bi_clock++;
+          if (s.bi_clock == 128u) {
+            if (s.bi_even > s.bi_odd) {
+              s.bi_polarity = 0;
+            } else if (s.bi_odd > s.bi_even) {
+              s.bi_polarity = 1;
             }
-            s.bi_clock++;
-            if (s.bi_clock == 128u) {
-              if (s.bi_even > s.bi_odd) {
-                s.bi_polarity = 0;
-              } else if (s.bi_odd > s.bi_even) {
-                s.bi_polarity = 1;
-              }
-              s.bi_even = 0.0f;
-              s.bi_odd = 0.0f;
-              s.bi_clock = 0;
+            s.bi_even = 0.0f;
+            s.bi_odd = 0.0f;
+            s.bi_clock = 0;
+          }
+          if (has) {
+            const bool bit = (bval != (s.delta_prev != 0));
+            s.delta_prev = bval ? 1 : 0;
+            if (s.n_bits < bits_cap) {
+              bout[s.n_bits] = bit ? 1 : 0;
             }
-            if (has) {
-              const bool bit = (bval != (s.delta_prev != 0));
-              s.delta_prev = bval ? 1 : 0;
-              if (s.n_bits < bits_cap) {
-                bout[s.n_bits] = bit ? 1 : 0;
-              }
-              s.n_bits++;
-            }
+            s.n_bits++;
           }
         }
-        // NCO::step (liquid_wrappers.cpp:125-139)
+      }
+      if (m > 0) {
+        // NCO::step of the group's last sample (after the loop filter moved the NCO)
         s.theta += s.dtheta;
-        const float pn = ncoPhaseDev(s.theta);
-        const float delta = unwrapDev(pn - s.prev_f0_phase);
-        s.prev_f0_phase = pn;
+        const float pnl = ncoPhaseDev(s.theta);
+        const float delta = unwrapDev(pnl - s.prev_f0_phase);
+        s.prev_f0_phase = pnl;
         s.phase0 = unwrapDev(s.phase0 + ((delta * 57000.f) / 57000.f));
-        s.since_reset++;
+        s.since_reset += (uint32_t)m;
+        ii += m;
       }
     }
     __syncthreads();
@@ -2489,16 +2612,30 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
                                                        acap, gcap);
 }
 
+void launchRdsResample(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch,
+                       const RdsState *st, const float *bank, float *r171, size_t r_pitch,
+                       int max_171, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+  dim3 grid((max_171 + RDS_RS_OUT - 1) / RDS_RS_OUT, nch);
+  k_rds_resample<<<grid, 128, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch,
+                                           k.rds_step, ch0);
+}
+
+void launchRdsDemod(RdsState *st, float2 *ring, const float *lpf, const float *mf, const float *dmf,
+                    const float *r171, size_t r_pitch, uint8_t *bits_out, uint32_t bits_cap,
+                    uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+  constexpr size_t smem = 2 * 32 * (LT + 4) * sizeof(float);
+  k_rds<<<(nch + 31) / 32, 32, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
+                                              bits_cap, bit_end, ch0, nch, k);
+}
+
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
                float *r171, size_t r_pitch, int max_171, uint8_t *bits_out, uint32_t bits_cap,
                uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  dim3 grid((max_171 + 127) / 128, nch);
-  k_rds_resample<<<grid, 128, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch,
-                                           k.rds_step, ch0);
-  constexpr size_t smem = 2 * 32 * (LT + 4) * sizeof(float);
-  k_rds<<<(nch + 31) / 32, 32, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
-                                              bits_cap, bit_end, ch0, nch, k);
+  launchRdsResample(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch, max_171, ch0, nch, k,
+                    stream);
+  launchRdsDemod(st, ring, lpf, mf, dmf, r171, r_pitch, bits_out, bits_cap, bit_end, ch0, nch, k,
+                 stream);
 }
 
 void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit_end, RdsState *st,

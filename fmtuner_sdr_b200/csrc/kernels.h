@@ -66,6 +66,12 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
                        cudaStream_t stream);
 // MPX -> 171 kHz (tile kernel) -> serial demodulator (lane kernel); max_171 >= every channel's
 // n171 of this call, r171 rows padded to whole 32-sample tiles
+void launchRdsResample(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch,
+                       const RdsState *st, const float *bank, float *r171, size_t r_pitch,
+                       int max_171, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+void launchRdsDemod(RdsState *st, float2 *ring, const float *lpf, const float *mf, const float *dmf,
+                    const float *r171, size_t r_pitch, uint8_t *bits_out, uint32_t bits_cap,
+                    uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
                float *r171, size_t r_pitch, int max_171, uint8_t *bits_out, uint32_t bits_cap,
