@@ -475,8 +475,8 @@ LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds", "rds_sync")
 # profiles/r01_top_kernels_ncu.csv (1250 channels x 8192 samples per launch; writes that were still
 # in L2 when the kernel ended are not in the figure).
 NCU_TRAFFIC_BYTES_PER_SAMPLE = {
-    "decimate": 25.9, "chanfir": 11.8, "pilot_fir": 4.4, "audio_lpf": 11.6, "stereo_pll": 12.7,
-    "dcblock": 12.2, "agc": 10.7, "freqdem": 9.7, "rds": 7.1, "afpost": 9.6,
+    "decimate": 25.8, "chanfir": 11.9, "pilot_fir": 4.4, "audio_lpf": 11.6, "stereo_pll": 12.5,
+    "dcblock": 12.1, "agc": 10.7, "freqdem": 9.3, "rds": 2.9, "rds_resample": 4.2, "afpost": 9.5,
 }
 
 

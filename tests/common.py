@@ -11,7 +11,9 @@ GROUP_KEYS = ("a", "b", "c", "d", "errors", "block_index")
 def rates(which: str):
     """'240k' = 2.4 MS/s / 10 (BASELINE configs 3-5); '256k' = 2.048 MS/s / 8 (unmodified main.cpp)."""
     return {"240k": (2_400_000, 10), "256k": (2_048_000, 8), "1024k": (1_024_000, 4),
-            "direct256k": (256_000, 1)}[which]
+            "direct256k": (256_000, 1),
+            # DSP rate above 2 x 171 kHz: the RDS resampler's window no longer fits its tile
+            "480k": (2_400_000, 5)}[which]
 
 
 def groups_equal(a: np.ndarray, b: np.ndarray, keys=GROUP_KEYS) -> bool:
