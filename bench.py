@@ -471,11 +471,12 @@ LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds", "rds_sync")
 
 
 # DRAM bytes per DSP-rate sample (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of
-# each stage, from the ncu --set full capture of this command committed as
-# profiles/r01_top_kernels_ncu.csv (1250 channels x 8192 samples per launch; writes that were still
-# in L2 when the kernel ended are not in the figure).
+# each stage, from `ncu --set full` captures: decimate, chanfir, pilot_fir, stereo_pll and audio_lpf
+# from the capture of the DEFAULT command (10,000 channels x 8192 samples per launch,
+# profiles/r01_top_kernels_ncu_default_10000ch.csv), the others from the 1250-channel command
+# (profiles/r01_top_kernels_ncu.csv; there, writes still in L2 when the kernel ended are not counted).
 NCU_TRAFFIC_BYTES_PER_SAMPLE = {
-    "decimate": 25.8, "chanfir": 11.9, "pilot_fir": 4.4, "audio_lpf": 11.6, "stereo_pll": 12.5,
+    "decimate": 27.8, "chanfir": 15.6, "pilot_fir": 7.6, "audio_lpf": 15.6, "stereo_pll": 15.7,
     "dcblock": 12.1, "agc": 10.7, "freqdem": 9.3, "rds": 2.9, "rds_resample": 4.2, "afpost": 9.5,
 }
 
@@ -514,7 +515,7 @@ def kernel_roofline(stage: str, stage_ms: float, C: int, B: int, clocks: dict) -
     return {"kernel": stage, "bound": "hbm", "achieved": alg[0] / t / 1e9, "peak": peak_hbm,
             "peak_source": how, "unit": "GB/s", "frac": alg[0] / t / 1e9 / peak_hbm,
             "traffic": (traffic * n) if traffic is not None else None,
-            "traffic_source": "ncu dram bytes per sample (profiles/r01_top_kernels_ncu.csv) x the "
+            "traffic_source": "ncu dram bytes per sample (profiles/r01_top_kernels_ncu*.csv) x the "
                               "samples of one launch",
             "algorithmic_bytes": alg[0], "launch_ms": launch_ms, "launches_per_step": B,
             "fp32": {"achieved_tflops": alg[1] / t / 1e12, "peak_tflops": fp32_peak,

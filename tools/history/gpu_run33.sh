@@ -1,10 +1,10 @@
 set -x
 mkdir -p gpurun_out
-for v in fu14 fu21 fu42; do
+for v in nt96 nt64; do
 FMGPU_LIB=$PWD/build/libfmgpu_$v.so timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/r33_bench_$v.json 2> gpurun_out/r33_bench_$v.err
 done
 timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/r33_bench.json 2> gpurun_out/r33_bench.err
-for v in r33_bench r33_bench_fu14 r33_bench_fu21 r33_bench_fu42; do python - $v <<'PY'
+for v in r33_bench r33_bench_nt96 r33_bench_nt64; do python - $v <<'PY'
 import json,sys
 try:
     d=json.loads(open(f'gpurun_out/{sys.argv[1]}.json').read().strip().splitlines()[-1])
