@@ -100,3 +100,20 @@ def test_engine_design_equals_oracle_design(orc_libm, iq_rate, decim):
             assert np.array_equal(a, b) and sa == sb
         (a, sa), (b, sb) = eng(8), orc_libm.design(4, 13, 0, np.float32(171000.0) / np.float32(fs))
         assert np.array_equal(a, b) and sa == sb
+
+
+def test_kaiser_design_against_scipy(orc_libm):
+    """Independent pin of liquid_firdes_kaiser as restated (Appendix A.1): the same taps from
+    scipy's Kaiser window and numpy's normalised sinc, to float rounding. The beta(As) rule is
+    Kaiser's, which scipy.signal.kaiser_beta also implements."""
+    from scipy.signal import kaiser_beta
+    from scipy.signal.windows import kaiser
+
+    for args, n, fc, att in (((0, 10, 28, 80.0), 280, 0.045, 80.0),     # 2.4 MS/s decimator
+                             ((0, 8, 28, 80.0), 224, 0.45 / 8, 80.0),    # 2.048 MS/s decimator
+                             ((1, 256000, 0), 81, 97000 / 256000, 60.0)):  # channel filter, 194 kHz
+        h, _ = orc_libm.design(*args)
+        assert h.size == n
+        t = np.arange(n) - (n - 1) / 2.0
+        ref = np.sinc(2.0 * fc * t) * kaiser(n, kaiser_beta(att), sym=True)
+        assert np.abs(h.astype(np.float64) - ref).max() < 2e-7, args

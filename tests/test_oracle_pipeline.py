@@ -120,3 +120,50 @@ def test_empty_and_null_arguments(orc_libm):
     a = L.orc_afpost_create(256000, 32000)
     assert L.orc_afpost_process(a, None, None, 0, None, None, 0) == 0
     L.orc_afpost_destroy(a)
+
+
+@pytest.mark.parametrize("iq_rate,decim", [(2_400_000, 10), (2_048_000, 8)])
+def test_front_end_against_scipy_float64_model(orc_libm, iq_rate, decim):
+    """Independent pin of stages a1/a2: the decimating FIR, the I/Q DC blockers, the
+    channel filter and the quadrature discriminator rebuilt from scipy.signal.lfilter in float64
+    — firdecim_crcf emits output n right after input n*M (Appendix A.7), iirfilt dc_blocker is
+    b = [1, -1], a = [1, -(1 - alpha)], freqdem is arg(conj(y[n-1]) y[n]) / (2 pi kf) — must give
+    the oracle's decimated IQ and MPX to float32 rounding."""
+    from scipy.signal import lfilter
+
+    fs = iq_rate // decim
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(3 * 8192 * decim)
+    ref = orc.Channel(orc_libm, orc.make_config(iq_rate=iq_rate, decimation=decim)).process(iq, debug=True)
+    x = ((iq[0::2].astype(np.float64) - 127.5) + 1j * (iq[1::2].astype(np.float64) - 127.5)) / 127.5
+    h, sc = orc_libm.design(0, decim, 28, 80.0)
+    dec = sc * lfilter(h.astype(np.float64), [1.0], x)[0::decim]
+    assert np.abs(dec - ref.dec.astype(np.complex128)).max() < 5e-6
+    w = lfilter([1.0, -1.0], [1.0, -(1.0 - 0.0005)], dec)
+    hc, sc1 = orc_libm.design(1, fs, 0)
+    z = sc1 * lfilter(hc.astype(np.float64), [1.0], w)
+    zp = np.concatenate([[0.0], z[:-1]])
+    mpx = np.angle(np.conj(zp) * z) / (2.0 * np.pi * 75000.0 / fs)
+    assert np.abs(mpx - ref.mpx).max() < 2e-4   # of a +-1.6 swing
+
+
+def test_audio_tail_against_scipy_float64_model(orc_libm):
+    """Independent pin of stage a9 (AFPostProcessor::process) at 2.048 MS/s / 8, where 256 kHz ->
+    32 kHz is exactly every 8th input through branch 0 of the 32-branch resampler: branch 0 as an
+    FIR (scipy.signal.lfilter, float64), decimation by 8, de-emphasis iirfilt b = [alpha],
+    a = [1, -(1 - alpha)] with alpha = dt / (tau + dt) at 50 us, DC blocker alpha = 0.005 must give
+    the oracle's 32 kHz audio from its own DSP-rate L/R."""
+    from scipy.signal import lfilter
+
+    iq_rate, decim = 2_048_000, 8
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(4 * 8192 * decim)
+    ref = orc.Channel(orc_libm, orc.make_config(iq_rate=iq_rate, decimation=decim)).process(iq, debug=True)
+    bank, step = orc_libm.design(4, 12, 0, np.float32(32000 / 256000))
+    assert int(step) == 8 << 24
+    h0 = bank.reshape(32, 24)[0].astype(np.float64)[::-1]   # stored oldest-sample-first
+    alpha = (1 / 32000) / (50e-6 + 1 / 32000)
+    for dsp, out in ((ref.sl, ref.left), (ref.sr, ref.right)):
+        y = lfilter(h0, [1.0], dsp.astype(np.float64))[0::8]
+        y = lfilter([alpha], [1.0, -(1.0 - alpha)], y)
+        y = lfilter([1.0, -1.0], [1.0, -(1.0 - 0.005)], y)
+        assert y.size == out.size
+        assert np.abs(y - out).max() < 2e-6
