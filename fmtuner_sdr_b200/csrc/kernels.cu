@@ -400,7 +400,18 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
       }
     };
     if (a_lo == 0 && a_hist == 0 && a_hi == tile_len) {
-      fill(std::true_type{});
+      if (M % 2 == 0) {
+        // even M: tile_len, RM and the skew are even, so elements (a, a + 1), a even, are one
+        // 16-byte aligned pair in shared memory: two 16-bit loads, one 128-bit store per lane
+#pragma unroll DECIM_FILL_UNROLL
+        for (unsigned a = 2 * t; a < (unsigned)tile_len; a += 2 * DECIM_NT) {
+          const float2 f0 = iqBytesToFloat(__ldg(p_in + a));
+          const float2 f1 = iqBytesToFloat(__ldg(p_in + a + 1));
+          *reinterpret_cast<float4 *>(xs + a + SK * (a / RM)) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        }
+      } else {
+        fill(std::true_type{});
+      }
     } else {
       fill(std::false_type{});
     }
