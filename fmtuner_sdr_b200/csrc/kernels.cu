@@ -810,6 +810,7 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
     const int a = t * R + j;
     win[j] = xs[a + (a >> 3)];
   }
+  const float2 *wp = xs + (R + 1) * (t + 1);  // as in k_fir_pair: immediate-offset window loads
   for (int i = 0; i < Lp / FMGPU_EXP_FIR_DIV; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
@@ -818,9 +819,9 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
       for (int j = 0; j < R; j++) {
         acc[j] = fma2<PACK>(h, win[(j + u) & (R - 1)], acc[j]);
       }
-      const int a = t * R + i + u + R;
-      win[u] = xs[a + (a >> 3)];
+      win[u] = wp[u];
     }
+    wp += R + 1;
   }
   float2 *out = ybuf + (size_t)c * y_pitch + Y_OFF;
 #pragma unroll
@@ -973,6 +974,7 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
     win[j] = fs_x[a + (a >> SH)];
   }
   int i = 0;
+  const float *wp = fs_x + (R + 1) * (t + 1);  // element t*R + i + u + R, see k_fir_pair
   for (; i + R <= Lp; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
@@ -981,9 +983,9 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
       for (int j = 0; j < R; j++) {
         acc[j] = fmaf(h, win[(j + u) & (R - 1)], acc[j]);
       }
-      const int a = t * R + i + u + R;
-      win[u] = fs_x[a + (a >> SH)];
+      win[u] = wp[u];
     }
+    wp += R + 1;
   }
   if (R == 16 && i < Lp) {  // Lp is a multiple of 8: one half round left
 #pragma unroll
@@ -993,8 +995,7 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
       for (int j = 0; j < R; j++) {
         acc[j] = fmaf(h, win[(j + u) & (R - 1)], acc[j]);
       }
-      const int a = t * R + i + u + R;
-      win[u] = fs_x[a + (a >> SH)];
+      win[u] = wp[u];
     }
   }
   float *out = job.out[z] + (size_t)c * job.out_pitch + job.out_off;
@@ -2549,6 +2550,10 @@ k_fir_pair(FirRealJob job, int pair_channels, int nch, const __grid_constant__ T
     const int a = t * R + j;
     win[j] = fp_x[a + (a >> 3)];
   }
+  // element a = t*R + i + u + R sits at a + (a >> 3) = (R + 1) * (t + 1 + i / R) + u: one pointer
+  // that advances by R + 1 per round, so every LDS has an immediate offset (the index arithmetic
+  // per load was 12 % of this kernel's instructions)
+  const float2 *wp = fp_x + (R + 1) * (t + 1);
   for (int i = 0; i < Lp / FMGPU_EXP_FIR_DIV; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
@@ -2557,9 +2562,9 @@ k_fir_pair(FirRealJob job, int pair_channels, int nch, const __grid_constant__ T
       for (int j = 0; j < R; j++) {
         acc[j] = fma2<true>(h, win[(j + u) & (R - 1)], acc[j]);
       }
-      const int a = t * R + i + u + R;
-      win[u] = fp_x[a + (a >> 3)];
+      win[u] = wp[u];
     }
+    wp += R + 1;
   }
   float *outa = job.out[0] + (size_t)ca * job.out_pitch + job.out_off;
   float *outb = (pair_channels ? job.out[0] : job.out[1]) + (size_t)cb * job.out_pitch + job.out_off;
