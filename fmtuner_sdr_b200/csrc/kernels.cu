@@ -165,7 +165,7 @@ __device__ __forceinline__ float2 iqBytesToFloat(uint32_t w) {
 #define FMGPU_LT 32
 #endif
 #ifndef FMGPU_ST
-#define FMGPU_ST 8
+#define FMGPU_ST 16
 #endif
 // samples per tile row of the lane kernels. The tiles of every lane kernel of a block sit in
 // shared memory for milliseconds while FIR CTAs of other blocks want the same SMs: small tiles
@@ -1028,7 +1028,7 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
 constexpr int STEREO_TILES = 23;
 constexpr int STEREO_THREADS = 128;
 #ifndef FMGPU_STEREO_MINB
-#define FMGPU_STEREO_MINB 8  // 64 registers per thread
+#define FMGPU_STEREO_MINB 6  // at most 85 registers per thread
 #endif
 
 __global__ void __launch_bounds__(STEREO_THREADS, FMGPU_STEREO_MINB)
