@@ -158,8 +158,9 @@ __device__ __forceinline__ float2 iqBytesToFloat(uint32_t w) {
 // tile between global and shared memory cooperatively (each instruction covers 128
 // contiguous bytes of ONE row; loads are cp.async so the next tile streams in while
 // the current one is processed) and every lane then reads its own row from shared
-// memory. Row pitches are multiples of 4 floats so rows move as 16-byte transfers; the
-// 4-way bank conflict that costs a lane kernel is noise next to its dependent-issue latency.
+// memory, four samples per 128-bit access: row pitches are multiples of 4 floats, so rows move as
+// 16-byte transfers and a warp's 128-bit row access is conflict-free (32-bit accesses of the same
+// rows hit only 8 banks).
 // ---------------------------------------------------------------------------
 #ifndef FMGPU_LT
 #define FMGPU_LT 32
@@ -167,9 +168,9 @@ __device__ __forceinline__ float2 iqBytesToFloat(uint32_t w) {
 #ifndef FMGPU_ST
 #define FMGPU_ST 16
 #endif
-// samples per tile row of the lane kernels. The tiles of every lane kernel of a block sit in
-// shared memory for milliseconds while FIR CTAs of other blocks want the same SMs: small tiles
-// leave the shared memory to them.
+// samples per tile row of the lane kernels (LT: k_dcblock, k_agc, k_rds; ST: k_stereo). Measured:
+// the shared memory the lane kernels hold does not move the 10,000-channel step;
+// shorter k_stereo tiles lengthen that kernel by 10 % (one block barrier per tile).
 // Timing experiments only (tools/gpu_exp_bounds.sh; results are WRONG with either set): the lane
 // kernels walk 1/FMGPU_EXP_LANE_DIV of their samples, the FIR kernels 1/FMGPU_EXP_FIR_DIV of their
 // taps. They bound what the step could gain from faster lane kernels or faster FIR kernels.
@@ -1038,8 +1039,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
          int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
   n_total /= FMGPU_EXP_LANE_DIV;
   constexpr int ST = STEREO_ST;  // samples per tile row
-  // 16-byte aligned rows; the delayed-MPX tile needs up to 3 extra samples + alignment. With
-  // ST = 16 the pitch of 20 floats spreads the 32 lanes over 8 banks (a pitch of 24 only over 4).
+  // 16-byte aligned rows, read and written by their lane four samples at a time; a pitch of ST + 4
+  // floats is odd in 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups
   constexpr int TP = ST + 4;
   constexpr int TS = 32 * TP;  // floats per tile
   extern __shared__ float sm_st[];
