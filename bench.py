@@ -171,12 +171,11 @@ def run_reference(args, rank: int):
     passes = 8
     for _ in range(max(1, args.warmup)):
         cpu_arm(iq, args.blocks, 1, threads)
-    t0 = time.perf_counter()
-    samples = 0
+    samples, dt = 0, 0.0
     for _ in range(args.steps):
-        s, _ = cpu_arm(iq, args.blocks, passes, threads)
-        samples += s
-    dt = time.perf_counter() - t0
+        s, d = cpu_arm(iq, args.blocks, passes, threads)   # d: the threads' decode time only (not the
+        samples += s                                        # construction of the pipeline objects)
+        dt += d
     value = samples / dt / 1e6
     sample_desc = (f"{threads} channels x {passes} passes x {args.blocks} blocks x {BLOCK * DECIM} IQ "
                    f"samples per step, {args.steps} steps, one channel per thread")
