@@ -167,3 +167,52 @@ def test_audio_tail_against_scipy_float64_model(orc_libm):
         y = lfilter([1.0, -1.0], [1.0, -(1.0 - 0.005)], y)
         assert y.size == out.size
         assert np.abs(y - out).max() < 2e-6
+
+
+def test_stereo_decoder_against_float64_model(orc_libm):
+    """Independent pin of stage a6 (StereoDecoder::processAudio) once locked and fully blended: pilot
+    band-pass as an FIR (scipy), an ideal float64 second-order PLL with liquid's loop constants
+    (alpha = bw, beta = sqrt(bw), bw = 0.01; error = pilot * sin(theta)), L-R = 2 d cos(2 theta) on the
+    MPX delayed by (N - 1) / 2 + 1 samples, the two 15 kHz low-pass filters. The only float32 effect
+    modelled is the blend recursion itself: b += (1 - b) * attack stalls at 1 - 9.1e-4 in float32
+    (the reference behaves the same), so L - R carries that gain."""
+    import math
+
+    from scipy.signal import lfilter
+
+    iq_rate, decim, nblk = 2_048_000, 8, 80
+    fs = iq_rate // decim
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(nblk * 8192 * decim)
+    ref = orc.Channel(orc_libm, orc.make_config(iq_rate=iq_rate, decimation=decim)).process(iq, debug=True)
+    assert ref.status["stereo"][-1] == 1
+    mpx = ref.mpx.astype(np.float64)
+    hp, scp = orc_libm.design(2, fs)
+    ha, sca = orc_libm.design(3, fs)
+    pilot = scp * lfilter(hp.astype(np.float64), [1.0], mpx)
+    theta, dtheta = 0.0, 2.0 * math.pi * 19000.0 / fs
+    c2 = np.empty(mpx.size)
+    for i in range(mpx.size):
+        err = pilot[i] * math.sin(theta)
+        dtheta += 0.01 * err
+        theta += 0.1 * err + dtheta
+        if theta > math.pi:
+            theta -= 2.0 * math.pi
+        c2[i] = math.cos(2.0 * theta)
+    delay = (hp.size - 1) // 2 + 1
+    d = np.concatenate([np.zeros(delay), mpx[:-delay]])
+    # float32 fixed point of the blend recursion (normal mode: attack tau 0.12 s)
+    attack = np.float32(1.0) - np.exp(np.float32(-1.0) / (np.float32(0.120) * np.float32(fs)))
+    b = np.float32(0.99)
+    while True:
+        nb = b + (np.float32(1.0) - b) * attack
+        if nb == b:
+            break
+        b = nb
+    assert 0.9985 < float(b) < 0.9995
+    lr = 2.0 * d * c2 * float(b)
+    sl = sca * lfilter(ha.astype(np.float64), [1.0], 0.5 * (d + lr))
+    sr = sca * lfilter(ha.astype(np.float64), [1.0], 0.5 * (d - lr))
+    k0 = (nblk - 2) * 8192
+    assert np.abs(sl[k0:] - ref.sl[k0:]).max() < 1e-4      # of a 0.42 swing
+    assert np.abs(sr[k0:] - ref.sr[k0:]).max() < 1e-4
+    assert np.abs((sl + sr)[k0:] - (ref.sl.astype(np.float64) + ref.sr)[k0:]).max() < 2e-6
