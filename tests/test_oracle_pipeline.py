@@ -216,3 +216,15 @@ def test_stereo_decoder_against_float64_model(orc_libm):
     assert np.abs(sl[k0:] - ref.sl[k0:]).max() < 1e-4      # of a 0.42 swing
     assert np.abs(sr[k0:] - ref.sr[k0:]).max() < 1e-4
     assert np.abs((sl + sr)[k0:] - (ref.sl.astype(np.float64) + ref.sr)[k0:]).max() < 2e-6
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_agc_only_scales_the_discriminator_input(orc_libm, mode):
+    """Physics pin of the pre-discriminator AGC (fm_demod.cpp:196-199): a positive real gain on y[n]
+    cannot move arg(conj(y[n-1]) y[n]), so MPX and audio with dsp_agc fast / slow equal the AGC-off
+    result to float32 rounding."""
+    iq = orc.config1_signal(fs_iq=2_400_000).generate(4 * 8192 * 10)
+    off = orc.Channel(orc_libm, orc.make_config(dsp_agc=0)).process(iq, debug=True)
+    on = orc.Channel(orc_libm, orc.make_config(dsp_agc=mode)).process(iq, debug=True)
+    assert np.abs(off.mpx - on.mpx).max() < 2e-6
+    assert np.abs(off.left - on.left).max() < 2e-6 and np.abs(off.right - on.right).max() < 2e-6
