@@ -250,3 +250,32 @@ print("decim8 ok")
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "decim8 ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_one_channel_reset_leaves_the_lanes_out_of_step(orc_fm):
+    """Retune of ONE channel of a batch (dspRuntime.reset + rdsReset, main.cpp:1028-1062) while its
+    neighbours keep going: afterwards the lanes of a warp sit at different /24 decimation phases,
+    different symbol-clock phases and different pilot-lock states, which the lane kernels (k_rds
+    walks groups that end at each lane's own decimation instant) must handle per lane."""
+    iq_rate, decim = rates("240k")
+    C, nblk = 5, 12
+    sig = [orc.config3_signal(300 + c, fs_iq=iq_rate) for c in range(C)]
+    first = np.stack([s.generate(3 * 8192 * decim) for s in sig])
+    rest = np.stack([s.generate(nblk * 8192 * decim, start_sample=3 * 8192 * decim) for s in sig])
+    eng = fm.Engine(fm.make_config(max_blocks=4), C, 0)
+    chans = [orc.Channel(orc_fm, orc.make_config()) for _ in range(C)]
+    a0, g0, s0, _ = run_engine_chunks(eng, first, 3, 3)
+    ref0 = [ch.process(first[c]) for c, ch in enumerate(chans)]
+    for victim, what, kw in ((1, fm.engine.RESET_ALL, dict(dsp=True, rds=True)),
+                             (3, fm.engine.RESET_DSP, dict(dsp=True, rds=False))):
+        eng.reset(what, victim)
+        chans[victim].reset(**kw)
+    a1, g1, s1, _ = run_engine_chunks(eng, rest, nblk, 4)
+    for c, ch in enumerate(chans):
+        ref1 = ch.process(rest[c])
+        assert np.array_equal(a0[c][0], ref0[c].left) and np.array_equal(a1[c][0], ref1.left), c
+        assert np.array_equal(a1[c][1], ref1.right), c
+        assert np.array_equal(s1[c], ref1.status), c
+        assert groups_equal(g1[c], ref1.groups), c
+    assert sum(len(g) for g in g1) > 0
+    eng.close()
