@@ -13,7 +13,9 @@ def rates(which: str):
     return {"240k": (2_400_000, 10), "256k": (2_048_000, 8), "1024k": (1_024_000, 4),
             "direct256k": (256_000, 1),
             # DSP rate above 2 x 171 kHz: the RDS resampler's window no longer fits its tile
-            "480k": (2_400_000, 5)}[which]
+            "480k": (2_400_000, 5),
+            # the smallest and the largest instantiated decimation factors
+            "m2": (480_000, 2), "m16": (3_840_000, 16)}[which]
 
 
 def groups_equal(a: np.ndarray, b: np.ndarray, keys=GROUP_KEYS) -> bool:

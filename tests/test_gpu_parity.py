@@ -27,7 +27,7 @@ def _compare_exact(eng_audio, eng_groups, eng_status, dbg, ref, decim):
     assert groups_equal(eng_groups, ref.groups)
 
 
-@pytest.mark.parametrize("rate", ["240k", "256k", "1024k", "direct256k", "480k"])
+@pytest.mark.parametrize("rate", ["240k", "256k", "1024k", "direct256k", "480k", "m2", "m16"])
 def test_config2_single_channel_bit_exact(orc_fm, orc_libm, rate):
     """BASELINE config 2: the config-1 multiplex on one channel, compared per block."""
     iq_rate, decim = rates(rate)
