@@ -16,8 +16,12 @@ are independent: they are sharded across ranks with no collective on the data pa
   e2e      same metric through the C-ABI host call (pinned host IQ in, audio/groups/status out)
   roofline dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak, plus
            its FP32 FMA rate (the FIR kernels are FP32-pipe-bound)
+  stage_ms every stage's kernels alone on one stream (the RDS branch as rds_resample / rds /
+           rds_sync); the dominant one is the kernel `roofline` describes
   cpu_baseline / --impl reference: the CPU oracle (restated reference pipeline, libm flavour)
-           on the host cores, one channel per thread.
+           on the host cores, one channel per thread; the decode time of the threads is timed.
+Multi-GPU runs give every rank NVML's ideal CPU affinity for its GPU before pinned host memory
+is allocated; a rank that cannot pin its buffers takes the e2e leg off for all ranks.
 """
 from __future__ import annotations
 
