@@ -230,6 +230,7 @@ public:
     create(firdes_kaiser(n, fc, As, mu), 2.0f * fc);
   }
   void reset() { w_.reset(); }
+  void set_scale(float scale) { scale_ = scale; }  // firfilt_crcf_set_scale
   void push(cf32 x) { w_.push(x); }
   cf32 execute() const {
     cf32 y = dot_c(hrev_.data(), w_.view(), w_.size());
@@ -287,6 +288,7 @@ public:
     w_.init(static_cast<unsigned>(h.size()));
   }
   void reset() { w_.reset(); }
+  void set_scale(float scale) { scale_ = scale; }  // firdecim_crcf_set_scale
   cf32 execute(const cf32 *x) {
     cf32 y{};
     for (unsigned i = 0; i < M_; i++) {
@@ -360,6 +362,8 @@ public:
     g_ = g0_;
     y2_ = 1.0f;
   }
+  void set_bandwidth(float bandwidth) { alpha_ = bandwidth; }  // agc_crcf_set_bandwidth
+  void set_gain(float gain) { g_ = gain; }                      // agc_crcf_set_gain
   cf32 execute(cf32 x) {
     cf32 y{x.re * g_, x.im * g_};
     const float e = (y.re * y.re) + (y.im * y.im);
@@ -407,6 +411,11 @@ public:
     theta_ = 0;
     dtheta_ = nco_constrain(f0_);
   }
+  void reset_zero() {  // nco_crcf_reset alone: phase and frequency to zero
+    theta_ = 0;
+    dtheta_ = 0;
+  }
+  void set_frequency(float freq) { dtheta_ = nco_constrain(freq); }  // nco_crcf_set_frequency
   void pll_set_bandwidth(float bw) {
     alpha_ = bw;
     beta_ = std::sqrt(bw);

@@ -16,7 +16,34 @@
 #include <new>
 #include <vector>
 
+#ifdef ORACLE_USE_REFERENCE
+// Third build (oracle/Makefile, target ref): the SAME harness over the reference's own classes,
+// compiled unmodified from /root/reference over liquid_shim/ -> oracle/_ref/libfmref.so.
+#include <algorithm>
+#include <complex>
+
+#include "af_post_processor.h"
+#include "dsp/liquid_primitives.h"
+#include "fm_demod.h"
+#include "rds_decoder.h"
+#include "redsea_port/dsp/subcarrier.hh"
+#include "stereo_decoder.h"
+
+namespace orc {
+using cf32 = std::complex<float>;
+using ::AFPostProcessor;
+using ::FMDemod;
+using ::RDSDecoder;
+using ::RDSGroup;
+using ::StereoDecoder;
+using ComplexDecimator = fm_tuner::dsp::liquid::ComplexDecimator;
+namespace m {
+inline const char *name() { return "reference"; }
+}  // namespace m
+}  // namespace orc
+#else
 #include "pipeline.hpp"
+#endif
 
 extern "C" {
 
@@ -86,8 +113,46 @@ public:
     }
     if (rds) {
       rds_.reset();
+#ifdef ORACLE_USE_REFERENCE
+      if (tap_) {
+        tap_->reset();  // RDSDecoder::Impl::reset, rds_decoder.cpp:23-27
+      }
+#endif
     }
   }
+
+#ifdef ORACLE_USE_REFERENCE
+  // RDSDecoder keeps its SubcarrierSet private and hands out groups only. For bit-level
+  // comparisons a second, public redsea::SubcarrierSet is fed the same MPX in the same chunks
+  // (rds_decoder.cpp:74-93); off unless orc_channel_enable_bits_tap was called.
+  void enableTap() {
+    if (!tap_) {
+      tap_ = std::make_unique<redsea::SubcarrierSet>(static_cast<float>(std::max(1, fs_)));
+    }
+  }
+  void tapBits(const float *mpx, size_t n) {
+    if (!tap_ || !mpx) {
+      return;
+    }
+    size_t offset = 0;
+    while (offset < n) {
+      const size_t chunk = std::min(static_cast<size_t>(redsea::kInputChunkSize), n - offset);
+      auto input = std::make_unique<redsea::MPXBuffer>();
+      input->used_size = chunk;
+      std::memcpy(input->data.data(), mpx + offset, chunk * sizeof(float));
+      const redsea::BitBuffer bits = tap_->chunkToBits(*input, 1);
+      for (const redsea::TimedBit &b : bits.bits[0]) {
+        all_bits_.push_back(b.value ? 1 : 0);
+      }
+      offset += chunk;
+    }
+  }
+  std::unique_ptr<redsea::SubcarrierSet> tap_;
+  std::vector<uint8_t> all_bits_;
+  std::vector<uint8_t> &allBits() { return all_bits_; }
+#else
+  std::vector<uint8_t> &allBits() { return rds_.allBits(); }
+#endif
 
   // one logical block: iq holds block_samples * decimation IQ pairs
   size_t processBlock(const uint8_t *iq, float *outL, float *outR, size_t cap,
@@ -116,6 +181,9 @@ public:
                                                          demodSamples)
                             : demod_.processSplit(iq, mpx_.data(), mono.data(), demodSamples);
       rds_.process(mpx_.data(), demodSamples, onGroup);
+#ifdef ORACLE_USE_REFERENCE
+      tapBits(mpx_.data(), demodSamples);
+#endif
       for (size_t i = 0; i < outSamples; i++) {
         const float v = mono[i] * 0.5f;
         outL[i] = v;
@@ -128,6 +196,9 @@ public:
         demod_.processSplit(iq, mpx_.data(), nullptr, demodSamples);
       }
       rds_.process(mpx_.data(), demodSamples, onGroup);
+#ifdef ORACLE_USE_REFERENCE
+      tapBits(mpx_.data(), demodSamples);
+#endif
       const size_t ss = stereo_.processAudio(mpx_.data(), sl_.data(), sr_.data(), demodSamples);
       outSamples = afpost_.process(sl_.data(), sr_.data(), ss, outL, outR, std::min(cap, n));
       stereoDetected = stereo_.isStereo();
@@ -250,9 +321,19 @@ long orc_channel_process(void *h, const uint8_t *iq, size_t n_blocks, float *out
   return static_cast<long>(total);
 }
 
+// reference build only: start collecting demodulated bits (no-op for the restated oracle, which
+// always collects them)
+void orc_channel_enable_bits_tap(void *h) {
+#ifdef ORACLE_USE_REFERENCE
+  static_cast<Channel *>(h)->enableTap();
+#else
+  (void)h;
+#endif
+}
+
 // every RDS bit demodulated so far (before block sync)
 size_t orc_channel_rds_bits(void *h, uint8_t *out, size_t cap) {
-  auto &v = static_cast<Channel *>(h)->rds_.allBits();
+  auto &v = static_cast<Channel *>(h)->allBits();
   if (out) {
     std::memcpy(out, v.data(), std::min(cap, v.size()));
   }
@@ -374,6 +455,7 @@ size_t orc_rds_process(void *h, const float *mpx, size_t n, orc_group *out, size
   });
   return k;
 }
+#ifndef ORACLE_USE_REFERENCE
 size_t orc_rds_bits(void *h, uint8_t *out, size_t cap) {
   auto &v = static_cast<RDSDecoder *>(h)->allBits();
   if (out) {
@@ -500,5 +582,6 @@ void orc_math_log(const float *x, float *r, size_t n) {
   }
 }
 uint32_t orc_nco_constrain(float x) { return orc::nco_constrain(x); }
+#endif  // !ORACLE_USE_REFERENCE
 
 }  // extern "C"

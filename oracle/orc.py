@@ -27,12 +27,18 @@ def build(force: bool = False) -> None:
 
     oracle_deps = ("oracle_capi.cpp", "pipeline.hpp", "liquid_restated.hpp", "Makefile",
                    os.path.join("..", "fmtuner_sdr_b200", "csrc", "fm_math.h"))
+    ref_deps = ("oracle_capi.cpp", "liquid_restated.hpp", "Makefile",
+                os.path.join("liquid_shim", "liquid_shim.cpp"),
+                os.path.join("liquid_shim", "liquid", "liquid.h"))
     need = force or stale("liboracle_libm.so", oracle_deps) or stale("liboracle_fm.so", oracle_deps) \
         or stale("libsiggen.so", ("siggen.cpp", "Makefile"))
     have_ref_src = os.path.isdir("/root/reference/src/redsea_port")
     ref_missing = have_ref_src and not all(
         os.path.exists(os.path.join(HERE, "_ref", f))
-        for f in ("libredsea_ref.so", "libsiglevel_ref.so", "libxdr_ref.so"))
+        for f in ("libredsea_ref.so", "libsiglevel_ref.so", "libxdr_ref.so", "libfmref.so",
+                  "libfmref_contract.so"))
+    if have_ref_src and not ref_missing:
+        ref_missing = stale(os.path.join("_ref", "libfmref.so"), ref_deps)
     if need or ref_missing:
         subprocess.run(["make", "-C", HERE, "--no-print-directory"], check=True,
                        stdout=subprocess.DEVNULL)
@@ -93,12 +99,29 @@ def _p(a, t):
 
 
 class OracleLib:
-    """One flavour of the oracle: math='libm' (faithful) or 'fm' (engine-shared kernels)."""
+    """One flavour of the oracle: math='libm' (faithful) or 'fm' (engine-shared kernels) are the
+    restated pipeline; 'ref' is the REFERENCE's own sources compiled unmodified over
+    liquid_shim/ (oracle/_ref/libfmref.so, -ffp-contract=off) and 'ref_contract' the same with
+    gcc's default FMA contraction. The reference flavours have the channel- and class-level
+    entry points only (no design getters, no block-sync / math hooks)."""
+
+    REF_LIBS = {"ref": "libfmref.so", "ref_contract": "libfmref_contract.so"}
+
+    @classmethod
+    def ref_path(cls, math: str = "ref") -> str:
+        return os.path.join(HERE, "_ref", cls.REF_LIBS[math])
+
+    @classmethod
+    def have_ref(cls, math: str = "ref") -> bool:
+        build()
+        return os.path.exists(cls.ref_path(math))
 
     def __init__(self, math: str = "fm"):
         build()
         self.math = math
-        self.lib = C.CDLL(os.path.join(HERE, f"liboracle_{math}.so"))
+        self.is_ref = math in self.REF_LIBS
+        path = self.ref_path(math) if self.is_ref else os.path.join(HERE, f"liboracle_{math}.so")
+        self.lib = C.CDLL(path)
         L = self.lib
         L.orc_math_name.restype = C.c_char_p
         L.orc_channel_create.restype = C.c_void_p
@@ -115,6 +138,7 @@ class OracleLib:
             C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_channel_rds_bits.restype = C.c_size_t
         L.orc_channel_rds_bits.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t]
+        L.orc_channel_enable_bits_tap.argtypes = [C.c_void_p]
         # class-level
         L.orc_decim_create.restype = C.c_void_p
         L.orc_decim_create.argtypes = [C.c_uint32, C.c_uint32, C.c_float]
@@ -174,6 +198,8 @@ class OracleLib:
         L.orc_rds_process.restype = C.c_size_t
         L.orc_rds_process.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.c_void_p,
                                       C.c_size_t]
+        if self.is_ref:
+            return
         L.orc_rds_bits.restype = C.c_size_t
         L.orc_rds_bits.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t]
         L.orc_blockstream_run.restype = C.c_size_t
@@ -270,6 +296,10 @@ class Channel:
             raise RuntimeError("oracle capacity exceeded")
         return ChannelResult(outL[:tot], outR[:tot], status, groups[:ng.value].copy(),
                              dec.view(np.complex64) if dec is not None else None, mpx, sl, sr)
+
+    def enable_bits_tap(self):
+        """Reference flavours: collect demodulated bits from now on (rds_bits())."""
+        self.L.lib.orc_channel_enable_bits_tap(self.h)
 
     def rds_bits(self) -> np.ndarray:
         n = self.L.lib.orc_channel_rds_bits(self.h, None, 0)
