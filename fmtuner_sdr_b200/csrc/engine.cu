@@ -98,11 +98,11 @@ struct fmgpu_engine {
   // consumer stage. Stage s of block q therefore runs beside stage s+1 of block q-1: the serial
   // one-lane-per-channel kernels of successive blocks overlap each other and the FIR kernels, and
   // the latency of a block is the slowest stage, not the sum of the stages.
-  // Scratch buffers are rings of K = max(2, max_blocks) block slots laid out contiguously in
+  // Scratch buffers are rings of K = max(3, max_blocks) block slots laid out contiguously in
   // time behind the halo, [H | slot 0 | slot 1 | ...]: block q lives in slot q % K, its FIR halo
   // is simply the tail of the previous slot, and only slot 0 needs the tail of slot K-1 copied
   // in front of it. A producer about to overwrite slot q % K first waits for the consumers of
-  // block q - K.
+  // block q - K + 1: they are the last readers of that slot (its tail is their halo).
   enum Stage {
     ST_H2D = 0, ST_DECIM, ST_DC, ST_CHAN, ST_AGC, ST_FD, ST_PILOT, ST_STEREO, ST_LPF, ST_AF, ST_RDS,
     ST_D2H, ST_COUNT
@@ -117,8 +117,8 @@ struct fmgpu_engine {
   static constexpr int kMaxGroups = 2;        // channel ranges with their own pipe (streams)
   int nGroups = 1;
   Pipe pipes[kMaxGroups];
-  int K = 2;             // ring slots
-  int ER = 3;            // events per stage (> K)
+  int K = 3;             // ring slots
+  int ER = 4;            // events per stage (> K)
   uint64_t seq = 0;      // logical blocks queued so far (slot = seq % K)
   bool headFresh = true; // the halo in front of slot 0 is already in place (start, reset, realign)
   bool asyncPending = false;
@@ -336,6 +336,21 @@ template <typename T>
 void zeroPrefix(T *buf, size_t pitch, size_t count, int lo, int hi, cudaStream_t s) {
   cudaMemset2DAsync(buf + static_cast<size_t>(lo) * pitch, pitch * sizeof(T), 0, count * sizeof(T),
                     static_cast<size_t>(hi - lo), s);
+}
+
+// One strided copy of the same `bytes` to `field` of every state struct of channels [lo, hi).
+template <typename S>
+int fillStateField(fmgpu_engine *e, S *base, size_t fieldOffset, const void *value,
+                          size_t bytes, int lo, int hi) {
+  const size_t cnt = static_cast<size_t>(hi - lo);
+  std::vector<uint8_t> rows(cnt * bytes);
+  for (size_t i = 0; i < cnt; i++) {
+    std::memcpy(rows.data() + i * bytes, value, bytes);
+  }
+  CK(cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(base + lo) + fieldOffset, sizeof(S), rows.data(),
+                       bytes, bytes, cnt, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // `rows` is pageable and about to go out of scope
+  return FMGPU_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -608,9 +623,13 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     for (int p : producers) {
       cudaStreamWaitEvent(P.run[st], ev(p, q), 0);
     }
-    if (q >= static_cast<uint64_t>(K)) {
+    // Block q overwrites ring slot q % K. Its last readers are not those of block q - K but of
+    // block q - K + 1, whose FIR / delay halo is the TAIL of that slot (only slot 0 reads a copied
+    // halo). With K >= 3 this still lets stage s of block q run beside stage s + 1 of block q - 1.
+    const uint64_t back = static_cast<uint64_t>(std::max(K - 1, 1));  // K = 1: the halo is a copy
+    if (q >= back) {
       for (int r : readers) {
-        cudaStreamWaitEvent(P.run[st], ev(r, q - K), 0);
+        cudaStreamWaitEvent(P.run[st], ev(r, q - back), 0);
       }
     }
   };
@@ -724,6 +743,13 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
                       out.groups, out.gcap, status, nb, 1, b, ch0, nch, s);
       launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
       launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, s);
+      if (last) {
+        // the call's group counts, from the stream that owns RdsState::n_groups: the next call's
+        // first k_prepare on this stream zeroes it again
+        launchStoreCounts(e->dAudioSt, e->dRds, nullptr, out.nGroups, ch0, nch, stereo ? 0 : 1,
+                          static_cast<uint32_t>(out.acap), out.gcap, s);
+        e->launches += 1;
+      }
     }
     e->launches += 5;
   }
@@ -826,7 +852,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     // the call's counts, once both branches have finished its last block
     cudaStreamWaitEvent(sAf, ev(E::ST_RDS, q), 0);
     Span sp(e, "commit", sAf);
-    launchStoreCounts(e->dAudioSt, e->dRds, out.nAudio, out.nGroups, ch0, nch, stereo ? 0 : 1,
+    launchStoreCounts(e->dAudioSt, e->dRds, out.nAudio, nullptr, ch0, nch, stereo ? 0 : 1,
                       static_cast<uint32_t>(out.acap), out.gcap, sAf);
     e->launches += 1;
   }
@@ -1132,7 +1158,9 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   e->nmax = static_cast<size_t>(e->N) * e->maxBlocks;
   // ring of K block slots per scratch buffer (see fmgpu_engine::Pipe); slots must start on
   // 16-byte boundaries for the cp.async tile loads, else every block goes through slot 0
-  e->K = (e->N % 32 == 0) ? std::max(2, e->maxBlocks) : 1;
+  // K >= 3: a producer waits for the readers of block q - K + 1 (their halo is the tail of the slot
+  // it overwrites), so three slots are what lets neighbouring stages of successive blocks overlap
+  e->K = (e->N % 32 == 0) ? std::max(3, e->maxBlocks) : 1;
   if (const char *rk = getenv("FMGPU_RING_K")) {  // deeper ring: stages may run further ahead
     if (e->K > 1) {
       e->K = std::max(e->K, std::min(16, atoi(rk)));
@@ -1332,6 +1360,10 @@ int fmgpu_dsp_rate(const fmgpu_engine *e) { return e ? e->fs : 0; }
 
 // ---- settings --------------------------------------------------------------
 int fmgpu_set_w0_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   return forChannels(e, channel, [&](int c) {
     e->hParams[c].w0_hz = std::clamp(bw_hz, 0, 400000);
     return FMGPU_OK;
@@ -1339,16 +1371,19 @@ int fmgpu_set_w0_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
 }
 
 int fmgpu_set_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
-  if (!e) {
+  if (!e || channel < -1 || channel >= e->C) {
     return FMGPU_EINVAL;
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
-  cudaSetDevice(e->device);
-  return forChannels(e, channel, [&](int c) {
+  CK(cudaSetDevice(e->device));
+  const int lo = (channel < 0) ? 0 : channel;
+  const int hi = (channel < 0) ? e->C : channel + 1;
+  std::vector<int> changed;
+  for (int c = lo; c < hi; c++) {
     ChanParams &p = e->hParams[c];
     const fmdesign::ChannelFilterSpec spec = fmdesign::channelFilterSpec(bw_hz, p.w0_hz, e->fs);
     if (spec.index == p.bandwidth_mode) {
-      return FMGPU_OK;  // fm_demod.cpp:114-116
+      continue;  // fm_demod.cpp:114-116
     }
     const int slot = filterSlot(e, spec.length, spec.cutoff, spec.atten);
     if (slot < 0) {
@@ -1357,13 +1392,24 @@ int fmgpu_set_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz) {
     }
     p.bandwidth_mode = spec.index;
     p.filt = slot;
-    e->paramsDirty = true;
-    // the FIR is re-created with an empty window (fm_demod.cpp:134); r_prev is kept
-    realign(e);  // queued blocks finish; the window (halo) sits in front of ring slot 0
-    zeroPrefix(e->dX2, e->x2Pitch, H_X2, c, c + 1, e->stream);
-    cudaStreamSynchronize(e->stream);
+    changed.push_back(c);
+  }
+  if (changed.empty()) {
     return FMGPU_OK;
-  });
+  }
+  e->paramsDirty = true;
+  // the FIR is re-created with an empty window (fm_demod.cpp:134); r_prev is kept
+  realign(e);  // queued blocks finish; the window (halo) sits in front of ring slot 0
+  for (size_t i = 0; i < changed.size();) {  // one memset per run of neighbouring channels
+    size_t j = i + 1;
+    while (j < changed.size() && changed[j] == changed[j - 1] + 1) {
+      j++;
+    }
+    zeroPrefix(e->dX2, e->x2Pitch, H_X2, changed[i], changed[j - 1] + 1, e->stream);
+    i = j;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return FMGPU_OK;
 }
 
 int fmgpu_set_bandwidth_mode(fmgpu_engine *e, int channel, int mode) {
@@ -1371,47 +1417,59 @@ int fmgpu_set_bandwidth_mode(fmgpu_engine *e, int channel, int mode) {
 }
 
 int fmgpu_set_agc_mode(fmgpu_engine *e, int channel, int mode) {
-  if (!e || mode < 0 || mode > 2) {
+  if (!e || mode < 0 || mode > 2 || channel < -1 || channel >= e->C) {
     return FMGPU_EINVAL;
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
-  cudaSetDevice(e->device);
-  return forChannels(e, channel, [&](int c) {
+  CK(cudaSetDevice(e->device));
+  const int lo = (channel < 0) ? 0 : channel;
+  const int hi = (channel < 0) ? e->C : channel + 1;
+  for (int c = lo; c < hi; c++) {
     ChanParams &p = e->hParams[c];
     p.agc_mode = mode;
-    e->paramsDirty = true;
     if (mode != 0) {
-      // AGC::init re-creates the object: gain 1, energy 1 (fm_demod.cpp:146-147)
       p.agc_alpha = (mode == 1) ? 0.01f : 0.001f;
-      const float init[2] = {1.0f, 1.0f};
-      cudaMemcpyAsync(&e->dDemod[c].agc_g, init, sizeof(init), cudaMemcpyHostToDevice, e->stream);
-      cudaStreamSynchronize(e->stream);
     }
-    return FMGPU_OK;
-  });
+  }
+  e->paramsDirty = true;
+  if (mode != 0) {
+    // AGC::init re-creates the object: gain 1, energy 1 (fm_demod.cpp:146-147). Blocks already
+    // queued finish first: an in-flight k_agc would write its own gain back over the reset.
+    syncPipes(e);
+    static_assert(offsetof(DemodState, agc_y2) == offsetof(DemodState, agc_g) + sizeof(float),
+                  "agc_g and agc_y2 are written as one pair");
+    const float init[2] = {1.0f, 1.0f};
+    return fillStateField(e, e->dDemod, offsetof(DemodState, agc_g), init, sizeof(init), lo, hi);
+  }
+  return FMGPU_OK;
 }
 
 int fmgpu_set_deemphasis_us(fmgpu_engine *e, int channel, int tau_us) {
-  if (!e) {
+  if (!e || channel < -1 || channel >= e->C) {
     return FMGPU_EINVAL;
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
-  cudaSetDevice(e->device);
-  return forChannels(e, channel, [&](int c) {
+  CK(cudaSetDevice(e->device));
+  const int lo = (channel < 0) ? 0 : channel;
+  const int hi = (channel < 0) ? e->C : channel + 1;
+  for (int c = lo; c < hi; c++) {
     ChanParams &p = e->hParams[c];
     deemphCoeffs(tau_us, e->cfg.output_rate, &p.deemph_on, &p.de_b0, &p.de_a1);
     deemphCoeffs(tau_us, e->cfg.output_rate, &p.mono_deemph_on, &p.mono_de_b0, &p.mono_de_a1);
-    e->paramsDirty = true;
-    if (tau_us > 0) {
-      // IIRFilterReal::init creates fresh filters: state cleared
-      const float z[2] = {0.0f, 0.0f};
-      cudaMemcpyAsync(e->dAudioSt[c].de_v1, z, sizeof(z), cudaMemcpyHostToDevice, e->stream);
-      cudaMemcpyAsync(&e->dAudioSt[c].mono_de_v1, z, sizeof(float), cudaMemcpyHostToDevice,
-                      e->stream);
-      cudaStreamSynchronize(e->stream);
+  }
+  e->paramsDirty = true;
+  if (tau_us > 0) {
+    // IIRFilterReal::init creates fresh filters: state cleared — once the queued blocks, whose
+    // k_audio_iir writes the state back, have finished
+    syncPipes(e);
+    const float z[2] = {0.0f, 0.0f};
+    int rc = fillStateField(e, e->dAudioSt, offsetof(AudioState, de_v1), z, sizeof(z), lo, hi);
+    if (rc == FMGPU_OK) {
+      rc = fillStateField(e, e->dAudioSt, offsetof(AudioState, mono_de_v1), z, sizeof(float), lo, hi);
     }
-    return FMGPU_OK;
-  });
+    return rc;
+  }
+  return FMGPU_OK;
 }
 
 int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz) {
@@ -1430,9 +1488,10 @@ int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz) {
 }
 
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
-  if (mode < 0 || mode > 2) {
+  if (!e || mode < 0 || mode > 2) {
     return FMGPU_EINVAL;
   }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   return forChannels(e, channel, [&](int c) {
     e->hParams[c].blend_mode = mode;
     e->paramsDirty = true;
@@ -1441,6 +1500,10 @@ int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
 }
 
 int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   return forChannels(e, channel, [&](int c) {
     e->hParams[c].force_mono = on ? 1 : 0;
     e->paramsDirty = true;
@@ -1449,6 +1512,10 @@ int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on) {
 }
 
 int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on) {
+  if (!e) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   return forChannels(e, channel, [&](int c) {
     e->hParams[c].force_stereo = on ? 1 : 0;
     e->paramsDirty = true;
