@@ -147,7 +147,7 @@ def test_config5_10000_channels_streamed_equals_joined():
     only in the streamed runs, so a producer overwriting a ring slot whose tail is still some
     reader's halo, or a count written from the wrong stream, shows up here."""
     import torch
-    C, calls, B, nd = 10_000, 4, 2, 9
+    C, calls, B, nd = 10_000, 8, 2, 9      # 16 blocks = 0.55 s: the first RDS groups appear
     nblk = calls * B
     base = _distinct(nd, nblk, 10.0, 40.0, seed=8)
     dev = torch.device("cuda", 0)
@@ -193,7 +193,7 @@ def test_config5_10000_channels_streamed_equals_joined():
         for i, name in enumerate(("audio", "n_audio", "groups", "n_groups", "status")):
             assert torch.equal(joined[k][i], streamed[k][i]), (k, name)
         total_groups += int(joined[k][3].sum().item())
-    assert total_groups > C       # the comparison saw real groups
+    assert total_groups > C // 2  # the comparison saw real groups
     # replicas agree inside the streamed run too
     last = streamed[-1]
     assert torch.equal(last[0][nd:2 * nd], last[0][:nd]) and torch.equal(last[3][nd:2 * nd], last[3][:nd])
