@@ -4,5 +4,6 @@ Python is plumbing only: `Engine` is a ctypes view of the C ABI in include/fmgpu
 (libfmgpu.so, hand-written sm_100a CUDA). There is no CPU fallback; creating an
 engine without a CUDA device raises.
 """
-from .engine import (Channelizer, Engine, EngineError, LevelSums, SignalLevel, SynthParams, GROUP_DTYPE, STATUS_DTYPE, XdrRdsFormatter, lib_path,  # noqa: F401
+from .engine import (RESET_AFPOST, RESET_ALL, RESET_DECIM, RESET_DEMOD, RESET_DSP, RESET_RDS, RESET_STEREO,  # noqa: F401
+                     Channelizer, Engine, EngineError, LevelSums, SignalLevel, SynthParams, GROUP_DTYPE, STATUS_DTYPE, XdrRdsFormatter, lib_path,  # noqa: F401
                      load_library, make_config, synth_iq)

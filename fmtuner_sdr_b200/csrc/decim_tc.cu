@@ -1,0 +1,488 @@
+// decim_tc.cu — the decimating FIR of ComplexDecimator::executeComplex
+// (/root/reference/src/dsp/liquid_primitives.cpp:461-499) on the 5th-generation tensor cores.
+//
+//   y_c[n] = scale * sum_i hrev[i] * x_c[n*M - (L-1) + i],   x = (byte - 127.5) / 127.5
+//
+// is evaluated as an INTEGER contraction: the uint8 IQ bytes are the A operand as they are (no
+// unpack, no conversion: TMA drops [128 channels x 128 bytes] boxes of the caller's buffer straight
+// into 128B-swizzled shared memory), and B is a constant banded (Toeplitz) matrix of the taps,
+// quantised to round(hrev * 2^26) and split into four signed base-128 digits ("limbs"):
+//
+//   D[channel][(limb, j, iq)] = sum_k A[channel][k] * B[(limb, j, iq)][k]       (tcgen05.mma kind::i8,
+//                                                                               u8 x s8 -> s32 in TMEM)
+//   k = byte offset inside the tile's window, j = 0..7 the tile's outputs, iq = byte parity.
+//
+// The int32 sums are exact; the epilogue recombines the limbs, removes the 127.5 offset in integer
+// arithmetic (255 * sum of the taps that see real samples) and rounds ONCE to float. The result is
+// the FIR to within one float rounding of the exact sum with taps good to 2^-27 — closer to the
+// real-number answer than the 280-term float chain of the reference, but not bit-identical to it
+// (the FP32 kernel k_decim in kernels.cu stays the bit-exact flavour).
+//
+// One CTA per SM, persistent over (128-channel row tile, time segment) work items:
+//   warp 0     TMA producer: 16 KB chunks (128 rows x 128 B) into a ring of shared-memory slots
+//   warp 1     allocates TMEM, issues the MMAs (one elected lane), frees ring slots with tcgen05.commit
+//   warps 2-5  epilogue: tcgen05.ld the 64 accumulator columns of a tile, recombine, store float2
+// Window of tile t (8 outputs): block-relative bytes [ADV*t - WS0, ADV*t - WS0 + 32*KS), ADV = 16*M,
+// WS0 = roundup(2L - 2, 32); the bytes in front of the block come from the per-channel history
+// buffer (hist tensor map), invalid history is byte 0 and is compensated in the offset term.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+
+namespace fmgpu {
+
+namespace {
+
+constexpr int TC_ROWS = 128;          // channels per tile (UMMA M)
+constexpr int TC_NO = 8;              // outputs per tile
+constexpr int TC_LIMBS = 4;
+constexpr int TC_N = TC_NO * 2 * TC_LIMBS;   // 64 accumulator columns (UMMA N)
+constexpr int TC_CHUNK = 128;         // bytes of K per ring slot row (one 128B swizzle atom)
+constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
+constexpr int TC_B_CHUNKS = 6;        // K extent of B: 6 * 128 = 768 bytes >= 32 * KS
+constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 48 KB
+constexpr int TC_RING = 10;           // A ring slots (160 KB)
+constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns
+constexpr int TC_THREADS = 192;
+constexpr int TC_SHIFT = 26;          // taps are quantised to 2^-26
+constexpr size_t TC_SMEM = 1024 + TC_B_BYTES + (size_t)TC_RING * TC_CHUNK_BYTES + 512;
+
+struct TcParams {
+  int M, L, n_out;
+  int adv;          // bytes per tile = 2 * M * TC_NO
+  int ws0;          // window start in front of the tile's first output sample, bytes
+  int ksteps;       // MMAs (32 bytes of K each) per tile
+  int halo_chunks;  // chunks in front of the block (from the history buffer)
+  int tiles;        // tiles per block = n_out / TC_NO
+  int tiles_per_seg;
+  int n_seg;
+  int row_tiles;
+  int ch0, nch;
+  float out_scale;  // scale / (255 * 2^26)
+};
+
+__device__ __forceinline__ uint32_t smemAddr(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tmaLoad2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x,
+                                          int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void ummaCommit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B swizzle, 8-row groups 1024 bytes apart (UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t smemDesc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFF);          // start address
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void ummaI8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmemLd16(uint32_t taddr, int32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr));
+}
+
+// work item w -> (row tile, first tile of the segment, tiles in it)
+__device__ __forceinline__ void workItem(const TcParams &p, int w, int *row, int *t0, int *nt) {
+  *row = w / p.n_seg;
+  const int s = w - *row * p.n_seg;
+  *t0 = s * p.tiles_per_seg;
+  *nt = min(p.tiles_per_seg, p.tiles - *t0);
+}
+// window of tile t in chunk space (chunk g holds block-relative bytes [128 (g - HC), +128))
+__device__ __forceinline__ int windowStart(const TcParams &p, int t) {
+  return p.adv * t - p.ws0 + TC_CHUNK * p.halo_chunks;   // >= 0
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CUtensorMap tm_hist,
+           const uint4 *__restrict__ b_image, const int2 *__restrict__ offs, const int *__restrict__ hist_valid,
+           float2 *__restrict__ x1, size_t x1_pitch, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smemAddr(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;
+  const uint32_t sA = base + TC_B_BYTES;
+  const uint32_t sBar = sA + TC_RING * TC_CHUNK_BYTES;
+  // barriers: full[RING], empty[RING], tfull[ACC], tempty[ACC]; then the TMEM base word
+  const uint32_t barFull = sBar, barEmpty = sBar + 8 * TC_RING, barTFull = sBar + 16 * TC_RING,
+                 barTEmpty = barTFull + 8 * TC_ACC, sTmem = barTEmpty + 8 * TC_ACC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_work = p.row_tiles * p.n_seg;
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  {  // B image: generic-proxy stores, made visible to the async proxy (UMMA) below
+    uint8_t *gen = smem_raw + (base - smemAddr(smem_raw));
+    uint4 *dst = reinterpret_cast<uint4 *>(gen);
+    for (int i = threadIdx.x; i < TC_B_BYTES / 16; i += TC_THREADS) {
+      dst[i] = __ldg(b_image + i);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_RING; i++) {
+      mbarInit(barFull + 8 * i, 1);
+      mbarInit(barEmpty + 8 * i, 1);
+    }
+    for (int i = 0; i < TC_ACC; i++) {
+      mbarInit(barTFull + 8 * i, 1);
+      mbarInit(barTEmpty + 8 * i, 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcFenceBefore();
+  __syncthreads();
+  tcFenceAfter();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+
+  if (warp == 0) {
+    // ===== TMA producer =====================================================================
+    if (lane == 0) {
+      uint32_t cnt = 0;   // chunks issued so far (ring position)
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int row, t0, nt;
+        workItem(p, w, &row, &t0, &nt);
+        const int g0 = windowStart(p, t0) / TC_CHUNK;
+        const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
+        const int y = p.ch0 + row * TC_ROWS;
+        for (int g = g0; g <= g1; g++, cnt++) {
+          const uint32_t slot = cnt % TC_RING;
+          const uint32_t use = cnt / TC_RING;
+          if (use > 0) {
+            mbarWait(barEmpty + 8 * slot, (use - 1) & 1);
+          }
+          mbarExpectTx(barFull + 8 * slot, TC_CHUNK_BYTES);
+          if (g < p.halo_chunks) {
+            tmaLoad2d(sA + slot * TC_CHUNK_BYTES, &tm_hist, barFull + 8 * slot,
+                      2 * H_IQ - TC_CHUNK * (p.halo_chunks - g), y);
+          } else {
+            tmaLoad2d(sA + slot * TC_CHUNK_BYTES, &tm_iq, barFull + 8 * slot,
+                      TC_CHUNK * (g - p.halo_chunks), y);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ========================================================================
+    if (lane == 0) {
+      // u8 x s8 -> s32, K-major A and B, N = 64, M = 128 (UMMA::InstrDescriptor)
+      const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((TC_N >> 3) << 17) | ((TC_ROWS >> 4) << 24);
+      uint32_t cnt0 = 0;  // ring position of the work item's first chunk
+      uint32_t tile_cnt = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int row, t0, nt;
+        workItem(p, w, &row, &t0, &nt);
+        const int g0 = windowStart(p, t0) / TC_CHUNK;
+        const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
+        int have = g0 - 1;    // chunks known to have landed
+        int freed = g0 - 1;   // chunks handed back to the producer
+        for (int i = 0; i < nt; i++, tile_cnt++) {
+          const int ws = windowStart(p, t0 + i);
+          const int ge = (ws + 32 * p.ksteps - 1) / TC_CHUNK;
+          const uint32_t acc = tile_cnt % TC_ACC;
+          const uint32_t ause = tile_cnt / TC_ACC;
+          if (ause > 0) {
+            mbarWait(barTEmpty + 8 * acc, (ause - 1) & 1);
+          }
+          while (have < ge) {
+            have++;
+            const uint32_t c = cnt0 + static_cast<uint32_t>(have - g0);
+            mbarWait(barFull + 8 * (c % TC_RING), (c / TC_RING) & 1);
+          }
+          tcFenceAfter();
+          const uint32_t d_tmem = tmem_base + acc * TC_N;
+          for (int ks = 0; ks < p.ksteps; ks++) {
+            const int byte = ws + 32 * ks;
+            const uint32_t c = cnt0 + static_cast<uint32_t>(byte / TC_CHUNK - g0);
+            const uint64_t a_desc =
+                smemDesc(sA + (c % TC_RING) * TC_CHUNK_BYTES + static_cast<uint32_t>(byte % TC_CHUNK));
+            const uint64_t b_desc = smemDesc(sB + (ks >> 2) * (TC_N * TC_CHUNK) + (ks & 3) * 32);
+            ummaI8(d_tmem, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+          }
+          ummaCommit(barTFull + 8 * acc);
+          // chunks in front of the next tile's window are finished once these MMAs are
+          const int keep = (i + 1 < nt) ? windowStart(p, t0 + i + 1) / TC_CHUNK : g1 + 1;
+          while (freed < keep - 1) {
+            freed++;
+            const uint32_t c = cnt0 + static_cast<uint32_t>(freed - g0);
+            ummaCommit(barEmpty + 8 * (c % TC_RING));
+          }
+        }
+        cnt0 += static_cast<uint32_t>(g1 - g0 + 1);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5 own TMEM lanes 32 * (warp % 4) ..) ===============================
+    const int q = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int need_hist = p.L - 1;
+    const int2 off_all = __ldg(offs);    // every tap sees a real sample
+    uint32_t tile_cnt = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int row, t0, nt;
+      workItem(p, w, &row, &t0, &nt);
+      const int c = p.ch0 + row * TC_ROWS + q * 32 + lane;
+      const bool live = c < p.ch0 + p.nch;
+      const int valid = live ? __ldg(hist_valid + c) : need_hist;
+      float2 *out = x1 + static_cast<size_t>(live ? c : p.ch0) * x1_pitch;
+      for (int i = 0; i < nt; i++, tile_cnt++) {
+        const uint32_t acc = tile_cnt % TC_ACC;
+        mbarWait(barTFull + 8 * acc, (tile_cnt / TC_ACC) & 1);
+        tcFenceAfter();
+        int32_t d[TC_N];
+        const uint32_t taddr = tmem_base + lane_base + acc * TC_N;
+        tmemLd16(taddr, d);
+        tmemLd16(taddr + 16, d + 16);
+        tmemLd16(taddr + 32, d + 32);
+        tmemLd16(taddr + 48, d + 48);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tcFenceBefore();
+        __syncwarp();
+        if (lane == 0) {
+          mbarArrive(barTEmpty + 8 * acc);
+        }
+        const int n0 = (t0 + i) * TC_NO;
+        float2 y[TC_NO];
+#pragma unroll
+        for (int j = 0; j < TC_NO; j++) {
+          // taps in front of the first real sample multiply byte 0: leave them out of the offset
+          int2 off = off_all;
+          const int missing = need_hist - p.M * (n0 + j) - valid;
+          if (missing > 0) {
+            off = __ldg(offs + min(missing, p.L));
+          }
+          float v[2];
+#pragma unroll
+          for (int iq = 0; iq < 2; iq++) {
+            const int col = j * 2 + iq;   // column of limb l: l * 16 + col, limb 0 = most significant
+            const int hi = (d[col] << 7) + d[16 + col];
+            const int lo = (d[32 + col] << 7) + d[48 + col];
+            const int ph = 2 * hi - off.x;   // offset term 255 * sum(hq) split the same way
+            const int pl = 2 * lo - off.y;
+            v[iq] = fmaf(static_cast<float>(ph), 16384.0f, static_cast<float>(pl)) * p.out_scale;
+          }
+          y[j] = make_float2(v[0], v[1]);
+        }
+        if (live) {
+          float4 *o4 = reinterpret_cast<float4 *>(out + n0);
+#pragma unroll
+          for (int j = 0; j < TC_NO; j += 2) {
+            o4[j >> 1] = make_float4(y[j].x, y[j].y, y[j + 1].x, y[j + 1].y);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  tcFenceBefore();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                              CUtensorMapFloatOOBfill);
+
+EncodeFn encodeFn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeFn>(p);
+    }
+  });
+  return fn;
+}
+
+// [rows][row_bytes] uint8 with `pitch` bytes between rows; boxes of 128 bytes x 128 rows, 128B swizzle
+bool encodeRows(CUtensorMap *map, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch) {
+  EncodeFn fn = encodeFn();
+  if (!fn) {
+    return false;
+  }
+  const cuuint64_t dims[2] = {row_bytes, rows};
+  const cuuint64_t strides[1] = {pitch};
+  const cuuint32_t box[2] = {TC_CHUNK, TC_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool decimTcSupported(int M, int L, int n_out) {
+  if (M < 2 || (M & 1) || L < M || n_out % TC_NO != 0) {
+    return false;   // the tile advance 16 * M must be a multiple of the 32-byte MMA K step
+  }
+  const int ws0 = ((2 * L - 2) + 31) / 32 * 32;
+  const int ksteps = (ws0 + 2 * M * (TC_NO - 1) + 2 + 31) / 32;
+  const int halo = (ws0 + TC_CHUNK - 1) / TC_CHUNK;
+  return ksteps <= 4 * TC_B_CHUNKS && halo * TC_CHUNK <= 2 * H_IQ && L - 1 <= H_IQ;
+}
+
+// Host: quantise the reversed taps, split them into limbs and lay the Toeplitz matrix B out the way
+// tcgen05.mma reads a K-major 128B-swizzled operand; plus the offset table (entry m: the taps from
+// index m on see real samples), each entry 255 * sum(hq) split as {hi, lo} with sum = hi*2^14 + lo.
+void decimTcBuildTables(int M, const std::vector<float> &hrev, std::vector<uint8_t> *b_image,
+                        std::vector<int32_t> *offs) {
+  const int L = static_cast<int>(hrev.size());
+  const int ws0 = ((2 * L - 2) + 31) / 32 * 32;
+  std::vector<long long> hq(L);
+  for (int i = 0; i < L; i++) {
+    hq[i] = std::llround(static_cast<double>(hrev[i]) * static_cast<double>(1 << TC_SHIFT));
+  }
+  b_image->assign(TC_B_BYTES, 0);
+  auto digit = [](long long v, int limb) {   // balanced base-128 digits, limb 0 most significant
+    int dg[TC_LIMBS];
+    for (int l = TC_LIMBS - 1; l >= 0; l--) {
+      long long r = ((v % 128) + 128) % 128;
+      if (r >= 64) {
+        r -= 128;
+      }
+      dg[l] = static_cast<int>(r);
+      v = (v - r) / 128;
+    }
+    return dg[limb];
+  };
+  for (int j = 0; j < TC_NO; j++) {
+    for (int i = 0; i < L; i++) {
+      for (int iq = 0; iq < 2; iq++) {
+        // sample i of output j's window is block-relative byte 2 (M (8 t + j) - (L - 1) + i) + iq
+        const int k = ws0 + 2 * (M * j - (L - 1) + i) + iq;   // byte inside the tile's window
+        for (int l = 0; l < TC_LIMBS; l++) {
+          const int n = l * 16 + j * 2 + iq;
+          const int kc = k / TC_CHUNK, kk = k % TC_CHUNK;
+          const size_t at = static_cast<size_t>(kc) * TC_N * TC_CHUNK + static_cast<size_t>(n) * TC_CHUNK +
+                            static_cast<size_t>(((kk >> 4) ^ (n & 7)) << 4) + (kk & 15);
+          (*b_image)[at] = static_cast<uint8_t>(static_cast<int8_t>(digit(hq[i], l)));
+        }
+      }
+    }
+  }
+  offs->assign(2 * (L + 1), 0);
+  long long suffix = 0;
+  for (int m = L; m >= 0; m--) {
+    if (m < L) {
+      suffix += hq[m];
+    }
+    const long long hi = suffix >> 14, lo = suffix & 16383;   // floor split, lo in [0, 2^14)
+    (*offs)[2 * m] = static_cast<int32_t>(255 * hi);
+    (*offs)[2 * m + 1] = static_cast<int32_t>(255 * lo);
+  }
+}
+
+cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, size_t iq_row_bytes,
+                          const uint8_t *hist, const int *hist_valid, int total_rows, float2 *x1,
+                          size_t x1_pitch, int n_out, int ch0, int nch, float scale,
+                          const uint8_t *b_image_dev, const int32_t *offs_dev, int sm_count,
+                          cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(k_decim_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(TC_SMEM));
+  });
+  if (attr_err != cudaSuccess) {
+    return attr_err;
+  }
+  TcParams p{};
+  p.M = M;
+  p.L = L;
+  p.n_out = n_out;
+  p.adv = 2 * M * TC_NO;
+  p.ws0 = ((2 * L - 2) + 31) / 32 * 32;
+  p.ksteps = (p.ws0 + 2 * M * (TC_NO - 1) + 2 + 31) / 32;
+  p.halo_chunks = (p.ws0 + TC_CHUNK - 1) / TC_CHUNK;
+  p.tiles = n_out / TC_NO;
+  p.row_tiles = (nch + TC_ROWS - 1) / TC_ROWS;
+  // segments: enough work items to fill the SMs several times over, at least 32 tiles each
+  int n_seg = std::max(1, (8 * sm_count + p.row_tiles - 1) / p.row_tiles);
+  n_seg = std::min(n_seg, std::max(1, p.tiles / 32));
+  p.tiles_per_seg = (p.tiles + n_seg - 1) / n_seg;
+  p.n_seg = (p.tiles + p.tiles_per_seg - 1) / p.tiles_per_seg;
+  p.ch0 = ch0;
+  p.nch = nch;
+  p.out_scale = static_cast<float>(static_cast<double>(scale) / (255.0 * static_cast<double>(1 << TC_SHIFT)));
+  CUtensorMap tm_iq, tm_hist;
+  if (!encodeRows(&tm_iq, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
+      !encodeRows(&tm_hist, hist, 2 * H_IQ, static_cast<uint64_t>(total_rows), 2 * H_IQ)) {
+    return cudaErrorInvalidValue;
+  }
+  const int grid = std::min(sm_count, p.row_tiles * p.n_seg);
+  k_decim_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm_iq, tm_hist, reinterpret_cast<const uint4 *>(b_image_dev),
+                                                   reinterpret_cast<const int2 *>(offs_dev), hist_valid, x1,
+                                                   x1_pitch, p);
+  return cudaGetLastError();
+}
+
+}  // namespace fmgpu

@@ -50,6 +50,13 @@ struct fmgpu_engine {
   TapsParam decParam{}, decParamRaw{}, pilParam{}, audParam{};
   int decPp = 0, decL = 0, pilLp = 0, pilL = 0, audLp = 0, audL = 0;
   float decScale = 1.0f;
+  // decimator arithmetic: 0 = FP32 FFMA2 kernel (bit-identical to the oracle's float chain),
+  // 1 = integer contraction on the tensor cores (decim_tc.cu; one rounding of the exact sum)
+  int decimMode = 0;
+  bool decimTcOk = false;
+  int smCount = 148;
+  uint8_t *dDecB = nullptr;
+  int32_t *dDecOffs = nullptr;
   std::vector<float> pilTaps, audTaps, rdsLpf;
   fmdesign::ResamplerDesign audRs, rdsRs;
   fmdesign::SymSyncDesign ss;
@@ -356,6 +363,24 @@ int fillStateField(fmgpu_engine *e, S *base, size_t fieldOffset, const void *val
 // ---------------------------------------------------------------------------
 // pipeline stages on channels [ch0, ch0 + nch)
 // ---------------------------------------------------------------------------
+// the decimating FIR of n_out outputs per channel into x1 (history in dHistIq), either flavour
+void runDecim(fmgpu_engine *e, const uint8_t *iq, size_t stride, float2 *x1, int n_out, int ch0,
+              int nch, cudaStream_t s) {
+  if (e->decimMode == 1 && e->decimTcOk && n_out % 8 == 0 && (stride & 15u) == 0 &&
+      (reinterpret_cast<uintptr_t>(iq) & 15u) == 0) {
+    const cudaError_t err =
+        launchDecimTc(e->M, e->decL, iq, stride, static_cast<size_t>(n_out) * e->M * 2, e->dHistIq,
+                      e->dHistValid, e->C, x1, e->pitch, n_out, ch0, nch, e->decScale, e->dDecB,
+                      e->dDecOffs, e->smCount, s);
+    if (err == cudaSuccess) {
+      return;
+    }
+    e->lastError = std::string("tensor-core decimator: ") + cudaGetErrorString(err);
+  }
+  launchDecim(e->M, iq, stride, e->dHistIq, e->dHistValid, x1, e->pitch, n_out, ch0, nch, e->decPp,
+              e->decL, e->decScale, e->decParam, e->decParamRaw, s);
+}
+
 void stageDecimate(fmgpu_engine *e, const uint8_t *iq, size_t stride, int n_out, int ch0, int nch,
                    cudaStream_t s) {
   Span sp(e, "decimate", s);
@@ -364,8 +389,7 @@ void stageDecimate(fmgpu_engine *e, const uint8_t *iq, size_t stride, int n_out,
     e->launches += 1;
     return;
   }
-  launchDecim(e->M, iq, stride, e->dHistIq, e->dHistValid, e->dX1, e->pitch, n_out, ch0, nch, e->decPp, e->decL,
-              e->decScale, e->decParam, e->decParamRaw, s);
+  runDecim(e, iq, stride, e->dX1, n_out, ch0, nch, s);
   launchCarryIq(e->dHistIq, e->dHistValid, iq, stride, static_cast<long>(n_out) * e->M, ch0, nch, s);
   e->launches += 2;
 }
@@ -645,8 +669,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     }
     {
       Span sp(e, "decimate", s);
-      launchDecim(e->M, iq, stride, e->dHistIq, e->dHistValid, e->dX1 + t0, e->pitch, N, ch0, nch,
-                  e->decPp, e->decL, e->decScale, e->decParam, e->decParamRaw, s);
+      runDecim(e, iq, stride, e->dX1 + t0, N, ch0, nch, s);
       launchCarryIq(e->dHistIq, e->dHistValid, iq, stride, static_cast<long>(N) * e->M, ch0, nch, s);
       e->launches += 2;
     }
@@ -1221,6 +1244,25 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(devAlloc(&e->dIq, C * e->iqPitch));
   CKC(devAlloc(&e->dHistIq, C * 2 * H_IQ));
   CKC(devAlloc(&e->dHistValid, C));
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) {
+      e->smCount = sms;
+    }
+    if (e->M > 1 && decimTcSupported(e->M, e->decL, e->N)) {
+      std::vector<uint8_t> bimg;
+      std::vector<int32_t> offs;
+      decimTcBuildTables(e->M, reversed(e->decTaps), &bimg, &offs);
+      CKC(devAlloc(&e->dDecB, bimg.size()));
+      CKC(devAlloc(&e->dDecOffs, offs.size()));
+      CKC(cudaMemcpy(e->dDecB, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
+      CKC(cudaMemcpy(e->dDecOffs, offs.data(), offs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      e->decimTcOk = true;
+    }
+    if (const char *dm = getenv("FMGPU_DECIM_MODE")) {
+      e->decimMode = (atoi(dm) == 1 && e->decimTcOk) ? 1 : 0;
+    }
+  }
   CKC(devAlloc(&e->dX1, C * e->pitch));
   CKC(devAlloc(&e->dX2, C * e->x2Pitch));
   CKC(devAlloc(&e->dY, C * e->yPitch));
@@ -1320,7 +1362,8 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
                   e->dAudBank, e->dRdsBank, e->dRdsLpf, e->dMf,     e->dDmf,     e->dParams,
                   e->dDemod,   e->dStereo, e->dAudioSt, e->dRds,    e->dGroups,  e->dStatus,
                   e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd,
-                  e->dAudio2,  e->dGroups2, e->dStatus2, e->dNAudio2, e->dNGroups2, e->dR171};
+                  e->dAudio2,  e->dGroups2, e->dStatus2, e->dNAudio2, e->dNGroups2, e->dR171,
+                  e->dDecB,    e->dDecOffs};
   for (void *p : ptrs) {
     if (p) {
       cudaFree(p);
@@ -1486,6 +1529,22 @@ int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz) {
   CK(cudaStreamSynchronize(e->stream));
   return FMGPU_OK;
 }
+
+int fmgpu_set_decimator_mode(fmgpu_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 1) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  if (mode == 1 && !e->decimTcOk) {
+    e->lastError = "tensor-core decimator: this decimation factor / tap count is not supported";
+    return FMGPU_EINVAL;
+  }
+  syncPipes(e);
+  e->decimMode = mode;
+  return FMGPU_OK;
+}
+
+int fmgpu_get_decimator_mode(const fmgpu_engine *e) { return e ? e->decimMode : FMGPU_EINVAL; }
 
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
   if (!e || mode < 0 || mode > 2) {

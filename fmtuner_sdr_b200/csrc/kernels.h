@@ -2,6 +2,8 @@
 #ifndef FMGPU_KERNELS_H_
 #define FMGPU_KERNELS_H_
 
+#include <vector>
+
 #include "engine.h"
 
 namespace fmgpu {
@@ -22,6 +24,17 @@ cudaError_t initRdsTables();
 void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
                  const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
                  const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream);
+// decim_tc.cu: the same FIR as an integer contraction on the tensor cores (tcgen05.mma kind::i8,
+// TMA-fed, accumulators in TMEM). Not bit-identical to launchDecim: one float rounding of the exact
+// sum instead of a 280-term float chain.
+bool decimTcSupported(int M, int L, int n_out);
+void decimTcBuildTables(int M, const std::vector<float> &hrev, std::vector<uint8_t> *b_image,
+                        std::vector<int32_t> *offs);
+cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, size_t iq_row_bytes,
+                          const uint8_t *hist, const int *hist_valid, int total_rows, float2 *x1,
+                          size_t x1_pitch, int n_out, int ch0, int nch, float scale,
+                          const uint8_t *b_image_dev, const int32_t *offs_dev, int sm_count,
+                          cudaStream_t stream);
 void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_pitch, int n,
                      int ch0, int nch, cudaStream_t stream);
 void launchCarryIq(uint8_t *hist, int *hist_valid, const uint8_t *iq, size_t iq_stride, long n_in,

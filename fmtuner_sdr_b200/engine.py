@@ -90,6 +90,8 @@ def load_library(build: bool = True):
                  "set_deemphasis_us", "set_blend_mode", "set_force_mono", "set_force_stereo"):
         getattr(L, f"fmgpu_{name}").argtypes = [vp, i32, i32]
     L.fmgpu_reset.argtypes = [vp, i32, C.c_uint]
+    L.fmgpu_set_decimator_mode.argtypes = [vp, i32]
+    L.fmgpu_get_decimator_mode.argtypes = [vp]
     L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
     L.fmgpu_set_stage_overlap.argtypes = [vp, i32]
     L.fmgpu_is_stereo.argtypes = [vp, i32]
@@ -225,6 +227,13 @@ class Engine:
 
     def set_force_stereo(self, on, channel=-1):
         self._check(self.L.fmgpu_set_force_stereo(self.h, channel, int(on)), "set_force_stereo")
+
+    def set_decimator_mode(self, mode: int):
+        """0 = FP32 chain (bit-identical to the oracle), 1 = tensor-core integer contraction."""
+        self._check(self.L.fmgpu_set_decimator_mode(self.h, mode), "set_decimator_mode")
+
+    def decimator_mode(self) -> int:
+        return self.L.fmgpu_get_decimator_mode(self.h)
 
     def set_pipeline_groups(self, groups: int):
         self._check(self.L.fmgpu_set_pipeline_groups(self.h, groups), "set_pipeline_groups")

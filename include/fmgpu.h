@@ -94,6 +94,14 @@ int fmgpu_set_w0_bandwidth_hz(fmgpu_engine *e, int channel, int bw_hz);/* FMDemo
 int fmgpu_set_agc_mode(fmgpu_engine *e, int channel, int mode);        /* FMDemod::setDspAgcMode    fm_demod.cpp:141-148 */
 int fmgpu_set_deemphasis_us(fmgpu_engine *e, int channel, int tau_us); /* FMDemod/AFPostProcessor::setDeemphasis */
 int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz);      /* FMDemod::setDeviation fm_demod.cpp:64-71 (all channels) */
+/* Arithmetic of the decimating FIR (ComplexDecimator::executeComplex, liquid_primitives.cpp:461-499),
+ * all channels. 0: FP32 FMA chain in the reference's summation order, bit-identical to the CPU
+ * oracle. 1: integer contraction on the tensor cores (uint8 samples x taps quantised to 2^-26,
+ * exact int32 sums, ONE float rounding): within ~1e-7 of mode 0, about 7x faster. FMGPU_EINVAL when
+ * the factor / tap count has no tensor-core form (odd factors, factor 16). The environment variable
+ * FMGPU_DECIM_MODE sets the mode an engine starts in. */
+int fmgpu_set_decimator_mode(fmgpu_engine *e, int mode);
+int fmgpu_get_decimator_mode(const fmgpu_engine *e);
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode);      /* StereoDecoder::setBlendMode */
 int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on);        /* StereoDecoder::setForceMono */
 int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on);      /* StereoDecoder::setForceStereo */
