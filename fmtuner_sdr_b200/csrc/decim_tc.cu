@@ -49,6 +49,9 @@ constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
 constexpr int TC_B_CHUNKS = 6;        // K extent of B: 6 * 128 = 768 bytes >= 32 * KS
 constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 48 KB
 constexpr int TC_RING = 10;           // A ring slots (160 KB)
+constexpr int TC_SUPER = 8;           // chunks per L2 prefetch unit: 1 KB of every row
+constexpr int TC_PF_ROWS = 32;        // rows per prefetch instruction
+constexpr int TC_PF_LEAD = 2;         // super-chunks the L2 prefetch runs ahead of the loads
 constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns
 constexpr int TC_THREADS = 192;
 constexpr int TC_SHIFT = 26;          // taps are quantised to 2^-26
@@ -101,6 +104,11 @@ __device__ __forceinline__ void tmaLoad2d(uint32_t dst, const CUtensorMap *map, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tmaPrefetchL2(const CUtensorMap *map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(x), "r"(y)
+               : "memory");
+}
 __device__ __forceinline__ void ummaCommit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -130,6 +138,20 @@ __device__ __forceinline__ void ummaI8(uint32_t tmem_d, uint64_t a_desc, uint64_
       : "memory");
 }
 
+// one lane of a converged warp; the region it guards is single-threaded and ptxas keeps its
+// warp-uniform operands in uniform registers (no waterfall loop around UTCIMMA / UTCBAR)
+__device__ __forceinline__ bool electOne() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmemLd16(uint32_t taddr, int32_t *v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
@@ -152,8 +174,100 @@ __device__ __forceinline__ int windowStart(const TcParams &p, int t) {
   return p.adv * t - p.ws0 + TC_CHUNK * p.halo_chunks;   // >= 0
 }
 
+constexpr int TC_MAX_KSTEPS = 4 * TC_B_CHUNKS;   // 24
+constexpr int TC_WIN_CHUNKS = 7;                 // a 768-byte window starting anywhere touches <= 7 chunks
+
+// The MMAs of one tile, fully unrolled for the window's phase PH (its start inside a chunk, in
+// 32-byte steps): every shared-memory offset is then an immediate. cb[r] / eb[r]: descriptor low
+// word and `empty` barrier of the window's r-th chunk; the first n_free chunks are released.
+template <int PH>
+__device__ __forceinline__ void issueTile(int ksteps, int n_free, const uint32_t (&cb)[TC_WIN_CHUNKS],
+                                          const uint32_t (&eb)[TC_WIN_CHUNKS], uint32_t b_lo0,
+                                          uint32_t desc_hi, uint32_t d_tmem, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < TC_MAX_KSTEPS; ks++) {
+    if (ks < ksteps) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int byte = 32 * PH + 32 * ks;
+      const int r = byte >> 7;
+      const uint32_t a_lo = cb[r] + ((byte & (TC_CHUNK - 1)) >> 4);
+      const uint32_t b_lo = b_lo0 + (ks >> 2) * ((TC_N * TC_CHUNK) >> 4) + (ks & 3) * 2;
+      const uint64_t a_desc = (static_cast<uint64_t>(desc_hi) << 32) | a_lo;
+      const uint64_t b_desc = (static_cast<uint64_t>(desc_hi) << 32) | b_lo;
+      if (ks == 0) {
+        ummaI8(d_tmem, a_desc, b_desc, idesc, 0u);
+      } else {
+        ummaI8(d_tmem, a_desc, b_desc, idesc, 1u);
+      }
+      const bool chunk_done = (((byte + 32) & (TC_CHUNK - 1)) == 0) || (ks + 1 == ksteps);
+      if (chunk_done && r < n_free) {
+        ummaCommit(eb[r]);
+      }
+    }
+  }
+}
+
+// the chunks a CTA loads, in order, across its work items
+struct ChunkCursor {
+  int w, stride, n_work, g, g1, gq0, y;
+  __device__ ChunkCursor(const TcParams &p, int w0, int stride_, int n_work_)
+      : w(w0), stride(stride_), n_work(n_work_), g(0), g1(-1), gq0(0), y(0) {
+    open(p);
+  }
+  __device__ void open(const TcParams &p) {
+    if (w < n_work) {
+      int row, t0, nt;
+      workItem(p, w, &row, &t0, &nt);
+      g = windowStart(p, t0) / TC_CHUNK;
+      g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
+      gq0 = max(g, p.halo_chunks);   // first chunk that comes from the IQ rows
+      y = p.ch0 + row * TC_ROWS;
+    }
+  }
+  __device__ bool valid() const { return w < n_work; }
+  __device__ void next(const TcParams &p) {
+    if (++g > g1) {
+      w += stride;
+      open(p);
+    }
+  }
+  // byte coordinate inside the history rows (chunks in front of the block) or the IQ rows
+  __device__ int x(const TcParams &p) const {
+    return g < p.halo_chunks ? 2 * H_IQ - TC_CHUNK * (p.halo_chunks - g) : TC_CHUNK * (g - p.halo_chunks);
+  }
+};
+
+// the same sequence in super-chunks (TC_SUPER chunks = 1 KB of every row) of the IQ rows
+struct SuperCursor {
+  int w, stride, n_work, sc, sc1, y;
+  __device__ SuperCursor(const TcParams &p, int w0, int stride_, int n_work_)
+      : w(w0), stride(stride_), n_work(n_work_), sc(0), sc1(-1), y(0) {
+    open(p);
+  }
+  __device__ void open(const TcParams &p) {
+    if (w < n_work) {
+      int row, t0, nt;
+      workItem(p, w, &row, &t0, &nt);
+      const int g0 = max(windowStart(p, t0) / TC_CHUNK, p.halo_chunks);
+      const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
+      sc = (g0 - p.halo_chunks) / TC_SUPER;
+      sc1 = (g1 - p.halo_chunks) / TC_SUPER;
+      y = p.ch0 + row * TC_ROWS;
+    }
+  }
+  __device__ bool valid() const { return w < n_work; }
+  __device__ void next(const TcParams &p) {
+    if (++sc > sc1) {
+      w += stride;
+      open(p);
+    }
+  }
+};
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CUtensorMap tm_hist,
+           const __grid_constant__ CUtensorMap tm_pf,
            const uint4 *__restrict__ b_image, const int2 *__restrict__ offs, const int *__restrict__ hist_valid,
            float2 *__restrict__ x1, size_t x1_pitch, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -199,45 +313,60 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
+    // A 128-row x 128-byte box touches 128 different DRAM pages for 128 bytes each, and the ring
+    // leaves room for only ~3 chunks beyond a tile's window: loading straight from DRAM ran at 29 %
+    // of the HBM peak (ncu r02). So a second cursor runs TC_PF_LEAD super-chunks (1 KB of every
+    // row) ahead and pulls them into L2 with cp.async.bulk.prefetch.tensor through a tensor map
+    // whose box is 1 KB x 32 rows — DRAM sees one contiguous kilobyte per row — and the loads into
+    // shared memory are L2 hits.
     if (lane == 0) {
-      uint32_t cnt = 0;   // chunks issued so far (ring position)
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        int row, t0, nt;
-        workItem(p, w, &row, &t0, &nt);
-        const int g0 = windowStart(p, t0) / TC_CHUNK;
-        const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
-        const int y = p.ch0 + row * TC_ROWS;
-        for (int g = g0; g <= g1; g++, cnt++) {
-          const uint32_t slot = cnt % TC_RING;
-          const uint32_t use = cnt / TC_RING;
-          if (use > 0) {
-            mbarWait(barEmpty + 8 * slot, (use - 1) & 1);
+      SuperCursor pf(p, blockIdx.x, gridDim.x, n_work);
+      auto prefetchOne = [&]() {
+        if (pf.valid()) {
+#pragma unroll
+          for (int r = 0; r < TC_ROWS; r += TC_PF_ROWS) {
+            tmaPrefetchL2(&tm_pf, pf.sc * (TC_SUPER * TC_CHUNK / 4), pf.y + r);
           }
-          mbarExpectTx(barFull + 8 * slot, TC_CHUNK_BYTES);
-          if (g < p.halo_chunks) {
-            tmaLoad2d(sA + slot * TC_CHUNK_BYTES, &tm_hist, barFull + 8 * slot,
-                      2 * H_IQ - TC_CHUNK * (p.halo_chunks - g), y);
-          } else {
-            tmaLoad2d(sA + slot * TC_CHUNK_BYTES, &tm_iq, barFull + 8 * slot,
-                      TC_CHUNK * (g - p.halo_chunks), y);
-          }
+          pf.next(p);
         }
+      };
+      for (int i = 0; i < TC_PF_LEAD; i++) {
+        prefetchOne();
+      }
+      uint32_t cnt = 0;   // chunks issued so far (ring position)
+      for (ChunkCursor ld(p, blockIdx.x, gridDim.x, n_work); ld.valid(); ld.next(p), cnt++) {
+        if (ld.g >= p.halo_chunks && (ld.g == ld.gq0 || ((ld.g - p.halo_chunks) & (TC_SUPER - 1)) == 0)) {
+          prefetchOne();   // the loads enter a new super-chunk: keep the lead
+        }
+        const uint32_t slot = cnt % TC_RING;
+        const uint32_t use = cnt / TC_RING;
+        if (use > 0) {
+          mbarWait(barEmpty + 8 * slot, (use - 1) & 1);
+        }
+        mbarExpectTx(barFull + 8 * slot, TC_CHUNK_BYTES);
+        tmaLoad2d(sA + slot * TC_CHUNK_BYTES, ld.g < p.halo_chunks ? &tm_hist : &tm_iq,
+                  barFull + 8 * slot, ld.x(p), ld.y);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer ========================================================================
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp keeps the (warp-uniform) books, one elected lane issues ======
+    {
       // u8 x s8 -> s32, K-major A and B, N = 64, M = 128 (UMMA::InstrDescriptor)
       const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((TC_N >> 3) << 17) | ((TC_ROWS >> 4) << 24);
-      uint32_t cnt0 = 0;  // ring position of the work item's first chunk
+      const uint32_t desc_hi = static_cast<uint32_t>(smemDesc(0) >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(smemDesc(sA));
+      const uint32_t b_lo0 = static_cast<uint32_t>(smemDesc(sB));
+      uint32_t ring = 0;    // ring slot and use count of the next chunk to wait for
+      uint32_t ring_use = 0;
       uint32_t tile_cnt = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         int row, t0, nt;
         workItem(p, w, &row, &t0, &nt);
         const int g0 = windowStart(p, t0) / TC_CHUNK;
         const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
-        int have = g0 - 1;    // chunks known to have landed
-        int freed = g0 - 1;   // chunks handed back to the producer
+        int have = g0 - 1;          // chunks known to have landed
+        int gs = g0;                // first chunk of the current window ...
+        uint32_t gs_slot = ring;    // ... and its ring slot
         for (int i = 0; i < nt; i++, tile_cnt++) {
           const int ws = windowStart(p, t0 + i);
           const int ge = (ws + 32 * p.ksteps - 1) / TC_CHUNK;
@@ -248,29 +377,46 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
           }
           while (have < ge) {
             have++;
-            const uint32_t c = cnt0 + static_cast<uint32_t>(have - g0);
-            mbarWait(barFull + 8 * (c % TC_RING), (c / TC_RING) & 1);
+            mbarWait(barFull + 8 * ring, ring_use & 1);
+            if (++ring == TC_RING) {
+              ring = 0;
+              ring_use++;
+            }
           }
           tcFenceAfter();
-          const uint32_t d_tmem = tmem_base + acc * TC_N;
-          for (int ks = 0; ks < p.ksteps; ks++) {
-            const int byte = ws + 32 * ks;
-            const uint32_t c = cnt0 + static_cast<uint32_t>(byte / TC_CHUNK - g0);
-            const uint64_t a_desc =
-                smemDesc(sA + (c % TC_RING) * TC_CHUNK_BYTES + static_cast<uint32_t>(byte % TC_CHUNK));
-            const uint64_t b_desc = smemDesc(sB + (ks >> 2) * (TC_N * TC_CHUNK) + (ks & 3) * 32);
-            ummaI8(d_tmem, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
-          }
-          ummaCommit(barTFull + 8 * acc);
-          // chunks in front of the next tile's window are finished once these MMAs are
+          // chunks in front of the next tile's window go back to the producer as soon as the MMAs
+          // that read them are done: a commit right behind the last K step inside them
           const int keep = (i + 1 < nt) ? windowStart(p, t0 + i + 1) / TC_CHUNK : g1 + 1;
-          while (freed < keep - 1) {
-            freed++;
-            const uint32_t c = cnt0 + static_cast<uint32_t>(freed - g0);
-            ummaCommit(barEmpty + 8 * (c % TC_RING));
+          const int n_free = keep - gs;
+          uint32_t cb[TC_WIN_CHUNKS], eb[TC_WIN_CHUNKS];   // descriptor / empty barrier per window chunk
+          {
+            uint32_t slot = gs_slot;
+#pragma unroll
+            for (int r = 0; r < TC_WIN_CHUNKS; r++) {
+              cb[r] = a_lo0 + slot * (TC_CHUNK_BYTES >> 4);
+              eb[r] = barEmpty + 8 * slot;
+              slot = (slot + 1 == TC_RING) ? 0 : slot + 1;
+            }
+          }
+          const uint32_t d_tmem = tmem_base + acc * TC_N;
+          const uint32_t tfull = barTFull + 8 * acc;
+          if (electOne()) {
+            switch ((ws & (TC_CHUNK - 1)) >> 5) {
+              case 0: issueTile<0>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              case 1: issueTile<1>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              case 2: issueTile<2>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              default: issueTile<3>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+            }
+            ummaCommit(tfull);
+          }
+          __syncwarp();
+          while (gs < keep) {   // the next window starts here
+            gs++;
+            if (++gs_slot == TC_RING) {
+              gs_slot = 0;
+            }
           }
         }
-        cnt0 += static_cast<uint32_t>(g1 - g0 + 1);
       }
     }
   } else {
@@ -378,6 +524,21 @@ bool encodeRows(CUtensorMap *map, const void *base, uint64_t row_bytes, uint64_t
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the same rows as uint32 words, boxes of 1 KB x TC_PF_ROWS rows, no swizzle: L2 prefetch only
+bool encodePrefetch(CUtensorMap *map, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch) {
+  EncodeFn fn = encodeFn();
+  if (!fn) {
+    return false;
+  }
+  const cuuint64_t dims[2] = {row_bytes / 4, rows};
+  const cuuint64_t strides[1] = {pitch};
+  const cuuint32_t box[2] = {TC_SUPER * TC_CHUNK / 4, TC_PF_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 bool decimTcSupported(int M, int L, int n_out) {
@@ -473,13 +634,14 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
   p.ch0 = ch0;
   p.nch = nch;
   p.out_scale = static_cast<float>(static_cast<double>(scale) / (255.0 * static_cast<double>(1 << TC_SHIFT)));
-  CUtensorMap tm_iq, tm_hist;
-  if (!encodeRows(&tm_iq, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
+  CUtensorMap tm_iq, tm_hist, tm_pf;
+  if (!encodePrefetch(&tm_pf, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
+      !encodeRows(&tm_iq, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
       !encodeRows(&tm_hist, hist, 2 * H_IQ, static_cast<uint64_t>(total_rows), 2 * H_IQ)) {
     return cudaErrorInvalidValue;
   }
   const int grid = std::min(sm_count, p.row_tiles * p.n_seg);
-  k_decim_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm_iq, tm_hist, reinterpret_cast<const uint4 *>(b_image_dev),
+  k_decim_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm_iq, tm_hist, tm_pf, reinterpret_cast<const uint4 *>(b_image_dev),
                                                    reinterpret_cast<const int2 *>(offs_dev), hist_valid, x1,
                                                    x1_pitch, p);
   return cudaGetLastError();
