@@ -6,4 +6,4 @@ engine without a CUDA device raises.
 """
 from .engine import (RESET_AFPOST, RESET_ALL, RESET_DECIM, RESET_DEMOD, RESET_DSP, RESET_RDS, RESET_STEREO,  # noqa: F401
                      Channelizer, Engine, EngineError, LevelSums, SignalLevel, SynthParams, GROUP_DTYPE, STATUS_DTYPE, XdrRdsFormatter, lib_path,  # noqa: F401
-                     load_library, make_config, synth_iq)
+                     load_library, make_config, measure_fp32_tflops, synth_iq)

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfmgpu.so")
 DROPIN_LIB = os.path.join(HERE, "libfmgpu_dropin.so")
-SOURCES = ["kernels.cu", "engine.cu", "decim_tc.cu", "channelizer.cu", "synth.cu", "design.cpp",
+SOURCES = ["kernels.cu", "engine.cu", "decim_tc.cu", "channelizer.cu", "synth.cu", "probe.cu", "design.cpp",
            "xdr_format.cpp"]
 HEADERS = ["engine.h", "kernels.h", "design.h", "fm_math.h", os.path.join("..", "..", "include", "fmgpu.h")]
 

@@ -29,7 +29,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -49,9 +51,6 @@ constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
 constexpr int TC_B_CHUNKS = 6;        // K extent of B: 6 * 128 = 768 bytes >= 32 * KS
 constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 48 KB
 constexpr int TC_RING = 10;           // A ring slots (160 KB)
-constexpr int TC_SUPER = 8;           // chunks per L2 prefetch unit: 1 KB of every row
-constexpr int TC_PF_ROWS = 32;        // rows per prefetch instruction
-constexpr int TC_PF_LEAD = 2;         // super-chunks the L2 prefetch runs ahead of the loads
 constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns
 constexpr int TC_THREADS = 192;
 constexpr int TC_SHIFT = 26;          // taps are quantised to 2^-26
@@ -103,11 +102,6 @@ __device__ __forceinline__ void tmaLoad2d(uint32_t dst, const CUtensorMap *map, 
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
-}
-__device__ __forceinline__ void tmaPrefetchL2(const CUtensorMap *map, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(x), "r"(y)
-               : "memory");
 }
 __device__ __forceinline__ void ummaCommit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -210,9 +204,9 @@ __device__ __forceinline__ void issueTile(int ksteps, int n_free, const uint32_t
 
 // the chunks a CTA loads, in order, across its work items
 struct ChunkCursor {
-  int w, stride, n_work, g, g1, gq0, y;
+  int w, stride, n_work, g, g1, y;
   __device__ ChunkCursor(const TcParams &p, int w0, int stride_, int n_work_)
-      : w(w0), stride(stride_), n_work(n_work_), g(0), g1(-1), gq0(0), y(0) {
+      : w(w0), stride(stride_), n_work(n_work_), g(0), g1(-1), y(0) {
     open(p);
   }
   __device__ void open(const TcParams &p) {
@@ -221,7 +215,6 @@ struct ChunkCursor {
       workItem(p, w, &row, &t0, &nt);
       g = windowStart(p, t0) / TC_CHUNK;
       g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
-      gq0 = max(g, p.halo_chunks);   // first chunk that comes from the IQ rows
       y = p.ch0 + row * TC_ROWS;
     }
   }
@@ -238,36 +231,8 @@ struct ChunkCursor {
   }
 };
 
-// the same sequence in super-chunks (TC_SUPER chunks = 1 KB of every row) of the IQ rows
-struct SuperCursor {
-  int w, stride, n_work, sc, sc1, y;
-  __device__ SuperCursor(const TcParams &p, int w0, int stride_, int n_work_)
-      : w(w0), stride(stride_), n_work(n_work_), sc(0), sc1(-1), y(0) {
-    open(p);
-  }
-  __device__ void open(const TcParams &p) {
-    if (w < n_work) {
-      int row, t0, nt;
-      workItem(p, w, &row, &t0, &nt);
-      const int g0 = max(windowStart(p, t0) / TC_CHUNK, p.halo_chunks);
-      const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
-      sc = (g0 - p.halo_chunks) / TC_SUPER;
-      sc1 = (g1 - p.halo_chunks) / TC_SUPER;
-      y = p.ch0 + row * TC_ROWS;
-    }
-  }
-  __device__ bool valid() const { return w < n_work; }
-  __device__ void next(const TcParams &p) {
-    if (++sc > sc1) {
-      w += stride;
-      open(p);
-    }
-  }
-};
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CUtensorMap tm_hist,
-           const __grid_constant__ CUtensorMap tm_pf,
            const uint4 *__restrict__ b_image, const int2 *__restrict__ offs, const int *__restrict__ hist_valid,
            float2 *__restrict__ x1, size_t x1_pitch, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -313,31 +278,12 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
-    // A 128-row x 128-byte box touches 128 different DRAM pages for 128 bytes each, and the ring
-    // leaves room for only ~3 chunks beyond a tile's window: loading straight from DRAM ran at 29 %
-    // of the HBM peak (ncu r02). So a second cursor runs TC_PF_LEAD super-chunks (1 KB of every
-    // row) ahead and pulls them into L2 with cp.async.bulk.prefetch.tensor through a tensor map
-    // whose box is 1 KB x 32 rows — DRAM sees one contiguous kilobyte per row — and the loads into
-    // shared memory are L2 hits.
+    // (An L2 prefetch running 1-3 KB per row ahead of these loads — cp.async.bulk.prefetch.tensor
+    // through a 1 KB x 32-row map — was measured and dropped: 1.7x the DRAM reads, same time. The
+    // kernel is bound by the tensor cores' shared-memory operand reads, not by these loads.)
     if (lane == 0) {
-      SuperCursor pf(p, blockIdx.x, gridDim.x, n_work);
-      auto prefetchOne = [&]() {
-        if (pf.valid()) {
-#pragma unroll
-          for (int r = 0; r < TC_ROWS; r += TC_PF_ROWS) {
-            tmaPrefetchL2(&tm_pf, pf.sc * (TC_SUPER * TC_CHUNK / 4), pf.y + r);
-          }
-          pf.next(p);
-        }
-      };
-      for (int i = 0; i < TC_PF_LEAD; i++) {
-        prefetchOne();
-      }
       uint32_t cnt = 0;   // chunks issued so far (ring position)
       for (ChunkCursor ld(p, blockIdx.x, gridDim.x, n_work); ld.valid(); ld.next(p), cnt++) {
-        if (ld.g >= p.halo_chunks && (ld.g == ld.gq0 || ((ld.g - p.halo_chunks) & (TC_SUPER - 1)) == 0)) {
-          prefetchOne();   // the loads enter a new super-chunk: keep the lead
-        }
         const uint32_t slot = cnt % TC_RING;
         const uint32_t use = cnt / TC_RING;
         if (use > 0) {
@@ -524,21 +470,6 @@ bool encodeRows(CUtensorMap *map, const void *base, uint64_t row_bytes, uint64_t
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// the same rows as uint32 words, boxes of 1 KB x TC_PF_ROWS rows, no swizzle: L2 prefetch only
-bool encodePrefetch(CUtensorMap *map, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch) {
-  EncodeFn fn = encodeFn();
-  if (!fn) {
-    return false;
-  }
-  const cuuint64_t dims[2] = {row_bytes / 4, rows};
-  const cuuint64_t strides[1] = {pitch};
-  const cuuint32_t box[2] = {TC_SUPER * TC_CHUNK / 4, TC_PF_ROWS};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 }  // namespace
 
 bool decimTcSupported(int M, int L, int n_out) {
@@ -634,14 +565,13 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
   p.ch0 = ch0;
   p.nch = nch;
   p.out_scale = static_cast<float>(static_cast<double>(scale) / (255.0 * static_cast<double>(1 << TC_SHIFT)));
-  CUtensorMap tm_iq, tm_hist, tm_pf;
-  if (!encodePrefetch(&tm_pf, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
-      !encodeRows(&tm_iq, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
+  CUtensorMap tm_iq, tm_hist;
+  if (!encodeRows(&tm_iq, iq, iq_row_bytes, static_cast<uint64_t>(total_rows), iq_stride) ||
       !encodeRows(&tm_hist, hist, 2 * H_IQ, static_cast<uint64_t>(total_rows), 2 * H_IQ)) {
     return cudaErrorInvalidValue;
   }
   const int grid = std::min(sm_count, p.row_tiles * p.n_seg);
-  k_decim_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm_iq, tm_hist, tm_pf, reinterpret_cast<const uint4 *>(b_image_dev),
+  k_decim_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm_iq, tm_hist, reinterpret_cast<const uint4 *>(b_image_dev),
                                                    reinterpret_cast<const int2 *>(offs_dev), hist_valid, x1,
                                                    x1_pitch, p);
   return cudaGetLastError();

@@ -90,6 +90,7 @@ def load_library(build: bool = True):
                  "set_deemphasis_us", "set_blend_mode", "set_force_mono", "set_force_stereo"):
         getattr(L, f"fmgpu_{name}").argtypes = [vp, i32, i32]
     L.fmgpu_reset.argtypes = [vp, i32, C.c_uint]
+    L.fmgpu_measure_fp32_tflops.argtypes = [i32, C.POINTER(C.c_double)]
     L.fmgpu_set_decimator_mode.argtypes = [vp, i32]
     L.fmgpu_get_decimator_mode.argtypes = [vp]
     L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
@@ -153,6 +154,15 @@ def load_library(build: bool = True):
 
 def _ptr(a):
     return a.ctypes.data if a is not None else None
+
+
+def measure_fp32_tflops(device: int = 0) -> float:
+    """The FP32 FMA roof of `device`, measured (fmgpu_measure_fp32_tflops)."""
+    out = C.c_double(0.0)
+    rc = load_library().fmgpu_measure_fp32_tflops(device, C.byref(out))
+    if rc != 0:
+        raise EngineError(f"fmgpu_measure_fp32_tflops failed ({rc})")
+    return out.value
 
 
 def synth_iq(device: int, params, fs_iq: float, n_samples: int, iq_dev_ptr: int,

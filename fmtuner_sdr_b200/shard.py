@@ -35,6 +35,17 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def sum_over_ranks(value: float, device=None) -> float:
+    """SUM-reduce a scalar over the default process group (identity when not initialised)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def aggregate_throughput(samples_per_rank_per_step: int, steps: int, world: int, max_ms: float) -> float:
     """Whole-job MS/s: all ranks' samples over the slowest rank's device time."""
     return world * samples_per_rank_per_step * steps / (max_ms * 1e-3) / 1e6

@@ -308,6 +308,10 @@ int fmgpu_debug_timeline(fmgpu_engine *e, const char **names, int *groups, float
 int fmgpu_enable_stage_timing(fmgpu_engine *e, int on);
 int fmgpu_get_stage_times(fmgpu_engine *e, const char **names, float *ms, int cap);
 
+/* Measurement aid (bench.py): the FP32 FMA rate of `device` in TFLOP/s (2 flop per FMA), measured
+ * with a register-resident packed-FMA loop on every SM — the roof the FIR kernels are held against. */
+int fmgpu_measure_fp32_tflops(int device, double *tflops_out);
+
 /* ---- on-device synthetic multiplex generator (bench.py input) ---- */
 typedef struct fmgpu_synth_params {
   float deviation_hz;   /* 22500..75000 */

@@ -7,6 +7,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_one_contract_line():
@@ -22,7 +24,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["config"]["workload"].startswith("BASELINE config 5")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # "reference": the reference's own sources (oracle/_ref/libfmref.so); "port" when it is not built
+    from oracle import orc
+    assert cb["kind"] == ("reference" if orc.OracleLib.have_ref("ref") else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "MS/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
