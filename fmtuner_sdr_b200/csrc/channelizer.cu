@@ -14,15 +14,31 @@
 // and the input before the first call equal to zero. m counts outputs since creation, so
 // consecutive calls continue the same stream (the last L-1 inputs are carried).
 //
-// Cost: L complex MACs per output = 153.6 GFMA/s for 100 channels of a 24 MS/s capture, 0.4 % of
-// the FP32 FMA rate of one B200 — the stage is evaluated directly in FP32 (W is exact to float
-// rounding; a bf16/tf32 tensor-core contraction would need split taps to hold the 60 dB stop band
-// and has nothing to win at this size). Lanes of a warp are 32 CHANNELS at the same output
-// instant: the input sample is a shared-memory broadcast, the taps W[n][k..k+31] one coalesced
-// 256-byte line, and every thread keeps 8 output instants so a tap is reused 8 times.
+// Two evaluations of that definition:
+//
+// * k_channelize_pp — the polyphase form, used whenever the carriers sit on a uniform grid
+//   nu_k = (k + c0) / P with P = Fs / spacing an integer (P = 120 for 24 MS/s and 200 kHz; the output
+//   rate Fs / D = 240 kS/s is 1.2x the spacing, so this is an oversampled bank, D = 100 != P):
+//       x'[s]  = x[s] exp(-j 2 pi c0 s / P)                 (c0 = first_center / spacing = -49.5:
+//                                                            a table of period 2P)
+//       u_r[m] = sum_{n : (mD - n) mod P = r} h[n] x'[mD - n]     (L MACs per output instant in all)
+//       y_k[m] = sum_{r=0}^{P-1} exp(-j 2 pi k r / P) u_r[m]      (a P-point DFT row per channel)
+//   One CTA takes 32 output instants: input tile (rotated on the fly) -> the P partial sums of every
+//   instant -> the DFT rows of this call's channels, everything in shared memory. Per output instant
+//   that is L + 2 P C real-times-complex / complex MACs instead of the L C of the direct form:
+//   13x fewer for the whole band, and the stage drops from 0.94 ms to well under 0.1 ms per 68 ms of
+//   signal (bench.py config4.channelizer). It stays in FP32: the DFT is a [C][P] x [P][32] complex
+//   contraction per CTA, 0.8 GFMA per step for the whole band — a tensor-core (tf32 / split-bf16)
+//   form would have to buy back its own operand conversion to save microseconds and would not
+//   hold the 2e-5 parity of the float64 model.
+// * k_channelize — the direct form (one complex tap table per channel), kept for carrier sets that
+//   are not a uniform grid. Lanes of a warp are 32 CHANNELS at the same output instant: the input
+//   sample is a shared-memory broadcast, the taps W[n][k..k+31] one coalesced 256-byte line, and
+//   every thread keeps 8 output instants so a tap is reused 8 times.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -41,6 +57,12 @@ struct fmgpu_channelizer {
   float2 *dW = nullptr;            // [L][Cpad]
   double *dNuD = nullptr;          // [Cpad]
   uint8_t *dHist = nullptr;        // last L-1 input samples (u8 pairs) of the previous call
+  // polyphase form (uniform grid): nu_k = (k + c0) / P
+  bool polyphase = false;
+  int P = 0, rotPeriod = 0;        // rotation table period (P * T, c0 * T integer)
+  float *dTaps = nullptr;          // [L]
+  float2 *dRot = nullptr;          // [rotPeriod] exp(-j 2 pi c0 s / P)
+  float2 *dTw = nullptr;           // [P] exp(-j 2 pi i / P)
   unsigned long long outCount = 0; // outputs produced so far (m of the next output)
   long histValid = 0;              // how many of the carried samples are real input (rest = 0)
   std::string lastError;
@@ -124,6 +146,92 @@ k_channelize(const uint8_t *__restrict__ iq, const uint8_t *__restrict__ hist, l
   }
 }
 
+constexpr int PP_TM = 32;         // output instants per CTA of the polyphase kernel
+constexpr int PP_THREADS = 256;
+
+__global__ void __launch_bounds__(PP_THREADS)
+k_channelize_pp(const uint8_t *__restrict__ iq, const uint8_t *__restrict__ hist, long hist_valid,
+                long n_in, const float *__restrict__ taps, const float2 *__restrict__ rot,
+                const float2 *__restrict__ tw, int L, int D, int P, int rot_period, int ch_first,
+                int ch_count, unsigned long long m_base, long n_out, float2 *__restrict__ out,
+                size_t out_stride) {
+  extern __shared__ float2 pp_smem[];
+  const int tile_len = (PP_TM - 1) * D + L;
+  float2 *xs = pp_smem;                       // [tile_len] rotated input, element a <-> sample m0*D-(L-1)+a
+  float2 *u = xs + tile_len;                  // [P][PP_TM + 1]
+  float2 *tws = u + (size_t)P * (PP_TM + 1);  // [P]
+  float *hs = reinterpret_cast<float *>(tws + P);   // [L]
+  const long m0 = (long)blockIdx.x * PP_TM;
+  const long s0 = m0 * D - (L - 1);           // call-relative sample index of tile element 0
+  constexpr float kScale = 1.0f / 127.5f;
+  const uchar2 *in2 = reinterpret_cast<const uchar2 *>(iq);
+  const uchar2 *hist2 = reinterpret_cast<const uchar2 *>(hist);
+  // absolute sample index of call-relative sample 0, modulo the rotation period
+  const unsigned long long abs0 = (m_base % (unsigned long long)rot_period) * (unsigned long long)D;
+  for (int a = threadIdx.x; a < tile_len; a += PP_THREADS) {
+    const long s = s0 + a;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (s < n_in && s >= -hist_valid) {
+      const uchar2 b = (s >= 0) ? in2[s] : hist2[(L - 1) + s];
+      const float xr = ((float)b.x - 127.5f) * kScale, xi = ((float)b.y - 127.5f) * kScale;
+      // (abs0 + s) mod period, s may be negative: add a multiple of the period first
+      const unsigned long long ai = abs0 + (unsigned long long)(s + (long)rot_period * (long)(L / rot_period + 2));
+      const float2 w = rot[ai % (unsigned long long)rot_period];
+      v = make_float2(xr * w.x - xi * w.y, xr * w.y + xi * w.x);
+    }
+    xs[a] = v;
+  }
+  for (int i = threadIdx.x; i < P; i += PP_THREADS) {
+    tws[i] = tw[i];
+  }
+  for (int i = threadIdx.x; i < L; i += PP_THREADS) {
+    hs[i] = taps[i];
+  }
+  __syncthreads();
+  // partial sums: item (m, r), r fastest -> consecutive lanes read consecutive samples and taps
+  for (int item = threadIdx.x; item < PP_TM * P; item += PP_THREADS) {
+    const int m = item / P, r = item - m * P;
+    const unsigned long long mabs = m_base + (unsigned long long)(m0 + m);
+    const int mdp = (int)(((mabs % (unsigned long long)P) * (unsigned long long)D) % (unsigned long long)P);
+    int n = mdp - r;                    // taps n = n0, n0 + P, ... see (mD - n) mod P = r
+    if (n < 0) {
+      n += P;
+    }
+    const float2 *xb = xs + (L - 1) + m * D;
+    float ar = 0.0f, ai = 0.0f;
+    for (; n < L; n += P) {
+      const float h = hs[n];
+      const float2 x = xb[-n];
+      ar = fmaf(h, x.x, ar);
+      ai = fmaf(h, x.y, ai);
+    }
+    u[(size_t)r * (PP_TM + 1) + m] = make_float2(ar, ai);
+  }
+  __syncthreads();
+  // DFT rows of this call's channels: item (kk, m), m fastest
+  for (int item = threadIdx.x; item < ch_count * PP_TM; item += PP_THREADS) {
+    const int kk = item / PP_TM, m = item - kk * PP_TM;
+    const int k = (ch_first + kk) % P;
+    float yr = 0.0f, yi = 0.0f;
+    int ti = 0;                          // (k * r) mod P
+    for (int r = 0; r < P; r++) {
+      const float2 w = tws[ti];
+      const float2 v = u[(size_t)r * (PP_TM + 1) + m];
+      yr = fmaf(w.x, v.x, yr);
+      yr = fmaf(-w.y, v.y, yr);
+      yi = fmaf(w.x, v.y, yi);
+      yi = fmaf(w.y, v.x, yi);
+      ti += k;
+      if (ti >= P) {
+        ti -= P;
+      }
+    }
+    if (m0 + m < n_out) {
+      out[(size_t)kk * out_stride + m0 + m] = make_float2(yr, yi);
+    }
+  }
+}
+
 // hist <- last H samples of (hist ++ in[0..n_in))
 __global__ void k_chan_carry(uint8_t *hist, const uint8_t *iq, long n_in, int H) {
   uchar2 *h = reinterpret_cast<uchar2 *>(hist);
@@ -188,7 +296,47 @@ int fmgpu_channelizer_create(int device, int wide_rate, int decimation, int n_ch
                       static_cast<float>(z->taps[n] * std::sin(ph)));
     }
   }
+  // uniform grid? P = Fs / spacing integer, c0 = first / spacing with c0 * T integer for a small T
+  std::vector<float2> rotTab, twTab;
+  {
+    const double pd = static_cast<double>(wide_rate) / spacing_hz;
+    const double c0 = first_center_hz / spacing_hz;
+    const int P = static_cast<int>(std::llround(pd));
+    int T = 0;
+    for (int t = 1; t <= 8 && T == 0; t++) {
+      if (std::fabs(c0 * t - std::round(c0 * t)) < 1e-9) {
+        T = t;
+      }
+    }
+    if (spacing_hz > 0.0 && P >= 2 && P <= 1024 && std::fabs(pd - P) < 1e-9 && T > 0 && n_channels <= P &&
+        getenv("FMGPU_CHANNELIZER_DIRECT") == nullptr) {
+      z->polyphase = true;
+      z->P = P;
+      z->rotPeriod = P * T;
+      rotTab.resize(z->rotPeriod);
+      for (int i = 0; i < z->rotPeriod; i++) {
+        // exp(-j 2 pi c0 i / P), the turn count reduced exactly: c0 * T is an integer
+        const long long num = std::llround(c0 * T) * static_cast<long long>(i);   // turns * (P T)
+        const long long red = ((num % z->rotPeriod) + z->rotPeriod) % z->rotPeriod;
+        const double ph = -2.0 * M_PI * static_cast<double>(red) / static_cast<double>(z->rotPeriod);
+        rotTab[i] = make_float2(static_cast<float>(std::cos(ph)), static_cast<float>(std::sin(ph)));
+      }
+      twTab.resize(P);
+      for (int i = 0; i < P; i++) {
+        const double ph = -2.0 * M_PI * static_cast<double>(i) / static_cast<double>(P);
+        twTab[i] = make_float2(static_cast<float>(std::cos(ph)), static_cast<float>(std::sin(ph)));
+      }
+    }
+  }
   bool ok = cudaSetDevice(device) == cudaSuccess;
+  if (z->polyphase) {
+    ok = ok && cudaMalloc(&z->dTaps, z->taps.size() * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc(&z->dRot, rotTab.size() * sizeof(float2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&z->dTw, twTab.size() * sizeof(float2)) == cudaSuccess;
+    ok = ok && cudaMemcpy(z->dTaps, z->taps.data(), z->taps.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(z->dRot, rotTab.data(), rotTab.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(z->dTw, twTab.data(), twTab.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
   ok = ok && cudaMalloc(&z->dW, W.size() * sizeof(float2)) == cudaSuccess;
   ok = ok && cudaMalloc(&z->dNuD, z->Cpad * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&z->dHist, static_cast<size_t>(z->L) * 2) == cudaSuccess;
@@ -217,6 +365,9 @@ void fmgpu_channelizer_destroy(fmgpu_channelizer *z) {
   cudaFree(z->dW);
   cudaFree(z->dNuD);
   cudaFree(z->dHist);
+  cudaFree(z->dTaps);
+  cudaFree(z->dRot);
+  cudaFree(z->dTw);
   delete z;
 }
 
@@ -257,10 +408,24 @@ int fmgpu_channelizer_process(fmgpu_channelizer *z, const uint8_t *iq_dev, size_
     z->lastError = "channelizer: filter too long for the shared-memory tile";
     return FMGPU_ERANGE;
   }
-  dim3 grid(static_cast<unsigned>((n_out + TM - 1) / TM), static_cast<unsigned>((ch_count + 31) / 32));
-  k_channelize<<<grid, 32 * WARPS, smem, s>>>(
-      iq_dev, z->dHist, z->histValid, static_cast<long>(n_in), z->dW, z->dNuD, z->L, z->D, z->Cpad, ch_first,
-      ch_count, z->outCount, n_out, reinterpret_cast<float2 *>(out_cf32_dev), out_stride_samples);
+  const size_t pp_smem = (static_cast<size_t>((PP_TM - 1) * z->D + z->L) + static_cast<size_t>(z->P) * (PP_TM + 1) +
+                          static_cast<size_t>(z->P)) * sizeof(float2) + static_cast<size_t>(z->L) * sizeof(float);
+  if (z->polyphase && pp_smem <= 200 * 1024) {
+    static bool pp_attr_done = false;
+    if (!pp_attr_done) {
+      cudaFuncSetAttribute(k_channelize_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      pp_attr_done = true;
+    }
+    k_channelize_pp<<<static_cast<unsigned>((n_out + PP_TM - 1) / PP_TM), PP_THREADS, pp_smem, s>>>(
+        iq_dev, z->dHist, z->histValid, static_cast<long>(n_in), z->dTaps, z->dRot, z->dTw, z->L, z->D, z->P,
+        z->rotPeriod, ch_first, ch_count, z->outCount, n_out, reinterpret_cast<float2 *>(out_cf32_dev),
+        out_stride_samples);
+  } else {
+    dim3 grid(static_cast<unsigned>((n_out + TM - 1) / TM), static_cast<unsigned>((ch_count + 31) / 32));
+    k_channelize<<<grid, 32 * WARPS, smem, s>>>(
+        iq_dev, z->dHist, z->histValid, static_cast<long>(n_in), z->dW, z->dNuD, z->L, z->D, z->Cpad, ch_first,
+        ch_count, z->outCount, n_out, reinterpret_cast<float2 *>(out_cf32_dev), out_stride_samples);
+  }
   const int H = z->L - 1;
   k_chan_carry<<<1, 512, static_cast<size_t>(H) * sizeof(uchar2), s>>>(z->dHist, iq_dev,
                                                                       static_cast<long>(n_in), H);

@@ -214,3 +214,44 @@ def test_config4_band_to_audio_and_rds(orc_fm):
     # an empty slot stays mono and silent of RDS
     for k in (20, 60):
         assert stereo_last[k] == 0 and sum(len(x) for x in groups[k]) == 0, k
+
+
+def test_polyphase_and_direct_forms_agree_and_polyphase_is_faster():
+    """The default evaluation is the polyphase bank (partial sums per commutator phase + one DFT row
+    per channel); FMGPU_CHANNELIZER_DIRECT=1 selects the direct form (one complex tap table per
+    channel). Same definition, so the same numbers to FP32 rounding — and the polyphase form must be
+    the faster one on the full band (config 4: 100 channels, two logical blocks per call)."""
+    import os
+
+    import torch
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(12)
+    n_in = 2 * 8192 * 100
+    iq = torch.from_numpy(rng.integers(0, 256, 2 * n_in, dtype=np.uint8)).to(dev)
+    n_out = n_in // 100
+    res, ms = {}, {}
+    for form in ("polyphase", "direct"):
+        if form == "direct":
+            os.environ["FMGPU_CHANNELIZER_DIRECT"] = "1"
+        try:
+            z = fm.Channelizer()
+        finally:
+            os.environ.pop("FMGPU_CHANNELIZER_DIRECT", None)
+        out = torch.zeros((100, n_out, 2), dtype=torch.float32, device=dev)
+        z.process(iq.data_ptr(), n_in, out.data_ptr(), n_out)      # first call: zero history
+        z.process(iq.data_ptr(), n_in, out.data_ptr(), n_out)      # second call: carried history
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            z.process(iq.data_ptr(), n_in, out.data_ptr(), n_out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms[form] = e0.elapsed_time(e1) / 5
+        res[form] = out.cpu().numpy()
+        z.close()
+    err = np.abs(res["polyphase"] - res["direct"]).max()
+    assert err < 2e-5, err
+    print(f"channelizer, 100 channels x {n_out} outputs: polyphase {ms['polyphase']:.3f} ms, "
+          f"direct {ms['direct']:.3f} ms")
+    assert ms["polyphase"] < 0.5 * ms["direct"], ms
