@@ -2084,6 +2084,29 @@ size_t fmgpu_decimate(fmgpu_engine *e, int channel, const uint8_t *iq, size_t in
   return stageFail(e, "decimate") ? 0 : n_out;
 }
 
+size_t fmgpu_decimate_u8(fmgpu_engine *e, int channel, const uint8_t *iq, size_t in_samples,
+                         uint8_t *out_u8, size_t out_capacity) {
+  STAGE_PROLOGUE(iq && out_u8 && in_samples > 0 && out_capacity > 0)
+  const size_t n_out = std::min({in_samples / static_cast<size_t>(e->M), out_capacity});
+  if (n_out == 0) {
+    return 0;
+  }
+  if (n_out > e->nmax) {
+    e->lastError = "decimate: more samples than the engine was sized for";
+    return 0;
+  }
+  uint8_t *row = e->dIq + static_cast<size_t>(channel) * e->iqPitch;
+  cudaMemcpyAsync(row, iq, n_out * e->M * 2, cudaMemcpyHostToDevice, s);
+  stageDecimate(e, e->dIq, e->iqPitch, static_cast<int>(n_out), channel, 1, s);
+  // the uint8 result goes back through the front of the channel's (already consumed) input row
+  launchRequantU8(e->dX1, e->pitch, e->dIq, e->iqPitch, static_cast<int>(n_out), channel, 1, s);
+  e->launches += 1;
+  cudaMemcpyAsync(out_u8, row, n_out * 2, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  e->lastN = static_cast<int>(n_out);
+  return stageFail(e, "decimate_u8") ? 0 : n_out;
+}
+
 static size_t demodCommon(fmgpu_engine *e, int channel, const uint8_t *iq_u8, const float *iq_cf32,
                           float *mpx_out, float *mono_out, size_t n, cudaStream_t s) {
   if (n > e->nmax) {

@@ -171,15 +171,6 @@ __device__ __forceinline__ float2 iqBytesToFloat(uint32_t w) {
 // samples per tile row of the lane kernels (LT: k_dcblock, k_agc, k_rds; ST: k_stereo). Measured:
 // the shared memory the lane kernels hold does not move the 10,000-channel step;
 // shorter k_stereo tiles lengthen that kernel by 10 % (one block barrier per tile).
-// Timing experiments only (tools/gpu_exp_bounds.sh; results are WRONG with either set): the lane
-// kernels walk 1/FMGPU_EXP_LANE_DIV of their samples, the FIR kernels 1/FMGPU_EXP_FIR_DIV of their
-// taps. They bound what the step could gain from faster lane kernels or faster FIR kernels.
-#ifndef FMGPU_EXP_LANE_DIV
-#define FMGPU_EXP_LANE_DIV 1
-#endif
-#ifndef FMGPU_EXP_FIR_DIV
-#define FMGPU_EXP_FIR_DIV 1
-#endif
 constexpr int LT = FMGPU_LT;
 constexpr int STEREO_ST = FMGPU_ST;
 
@@ -445,7 +436,7 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
   for (int u = 0; u < 3; u++) {
     loadSeg(seg[u], tbase + u * M);  // u < 4: no skew element yet
   }
-  for (int pp = 0; pp < Pp / FMGPU_EXP_FIR_DIV; pp += 4) {
+  for (int pp = 0; pp < Pp; pp += 4) {
 #pragma unroll
     for (int ps = 0; ps < 4; ps++) {
       const int u = pp + ps + 3;
@@ -471,139 +462,6 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
 }
 
 // ---------------------------------------------------------------------------
-// K1, eight outputs per thread. k_decim above is bound by shared-memory bandwidth: with 4 outputs
-// per thread one LDS.64 feeds 4 FFMA2, which needs the full 128 B/clk/SM at the full FMA rate (ncu
-// r01: LSU data pipe 81 %, FMA pipe 55 %). Holding 8 outputs' worth of sample segments in registers
-// (8 x M complex) does not fit. Instead the second set of four outputs runs FOUR TAP SEGMENTS
-// BEHIND the first: at step tau outputs 0..3 apply tap segment tau to sample segments tau..tau+3,
-// and outputs 4..7 apply tap segment tau-4 to segments (tau-4)+4.. = the SAME four segments. Every
-// segment read from shared memory now feeds 8 FFMA2 with the same 4-segment register ring, and each
-// output still sees its taps in ascending order (oldest sample first): bit-identical results.
-// ---------------------------------------------------------------------------
-#ifndef FMGPU_DECIM8_NT
-#define FMGPU_DECIM8_NT 64
-#endif
-constexpr int DECIM8_NT = FMGPU_DECIM8_NT;
-
-template <int M, bool PACK>
-__global__ void __launch_bounds__(DECIM8_NT)
-k_decim8(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
-         const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
-         int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
-  constexpr int R = 8;
-  constexpr int T = DECIM8_NT * R;
-  constexpr int RM = R * M;
-  extern __shared__ float2 xs[];
-  const int c = blockIdx.y + ch0;
-  const int n0 = blockIdx.x * T;
-  const int t = threadIdx.x;
-  const long o = (long)(n0 - Pp) * M + 1;  // stream index of tile element 0
-  const int tile_len = (T + Pp - 1) * M;
-  const long v0 = o + H_IQ;                // virtual index (history first)
-  const long n_in = (long)n_out * M;
-  const unsigned short *in_c = reinterpret_cast<const unsigned short *>(iq + (size_t)c * iq_stride);
-  const unsigned short *hist_c = reinterpret_cast<const unsigned short *>(hist) + (size_t)c * H_IQ;
-  const long v_first_valid = H_IQ - hist_valid[c];
-  {  // tile fill, as in k_decim (one skew element per RM samples: odd per-thread stride)
-    const int a_lo = (int)max(0L, min((long)tile_len, v_first_valid - v0));
-    const int a_hi = (int)max(0L, min((long)tile_len, n_in + H_IQ - v0));
-    const int a_hist = (int)max(0L, min((long)tile_len, (long)H_IQ - v0));
-    const unsigned short *p_hist = hist_c + v0;
-    const unsigned short *p_in = in_c + (v0 - H_IQ);
-    auto fill = [&](auto fast_tag) {
-      constexpr bool FAST = decltype(fast_tag)::value;
-#pragma unroll 6
-      for (unsigned a = t; a < (unsigned)tile_len; a += DECIM8_NT) {
-        uint32_t w = 0;
-        bool ok = true;
-        if (FAST) {
-          w = __ldg(p_in + a);
-        } else {
-          ok = ((int)a >= a_lo) && ((int)a < a_hi);
-          if (ok) {
-            w = __ldg((((int)a < a_hist) ? p_hist : p_in) + a);
-          }
-        }
-        float2 f = iqBytesToFloat(w);
-        if (!FAST && !ok) {
-          f = make_float2(0.0f, 0.0f);
-        }
-        xs[a + a / RM] = f;
-      }
-    };
-    if (a_lo == 0 && a_hist == 0 && a_hi == tile_len) {
-      fill(std::true_type{});
-    } else {
-      fill(std::false_type{});
-    }
-  }
-  __syncthreads();
-
-  float2 accA[4], accB[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    accA[j] = make_float2(0.0f, 0.0f);
-    accB[j] = make_float2(0.0f, 0.0f);
-  }
-  float2 seg[4][M];
-  const int tbase = t * (RM + 1);
-#pragma unroll
-  for (int u = 0; u < 3; u++) {
-#pragma unroll
-    for (int r = 0; r < M; r++) {
-      seg[u][r] = xs[tbase + u * M + r];  // u < 8: no skew element yet
-    }
-  }
-  // groups of four steps (ring slots are compile-time). Outputs 0..3 run tap segments 0..Pp-1 at
-  // steps 0..Pp-1, outputs 4..7 the same segments at steps 4..Pp+3; both branches are uniform.
-  const int PpE = Pp / FMGPU_EXP_FIR_DIV;
-  for (int tau0 = 0; tau0 <= PpE; tau0 += 4) {
-    const bool a_on = tau0 < PpE;
-    const bool b_on = tau0 >= 4;
-#pragma unroll
-    for (int ps = 0; ps < 4; ps++) {
-      const int u = tau0 + ps + 3;
-      const int sb = tbase + u * M + (u >> 3);
-#pragma unroll
-      for (int r = 0; r < M; r++) {
-        seg[(ps + 3) & 3][r] = xs[sb + r];
-      }
-      if (a_on) {
-#pragma unroll
-        for (int r = 0; r < M; r++) {
-          const float h = taps.h[(tau0 + ps) * M + r];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            accA[j] = fma2<PACK>(h, seg[(j + ps) & 3][r], accA[j]);
-          }
-        }
-      }
-      if (b_on) {
-#pragma unroll
-        for (int r = 0; r < M; r++) {
-          const float h = taps.h[(tau0 + ps - 4) * M + r];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            accB[j] = fma2<PACK>(h, seg[(j + ps) & 3][r], accB[j]);
-          }
-        }
-      }
-    }
-  }
-
-  float2 *out = x1 + (size_t)c * x1_pitch;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int n = n0 + R * t + j;
-    if (n < n_out) {
-      out[n] = make_float2(accA[j].x * scale, accA[j].y * scale);
-    }
-    if (n + 4 < n_out) {
-      out[n + 4] = make_float2(accB[j].x * scale, accB[j].y * scale);
-    }
-  }
-}
-
 // generic fallback for decimation factors without an instantiation
 __global__ void k_decim_generic(const uint8_t *__restrict__ iq, size_t iq_stride,
                                 const uint8_t *__restrict__ hist,
@@ -648,6 +506,22 @@ __global__ void k_convert_u8(const uint8_t *__restrict__ iq, size_t iq_stride,
       make_float2(((float)b.x - 127.5f) * kScale, ((float)b.y - 127.5f) * kScale);
 }
 
+// ComplexDecimator::execute: the decimated sample back to uint8 (liquid_primitives.cpp:452-456):
+// clamp(y * 127.5 + 127.5, 0, 255), truncated
+__global__ void k_requant_u8(const float2 *__restrict__ x1, size_t x1_pitch, uint8_t *__restrict__ out,
+                             size_t out_stride, int n, int ch0) {
+  const int c = blockIdx.y + ch0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  const float2 y = x1[(size_t)c * x1_pitch + i];
+  const float vi = fminf(fmaxf(__fadd_rn(__fmul_rn(y.x, 127.5f), 127.5f), 0.0f), 255.0f);
+  const float vq = fminf(fmaxf(__fadd_rn(__fmul_rn(y.y, 127.5f), 127.5f), 0.0f), 255.0f);
+  reinterpret_cast<uchar2 *>(out + (size_t)c * out_stride)[i] =
+      make_uchar2((unsigned char)vi, (unsigned char)vq);
+}
+
 // ---------------------------------------------------------------------------
 // S1: I/Q DC blockers (iirfilt dc_blocker, alpha = 0.0005) + clip statistics.
 // One lane per channel; fm_demod.cpp:150-208.
@@ -657,7 +531,6 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
           size_t iq_stride, float2 *__restrict__ x2, size_t x2_pitch, DemodState *st,
           fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total, int ch0,
           int nch, float a1) {
-  n_total /= FMGPU_EXP_LANE_DIV;
   // ONE warp per 32 channels, one lane per channel: the warp prefetches its next input tile
   // (cp.async), runs the recursions on the current one and writes the finished tile back itself.
   // (A separate mover warp doubles the registers and warp slots this kernel keeps from the FIR
@@ -812,7 +685,7 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
     win[j] = xs[a + (a >> 3)];
   }
   const float2 *wp = xs + (R + 1) * (t + 1);  // as in k_fir_pair: immediate-offset window loads
-  for (int i = 0; i < Lp / FMGPU_EXP_FIR_DIV; i += R) {
+  for (int i = 0; i < Lp; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
       const float h = hs[i + u];
@@ -838,7 +711,6 @@ k_chanfir(const float2 *__restrict__ x2, size_t x2_pitch, float2 *__restrict__ y
 __global__ void __launch_bounds__(32)
 k_agc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total, int ch0,
       int nch) {
-  n_total /= FMGPU_EXP_LANE_DIV;
   // ONE warp per 32 channels (see k_dcblock): prefetch the next tile, run the AGC recursion in
   // place on the current one, write it back. Two tiles.
   constexpr int TP = 2 * LT + 4;
@@ -1037,7 +909,6 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
          size_t pilot_pitch, float *__restrict__ lraw, float *__restrict__ rraw, size_t lr_pitch,
          StereoState *st, const ChanParams *cp, fmgpu_block_status *status, int status_pitch,
          int nblk, int blk_len, int n_total, int ch0, int nch, EngineConst k) {
-  n_total /= FMGPU_EXP_LANE_DIV;
   constexpr int ST = STEREO_ST;  // samples per tile row
   // 16-byte aligned rows, read and written by their lane four samples at a time; a pitch of ST + 4
   // floats is odd in 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups
@@ -1920,7 +1791,7 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
 
   uint32_t produced = 0;
   const uint32_t n171 = active ? s.n171 : 0u;
-  const int nchunks = (int)((s_nmax / FMGPU_EXP_LANE_DIV + LT - 1) / LT);
+  const int nchunks = (int)((s_nmax + LT - 1) / LT);
   // tile element ii of chunk ck <-> 171 kHz sample ck*LT + ii (rows are padded to whole tiles)
   auto prefetch = [&](int ck) {
     constexpr int cpr = LT / 4;
@@ -2380,53 +2251,9 @@ static bool usePackedFma() {
     break;                                                                                       \
   }
 
-#define FMGPU_DECIM8_CASE(MM)                                                                    \
-  case MM: {                                                                                     \
-    constexpr int T = 8 * DECIM8_NT;                                                             \
-    const int tile_len = (T + Pp - 1) * MM;                                                      \
-    const size_t smem = (size_t)(tile_len + tile_len / (8 * MM) + 2) * sizeof(float2);           \
-    static bool attr_done = false;                                                               \
-    if (!attr_done) {                                                                            \
-      cudaFuncSetAttribute(k_decim8<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                           160 * 1024);                                                          \
-      cudaFuncSetAttribute(k_decim8<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                           160 * 1024);                                                          \
-      attr_done = true;                                                                          \
-    }                                                                                            \
-    dim3 grid((n_out + T - 1) / T, nch);                                                         \
-    if (usePackedFma()) {                                                                        \
-      k_decim8<MM, true><<<grid, DECIM8_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1, \
-                                                            x1_pitch, n_out, ch0, Pp, scale,     \
-                                                            taps);                               \
-    } else {                                                                                     \
-      k_decim8<MM, false><<<grid, DECIM8_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid,    \
-                                                             x1, x1_pitch, n_out, ch0, Pp,       \
-                                                             scale, taps);                       \
-    }                                                                                            \
-    return;                                                                                      \
-  }
-
-// FMGPU_DECIM8=1 selects the eight-outputs-per-thread decimator (bit-identical; slower so far:
-// 139 registers leave 10 warps per SM)
-static bool useDecim8() {
-  static const bool v = [] {
-    const char *e = getenv("FMGPU_DECIM8");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
 void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist,
                  const int *hist_valid, float2 *x1, size_t x1_pitch, int n_out, int ch0, int nch, int Pp, int L, float scale,
                  const TapsParam &taps, const TapsParam &taps_unpadded, cudaStream_t stream) {
-  if (useDecim8()) {  // the factors of the BASELINE configurations (2.048 MS/s / 8, 2.4 MS/s / 10)
-    switch (M) {
-      FMGPU_DECIM8_CASE(8)
-      FMGPU_DECIM8_CASE(10)
-    default:
-      break;
-    }
-  }
   switch (M) {
     FMGPU_DECIM_CASE(2)
     FMGPU_DECIM_CASE(4)
@@ -2447,6 +2274,12 @@ void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_
                      int ch0, int nch, cudaStream_t stream) {
   dim3 grid((n + 255) / 256, nch);
   k_convert_u8<<<grid, 256, 0, stream>>>(iq, iq_stride, x1, x1_pitch, n, ch0);
+}
+
+void launchRequantU8(const float2 *x1, size_t x1_pitch, uint8_t *out, size_t out_stride, int n, int ch0,
+                     int nch, cudaStream_t stream) {
+  dim3 grid((n + 255) / 256, nch);
+  k_requant_u8<<<grid, 256, 0, stream>>>(x1, x1_pitch, out, out_stride, n, ch0);
 }
 
 void launchCarryIq(uint8_t *hist, int *hist_valid, const uint8_t *iq, size_t iq_stride, long n_in,
@@ -2555,7 +2388,7 @@ k_fir_pair(FirRealJob job, int pair_channels, int nch, const __grid_constant__ T
   // that advances by R + 1 per round, so every LDS has an immediate offset (the index arithmetic
   // per load was 12 % of this kernel's instructions)
   const float2 *wp = fp_x + (R + 1) * (t + 1);
-  for (int i = 0; i < Lp / FMGPU_EXP_FIR_DIV; i += R) {
+  for (int i = 0; i < Lp; i += R) {
 #pragma unroll
     for (int u = 0; u < R; u++) {
       const float h = taps.h[i + u];

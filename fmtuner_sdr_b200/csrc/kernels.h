@@ -37,6 +37,8 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
                           cudaStream_t stream);
 void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_pitch, int n,
                      int ch0, int nch, cudaStream_t stream);
+void launchRequantU8(const float2 *x1, size_t x1_pitch, uint8_t *out, size_t out_stride, int n, int ch0,
+                     int nch, cudaStream_t stream);
 void launchCarryIq(uint8_t *hist, int *hist_valid, const uint8_t *iq, size_t iq_stride, long n_in,
                    int ch0, int nch, cudaStream_t stream);
 void launchCarryF32(float *buf, size_t pitch, int H, size_t n, int ch0, int nch,

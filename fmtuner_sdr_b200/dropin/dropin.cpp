@@ -150,9 +150,7 @@ void ComplexDecimator::init(std::uint32_t factor, std::uint32_t tapsPerPhase, fl
     engine_ = nullptr;
   }
   factor_ = factor;
-  if (factor_ == 1) {
-    return;
-  }
+  // factor 1 is a pure convert (liquid_primitives.cpp:468-478): it runs on the device as well
   engine_ = makeEngine(256000 * static_cast<int>(factor), static_cast<int>(factor), 32000,
                        static_cast<int>(std::max<std::uint32_t>(4, tapsPerPhase)),
                        static_cast<int>(std::lround(stopBandAtten)));
@@ -170,19 +168,25 @@ std::size_t ComplexDecimator::executeComplex(const uint8_t *iqIn, std::size_t in
   if (!iqIn || !iqOut || inSamples == 0 || outCapacity == 0) {
     return 0;
   }
-  if (factor_ == 1) {
-    static constexpr float kScale = 1.0f / 127.5f;
-    const std::size_t n = std::min(inSamples, outCapacity);
-    for (std::size_t i = 0; i < n; i++) {
-      iqOut[i] = std::complex<float>((static_cast<float>(iqIn[2 * i]) - 127.5f) * kScale,
-                                     (static_cast<float>(iqIn[2 * i + 1]) - 127.5f) * kScale);
-    }
-    return n;
+  if (!engine_ && factor_ == 1) {
+    engine_ = makeEngine(256000, 1, 32000);
   }
   if (!engine_) {
     return 0;
   }
-  return fmgpu_decimate(engine_, 0, iqIn, inSamples, reinterpret_cast<float *>(iqOut), outCapacity);
+  // (blocks longer than the engine was sized for go through in pieces)
+  std::size_t done = 0;
+  const std::size_t want = std::min(inSamples / factor_, outCapacity);
+  while (done < want) {
+    const std::size_t n = std::min<std::size_t>(kMaxBlock, want - done);
+    const std::size_t got = fmgpu_decimate(engine_, 0, iqIn + 2 * done * factor_, n * factor_,
+                                           reinterpret_cast<float *>(iqOut + done), n);
+    if (got == 0) {
+      break;
+    }
+    done += got;
+  }
+  return done;
 }
 
 std::size_t ComplexDecimator::execute(const uint8_t *iqIn, std::size_t inSamples, uint8_t *iqOut,
@@ -192,19 +196,24 @@ std::size_t ComplexDecimator::execute(const uint8_t *iqIn, std::size_t inSamples
   }
   if (factor_ == 1) {
     const std::size_t n = std::min(inSamples, outCapacity);
-    std::copy_n(iqIn, n * 2, iqOut);
+    std::copy_n(iqIn, n * 2, iqOut);   // a byte copy, as in the reference (:431-435)
     return n;
   }
-  std::vector<std::complex<float>> tmp(std::min(inSamples / factor_, outCapacity));
-  const std::size_t n = executeComplex(iqIn, inSamples, tmp.data(), tmp.size());
-  for (std::size_t b = 0; b < n; b++) {
-    // re-quantisation as in liquid_primitives.cpp:452-456
-    const float i = std::clamp((tmp[b].real() * 127.5f) + 127.5f, 0.0f, 255.0f);
-    const float q = std::clamp((tmp[b].imag() * 127.5f) + 127.5f, 0.0f, 255.0f);
-    iqOut[2 * b] = static_cast<uint8_t>(i);
-    iqOut[2 * b + 1] = static_cast<uint8_t>(q);
+  if (!engine_) {
+    return 0;
   }
-  return n;
+  std::size_t done = 0;
+  const std::size_t want = std::min(inSamples / factor_, outCapacity);
+  while (done < want) {   // decimated and re-quantised on the device (fmgpu_decimate_u8)
+    const std::size_t n = std::min<std::size_t>(kMaxBlock, want - done);
+    const std::size_t got =
+        fmgpu_decimate_u8(engine_, 0, iqIn + 2 * done * factor_, n * factor_, iqOut + 2 * done, n);
+    if (got == 0) {
+      break;
+    }
+    done += got;
+  }
+  return done;
 }
 
 }  // namespace fm_tuner::dsp::liquid

@@ -33,7 +33,9 @@ public:
   std::uint32_t factor() const { return factor_; }
 
 private:
-  fmgpu_engine *engine_ = nullptr;
+  // mutable: a default-constructed decimator (factor 1, never initialised) converts as the
+  // reference's does, and gets its engine on first use
+  mutable fmgpu_engine *engine_ = nullptr;
   std::uint32_t factor_ = 1;
 };
 

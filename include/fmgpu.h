@@ -13,7 +13,9 @@
  * method that returns a sample count return that count and 0 for null / empty
  * arguments, as the reference does (stereo_decoder.cpp:94-96,
  * af_post_processor.cpp:50-53, rds_decoder.cpp:76-78, liquid_primitives.cpp:465-467).
- * There is no CPU fallback: every call fails with FMGPU_ENODEV without a CUDA device.
+ * There is no CPU fallback: every call fails with FMGPU_ENODEV without a CUDA device, and every
+ * sample-rate operation of the path — the factor-1 convert and the uint8 re-quantisation of
+ * ComplexDecimator::execute included — runs on the device.
  */
 #ifndef FMGPU_H_
 #define FMGPU_H_
@@ -254,6 +256,10 @@ int fmgpu_set_pipeline_groups(fmgpu_engine *e, int groups);
 /* ComplexDecimator::executeComplex  liquid_primitives.cpp:461-499 ; out = interleaved re,im */
 size_t fmgpu_decimate(fmgpu_engine *e, int channel, const uint8_t *iq, size_t in_samples,
                       float *out_cf32, size_t out_capacity);
+/* ComplexDecimator::execute  liquid_primitives.cpp:422-459 ; uint8 I,Q pairs out (re-quantised on
+ * the device: clamp(y * 127.5 + 127.5, 0, 255), truncated) */
+size_t fmgpu_decimate_u8(fmgpu_engine *e, int channel, const uint8_t *iq, size_t in_samples,
+                         uint8_t *out_u8, size_t out_capacity);
 /* FMDemod::processSplit (uint8 IQ at the DSP rate)  fm_demod.cpp:245-259 */
 size_t fmgpu_demod_u8(fmgpu_engine *e, int channel, const uint8_t *iq, float *mpx_out,
                       float *mono_out, size_t n);

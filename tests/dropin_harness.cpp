@@ -120,6 +120,12 @@ int main(int argc, char **argv) {
     std::fwrite(b.data(), sizeof(float), n, fx);
     const size_t k2 = d3.downsampleAudio(b.data(), c.data(), n);
     std::fwrite(c.data(), sizeof(float), k2, fx);
+    // a default-constructed ComplexDecimator (factor 1, never initialised): the pure convert of
+    // liquid_primitives.cpp:468-478
+    fm_tuner::dsp::liquid::ComplexDecimator d4;
+    std::vector<std::complex<float>> conv(n);
+    const size_t k3 = d4.executeComplex(iq.data(), n, conv.data(), n);
+    std::fwrite(conv.data(), sizeof(std::complex<float>), k3, fx);
     std::fclose(fx);
   }
   return 0;

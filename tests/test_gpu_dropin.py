@@ -59,7 +59,9 @@ def _check_extra(orc_fm, iq, iq_rate, decim, prefix):
     assert np.array_equal(fl[na:na + n], b)
     c = np.zeros(n, np.float32)
     kc = L.orc_demod_downsample(h, b.ctypes.data_as(F), c.ctypes.data_as(F), n)
-    assert np.array_equal(fl[na + n:na + n + kc], c[:kc]) and fl.size == na + n + kc
+    assert np.array_equal(fl[na + n:na + n + kc], c[:kc]) and fl.size == na + n + kc + 2 * n
+    conv = (iq[:2 * n].astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)
+    assert np.array_equal(fl[na + n + kc:], conv)       # factor-1 convert, done on the device
     L.orc_demod_destroy(h)
 
 
