@@ -50,7 +50,10 @@ constexpr int TC_CHUNK = 128;         // bytes of K per ring slot row (one 128B 
 constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
 constexpr int TC_B_CHUNKS = 6;        // K extent of B: 6 * 128 = 768 bytes >= 32 * KS
 constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 48 KB
-constexpr int TC_RING = 10;           // A ring slots (160 KB)
+#ifndef FMGPU_TC_RING
+#define FMGPU_TC_RING 10
+#endif
+constexpr int TC_RING = FMGPU_TC_RING;   // A ring slots of 16 KB (a tile's window touches up to 7)
 constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns
 constexpr int TC_THREADS = 192;
 constexpr int TC_SHIFT = 26;          // taps are quantised to 2^-26

@@ -159,6 +159,18 @@ FM_HD float fm_atan2f(float y, float x) {
 
 // ---- exp / log ------------------------------------------------------------
 FM_HD float fm_expf(float x) {
+  if (fabsf(x) < 0.34f) {
+    // k = rint(x * log2(e)) = 0: the reduction leaves r = x and both scale factors are 1.0f, so
+    // this shortcut returns the bits of the general path below (the AGCs only ever call exp with
+    // |x| = 0.5 * alpha * |log(energy)| << 0.34)
+    const float z0 = FM_MUL(x, x);
+    float p0 = FM_FMA(x, 1.9875691500e-4f, 1.3981999507e-3f);
+    p0 = FM_FMA(p0, x, 8.3334519073e-3f);
+    p0 = FM_FMA(p0, x, 4.1665795894e-2f);
+    p0 = FM_FMA(p0, x, 1.6666665459e-1f);
+    p0 = FM_FMA(p0, x, 5.0000001201e-1f);
+    return FM_ADD(FM_FMA(p0, z0, x), 1.0f);
+  }
   x = fm_clampf(x, -87.0f, 88.0f);
   const float kf = rintf(FM_MUL(x, 1.44269504088896341f));
   float r = FM_FMA(kf, -0.693359375f, x);

@@ -81,8 +81,20 @@ cudaError_t initRdsTables() {
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------
+// liquid's nco_crcf goes through double twice: constrain() evaluates (float)((double)theta / 2pi)
+// and get_phase() (float)(2pi * (double)(float)theta / 2^32). A float -> double -> float round trip
+// costs ~46 cycles of the PLL's serial chain on B200 (F2F pair 38, DMUL 8; r01 latency microbench).
+// Both products are evaluated here in float as a two-term product with the exact error of the
+// leading term (p = x*hi; e = fma(x, hi, -p); p + fma(x, lo, e)), which is bit-identical:
+// tools/nco_float_form_proof.cpp compares EVERY input — all 3.19e9 finite floats below 2^63 for the
+// resulting uint32 of constrain(), all 83,886,081 possible (float)theta for the phase — with the
+// double form: 0 mismatches (profiles/r02_nco_float_form_proof.txt).
 __device__ __forceinline__ uint32_t ncoConstrainDev(float theta) {
-  const float p = (float)((double)theta * 0.159154943091895);
+  constexpr float kHi = 0x1.45f306p-3f;   // (float)(1 / 2pi), 0.159154943091895 as liquid writes it
+  constexpr float kLo = 0x1.b9390ep-28f;  // (float)(0.159154943091895 - kHi)
+  const float p0 = __fmul_rn(theta, kHi);
+  const float e = __fmaf_rn(theta, kHi, -p0);
+  const float p = __fadd_rn(p0, __fmaf_rn(theta, kLo, e));
   float fpart = p - truncf(p);  // == p - (float)(long)p for every |p| < 2^63
   if (fpart < 0.0f) {
     fpart = fpart + 1.0f;
@@ -93,7 +105,12 @@ __device__ __forceinline__ uint32_t ncoConstrainDev(float theta) {
 }
 
 __device__ __forceinline__ float ncoPhaseDev(uint32_t theta) {
-  return (float)(6.283185307179586 * (double)((float)theta) / 4294967296.0);
+  constexpr float kHi = (float)(6.283185307179586 / 4294967296.0);
+  constexpr float kLo = (float)(6.283185307179586 / 4294967296.0 - (double)kHi);
+  const float t = __uint2float_rn(theta);
+  const float p0 = __fmul_rn(t, kHi);
+  const float e = __fmaf_rn(t, kHi, -p0);
+  return __fadd_rn(p0, __fmaf_rn(t, kLo, e));
 }
 
 __device__ __forceinline__ float unwrapDev(float p) {
