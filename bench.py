@@ -72,8 +72,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--decim-mode", default="tc", choices=["tc", "fp32"],
-                    help="decimator arithmetic: tc = tcgen05 int8 contraction (fmgpu_set_decimator_mode 1), "
-                         "fp32 = the FFMA2 chain that is bit-identical to the CPU oracle (mode 0)")
+                    help="arithmetic: tc = the engine's fast forms (tcgen05 int8 decimator, "
+                         "fmgpu_set_decimator_mode 1; de-emphasis / DC blocker as a warp-shuffle scan, "
+                         "fmgpu_set_audio_iir_mode 1); fp32 = the reference's summation order everywhere, "
+                         "bit-identical to the CPU oracle (modes 0)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the strong-scaling, config-4 and H2D-roof records")
     return ap.parse_args()
@@ -235,8 +237,11 @@ def workload_config(args, channels_this_arm: int) -> dict:
                     "SNR 10-40 dB, blend soft/normal/aggressive by c%3, dsp_agc fast, stereo + RDS",
         "channels_per_gpu": args.channels, "blocks_per_step": args.blocks,
         "pipeline_groups": args.groups,
-        "decimator": ("tcgen05 int8 contraction, TMA-fed, accumulators in TMEM (decim_tc.cu, mode 1)"
-                      if args.decim_mode == "tc" else "FP32 FFMA2 chain, bit-identical to the oracle (mode 0)"),
+        "arithmetic": ("fast forms where they exist: decimator = tcgen05 int8 contraction, TMA-fed, "
+                       "accumulators in TMEM (decim_tc.cu, fmgpu_set_decimator_mode 1); de-emphasis + DC "
+                       "blocker = warp-shuffle scan (fmgpu_set_audio_iir_mode 1); every other stage in "
+                       "the reference's summation order" if args.decim_mode == "tc" else
+                       "reference order everywhere: bit-identical to the CPU oracle (modes 0)"),
         "step_submission": "joined per step" if args.sync_steps else
                            "streamed (async steps, one join before the closing event)",
         "block_samples": BLOCK, "iq_rate": IQ_RATE, "decimation": DECIM,
@@ -285,6 +290,7 @@ class Workload:
                                             dsp_agc=1), channels, local_rank)
         self.eng.set_pipeline_groups(args.groups)
         self.eng.set_decimator_mode(1 if args.decim_mode == "tc" else 0)
+        self.eng.set_audio_iir_mode(1 if args.decim_mode == "tc" else 0)
         for m in (0, 2):   # blend mode = global channel id % 3 (1 = normal is the engine default)
             for c, g in enumerate(global_ids):
                 if g % 3 == m:

@@ -1481,6 +1481,105 @@ __global__ void k_audio_iir(float *audio, size_t acap, AudioState *au, const Cha
   }
 }
 
+// S6 as a warp-shuffle parallel scan (north_star item 5): the same two first-order recursions,
+// one WARP per (channel, side) row, 32 frames per step. Both filters are affine in their state,
+//     v[j] = x[j] + r v[j-1]     (de-emphasis: r = -a1;  DC blocker: r = 1 - alpha),
+// so a Kogge-Stone scan over the lanes (5 rounds of shfl_up + fma with r^1, r^2, ... r^16) gives
+// every lane its v[j] from the 32 inputs and the state carried in, and the row is read and
+// written with coalesced 128-byte accesses instead of one scattered word per lane. The scan adds
+// the terms in a different order than the serial loop: results agree to float rounding (~1e-7),
+// not bit for bit, so it is the engine's FAST form (fmgpu_set_audio_iir_mode(1)); the lane
+// recursion above stays the bit-exact one. Stereo rows only (the mono chain keeps the recursion).
+__global__ void __launch_bounds__(128)
+k_audio_iir_scan(float *audio, size_t acap, AudioState *au, const ChanParams *cp, int ch0, int nch,
+                 float dc_a1, int clamp) {
+  const int lane = threadIdx.x & 31;
+  const int row_id = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row_id >= 2 * nch) {
+    return;
+  }
+  const int c = ch0 + (row_id >> 1);
+  const int side = row_id & 1;
+  AudioState *a = &au[c];
+  const ChanParams p = cp[c];
+  const uint32_t ob = min((uint32_t)acap, a->out_base);
+  const uint32_t n = min((uint32_t)acap - ob, a->n_out);
+  float *row = audio + ((size_t)c * 2 + side) * acap + ob;
+  const bool de = p.deemph_on != 0;
+  const float b0 = p.de_b0;
+  const float r1 = -p.de_a1;   // de-emphasis pole
+  const float r2 = -dc_a1;     // DC blocker pole
+  // r^(2^k) for the scan rounds and r^(lane+1) for the carried state
+  float p1[5], p2[5];
+  p1[0] = r1;
+  p2[0] = r2;
+#pragma unroll
+  for (int k = 1; k < 5; k++) {
+    p1[k] = p1[k - 1] * p1[k - 1];
+    p2[k] = p2[k - 1] * p2[k - 1];
+  }
+  float s1 = 1.0f, s2 = 1.0f;   // r^(lane+1) by binary exponentiation of lane + 1
+  {
+    const int e = lane + 1;
+    float q1 = r1, q2 = r2;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if ((e >> k) & 1) {
+        s1 *= q1;
+        s2 *= q2;
+      }
+      q1 *= q1;
+      q2 *= q2;
+    }
+  }
+  float dv = a->de_v1[side];
+  float cv = a->dc_v1[side];
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    float x = (i < n) ? row[i] : 0.0f;
+    if (de) {
+      float v = x;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const float t = __shfl_up_sync(0xffffffffu, v, 1 << k);
+        if (lane >= (1 << k)) {
+          v = fmaf(p1[k], t, v);
+        }
+      }
+      v = fmaf(s1, dv, v);   // v0[j] of the serial loop
+      x = b0 * v;
+      const uint32_t last = min(31u, n - 1 - i0);
+      dv = __shfl_sync(0xffffffffu, v, last);
+    }
+    float w = x;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const float t = __shfl_up_sync(0xffffffffu, w, 1 << k);
+      if (lane >= (1 << k)) {
+        w = fmaf(p2[k], t, w);
+      }
+    }
+    w = fmaf(s2, cv, w);
+    float wp = __shfl_up_sync(0xffffffffu, w, 1);
+    if (lane == 0) {
+      wp = cv;
+    }
+    float y = w - wp;
+    if (clamp) {
+      y = fm_clampf(y, -1.0f, 1.0f);
+    }
+    if (i < n) {
+      row[i] = y;
+    }
+    const uint32_t last = min(31u, n - 1 - i0);
+    cv = __shfl_sync(0xffffffffu, w, last);
+  }
+  if (lane == 0) {
+    a->de_v1[side] = dv;
+    a->dc_v1[side] = cv;
+  }
+}
+
 __global__ void k_store_counts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,
                                uint32_t *n_groups, int ch0, int nch, int mono, uint32_t acap,
                                uint32_t gcap) {
@@ -2520,6 +2619,11 @@ void launchAudioIir(float *audio, size_t acap, AudioState *au, const ChanParams 
   const int lanes = mono ? nch : 2 * nch;
   k_audio_iir<<<(lanes + 31) / 32, 32, 0, stream>>>(audio, acap, au, cp, ch0, nch, dc_a1, mono,
                                                    clamp, mono_dup);
+}
+
+void launchAudioIirScan(float *audio, size_t acap, AudioState *au, const ChanParams *cp, int ch0,
+                        int nch, float dc_a1, int clamp, cudaStream_t stream) {
+  k_audio_iir_scan<<<(2 * nch + 3) / 4, 128, 0, stream>>>(audio, acap, au, cp, ch0, nch, dc_a1, clamp);
 }
 
 void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,

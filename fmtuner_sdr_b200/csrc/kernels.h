@@ -76,6 +76,9 @@ void launchResample(const float *in0, const float *in1, size_t in_pitch, int in_
                     int ch0, int nch, cudaStream_t stream);
 void launchAudioIir(float *audio, size_t acap, AudioState *au, const ChanParams *cp, int ch0,
                     int nch, float dc_a1, int mono, int clamp, int mono_dup, cudaStream_t stream);
+// de-emphasis + DC blocker of the stereo rows as a warp-shuffle affine scan (fast arithmetic)
+void launchAudioIirScan(float *audio, size_t acap, AudioState *au, const ChanParams *cp, int ch0,
+                        int nch, float dc_a1, int clamp, cudaStream_t stream);
 void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_audio,
                        uint32_t *n_groups, int ch0, int nch, int mono, uint32_t acap, uint32_t gcap,
                        cudaStream_t stream);

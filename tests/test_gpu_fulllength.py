@@ -49,15 +49,17 @@ def audio_start(status, extra_blocks=2, never=8):
     return int(status["n_audio"][:blk].sum()), (int(on[0]) if on.size else -1)
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["fp32-chain", "tensor-core"])
+@pytest.mark.parametrize("mode", [0, 1], ids=["reference-order", "fast-arithmetic"])
 @pytest.mark.parametrize("rate,nblk", [("240k", 293), ("256k", 313)])
 def test_config1_ten_seconds(orc_fm, rate, nblk, mode):
-    """mode 0: the FP32 decimator (the oracle's summation order) — bit for bit. mode 1: the
-    tensor-core decimator (bench.py's default) — the tolerance gates against the faithful flavour."""
+    """mode 0: the reference's summation order everywhere — bit for bit. mode 1: the engine's fast
+    arithmetic (tensor-core decimator + scan de-emphasis, bench.py's default) — the tolerance
+    gates against the faithful flavour."""
     iq_rate, decim = rates(rate)
     iq = orc.config1_signal(fs_iq=iq_rate).generate(nblk * 8192 * decim)
     eng = fm.Engine(fm.make_config(iq_rate=iq_rate, decimation=decim, max_blocks=8), 1, 0)
     eng.set_decimator_mode(mode)
+    eng.set_audio_iir_mode(mode)       # mode 1 = the engine's fast arithmetic, as bench.py runs it
     audio, groups, status, dbg = run_engine_chunks(eng, iq.reshape(1, -1), nblk, 8, debug_channel=0)
     eng.close()
     a, g, st = audio[0], groups[0], status[0]
@@ -89,7 +91,7 @@ def _sweep_signal(c, n_ch, iq_rate):
     return s
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["fp32-chain", "tensor-core"])
+@pytest.mark.parametrize("mode", [0, 1], ids=["reference-order", "fast-arithmetic"])
 def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
     iq_rate, decim = rates("240k")
     n_ch, nblk, chunk, per_pass = 320, 88, 8, 80     # 88 blocks = 3.0 s
@@ -113,6 +115,7 @@ def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
             eng = fm.Engine(fm.make_config(iq_rate=iq_rate, decimation=decim, max_blocks=chunk,
                                            dsp_agc=1), len(chans), 0)
             eng.set_decimator_mode(mode)
+            eng.set_audio_iir_mode(mode)
             for i, c in enumerate(chans):
                 eng.set_blend_mode(c % 3, i)
             audio, groups, status, _ = run_engine_chunks(eng, np.stack([x[0] for x in cpu]), nblk, chunk)
@@ -178,7 +181,8 @@ def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
             audio_snr_db_min=min(r["audio_snr_db"] for r in b)))
     out = dict(config="BASELINE config 5: 320 channels x 3 s, SNR 10-40 dB, blend c%3, dsp_agc fast",
                reference_flavour=faith_lib.math,
-               decimator=("tensor-core int8 contraction (mode 1)" if mode else "FP32 chain (mode 0)"),
+               arithmetic=("fast: tensor-core int8 decimator + scan de-emphasis (modes 1)" if mode else
+                           "reference order everywhere (modes 0)"),
                buckets=table)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"parity_sweep_mode{mode}.json"), "w") as f:
