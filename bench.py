@@ -74,7 +74,7 @@ def parse_args():
     ap.add_argument("--decim-mode", default="tc", choices=["tc", "fp32"],
                     help="arithmetic: tc = the engine's fast forms (tcgen05 int8 decimator, "
                          "fmgpu_set_decimator_mode 1; de-emphasis / DC blocker as a warp-shuffle scan, "
-                         "fmgpu_set_audio_iir_mode 1); fp32 = the reference's summation order everywhere, "
+                         "fmgpu_set_scan_mode 1); fp32 = the reference's summation order everywhere, "
                          "bit-identical to the CPU oracle (modes 0)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the strong-scaling, config-4 and H2D-roof records")
@@ -239,7 +239,7 @@ def workload_config(args, channels_this_arm: int) -> dict:
         "pipeline_groups": args.groups,
         "arithmetic": ("fast forms where they exist: decimator = tcgen05 int8 contraction, TMA-fed, "
                        "accumulators in TMEM (decim_tc.cu, fmgpu_set_decimator_mode 1); de-emphasis + DC "
-                       "blocker = warp-shuffle scan (fmgpu_set_audio_iir_mode 1); every other stage in "
+                       "blocker = warp-shuffle scan (fmgpu_set_scan_mode 1); every other stage in "
                        "the reference's summation order" if args.decim_mode == "tc" else
                        "reference order everywhere: bit-identical to the CPU oracle (modes 0)"),
         "step_submission": "joined per step" if args.sync_steps else
@@ -290,7 +290,7 @@ class Workload:
                                             dsp_agc=1), channels, local_rank)
         self.eng.set_pipeline_groups(args.groups)
         self.eng.set_decimator_mode(1 if args.decim_mode == "tc" else 0)
-        self.eng.set_audio_iir_mode(1 if args.decim_mode == "tc" else 0)
+        self.eng.set_scan_mode(1 if args.decim_mode == "tc" else 0)
         for m in (0, 2):   # blend mode = global channel id % 3 (1 = normal is the engine default)
             for c, g in enumerate(global_ids):
                 if g % 3 == m:

@@ -53,9 +53,10 @@ struct fmgpu_engine {
   // decimator arithmetic: 0 = FP32 FFMA2 kernel (bit-identical to the oracle's float chain),
   // 1 = integer contraction on the tensor cores (decim_tc.cu; one rounding of the exact sum)
   int decimMode = 0;
-  // de-emphasis + DC blocker of the batched stereo path: 0 = serial lane recursion (bit-identical
-  // to the oracle), 1 = warp-shuffle parallel scan (k_audio_iir_scan; float rounding differs)
-  int iirMode = 0;
+  // linear first-order recursions of the batched path (I/Q DC blockers; de-emphasis + DC blocker at
+  // 32 kHz): 0 = serial lane recursions (bit-identical to the oracle), 1 = warp-shuffle parallel
+  // scans (k_dcblock_scan, k_audio_iir_scan; float rounding differs)
+  int scanMode = 0;
   bool decimTcOk = false;
   int smCount = 148;
   uint8_t *dDecB = nullptr;
@@ -692,7 +693,11 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       launchCarryF2(e->dX2, e->x2Pitch, H_X2, ringEnd, ch0, nch, s);
       e->launches += 1;
     }
-    if (xcf) {
+    if (e->scanMode == 1 && (xcf || decim)) {
+      // float input: the two recursions as a warp-shuffle scan (fast arithmetic)
+      launchDcBlockScan(xcf ? xcf : e->dX1 + t0, xcf ? xcfStride : e->pitch, e->dX2 + t0, e->x2Pitch,
+                        e->dDemod, status, nb, N, ch0, nch, e->k.dc_a1_iq, s);
+    } else if (xcf) {
       // complex-float input at the DSP rate (FMDemod::processSplitComplex): read in place
       launchDcBlock(xcf, xcfStride, nullptr, 0, e->dX2 + t0, e->x2Pitch, e->dDemod, status, nb, 1, N,
                     N, ch0, nch, e->k.dc_a1_iq, s);
@@ -851,7 +856,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
           out.acap, static_cast<size_t>((static_cast<double>(N) * 16777216.0) / e->k.aud_step) + 2));
       launchResample(e->dLf + t0, e->dRf + t0, e->lfPitch, H_LF, nullptr, 0, out.audio, out.acap,
                      e->dAudBank, AUD_RS_LEN, e->k.aud_step, e->dAudioSt, 0, maxOut, ch0, nch, sAf);
-      if (e->iirMode == 1) {
+      if (e->scanMode == 1) {
         launchAudioIirScan(out.audio, out.acap, e->dAudioSt, e->dParams, ch0, nch, e->k.dc_a1_af, 1, sAf);
       } else {
         launchAudioIir(out.audio, out.acap, e->dAudioSt, e->dParams, ch0, nch, e->k.dc_a1_af, 0, 1, 0,
@@ -1269,8 +1274,8 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
     if (const char *dm = getenv("FMGPU_DECIM_MODE")) {
       e->decimMode = (atoi(dm) == 1 && e->decimTcOk) ? 1 : 0;
     }
-    if (const char *im = getenv("FMGPU_IIR_MODE")) {
-      e->iirMode = (atoi(im) == 1) ? 1 : 0;
+    if (const char *im = getenv("FMGPU_SCAN_MODE")) {
+      e->scanMode = (atoi(im) == 1) ? 1 : 0;
     }
   }
   CKC(devAlloc(&e->dX1, C * e->pitch));
@@ -1556,17 +1561,17 @@ int fmgpu_set_decimator_mode(fmgpu_engine *e, int mode) {
 
 int fmgpu_get_decimator_mode(const fmgpu_engine *e) { return e ? e->decimMode : FMGPU_EINVAL; }
 
-int fmgpu_set_audio_iir_mode(fmgpu_engine *e, int mode) {
+int fmgpu_set_scan_mode(fmgpu_engine *e, int mode) {
   if (!e || mode < 0 || mode > 1) {
     return FMGPU_EINVAL;
   }
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   syncPipes(e);
-  e->iirMode = mode;
+  e->scanMode = mode;
   return FMGPU_OK;
 }
 
-int fmgpu_get_audio_iir_mode(const fmgpu_engine *e) { return e ? e->iirMode : FMGPU_EINVAL; }
+int fmgpu_get_scan_mode(const fmgpu_engine *e) { return e ? e->scanMode : FMGPU_EINVAL; }
 
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
   if (!e || mode < 0 || mode > 2) {

@@ -663,6 +663,104 @@ k_dcblock(const float2 *__restrict__ x1, size_t x1_pitch, const uint8_t *__restr
   }
 }
 
+// S1 as a warp-shuffle parallel scan (see k_audio_iir_scan): one WARP per channel, 32 complex
+// samples per step, I and Q in one packed FMA. v0[j] = x[j] + r v0[j-1] with r = 1 - alpha is affine
+// in the carried state, so five Kogge-Stone rounds (shfl_up + fma with r, r^2, ... r^16) give every
+// lane its v0[j]; y[j] = v0[j] - v0[j-1]. Float input only (decimated IQ or the complex-float path),
+// one logical block per launch. Fast arithmetic: agrees with k_dcblock to float rounding.
+__global__ void __launch_bounds__(128)
+k_dcblock_scan(const float2 *__restrict__ x1, size_t x1_pitch, float2 *__restrict__ x2, size_t x2_pitch,
+               DemodState *st, fmgpu_block_status *status, int status_pitch, int n_total, int ch0,
+               int nch, float a1) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= nch) {
+    return;
+  }
+  const int c = ch0 + row;
+  const float r = -a1;
+  float pw[5];
+  pw[0] = r;
+#pragma unroll
+  for (int k = 1; k < 5; k++) {
+    pw[k] = pw[k - 1] * pw[k - 1];
+  }
+  float sl = 1.0f;   // r^(lane + 1)
+  {
+    float q = r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if (((lane + 1) >> k) & 1) {
+        sl *= q;
+      }
+      q *= q;
+    }
+  }
+  float2 carry = make_float2(st[c].dc_i, st[c].dc_q);
+  const float2 *in = x1 + (size_t)c * x1_pitch;
+  float2 *out = x2 + (size_t)c * x2_pitch + H_X2;
+  int clip = 0;
+  // U chunks of 32 samples per iteration: their loads and scan rounds are independent of each other
+  // (instruction-level parallelism against the global-memory latency); only the carried state
+  // links them, one fma and one broadcast per chunk
+  constexpr int U = 4;
+  for (int i0 = 0; i0 < n_total; i0 += 32 * U) {
+    float2 v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = i0 + 32 * u + lane;
+      ok[u] = i < n_total;
+      v[u] = ok[u] ? in[i] : make_float2(0.0f, 0.0f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      clip += __popc(__ballot_sync(0xffffffffu, ok[u] && (fabsf(v[u].x) >= 0.995f || fabsf(v[u].y) >= 0.995f)));
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float2 t;
+        t.x = __shfl_up_sync(0xffffffffu, v[u].x, 1 << k);
+        t.y = __shfl_up_sync(0xffffffffu, v[u].y, 1 << k);
+        if (lane >= (1 << k)) {
+          v[u] = fma2<true>(pw[k], t, v[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int base = i0 + 32 * u;
+      if (base < n_total) {   // warp-uniform
+        v[u] = fma2<true>(sl, carry, v[u]);   // v0[j] of the serial loop
+        float2 p;
+        p.x = __shfl_up_sync(0xffffffffu, v[u].x, 1);
+        p.y = __shfl_up_sync(0xffffffffu, v[u].y, 1);
+        if (lane == 0) {
+          p = carry;
+        }
+        if (ok[u]) {
+          out[base + lane] = make_float2(v[u].x - p.x, v[u].y - p.y);
+        }
+        const int last = min(31, n_total - 1 - base);
+        carry.x = __shfl_sync(0xffffffffu, v[u].x, last);
+        carry.y = __shfl_sync(0xffffffffu, v[u].y, last);
+      }
+    }
+  }
+  if (lane == 0) {
+    st[c].dc_i = carry.x;
+    st[c].dc_q = carry.y;
+    st[c].clipping = (clip > 0) ? 1 : 0;
+    const float ratio = (float)clip / (float)n_total;
+    st[c].clip_ratio = ratio;
+    if (status) {
+      status[(size_t)c * status_pitch].clip_ratio = ratio;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K2: channel filter (firfilt_crcf, 81/121 real taps on complex data, per-channel
 // bandwidth). 128 threads x 8 consecutive complex outputs, sliding register window.
@@ -1534,45 +1632,68 @@ k_audio_iir_scan(float *audio, size_t acap, AudioState *au, const ChanParams *cp
   }
   float dv = a->de_v1[side];
   float cv = a->dc_v1[side];
-  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    float x = (i < n) ? row[i] : 0.0f;
+  // U chunks per iteration: independent loads and scan rounds; the carried states link them
+  constexpr int U = 4;
+  for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
+    float x[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t i = i0 + 32 * u + lane;
+      x[u] = (i < n) ? row[i] : 0.0f;
+    }
     if (de) {
-      float v = x;
 #pragma unroll
       for (int k = 0; k < 5; k++) {
-        const float t = __shfl_up_sync(0xffffffffu, v, 1 << k);
-        if (lane >= (1 << k)) {
-          v = fmaf(p1[k], t, v);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const float t = __shfl_up_sync(0xffffffffu, x[u], 1 << k);
+          if (lane >= (1 << k)) {
+            x[u] = fmaf(p1[k], t, x[u]);
+          }
         }
       }
-      v = fmaf(s1, dv, v);   // v0[j] of the serial loop
-      x = b0 * v;
-      const uint32_t last = min(31u, n - 1 - i0);
-      dv = __shfl_sync(0xffffffffu, v, last);
-    }
-    float w = x;
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-      const float t = __shfl_up_sync(0xffffffffu, w, 1 << k);
-      if (lane >= (1 << k)) {
-        w = fmaf(p2[k], t, w);
+      for (int u = 0; u < U; u++) {
+        const uint32_t base = i0 + 32 * u;
+        if (base < n) {   // warp-uniform
+          const float v = fmaf(s1, dv, x[u]);   // v0[j] of the serial loop
+          dv = __shfl_sync(0xffffffffu, v, min(31u, n - 1 - base));
+          x[u] = b0 * v;
+          if (base + lane >= n) {
+            x[u] = 0.0f;   // nothing past the row's end enters the second scan
+          }
+        }
       }
     }
-    w = fmaf(s2, cv, w);
-    float wp = __shfl_up_sync(0xffffffffu, w, 1);
-    if (lane == 0) {
-      wp = cv;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float t = __shfl_up_sync(0xffffffffu, x[u], 1 << k);
+        if (lane >= (1 << k)) {
+          x[u] = fmaf(p2[k], t, x[u]);
+        }
+      }
     }
-    float y = w - wp;
-    if (clamp) {
-      y = fm_clampf(y, -1.0f, 1.0f);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t base = i0 + 32 * u;
+      if (base < n) {   // warp-uniform
+        const float w = fmaf(s2, cv, x[u]);
+        float wp = __shfl_up_sync(0xffffffffu, w, 1);
+        if (lane == 0) {
+          wp = cv;
+        }
+        float y = w - wp;
+        if (clamp) {
+          y = fm_clampf(y, -1.0f, 1.0f);
+        }
+        if (base + lane < n) {
+          row[base + lane] = y;
+        }
+        cv = __shfl_sync(0xffffffffu, w, min(31u, n - 1 - base));
+      }
     }
-    if (i < n) {
-      row[i] = y;
-    }
-    const uint32_t last = min(31u, n - 1 - i0);
-    cv = __shfl_sync(0xffffffffu, w, last);
   }
   if (lane == 0) {
     a->de_v1[side] = dv;
@@ -2427,6 +2548,13 @@ void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size
   k_dcblock<<<(nch + 31) / 32, 32, smem, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
                                                status, status_pitch, nblk, blk_len, n_total, ch0,
                                                nch, a1);
+}
+
+void launchDcBlockScan(const float2 *x1, size_t x1_pitch, float2 *x2, size_t x2_pitch, DemodState *st,
+                       fmgpu_block_status *status, int status_pitch, int n_total, int ch0, int nch,
+                       float a1, cudaStream_t stream) {
+  k_dcblock_scan<<<(nch + 3) / 4, 128, 0, stream>>>(x1, x1_pitch, x2, x2_pitch, st, status, status_pitch,
+                                                   n_total, ch0, nch, a1);
 }
 
 void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pitch,

@@ -51,6 +51,10 @@ void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size
                    float2 *x2, size_t x2_pitch, DemodState *st, fmgpu_block_status *status,
                    int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, float a1,
                    cudaStream_t stream);
+// the I/Q DC blockers of one logical block as a warp-shuffle scan (float input; fast arithmetic)
+void launchDcBlockScan(const float2 *x1, size_t x1_pitch, float2 *x2, size_t x2_pitch, DemodState *st,
+                       fmgpu_block_status *status, int status_pitch, int n_total, int ch0, int nch,
+                       float a1, cudaStream_t stream);
 void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pitch,
                    const float *chan_taps, const int *chan_lp, const float *chan_scale,
                    const ChanParams *cp, int n_total, int ch0, int nch, cudaStream_t stream);

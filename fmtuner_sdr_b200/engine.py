@@ -93,8 +93,8 @@ def load_library(build: bool = True):
     L.fmgpu_measure_fp32_tflops.argtypes = [i32, C.POINTER(C.c_double)]
     L.fmgpu_set_decimator_mode.argtypes = [vp, i32]
     L.fmgpu_get_decimator_mode.argtypes = [vp]
-    L.fmgpu_set_audio_iir_mode.argtypes = [vp, i32]
-    L.fmgpu_get_audio_iir_mode.argtypes = [vp]
+    L.fmgpu_set_scan_mode.argtypes = [vp, i32]
+    L.fmgpu_get_scan_mode.argtypes = [vp]
     L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
     L.fmgpu_set_stage_overlap.argtypes = [vp, i32]
     L.fmgpu_is_stereo.argtypes = [vp, i32]
@@ -247,12 +247,12 @@ class Engine:
     def decimator_mode(self) -> int:
         return self.L.fmgpu_get_decimator_mode(self.h)
 
-    def set_audio_iir_mode(self, mode: int):
+    def set_scan_mode(self, mode: int):
         """0 = serial lane recursion (bit-identical to the oracle), 1 = warp-shuffle parallel scan."""
-        self._check(self.L.fmgpu_set_audio_iir_mode(self.h, mode), "set_audio_iir_mode")
+        self._check(self.L.fmgpu_set_scan_mode(self.h, mode), "set_scan_mode")
 
-    def audio_iir_mode(self) -> int:
-        return self.L.fmgpu_get_audio_iir_mode(self.h)
+    def scan_mode(self) -> int:
+        return self.L.fmgpu_get_scan_mode(self.h)
 
     def set_pipeline_groups(self, groups: int):
         self._check(self.L.fmgpu_set_pipeline_groups(self.h, groups), "set_pipeline_groups")

@@ -104,12 +104,14 @@ int fmgpu_set_deviation_hz(fmgpu_engine *e, double deviation_hz);      /* FMDemo
  * FMGPU_DECIM_MODE sets the mode an engine starts in. */
 int fmgpu_set_decimator_mode(fmgpu_engine *e, int mode);
 int fmgpu_get_decimator_mode(const fmgpu_engine *e);
-/* De-emphasis + DC blocker of the batched stereo path (af_post_processor.cpp:66-71), all channels.
- * 0: the serial recursion, one lane per (channel, side), bit-identical to the CPU oracle. 1: the
- * same two first-order filters as a warp-shuffle parallel scan (one warp per row, coalesced):
- * results agree to float rounding (~1e-7 of full scale). FMGPU_IIR_MODE sets the starting mode. */
-int fmgpu_set_audio_iir_mode(fmgpu_engine *e, int mode);
-int fmgpu_get_audio_iir_mode(const fmgpu_engine *e);
+/* The linear first-order recursions of the batched path — the I/Q DC blockers in front of the
+ * channel filter (fm_demod.cpp:37-38,164-165) and de-emphasis + DC blocker at 32 kHz
+ * (af_post_processor.cpp:66-71) — all channels. 0: serial recursions, one lane per channel,
+ * bit-identical to the CPU oracle. 1: the same filters as warp-shuffle parallel scans (one warp per
+ * channel row, coalesced accesses; north_star item 5): results agree to float rounding (~1e-7 of
+ * full scale), not bit for bit. FMGPU_SCAN_MODE sets the mode an engine starts in. */
+int fmgpu_set_scan_mode(fmgpu_engine *e, int mode);
+int fmgpu_get_scan_mode(const fmgpu_engine *e);
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode);      /* StereoDecoder::setBlendMode */
 int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on);        /* StereoDecoder::setForceMono */
 int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on);      /* StereoDecoder::setForceStereo */
