@@ -8,9 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfmgpu.so")
 DROPIN_LIB = os.path.join(HERE, "libfmgpu_dropin.so")
-SOURCES = ["kernels.cu", "engine.cu", "decim_tc.cu", "channelizer.cu", "synth.cu", "probe.cu", "design.cpp",
+SOURCES = ["kernels.cu", "engine.cu", "decim_tc.cu", "fir_tc.cu", "channelizer.cu", "synth.cu", "probe.cu", "design.cpp",
            "xdr_format.cpp"]
-HEADERS = ["engine.h", "kernels.h", "design.h", "fm_math.h", os.path.join("..", "..", "include", "fmgpu.h")]
+HEADERS = ["engine.h", "kernels.h", "tc_common.cuh", "design.h", "fm_math.h", os.path.join("..", "..", "include", "fmgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

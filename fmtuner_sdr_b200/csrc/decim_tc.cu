@@ -37,10 +37,13 @@
 #include <vector>
 
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace fmgpu {
 
 namespace {
+
+using namespace tc;
 
 constexpr int TC_ROWS = 128;          // channels per tile (UMMA M)
 constexpr int TC_NO = 8;              // outputs per tile
@@ -50,14 +53,23 @@ constexpr int TC_CHUNK = 128;         // bytes of K per ring slot row (one 128B 
 constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
 constexpr int TC_B_CHUNKS = 6;        // K extent of B: 6 * 128 = 768 bytes >= 32 * KS
 constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 48 KB
-#ifndef FMGPU_TC_RING
-#define FMGPU_TC_RING 10
-#endif
-constexpr int TC_RING = FMGPU_TC_RING;   // A ring slots of 16 KB (a tile's window touches up to 7)
-constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns
+// A ring slots of 16 KB in shared memory: TcParams::ring, a launch parameter. With the A operand in
+// shared memory a tile's window touches up to 7 slots (default 10: three in flight); with the A
+// operand in TMEM a slot is free again as soon as its four tcgen05.cp retire, so the ring only covers
+// the TMA latency and the CTA leaves shared memory to the kernels that run beside it.
+constexpr int TC_RING_SMEM_A = 10;
+constexpr int TC_RING_TMEM_A = 5;
+constexpr int TC_RING_MAX = 10;
+constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns (A operand from shared memory)
+// A operand from TMEM: columns [0, 256) hold a ring of eight chunks (32 columns = 128 bytes of K
+// per lane), columns [256, 512) four accumulator slots
+constexpr bool TC_ATMEM_DEFAULT = true;
+constexpr int TC_A_SLOTS = 8;
+constexpr int TC_A_COLS = 32;
+constexpr int TC_ACC_TS = 4;
 constexpr int TC_THREADS = 192;
 constexpr int TC_SHIFT = 26;          // taps are quantised to 2^-26
-constexpr size_t TC_SMEM = 1024 + TC_B_BYTES + (size_t)TC_RING * TC_CHUNK_BYTES + 512;
+constexpr size_t tcSmemBytes(int ring) { return 1024 + TC_B_BYTES + (size_t)ring * TC_CHUNK_BYTES + 512; }
 
 struct TcParams {
   int M, L, n_out;
@@ -70,94 +82,9 @@ struct TcParams {
   int n_seg;
   int row_tiles;
   int ch0, nch;
+  int ring;         // shared-memory ring slots
   float out_scale;  // scale / (255 * 2^26)
 };
-
-__device__ __forceinline__ uint32_t smemAddr(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tmaLoad2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x,
-                                          int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void ummaCommit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B swizzle, 8-row groups 1024 bytes apart (UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t smemDesc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFF);          // start address
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset
-  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void ummaI8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// one lane of a converged warp; the region it guards is single-threaded and ptxas keeps its
-// warp-uniform operands in uniform registers (no waterfall loop around UTCIMMA / UTCBAR)
-__device__ __forceinline__ bool electOne() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void tmemLd16(uint32_t taddr, int32_t *v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-      "%14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-        "=r"(v[15])
-      : "r"(taddr));
-}
 
 // work item w -> (row tile, first tile of the segment, tiles in it)
 __device__ __forceinline__ void workItem(const TcParams &p, int w, int *row, int *t0, int *nt) {
@@ -177,29 +104,32 @@ constexpr int TC_WIN_CHUNKS = 7;                 // a 768-byte window starting a
 // The MMAs of one tile, fully unrolled for the window's phase PH (its start inside a chunk, in
 // 32-byte steps): every shared-memory offset is then an immediate. cb[r] / eb[r]: descriptor low
 // word and `empty` barrier of the window's r-th chunk; the first n_free chunks are released.
-template <int PH>
-__device__ __forceinline__ void issueTile(int ksteps, int n_free, const uint32_t (&cb)[TC_WIN_CHUNKS],
+template <int PH, bool ATMEM, int KS>
+__device__ __forceinline__ void issueTile(int ksteps_rt, int n_free, const uint32_t (&cb)[TC_WIN_CHUNKS],
                                           const uint32_t (&eb)[TC_WIN_CHUNKS], uint32_t b_lo0,
                                           uint32_t desc_hi, uint32_t d_tmem, uint32_t idesc) {
+  // KS > 0: the K-step count is a compile-time constant (23 for /10, 18 for /8): no per-step test
+  const int ksteps = (KS > 0) ? KS : ksteps_rt;
 #pragma unroll
-  for (int ks = 0; ks < TC_MAX_KSTEPS; ks++) {
-    if (ks < ksteps) {
+  for (int ks = 0; ks < ((KS > 0) ? KS : TC_MAX_KSTEPS); ks++) {
+    if (KS > 0 || ks < ksteps) {
       constexpr int dummy = 0;
       (void)dummy;
       const int byte = 32 * PH + 32 * ks;
       const int r = byte >> 7;
-      const uint32_t a_lo = cb[r] + ((byte & (TC_CHUNK - 1)) >> 4);
       const uint32_t b_lo = b_lo0 + (ks >> 2) * ((TC_N * TC_CHUNK) >> 4) + (ks & 3) * 2;
-      const uint64_t a_desc = (static_cast<uint64_t>(desc_hi) << 32) | a_lo;
       const uint64_t b_desc = (static_cast<uint64_t>(desc_hi) << 32) | b_lo;
-      if (ks == 0) {
-        ummaI8(d_tmem, a_desc, b_desc, idesc, 0u);
+      if (ATMEM) {
+        const uint32_t a_col = cb[r] + ((byte & (TC_CHUNK - 1)) >> 2);   // 4 bytes of K per column
+        ummaI8Ts(d_tmem, a_col, b_desc, idesc, ks == 0 ? 0u : 1u);
       } else {
-        ummaI8(d_tmem, a_desc, b_desc, idesc, 1u);
-      }
-      const bool chunk_done = (((byte + 32) & (TC_CHUNK - 1)) == 0) || (ks + 1 == ksteps);
-      if (chunk_done && r < n_free) {
-        ummaCommit(eb[r]);
+        const uint32_t a_lo = cb[r] + ((byte & (TC_CHUNK - 1)) >> 4);
+        const uint64_t a_desc = (static_cast<uint64_t>(desc_hi) << 32) | a_lo;
+        ummaI8(d_tmem, a_desc, b_desc, idesc, ks == 0 ? 0u : 1u);
+        const bool chunk_done = (((byte + 32) & (TC_CHUNK - 1)) == 0) || (ks + 1 == ksteps);
+        if (chunk_done && r < n_free) {
+          ummaCommit(eb[r]);
+        }
       }
     }
   }
@@ -234,18 +164,22 @@ struct ChunkCursor {
   }
 };
 
+template <bool ATMEM, int KS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CUtensorMap tm_hist,
            const uint4 *__restrict__ b_image, const int2 *__restrict__ offs, const int *__restrict__ hist_valid,
            float2 *__restrict__ x1, size_t x1_pitch, const TcParams p) {
+  constexpr int NACC = ATMEM ? TC_ACC_TS : TC_ACC;
+  constexpr uint32_t ACC_COL0 = ATMEM ? TC_A_SLOTS * TC_A_COLS : 0;   // first accumulator column
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smemAddr(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;
   const uint32_t sA = base + TC_B_BYTES;
-  const uint32_t sBar = sA + TC_RING * TC_CHUNK_BYTES;
+  const int RING = p.ring;
+  const uint32_t sBar = sA + RING * TC_CHUNK_BYTES;
   // barriers: full[RING], empty[RING], tfull[ACC], tempty[ACC]; then the TMEM base word
-  const uint32_t barFull = sBar, barEmpty = sBar + 8 * TC_RING, barTFull = sBar + 16 * TC_RING,
-                 barTEmpty = barTFull + 8 * TC_ACC, sTmem = barTEmpty + 8 * TC_ACC;
+  const uint32_t barFull = sBar, barEmpty = sBar + 8 * RING, barTFull = sBar + 16 * RING,
+                 barTEmpty = barTFull + 8 * NACC, sTmem = barTEmpty + 8 * NACC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_work = p.row_tiles * p.n_seg;
 
@@ -258,11 +192,11 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
     }
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_RING; i++) {
+    for (int i = 0; i < RING; i++) {
       mbarInit(barFull + 8 * i, 1);
       mbarInit(barEmpty + 8 * i, 1);
     }
-    for (int i = 0; i < TC_ACC; i++) {
+    for (int i = 0; i < NACC; i++) {
       mbarInit(barTFull + 8 * i, 1);
       mbarInit(barTEmpty + 8 * i, 4);   // one arrival per epilogue warp
     }
@@ -285,16 +219,18 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
     // through a 1 KB x 32-row map — was measured and dropped: 1.7x the DRAM reads, same time. The
     // kernel is bound by the tensor cores' shared-memory operand reads, not by these loads.)
     if (lane == 0) {
-      uint32_t cnt = 0;   // chunks issued so far (ring position)
-      for (ChunkCursor ld(p, blockIdx.x, gridDim.x, n_work); ld.valid(); ld.next(p), cnt++) {
-        const uint32_t slot = cnt % TC_RING;
-        const uint32_t use = cnt / TC_RING;
+      uint32_t slot = 0, use = 0;   // ring position of the next chunk
+      for (ChunkCursor ld(p, blockIdx.x, gridDim.x, n_work); ld.valid(); ld.next(p)) {
         if (use > 0) {
           mbarWait(barEmpty + 8 * slot, (use - 1) & 1);
         }
         mbarExpectTx(barFull + 8 * slot, TC_CHUNK_BYTES);
         tmaLoad2d(sA + slot * TC_CHUNK_BYTES, ld.g < p.halo_chunks ? &tm_hist : &tm_iq,
                   barFull + 8 * slot, ld.x(p), ld.y);
+        if (++slot == static_cast<uint32_t>(RING)) {
+          slot = 0;
+          use++;
+        }
       }
     }
   } else if (warp == 1) {
@@ -307,6 +243,7 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
       const uint32_t b_lo0 = static_cast<uint32_t>(smemDesc(sB));
       uint32_t ring = 0;    // ring slot and use count of the next chunk to wait for
       uint32_t ring_use = 0;
+      uint32_t a_slot = 0;  // ATMEM: TMEM slot of the next chunk to copy
       uint32_t tile_cnt = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         int row, t0, nt;
@@ -315,19 +252,37 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
         const int g1 = (windowStart(p, t0 + nt - 1) + 32 * p.ksteps - 1) / TC_CHUNK;
         int have = g0 - 1;          // chunks known to have landed
         int gs = g0;                // first chunk of the current window ...
-        uint32_t gs_slot = ring;    // ... and its ring slot
+        uint32_t gs_slot = ATMEM ? a_slot : ring;   // ... and its slot (TMEM A ring / smem ring)
         for (int i = 0; i < nt; i++, tile_cnt++) {
           const int ws = windowStart(p, t0 + i);
           const int ge = (ws + 32 * p.ksteps - 1) / TC_CHUNK;
-          const uint32_t acc = tile_cnt % TC_ACC;
-          const uint32_t ause = tile_cnt / TC_ACC;
+          const uint32_t acc = tile_cnt % NACC;
+          const uint32_t ause = tile_cnt / NACC;
           if (ause > 0) {
             mbarWait(barTEmpty + 8 * acc, (ause - 1) & 1);
           }
           while (have < ge) {
             have++;
             mbarWait(barFull + 8 * ring, ring_use & 1);
-            if (++ring == TC_RING) {
+            if (ATMEM) {
+              // the chunk goes to TMEM once (4 x tcgen05.cp 128x256b = 128 lanes x 32 bytes each), every
+              // MMA that uses it reads it from there, and its shared-memory slot is free as soon as
+              // the copies retire. cp and mma execute in issue order, so a later copy into the same
+              // TMEM slot cannot overtake the MMAs still reading it (a window spans <= 7 of 8 slots).
+              tcFenceAfter();
+              if (electOne()) {
+                const uint32_t a_col = tmem_base + a_slot * TC_A_COLS;
+                const uint32_t src = a_lo0 + ring * (TC_CHUNK_BYTES >> 4);
+#pragma unroll
+                for (int sstep = 0; sstep < 4; sstep++) {
+                  tmemCp128x256(a_col + sstep * 8, (static_cast<uint64_t>(desc_hi) << 32) | (src + 2 * sstep));
+                }
+                ummaCommit(barEmpty + 8 * ring);
+              }
+              __syncwarp();
+              a_slot = (a_slot + 1 == TC_A_SLOTS) ? 0 : a_slot + 1;
+            }
+            if (++ring == static_cast<uint32_t>(RING)) {
               ring = 0;
               ring_use++;
             }
@@ -342,26 +297,32 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
             uint32_t slot = gs_slot;
 #pragma unroll
             for (int r = 0; r < TC_WIN_CHUNKS; r++) {
-              cb[r] = a_lo0 + slot * (TC_CHUNK_BYTES >> 4);
-              eb[r] = barEmpty + 8 * slot;
-              slot = (slot + 1 == TC_RING) ? 0 : slot + 1;
+              if (ATMEM) {
+                cb[r] = tmem_base + slot * TC_A_COLS;   // TMEM column of the chunk
+                eb[r] = 0;
+                slot = (slot + 1 == TC_A_SLOTS) ? 0 : slot + 1;
+              } else {
+                cb[r] = a_lo0 + slot * (TC_CHUNK_BYTES >> 4);
+                eb[r] = barEmpty + 8 * slot;
+                slot = (slot + 1 == static_cast<uint32_t>(RING)) ? 0 : slot + 1;
+              }
             }
           }
-          const uint32_t d_tmem = tmem_base + acc * TC_N;
+          const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * TC_N;
           const uint32_t tfull = barTFull + 8 * acc;
           if (electOne()) {
             switch ((ws & (TC_CHUNK - 1)) >> 5) {
-              case 0: issueTile<0>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
-              case 1: issueTile<1>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
-              case 2: issueTile<2>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
-              default: issueTile<3>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              case 0: issueTile<0, ATMEM, KS>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              case 1: issueTile<1, ATMEM, KS>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              case 2: issueTile<2, ATMEM, KS>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
+              default: issueTile<3, ATMEM, KS>(p.ksteps, n_free, cb, eb, b_lo0, desc_hi, d_tmem, idesc); break;
             }
             ummaCommit(tfull);
           }
           __syncwarp();
           while (gs < keep) {   // the next window starts here
             gs++;
-            if (++gs_slot == TC_RING) {
+            if (++gs_slot == static_cast<uint32_t>(ATMEM ? TC_A_SLOTS : RING)) {
               gs_slot = 0;
             }
           }
@@ -383,11 +344,11 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
       const int valid = live ? __ldg(hist_valid + c) : need_hist;
       float2 *out = x1 + static_cast<size_t>(live ? c : p.ch0) * x1_pitch;
       for (int i = 0; i < nt; i++, tile_cnt++) {
-        const uint32_t acc = tile_cnt % TC_ACC;
-        mbarWait(barTFull + 8 * acc, (tile_cnt / TC_ACC) & 1);
+        const uint32_t acc = tile_cnt % NACC;
+        mbarWait(barTFull + 8 * acc, (tile_cnt / NACC) & 1);
         tcFenceAfter();
         int32_t d[TC_N];
-        const uint32_t taddr = tmem_base + lane_base + acc * TC_N;
+        const uint32_t taddr = tmem_base + lane_base + ACC_COL0 + acc * TC_N;
         tmemLd16(taddr, d);
         tmemLd16(taddr + 16, d + 16);
         tmemLd16(taddr + 32, d + 32);
@@ -437,25 +398,6 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
-}
-
-using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                              CUtensorMapFloatOOBfill);
-
-EncodeFn encodeFn() {
-  static EncodeFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeFn>(p);
-    }
-  });
-  return fn;
 }
 
 // [rows][row_bytes] uint8 with `pitch` bytes between rows; boxes of 128 bytes x 128 rows, 128B swizzle
@@ -544,8 +486,18 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_decim_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(TC_SMEM));
+    auto set = [](const void *f) {
+      return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(tcSmemBytes(TC_RING_MAX)));
+    };
+    const void *fs[] = {(const void *)k_decim_tc<false, 23>, (const void *)k_decim_tc<false, 18>,
+                        (const void *)k_decim_tc<false, 0>,  (const void *)k_decim_tc<true, 23>,
+                        (const void *)k_decim_tc<true, 18>,  (const void *)k_decim_tc<true, 0>};
+    for (const void *f : fs) {
+      if (attr_err == cudaSuccess) {
+        attr_err = set(f);
+      }
+    }
   });
   if (attr_err != cudaSuccess) {
     return attr_err;
@@ -574,9 +526,41 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
     return cudaErrorInvalidValue;
   }
   const int grid = std::min(sm_count, p.row_tiles * p.n_seg);
-  k_decim_tc<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm_iq, tm_hist, reinterpret_cast<const uint4 *>(b_image_dev),
-                                                   reinterpret_cast<const int2 *>(offs_dev), hist_valid, x1,
-                                                   x1_pitch, p);
+  // FMGPU_TC_ATMEM / FMGPU_TC_RING: measurement overrides (A operand from shared memory; ring depth)
+  static const bool a_from_tmem = [] {
+    const char *v = getenv("FMGPU_TC_ATMEM");
+    return v ? atoi(v) != 0 : TC_ATMEM_DEFAULT;
+  }();
+  static const int ring_slots = [] {
+    const char *v = getenv("FMGPU_TC_RING");
+    const int dflt = a_from_tmem ? TC_RING_TMEM_A : TC_RING_SMEM_A;
+    const int r = v ? atoi(v) : dflt;
+    return std::min(TC_RING_MAX, std::max(a_from_tmem ? 2 : 8, r));
+  }();
+  p.ring = ring_slots;
+  const size_t smem_bytes = tcSmemBytes(ring_slots);
+  const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
+  const int2 *of = reinterpret_cast<const int2 *>(offs_dev);
+#define FMGPU_TC_LAUNCH(AT, KSV)                                                                          \
+  k_decim_tc<AT, KSV><<<grid, TC_THREADS, smem_bytes, stream>>>(tm_iq, tm_hist, bi, of, hist_valid, x1, x1_pitch, p)
+  if (a_from_tmem) {
+    if (p.ksteps == 23) {
+      FMGPU_TC_LAUNCH(true, 23);
+    } else if (p.ksteps == 18) {
+      FMGPU_TC_LAUNCH(true, 18);
+    } else {
+      FMGPU_TC_LAUNCH(true, 0);
+    }
+  } else {
+    if (p.ksteps == 23) {
+      FMGPU_TC_LAUNCH(false, 23);
+    } else if (p.ksteps == 18) {
+      FMGPU_TC_LAUNCH(false, 18);
+    } else {
+      FMGPU_TC_LAUNCH(false, 0);
+    }
+  }
+#undef FMGPU_TC_LAUNCH
   return cudaGetLastError();
 }
 

@@ -57,7 +57,12 @@ struct fmgpu_engine {
   // 32 kHz): 0 = serial lane recursions (bit-identical to the oracle), 1 = warp-shuffle parallel
   // scans (k_dcblock_scan, k_audio_iir_scan; float rounding differs)
   int scanMode = 0;
-  bool decimTcOk = false;
+  // real-tap FIRs of the stereo decoder (pilot band-pass, L/R low-pass): 0 = FP32 FFMA2 chains
+  // (bit-identical to the oracle), 1 = exact integer contractions on the tensor cores (fir_tc.cu)
+  int firMode = 0;
+  bool decimTcOk = false, pilTcOk = false, audTcOk = false;
+  FirTcTables pilTc{}, audTc{};
+  uint8_t *dPilB = nullptr, *dAudB = nullptr;
   int smCount = 148;
   uint8_t *dDecB = nullptr;
   int32_t *dDecOffs = nullptr;
@@ -385,6 +390,20 @@ void runDecim(fmgpu_engine *e, const uint8_t *iq, size_t stride, float2 *x1, int
               e->decL, e->decScale, e->decParam, e->decParamRaw, s);
 }
 
+// a real-tap FIR of the stereo decoder, either flavour. data_shift: fixed-point scale of the
+// tensor-core form (the multiplex is bounded by pi * fd_ref < 2; the matrix outputs by 3x that)
+void runFirReal(fmgpu_engine *e, const FirRealJob &j, int nsig, int nch, const TapsParam &taps, bool tc_ok,
+                const FirTcTables &t, const uint8_t *b_dev, int data_shift, cudaStream_t s) {
+  if (e->firMode == 1 && tc_ok && j.n_total % 32 == 0) {
+    const cudaError_t err = launchFirTc(j, nsig, nch, t, b_dev, data_shift, e->smCount, s);
+    if (err == cudaSuccess) {
+      return;
+    }
+    e->lastError = std::string("tensor-core FIR: ") + cudaGetErrorString(err);
+  }
+  launchFirReal(j, nsig, nch, taps, s);
+}
+
 void stageDecimate(fmgpu_engine *e, const uint8_t *iq, size_t stride, int n_out, int ch0, int nch,
                    cudaStream_t s) {
   Span sp(e, "decimate", s);
@@ -468,7 +487,7 @@ void stageStereo(fmgpu_engine *e, fmgpu_block_status *status, int nblk, int blk_
     j.Lp = e->pilLp;
     j.scale = 1.0f;
     j.ch0 = ch0;
-    launchFirReal(j, 1, nch, e->pilParam, s);
+    runFirReal(e, j, 1, nch, e->pilParam, e->pilTcOk, e->pilTc, e->dPilB, 22, s);
   }
   hop(s, lane, ev);
   {
@@ -492,7 +511,7 @@ void stageStereo(fmgpu_engine *e, fmgpu_block_status *status, int nblk, int blk_
     j.Lp = e->audLp;
     j.scale = e->k.aud_scale;
     j.ch0 = ch0;
-    launchFirReal(j, 2, nch, e->audParam, s);
+    runFirReal(e, j, 2, nch, e->audParam, e->audTcOk, e->audTc, e->dAudB, 20, s);
     launchCarryF32(e->dLraw, e->lrPitch, H_LR, n, ch0, nch, s);
     launchCarryF32(e->dRraw, e->lrPitch, H_LR, n, ch0, nch, s);
     launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, n, ch0, nch, s);
@@ -803,7 +822,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       j.Lp = e->pilLp;
       j.scale = 1.0f;
       j.ch0 = ch0;
-      launchFirReal(j, 1, nch, e->pilParam, s);
+      runFirReal(e, j, 1, nch, e->pilParam, e->pilTcOk, e->pilTc, e->dPilB, 22, s);
       e->launches += 1;
     }
     done(E::ST_PILOT);
@@ -843,7 +862,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       j.Lp = e->audLp;
       j.scale = e->k.aud_scale;
       j.ch0 = ch0;
-      launchFirReal(j, 2, nch, e->audParam, s);
+      runFirReal(e, j, 2, nch, e->audParam, e->audTcOk, e->audTc, e->dAudB, 20, s);
       e->launches += 1;
     }
     done(E::ST_LPF);
@@ -1271,6 +1290,21 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
       CKC(cudaMemcpy(e->dDecOffs, offs.data(), offs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
       e->decimTcOk = true;
     }
+    if (firTcSupported(e->pilParam.h, e->pilLp, H_MPX)) {
+      firTcBuildTables(e->pilParam.h, e->pilLp, &e->pilTc);
+      CKC(devAlloc(&e->dPilB, e->pilTc.b_image.size()));
+      CKC(cudaMemcpy(e->dPilB, e->pilTc.b_image.data(), e->pilTc.b_image.size(), cudaMemcpyHostToDevice));
+      e->pilTcOk = true;
+    }
+    if (firTcSupported(e->audParam.h, e->audLp, H_LR)) {
+      firTcBuildTables(e->audParam.h, e->audLp, &e->audTc);
+      CKC(devAlloc(&e->dAudB, e->audTc.b_image.size()));
+      CKC(cudaMemcpy(e->dAudB, e->audTc.b_image.data(), e->audTc.b_image.size(), cudaMemcpyHostToDevice));
+      e->audTcOk = true;
+    }
+    if (const char *fm = getenv("FMGPU_FIR_MODE")) {
+      e->firMode = (atoi(fm) == 1 && e->pilTcOk && e->audTcOk) ? 1 : 0;
+    }
     if (const char *dm = getenv("FMGPU_DECIM_MODE")) {
       e->decimMode = (atoi(dm) == 1 && e->decimTcOk) ? 1 : 0;
     }
@@ -1378,7 +1412,7 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
                   e->dDemod,   e->dStereo, e->dAudioSt, e->dRds,    e->dGroups,  e->dStatus,
                   e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd,
                   e->dAudio2,  e->dGroups2, e->dStatus2, e->dNAudio2, e->dNGroups2, e->dR171,
-                  e->dDecB,    e->dDecOffs};
+                  e->dDecB,    e->dDecOffs, e->dPilB, e->dAudB};
   for (void *p : ptrs) {
     if (p) {
       cudaFree(p);
@@ -1572,6 +1606,22 @@ int fmgpu_set_scan_mode(fmgpu_engine *e, int mode) {
 }
 
 int fmgpu_get_scan_mode(const fmgpu_engine *e) { return e ? e->scanMode : FMGPU_EINVAL; }
+
+int fmgpu_set_fir_mode(fmgpu_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 1) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  if (mode == 1 && !(e->pilTcOk && e->audTcOk)) {
+    e->lastError = "tensor-core FIRs: this pilot / audio filter length is not supported";
+    return FMGPU_EINVAL;
+  }
+  syncPipes(e);
+  e->firMode = mode;
+  return FMGPU_OK;
+}
+
+int fmgpu_get_fir_mode(const fmgpu_engine *e) { return e ? e->firMode : FMGPU_EINVAL; }
 
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
   if (!e || mode < 0 || mode > 2) {

@@ -1,0 +1,567 @@
+// fir_tc.cu — the real-tap FIRs of the stereo decoder on the 5th-generation tensor cores: the 19 kHz
+// pilot band-pass and the L/R 15 kHz low-pass (/root/reference/src/stereo_decoder.cpp:25-63,172-173,
+// 233-239; liquid firfilt_rrrf_execute, one float chain of 305 / 121 terms per output there).
+//
+//   y_r[n] = scale * sum_i h[i] * x_r[n - (Lp-1) + i]          r = a row (channel, or channel x {L, R})
+//
+// evaluated as an EXACT INTEGER contraction, like the decimator of decim_tc.cu, but for float data:
+//   * the samples become 24-bit offset-binary fixed point, q = rni(x * 2^d) + 2^23 (d = 22 for the
+//     multiplex, |x| < 2: one rounding of 1.2e-7, the float ulp at that magnitude; d = 20 for the
+//     matrix outputs, |x| < 8), split into three unsigned byte planes;
+//   * the taps become round(h * 2^S) (S: the largest tap fills 23 bits), split into three signed
+//     base-256 digits; B is the banded (Toeplitz) matrix of those digits, [K = window][N = 3 x 32];
+//   * tcgen05.mma kind::i8 (u8 x s8 -> s32), M = 128 rows, N = 96, K = 32 per instruction. Plane a
+//     accumulates into columns [32 a, 32 a + 96) of one 160-column accumulator, so that products of
+//     equal weight 256^(a + l) share a column: five limb sets of 32 outputs;
+//   * the epilogue removes the 2^23 offset limb-wise in integers (2^23 * sum of the integer taps) and
+//     recombines the five limbs in float, most significant first.
+// The result is the FIR of the quantised samples with taps good to 2^-S, to within three float
+// roundings of the exact sum: closer to the real-number answer than the reference's float chain,
+// not bit-identical to it (k_fir_pair in kernels.cu stays the bit-exact flavour).
+//
+// No operand of the data ever sits in shared memory in MMA layout: the A operand lives in TENSOR
+// MEMORY. One persistent CTA per SM, ten warps:
+//   warp 0     TMA producer: [128 rows x 32 floats] boxes of the input rows -> staging ring
+//   warp 1     allocates TMEM, issues the MMAs (one elected lane; A from TMEM, B from shared memory)
+//   warps 2-5  epilogue: tcgen05.ld the accumulator, recombine, stage in 128B-swizzled shared memory,
+//              one TMA store of [32 rows x 32 floats] per warp and tile; then zero the accumulator
+//              (tcgen05.st) so that every MMA accumulates
+//   warps 6-9  converters: staged floats -> fixed point -> three byte planes -> tcgen05.st into the
+//              TMEM ring of 32-sample sub-chunks (lane = row, 8 columns = 32 bytes of K per plane)
+// A tile is 32 outputs of 128 rows; its window is KS sub-chunks (KS = WS0/32 + 1, WS0 = the taps'
+// reach rounded up to 32), and consecutive tiles of a row tile share all but one of them. Every CTA
+// owns one contiguous range of the (row tile, time) tile sequence: perfect balance, and the window
+// is primed once per range (and once more where the range crosses into the next row tile).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace fmgpu {
+
+namespace {
+
+using namespace tc;
+
+constexpr int FT_ROWS = 128;          // rows per tile (UMMA M)
+constexpr int FT_NO = 32;             // outputs per tile = samples per sub-chunk
+constexpr int FT_PLANES = 3;          // data bytes
+constexpr int FT_DIGITS = 3;          // tap digits
+constexpr int FT_N = FT_DIGITS * FT_NO;                    // 96 (UMMA N)
+constexpr int FT_LIMBS = FT_PLANES + FT_DIGITS - 1;        // 5 limb sets
+constexpr int FT_ACC_COLS = FT_LIMBS * FT_NO;              // 160 TMEM columns per accumulator
+constexpr int FT_SLOT_COLS = FT_PLANES * 8;                // 24 TMEM columns per sub-chunk slot
+constexpr int FT_BCHUNK = FT_N * 128;                      // bytes of one 128-byte K chunk of B (12 KB)
+constexpr int FT_MAX_KS = 12;
+constexpr int FT_B_BYTES = ((FT_MAX_KS + 3) / 4) * FT_BCHUNK;   // 36 KB
+constexpr int FT_NSTG = 4;                                 // float staging slots (16 KB each)
+constexpr int FT_STG_BYTES = FT_ROWS * FT_NO * 4;
+constexpr int FT_OUT_BYTES = 32 * FT_NO * 4;               // one epilogue warp's staging tile (4 KB)
+constexpr int FT_THREADS = 320;
+constexpr size_t FT_SMEM = 1024 + FT_B_BYTES + FT_NSTG * FT_STG_BYTES + 8 * FT_OUT_BYTES + 512;
+
+struct FirTcParams {
+  int tiles_row;      // tiles per row = n_total / 32
+  int row_tiles;      // 128-row tiles per signal
+  int nsig;
+  int tiles_total;    // nsig * row_tiles * tiles_row
+  int in_x0;          // float index inside an input row of tile 0's window start (in_off - WS0)
+  int out_x0;         // float index inside an output row of output 0
+  int off2, off3, off4;   // 2^23 * sum(hq) as limbs 2..4 (limbs 0, 1 are zero)
+  float dscale;       // 2^data_shift: samples are quantised to 2^-data_shift
+  float out_scale;    // scale / 2^(S + data_shift)
+};
+
+// CTA b owns tiles [lo, hi) of the (signal, row tile, time) sequence
+__device__ __forceinline__ void tileRange(const FirTcParams &p, int *lo, int *hi) {
+  const long long t = p.tiles_total;
+  *lo = static_cast<int>(t * blockIdx.x / gridDim.x);
+  *hi = static_cast<int>(t * (blockIdx.x + 1) / gridDim.x);
+}
+// the run of tiles starting at `cur` that stays inside one row tile: (signal, row tile, first tile, count)
+__device__ __forceinline__ void nextRun(const FirTcParams &p, int cur, int hi, int *sig, int *rt, int *t0,
+                                        int *nt) {
+  const int r = cur / p.tiles_row;
+  *t0 = cur - r * p.tiles_row;
+  *nt = min(hi - cur, p.tiles_row - *t0);
+  *sig = r / p.row_tiles;
+  *rt = r - *sig * p.row_tiles;
+}
+
+template <int KS, int RING, int NACC>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+         const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
+         const uint4 *__restrict__ b_image, const FirTcParams p) {
+  static_assert(NACC * FT_ACC_COLS + RING * FT_SLOT_COLS <= 512, "TMEM budget");
+  static_assert(RING >= KS + 1, "ring must hold a window and one sub-chunk in flight");
+  constexpr uint32_t A_COL0 = NACC * FT_ACC_COLS;   // accumulators first, the A ring behind them
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smemAddr(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;
+  const uint32_t sStg = sB + FT_B_BYTES;
+  const uint32_t sOut = sStg + FT_NSTG * FT_STG_BYTES;
+  const uint32_t sBar = sOut + 8 * FT_OUT_BYTES;
+  const uint32_t barSFull = sBar, barSEmpty = barSFull + 8 * FT_NSTG, barAFull = barSEmpty + 8 * FT_NSTG,
+                 barAEmpty = barAFull + 8 * RING, barTFull = barAEmpty + 8 * RING,
+                 barTEmpty = barTFull + 8 * NACC, sTmem = barTEmpty + 8 * NACC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int lo, hi;
+  tileRange(p, &lo, &hi);
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  {
+    uint8_t *gen = smem_raw + (base - smemAddr(smem_raw));
+    uint4 *dst = reinterpret_cast<uint4 *>(gen);
+    for (int i = threadIdx.x; i < ((KS + 3) / 4) * FT_BCHUNK / 16; i += FT_THREADS) {
+      dst[i] = __ldg(b_image + i);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FT_NSTG; i++) {
+      mbarInit(barSFull + 8 * i, 1);
+      mbarInit(barSEmpty + 8 * i, 4);   // one arrival per converter warp
+    }
+    for (int i = 0; i < RING; i++) {
+      mbarInit(barAFull + 8 * i, 4);    // one arrival per converter warp
+      mbarInit(barAEmpty + 8 * i, 1);   // tcgen05.commit
+    }
+    for (int i = 0; i < NACC; i++) {
+      mbarInit(barTFull + 8 * i, 1);    // tcgen05.commit
+      mbarInit(barTEmpty + 8 * i, 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fenceProxyAsync();
+  tcFenceBefore();
+  __syncthreads();
+  tcFenceAfter();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+
+  if (warp == 0) {
+    // ===== TMA producer ======================================================================
+    if (lane == 0) {
+      uint32_t stg = 0, use = 0;
+      for (int cur = lo; cur < hi;) {
+        int sig, rt, t0, nt;
+        nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
+        const CUtensorMap *map = sig ? &tm_in1 : &tm_in0;
+        const int nsub = nt + KS - 1;
+        for (int g = 0; g < nsub; g++) {
+          if (use > 0) {
+            mbarWait(barSEmpty + 8 * stg, (use - 1) & 1);
+          }
+          mbarExpectTx(barSFull + 8 * stg, FT_STG_BYTES);
+          tmaLoad2d(sStg + stg * FT_STG_BYTES, map, barSFull + 8 * stg, p.in_x0 + FT_NO * (t0 + g),
+                    rt * FT_ROWS);
+          if (++stg == FT_NSTG) {
+            stg = 0;
+            use++;
+          }
+        }
+        cur += nt;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ========================================================================
+    // u8 x s8 -> s32, K-major B, N = 96, M = 128 (UMMA::InstrDescriptor)
+    const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((FT_N >> 3) << 17) | ((FT_ROWS >> 4) << 24);
+    const uint32_t desc_hi = static_cast<uint32_t>(smemDesc(0) >> 32);
+    const uint32_t b_lo0 = static_cast<uint32_t>(smemDesc(sB));
+    uint32_t tile_cnt = 0;
+    uint32_t win_slot = 0;        // ring slot of the window's first sub-chunk
+    uint32_t wait_slot = 0, wait_use = 0;   // next sub-chunk to wait for
+    for (int cur = lo; cur < hi;) {
+      int sig, rt, t0, nt;
+      nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
+      int landed = 0;             // sub-chunks of this run known to be in TMEM
+      for (int i = 0; i < nt; i++, tile_cnt++) {
+        const uint32_t acc = tile_cnt % NACC;
+        mbarWait(barTEmpty + 8 * acc, (tile_cnt / NACC) & 1);   // zeroed by the epilogue
+        while (landed < i + KS) {
+          mbarWait(barAFull + 8 * wait_slot, wait_use & 1);
+          landed++;
+          if (++wait_slot == RING) {
+            wait_slot = 0;
+            wait_use++;
+          }
+        }
+        tcFenceAfter();
+        if (electOne()) {
+          const uint32_t d0 = tmem_base + acc * FT_ACC_COLS;
+#pragma unroll
+          for (int a = 0; a < FT_PLANES; a++) {
+            uint32_t slot = win_slot;
+#pragma unroll
+            for (int k = 0; k < KS; k++) {
+              const uint32_t a_col = tmem_base + A_COL0 + slot * FT_SLOT_COLS + a * 8;
+              const uint32_t b_lo = b_lo0 + (k >> 2) * (FT_BCHUNK >> 4) + (k & 3) * 2;
+              ummaI8Ts(d0 + a * FT_NO, a_col, (static_cast<uint64_t>(desc_hi) << 32) | b_lo, idesc, 1u);
+              slot = (slot + 1 == RING) ? 0 : slot + 1;
+            }
+          }
+          ummaCommit(barTFull + 8 * acc);
+          // the window moves on by one sub-chunk; the run's last tile releases all of them
+          ummaCommit(barAEmpty + 8 * win_slot);
+          if (i + 1 == nt) {
+            uint32_t slot = win_slot;
+#pragma unroll
+            for (int k = 1; k < KS; k++) {
+              slot = (slot + 1 == RING) ? 0 : slot + 1;
+              ummaCommit(barAEmpty + 8 * slot);
+            }
+          }
+        }
+        __syncwarp();
+        win_slot = (win_slot + 1 == RING) ? 0 : win_slot + 1;
+      }
+      // the next run starts behind this run's last window
+      win_slot += KS - 1;
+      if (win_slot >= RING) {
+        win_slot -= RING;
+      }
+      cur += nt;
+    }
+  } else if (warp < 6) {
+    // ===== epilogue (warps 2..5 own TMEM lanes 32 * (warp % 4) ..) ==============================
+    const int q = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < NACC * FT_ACC_COLS; c += 8) {
+      tmemSt8(tmem_base + lane_base + c, zero);
+    }
+    tmemWaitSt();
+    tcFenceBefore();
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = 0; i < NACC; i++) {
+        mbarArrive(barTEmpty + 8 * i);
+      }
+    }
+    const uint32_t my_out = sOut + q * 2 * FT_OUT_BYTES;
+    uint32_t tile_cnt = 0;
+    for (int cur = lo; cur < hi;) {
+      int sig, rt, t0, nt;
+      nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
+      const CUtensorMap *map = sig ? &tm_out1 : &tm_out0;
+      for (int i = 0; i < nt; i++, tile_cnt++) {
+        const uint32_t acc = tile_cnt % NACC;
+        mbarWait(barTFull + 8 * acc, (tile_cnt / NACC) & 1);
+        tcFenceAfter();
+        // the TMA store that read this staging buffer two tiles ago has to be done with it
+        if (lane == 0) {
+          bulkWaitRead<1>();
+        }
+        __syncwarp();
+        const uint32_t buf = my_out + (tile_cnt & 1) * FT_OUT_BYTES;
+        const uint32_t taddr = tmem_base + lane_base + acc * FT_ACC_COLS;
+#pragma unroll 1
+        for (int jg = 0; jg < FT_NO / 8; jg++) {
+          int32_t d[FT_LIMBS][8];
+#pragma unroll
+          for (int s = 0; s < FT_LIMBS; s++) {
+            tmemLd8(taddr + s * FT_NO + jg * 8, d[s]);
+          }
+          tmemWaitLd();
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float f = static_cast<float>(d[4][j] - p.off4);
+            f = fmaf(f, 256.0f, static_cast<float>(d[3][j] - p.off3));
+            f = fmaf(f, 256.0f, static_cast<float>(d[2][j] - p.off2));
+            f = fmaf(f, 256.0f, static_cast<float>(d[1][j]));
+            f = fmaf(f, 256.0f, static_cast<float>(d[0][j]));
+            y[j] = f * p.out_scale;
+          }
+          // row `lane` of the [32 rows x 128 bytes] tile, 16-byte units XOR-swizzled like the tensor map
+          const uint32_t row = buf + lane * 128;
+          const uint32_t u0 = static_cast<uint32_t>((2 * jg) ^ (lane & 7)) << 4;
+          const uint32_t u1 = static_cast<uint32_t>((2 * jg + 1) ^ (lane & 7)) << 4;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + u0), "f"(y[0]), "f"(y[1]),
+                       "f"(y[2]), "f"(y[3])
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + u1), "f"(y[4]), "f"(y[5]),
+                       "f"(y[6]), "f"(y[7])
+                       : "memory");
+        }
+        // every MMA accumulates: hand the accumulator back zeroed
+#pragma unroll
+        for (int c = 0; c < FT_ACC_COLS; c += 8) {
+          tmemSt8(taddr + c, zero);
+        }
+        tmemWaitSt();
+        tcFenceBefore();
+        fenceProxyAsync();
+        __syncwarp();
+        if (lane == 0) {
+          mbarArrive(barTEmpty + 8 * acc);
+          tmaStore2d(map, buf, p.out_x0 + FT_NO * (t0 + i), rt * FT_ROWS + q * 32);
+          bulkCommit();
+        }
+      }
+      cur += nt;
+    }
+    if (lane == 0) {
+      bulkWait<0>();
+    }
+  } else {
+    // ===== converters (warps 6..9 own TMEM lanes 32 * (warp % 4) ..) =============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const float dscale = p.dscale;
+    uint32_t stg = 0, stg_use = 0, slot = 0, slot_use = 0;
+    for (int cur = lo; cur < hi;) {
+      int sig, rt, t0, nt;
+      nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
+      const int nsub = nt + KS - 1;
+      for (int g = 0; g < nsub; g++) {
+        mbarWait(barSFull + 8 * stg, stg_use & 1);
+        // my row of the [128 rows x 128 bytes] staging tile (128B-swizzled by the TMA)
+        const uint32_t src = sStg + stg * FT_STG_BYTES + row * 128;
+        float x[FT_NO];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const uint32_t at = src + (static_cast<uint32_t>(u ^ (row & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x[4 * u]), "=f"(x[4 * u + 1]), "=f"(x[4 * u + 2]), "=f"(x[4 * u + 3])
+                       : "r"(at));
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbarArrive(barSEmpty + 8 * stg);
+        }
+        if (++stg == FT_NSTG) {
+          stg = 0;
+          stg_use++;
+        }
+        uint32_t pl[FT_PLANES][8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          uint32_t qv[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float t = x[4 * u + e] * dscale;
+            t = fminf(fmaxf(t, -8388608.0f), 8388607.0f);
+            qv[e] = static_cast<uint32_t>(__float2int_rn(t) + 8388608);
+          }
+          const uint32_t a01 = __byte_perm(qv[0], qv[1], 0x5140);   // q0.b0 q1.b0 q0.b1 q1.b1
+          const uint32_t a23 = __byte_perm(qv[2], qv[3], 0x5140);
+          const uint32_t c01 = __byte_perm(qv[0], qv[1], 0x0062);   // q0.b2 q1.b2
+          const uint32_t c23 = __byte_perm(qv[2], qv[3], 0x0062);
+          pl[0][u] = __byte_perm(a01, a23, 0x5410);
+          pl[1][u] = __byte_perm(a01, a23, 0x7632);
+          pl[2][u] = __byte_perm(c01, c23, 0x5410);
+        }
+        if (slot_use > 0) {
+          mbarWait(barAEmpty + 8 * slot, (slot_use - 1) & 1);
+          tcFenceAfter();
+        }
+        const uint32_t taddr = tmem_base + lane_base + A_COL0 + slot * FT_SLOT_COLS;
+#pragma unroll
+        for (int a = 0; a < FT_PLANES; a++) {
+          tmemSt8(taddr + a * 8, pl[a]);
+        }
+        tmemWaitSt();
+        tcFenceBefore();
+        __syncwarp();
+        if (lane == 0) {
+          mbarArrive(barAFull + 8 * slot);
+        }
+        if (++slot == RING) {
+          slot = 0;
+          slot_use++;
+        }
+      }
+      cur += nt;
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  tcFenceBefore();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// float rows [rows][row_floats] with `pitch` floats between rows; boxes of 32 floats x box_rows, 128B swizzle
+bool encodeFloatRows(CUtensorMap *map, const float *base, uint64_t row_floats, uint64_t rows, uint64_t pitch,
+                     uint32_t box_rows) {
+  EncodeFn fn = encodeFn();
+  if (!fn) {
+    return false;
+  }
+  const cuuint64_t dims[2] = {row_floats, rows};
+  const cuuint64_t strides[1] = {pitch * sizeof(float)};
+  const cuuint32_t box[2] = {FT_NO, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// first tap that is not zero (the designs are padded in front to a multiple of 8)
+int firstTap(const float *h, int Lp) {
+  int i0 = 0;
+  while (i0 < Lp - 1 && h[i0] == 0.0f) {
+    i0++;
+  }
+  return i0;
+}
+
+}  // namespace
+
+int firTcKsteps(const float *h, int Lp) {
+  const int reach = Lp - 1 - firstTap(h, Lp);       // oldest sample a tap touches, relative to the output
+  const int ws0 = (reach + FT_NO - 1) / FT_NO * FT_NO;
+  return ws0 / FT_NO + 1;
+}
+
+bool firTcSupported(const float *h, int Lp, int in_off) {
+  const int ks = firTcKsteps(h, Lp);
+  return (ks == 5 || ks == 11 || ks == 12) && (ks - 1) * FT_NO <= in_off;
+}
+
+// Host: integer taps, their digits, and the B image the way tcgen05.mma reads a K-major,
+// 128B-swizzled operand: [K chunk of 128 bytes][n = digit * 32 + output j][128 bytes of k].
+void firTcBuildTables(const float *h, int Lp, FirTcTables *t) {
+  const int ks = firTcKsteps(h, Lp);
+  const int ws0 = (ks - 1) * FT_NO;
+  float hmax = 0.0f;
+  for (int i = 0; i < Lp; i++) {
+    hmax = std::max(hmax, std::fabs(h[i]));
+  }
+  // three balanced base-256 digits hold |v| <= 127 * 65536 + 127 * 256 + 127
+  int shift = 0;
+  while (shift < 40 && std::ldexp(static_cast<double>(hmax), shift + 1) <= 8355711.0) {
+    shift++;
+  }
+  t->shift = shift;
+  t->ksteps = ks;
+  t->b_image.assign(static_cast<size_t>((ks + 3) / 4) * FT_BCHUNK, 0);
+  long long hsum = 0;
+  for (int i = 0; i < Lp; i++) {
+    long long v = std::llround(std::ldexp(static_cast<double>(h[i]), shift));
+    hsum += v;
+    if (v == 0) {
+      continue;
+    }
+    int dg[FT_DIGITS];
+    for (int l = 0; l < FT_DIGITS; l++) {   // digit 0 least significant
+      long long r = ((v % 256) + 256) % 256;
+      if (r >= 128) {
+        r -= 256;
+      }
+      dg[l] = static_cast<int>(r);
+      v = (v - r) / 256;
+    }
+    for (int j = 0; j < FT_NO; j++) {
+      const int k = ws0 + j - (Lp - 1) + i;   // byte of the tile's window that tap i of output j reads
+      if (k < 0) {
+        continue;   // cannot happen: ws0 covers the first non-zero tap
+      }
+      const int kc = k / 128, kk = k % 128;
+      for (int l = 0; l < FT_DIGITS; l++) {
+        const int n = l * FT_NO + j;
+        const size_t at = static_cast<size_t>(kc) * FT_BCHUNK + static_cast<size_t>(n) * 128 +
+                          static_cast<size_t>(((kk >> 4) ^ (n & 7)) << 4) + (kk & 15);
+        t->b_image[at] = static_cast<uint8_t>(static_cast<int8_t>(dg[l]));
+      }
+    }
+  }
+  // 2^23 * hsum = 256^2 * 128 * hsum, in limbs 2, 3, 4 (digits of hsum in base 256, floor form)
+  const long long h0 = ((hsum % 256) + 256) % 256;
+  const long long r1 = (hsum - h0) / 256;
+  const long long h1 = ((r1 % 256) + 256) % 256;
+  const long long h2 = (r1 - h1) / 256;
+  t->off[0] = static_cast<int32_t>(128 * h0);
+  t->off[1] = static_cast<int32_t>(128 * h1);
+  t->off[2] = static_cast<int32_t>(128 * h2);
+}
+
+cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
+                        const uint8_t *b_image_dev, int data_shift, int sm_count, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    const void *fs[] = {(const void *)k_fir_tc<5, 8, 2>, (const void *)k_fir_tc<11, 14, 1>,
+                        (const void *)k_fir_tc<12, 14, 1>};
+    for (const void *f : fs) {
+      if (attr_err == cudaSuccess) {
+        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(FT_SMEM));
+      }
+    }
+  });
+  if (attr_err != cudaSuccess) {
+    return attr_err;
+  }
+  if (job.n_total % FT_NO != 0 || nsig < 1 || nsig > 2 || nch < 1) {
+    return cudaErrorInvalidValue;
+  }
+  const int ws0 = (t.ksteps - 1) * FT_NO;
+  if (ws0 > job.in_off) {
+    return cudaErrorInvalidValue;
+  }
+  FirTcParams p{};
+  p.tiles_row = job.n_total / FT_NO;
+  p.row_tiles = (nch + FT_ROWS - 1) / FT_ROWS;
+  p.nsig = nsig;
+  p.tiles_total = nsig * p.row_tiles * p.tiles_row;
+  p.in_x0 = job.in_off - ws0;
+  p.out_x0 = job.out_off;
+  p.off2 = t.off[0];
+  p.off3 = t.off[1];
+  p.off4 = t.off[2];
+  p.dscale = static_cast<float>(std::ldexp(1.0, data_shift));
+  p.out_scale = static_cast<float>(std::ldexp(static_cast<double>(job.scale), -(t.shift + data_shift)));
+  CUtensorMap tm_in[2], tm_out[2];
+  for (int s = 0; s < 2; s++) {
+    const int ss = s < nsig ? s : 0;
+    const float *in = job.in[ss] + static_cast<size_t>(job.ch0) * job.in_pitch;
+    float *out = job.out[ss] + static_cast<size_t>(job.ch0) * job.out_pitch;
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u) ||
+        (job.in_pitch & 3u) || (job.out_pitch & 3u)) {
+      return cudaErrorInvalidValue;
+    }
+    if (!encodeFloatRows(&tm_in[s], in, static_cast<uint64_t>(job.in_off + job.n_total),
+                         static_cast<uint64_t>(nch), job.in_pitch, FT_ROWS) ||
+        !encodeFloatRows(&tm_out[s], out, static_cast<uint64_t>(job.out_off + job.n_total),
+                         static_cast<uint64_t>(nch), job.out_pitch, 32)) {
+      return cudaErrorInvalidValue;
+    }
+  }
+  const int grid = std::min(sm_count, p.tiles_total);
+  const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
+  switch (t.ksteps) {
+    case 5:
+      k_fir_tc<5, 8, 2><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      break;
+    case 11:
+      k_fir_tc<11, 14, 1><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      break;
+    case 12:
+      k_fir_tc<12, 14, 1><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fmgpu

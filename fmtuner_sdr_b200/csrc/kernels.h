@@ -35,6 +35,23 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
                           size_t x1_pitch, int n_out, int ch0, int nch, float scale,
                           const uint8_t *b_image_dev, const int32_t *offs_dev, int sm_count,
                           cudaStream_t stream);
+// fir_tc.cu: the real-tap FIRs of the stereo decoder (pilot band-pass, L/R low-pass) as exact integer
+// contractions on the tensor cores: samples as 24-bit fixed point in three byte planes (A operand in
+// TMEM), taps as three signed base-256 digits (banded B matrix in shared memory), int32 accumulators
+// in TMEM. Not bit-identical to launchFirReal: the exact sum of quantised terms, rounded at the end.
+struct FirTcTables {
+  std::vector<uint8_t> b_image;
+  int32_t off[3];   // 2^23 * sum(integer taps), limbs 2..4
+  int shift;        // taps are quantised to 2^-shift
+  int ksteps;       // 32-sample sub-chunks per tile window
+};
+int firTcKsteps(const float *h, int Lp);
+bool firTcSupported(const float *h, int Lp, int in_off);
+void firTcBuildTables(const float *h, int Lp, FirTcTables *t);
+// data_shift: samples are quantised to 2^-data_shift and must satisfy |x| < 2^(23 - data_shift)
+// (larger values saturate)
+cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
+                        const uint8_t *b_image_dev, int data_shift, int sm_count, cudaStream_t stream);
 void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_pitch, int n,
                      int ch0, int nch, cudaStream_t stream);
 void launchRequantU8(const float2 *x1, size_t x1_pitch, uint8_t *out, size_t out_stride, int n, int ch0,

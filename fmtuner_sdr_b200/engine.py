@@ -95,6 +95,8 @@ def load_library(build: bool = True):
     L.fmgpu_get_decimator_mode.argtypes = [vp]
     L.fmgpu_set_scan_mode.argtypes = [vp, i32]
     L.fmgpu_get_scan_mode.argtypes = [vp]
+    L.fmgpu_set_fir_mode.argtypes = [vp, i32]
+    L.fmgpu_get_fir_mode.argtypes = [vp]
     L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
     L.fmgpu_set_stage_overlap.argtypes = [vp, i32]
     L.fmgpu_is_stereo.argtypes = [vp, i32]
@@ -253,6 +255,13 @@ class Engine:
 
     def scan_mode(self) -> int:
         return self.L.fmgpu_get_scan_mode(self.h)
+
+    def set_fir_mode(self, mode: int):
+        """0 = FP32 pilot band-pass / L-R low-pass (bit-exact flavour), 1 = tensor-core integer form."""
+        self._check(self.L.fmgpu_set_fir_mode(self.h, mode), "set_fir_mode")
+
+    def fir_mode(self) -> int:
+        return self.L.fmgpu_get_fir_mode(self.h)
 
     def set_pipeline_groups(self, groups: int):
         self._check(self.L.fmgpu_set_pipeline_groups(self.h, groups), "set_pipeline_groups")

@@ -112,6 +112,14 @@ int fmgpu_get_decimator_mode(const fmgpu_engine *e);
  * full scale), not bit for bit. FMGPU_SCAN_MODE sets the mode an engine starts in. */
 int fmgpu_set_scan_mode(fmgpu_engine *e, int mode);
 int fmgpu_get_scan_mode(const fmgpu_engine *e);
+/* Arithmetic of the stereo decoder's real-tap FIRs — the 19 kHz pilot band-pass and the L/R 15 kHz
+ * low-pass (stereo_decoder.cpp:25-63,172-173,233-239) — all channels. 0: FP32 FMA chains in the
+ * reference's summation order, bit-identical to the CPU oracle. 1: exact integer contractions on the
+ * tensor cores (samples as 24-bit fixed point, taps as 24-bit integers, int32 sums in TMEM, rounded
+ * at the end): within ~2e-7 of mode 0. FMGPU_EINVAL when a filter length has no tensor-core form.
+ * FMGPU_FIR_MODE sets the mode an engine starts in. */
+int fmgpu_set_fir_mode(fmgpu_engine *e, int mode);
+int fmgpu_get_fir_mode(const fmgpu_engine *e);
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode);      /* StereoDecoder::setBlendMode */
 int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on);        /* StereoDecoder::setForceMono */
 int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on);      /* StereoDecoder::setForceStereo */
