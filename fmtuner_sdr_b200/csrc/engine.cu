@@ -2410,6 +2410,8 @@ size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, siz
   case 2: base = e->dLf + c * e->lfPitch + H_LF; break;
   case 3: base = e->dRf + c * e->lfPitch + H_LF; break;
   case 4: base = e->dPilot + c * e->pitch; break;
+  case 5: base = e->dLraw + c * e->lrPitch + H_LR; break;
+  case 6: base = e->dRraw + c * e->lrPitch + H_LR; break;
   default: return 0;
   }
   size_t written = 0;

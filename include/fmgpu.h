@@ -310,7 +310,8 @@ size_t fmgpu_design_host(const fmgpu_config *cfg, int which, int bw_hz, float *o
                          float *scale);
 /* Intermediate device buffers of the last fmgpu_process_* call, copied to the host:
  * which: 0 decimated cf32 (2 floats/sample), 1 MPX, 2 stereo left at the DSP rate,
- * 3 stereo right, 4 pilot band-pass output. Returns floats written. */
+ * 3 stereo right, 4 pilot band-pass output, 5 / 6 the matrix outputs L / R in front of the 15 kHz
+ * low-pass. Returns floats written. */
 size_t fmgpu_debug_read(fmgpu_engine *e, int which, int channel, float *out, size_t cap);
 /* Every RDS bit demodulated by `channel` during the last call (before block sync). */
 size_t fmgpu_debug_rds_bits(fmgpu_engine *e, int channel, uint8_t *out, size_t cap);

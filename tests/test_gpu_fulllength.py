@@ -62,6 +62,7 @@ def test_config1_ten_seconds(orc_fm, rate, nblk, mode):
     eng = fm.Engine(fm.make_config(iq_rate=iq_rate, decimation=decim, max_blocks=8), 1, 0)
     eng.set_decimator_mode(mode)
     eng.set_scan_mode(mode)       # mode 1 = the engine's fast arithmetic, as bench.py runs it
+    eng.set_fir_mode(mode)
     audio, groups, status, dbg = run_engine_chunks(eng, iq.reshape(1, -1), nblk, 8, debug_channel=0)
     eng.close()
     a, g, st = audio[0], groups[0], status[0]
@@ -118,6 +119,7 @@ def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
                                            dsp_agc=1), len(chans), 0)
             eng.set_decimator_mode(mode)
             eng.set_scan_mode(mode)
+            eng.set_fir_mode(mode)
             for i, c in enumerate(chans):
                 eng.set_blend_mode(c % 3, i)
             audio, groups, status, _ = run_engine_chunks(eng, np.stack([x[0] for x in cpu]), nblk, chunk)
