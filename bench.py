@@ -75,7 +75,9 @@ def parse_args():
                     help="arithmetic: tc = the engine's fast forms (tcgen05 int8 decimator, "
                          "fmgpu_set_decimator_mode 1; de-emphasis / DC blocker as a warp-shuffle scan, "
                          "fmgpu_set_scan_mode 1; pilot band-pass and L/R low-pass as tcgen05 int8 "
-                         "contractions, fmgpu_set_fir_mode 1); fp32 = the reference's summation order everywhere, "
+                         "contractions, fmgpu_set_fir_mode 1; channel filter + discriminator fused into one "
+                         "tensor-core kernel, AGC elided, fmgpu_set_demod_mode 1); fp32 = the reference's "
+                         "summation order everywhere, "
                          "bit-identical to the CPU oracle (modes 0)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the strong-scaling, config-4 and H2D-roof records")
@@ -242,7 +244,9 @@ def workload_config(args, channels_this_arm: int) -> dict:
                        "accumulators in TMEM (decim_tc.cu, fmgpu_set_decimator_mode 1); de-emphasis + DC "
                        "blocker = warp-shuffle scan (fmgpu_set_scan_mode 1); pilot band-pass + L/R low-pass = "
                        "tcgen05 int8 contractions on 24-bit fixed-point samples, A operand in TMEM (fir_tc.cu, "
-                       "fmgpu_set_fir_mode 1); every other stage in "
+                       "fmgpu_set_fir_mode 1); channel filter + discriminator = one tcgen05 int8 kernel, the "
+                       "pre-discriminator AGC (a positive real gain the discriminator cannot see) elided "
+                       "(fmgpu_set_demod_mode 1); every other stage in "
                        "the reference's summation order" if args.decim_mode == "tc" else
                        "reference order everywhere: bit-identical to the CPU oracle (modes 0)"),
         "step_submission": "joined per step" if args.sync_steps else
@@ -295,6 +299,7 @@ class Workload:
         self.eng.set_decimator_mode(1 if args.decim_mode == "tc" else 0)
         self.eng.set_scan_mode(1 if args.decim_mode == "tc" else 0)
         self.eng.set_fir_mode(1 if args.decim_mode == "tc" else 0)
+        self.eng.set_demod_mode(1 if args.decim_mode == "tc" else 0)
         for m in (0, 2):   # blend mode = global channel id % 3 (1 = normal is the engine default)
             for c, g in enumerate(global_ids):
                 if g % 3 == m:
@@ -696,7 +701,7 @@ def config4_record(fm, shard, args, rank, local_rank, world, stream, barrier):
     return rec
 
 
-TILE_STAGES = ("decimate", "chanfir", "freqdem", "pilot_fir", "audio_lpf", "afpost", "rds_resample")
+TILE_STAGES = ("decimate", "chanfir", "chan_demod", "freqdem", "pilot_fir", "audio_lpf", "afpost", "rds_resample")
 LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds", "rds_sync")
 
 # DRAM bytes per DSP-rate sample (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu
@@ -728,6 +733,8 @@ def stage_figures(stage: str, stage_ms: float, C: int, B: int, peak_hbm: float, 
     alg = {   # stage: (bytes, flops, bound)
         "decimate": (2.0 * n * DECIM + 8.0 * n, 2.0 * 2 * 280 * n, "hbm" if decim_mode == "tc" else "fp32"),
         "chanfir": (8.0 * n + 8.0 * n, 2.0 * 2 * 81 * n, "fp32"),
+        # fused channel filter + discriminator (fir_tc.cu): complex samples in, MPX out
+        "chan_demod": (8.0 * n + 4.0 * n, 2.0 * 2 * 81 * n + 30.0 * n, "hbm"),
         # tensor-core forms (fir_tc.cu): the FP32 pipe is out of the picture, HBM is the roof
         "pilot_fir": (4.0 * n + 4.0 * n, 2.0 * 305 * n, "hbm" if decim_mode == "tc" else "fp32"),
         "audio_lpf": (8.0 * n + 8.0 * n, 2.0 * 2 * 121 * n, "hbm" if decim_mode == "tc" else "fp32"),

@@ -60,6 +60,10 @@ struct fmgpu_engine {
   // real-tap FIRs of the stereo decoder (pilot band-pass, L/R low-pass): 0 = FP32 FFMA2 chains
   // (bit-identical to the oracle), 1 = exact integer contractions on the tensor cores (fir_tc.cu)
   int firMode = 0;
+  // channel filter -> AGC -> discriminator: 0 = three kernels in the reference's arithmetic
+  // (bit-identical to the oracle), 1 = one tensor-core kernel (fir_tc.cu: integer channel filter,
+  // discriminator in its epilogue; the AGC cannot change the discriminator's output and is left out)
+  int demodMode = 0;
   bool decimTcOk = false, pilTcOk = false, audTcOk = false;
   FirTcTables pilTc{}, audTc{};
   uint8_t *dPilB = nullptr, *dAudB = nullptr;
@@ -75,6 +79,10 @@ struct fmgpu_engine {
     std::vector<float> taps;
     float scale;
     int lp;
+    // tensor-core form (fir_tc.cu): integer taps' digits as a B image on the device
+    FirTcTables tc{};
+    uint8_t *dB = nullptr;
+    bool tcOk = false;
   };
   std::vector<ChanFilter> filters;
   std::map<std::tuple<unsigned, float, float>, int> filterIndex;
@@ -279,6 +287,18 @@ int filterSlot(fmgpu_engine *e, unsigned len, float cutoff, float atten) {
              CHAN_TAPS_PITCH * sizeof(float), cudaMemcpyHostToDevice);
   cudaMemcpy(e->dChanLp + slot, &f.lp, sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(e->dChanScale + slot, &f.scale, sizeof(float), cudaMemcpyHostToDevice);
+  {
+    const float *h = row.data() + (CHAN_TAPS_PITCH - f.lp);   // the padded taps as k_chanfir reads them
+    if (chanTcSupported(h, f.lp, H_X2)) {
+      firTcBuildTables(h, f.lp, &f.tc);
+      void *d = nullptr;
+      if (cudaMalloc(&d, f.tc.b_image.size()) == cudaSuccess &&
+          cudaMemcpy(d, f.tc.b_image.data(), f.tc.b_image.size(), cudaMemcpyHostToDevice) == cudaSuccess) {
+        f.dB = static_cast<uint8_t *>(d);
+        f.tcOk = true;
+      }
+    }
+  }
   e->filters.push_back(std::move(f));
   e->filterIndex[key] = slot;
   return slot;
@@ -728,7 +748,44 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     e->launches += 1;
   }
   done(E::ST_DC);
-  {
+  // fused tensor-core form of channel filter + discriminator: every channel of the range on the same
+  // channel filter, and that filter has a tensor-core image
+  int fusedFilt = -1;
+  if (e->demodMode == 1 && N % 32 == 0) {
+    fusedFilt = e->hParams[ch0].filt;
+    for (int c = ch0 + 1; c < ch0 + nch && fusedFilt >= 0; c++) {
+      if (e->hParams[c].filt != fusedFilt) {
+        fusedFilt = -1;
+      }
+    }
+    if (fusedFilt >= 0 && !e->filters[fusedFilt].tcOk) {
+      fusedFilt = -1;
+    }
+  }
+  if (fusedFilt >= 0) {
+    // one kernel on the channel-filter stream: reads x2, writes MPX (and the discriminator's carried
+    // sample into the y row); the AGC and discriminator stages of this block are empty
+    cudaStream_t s = P.run[E::ST_CHAN];
+    if (stereo) {
+      need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD, E::ST_PILOT, E::ST_STEREO, E::ST_RDS});
+    } else {
+      need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD, E::ST_RDS, E::ST_AF});
+    }
+    Span sp(e, "chan_demod", s);
+    if (carry) {
+      launchCarryF2(e->dY, e->yPitch, Y_OFF, ringEnd, ch0, nch, s);  // slot Y_OFF-1 <- last output
+      launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, ringEnd, ch0, nch, s);
+      e->launches += 2;
+    }
+    const auto &f = e->filters[fusedFilt];
+    const cudaError_t err =
+        launchChanDemodTc(e->dX2 + t0, e->x2Pitch, H_X2, e->dY + t0, e->yPitch, e->dMpx + t0, e->mpxPitch,
+                          H_MPX, N, ch0, nch, f.scale, e->k.fd_ref, f.tc, f.dB, 21, e->smCount, s);
+    if (err != cudaSuccess) {
+      e->lastError = std::string("tensor-core channel filter + discriminator: ") + cudaGetErrorString(err);
+    }
+    e->launches += 1;
+  } else {
     cudaStream_t s = P.run[E::ST_CHAN];
     need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD});
     Span sp(e, "chanfir", s);
@@ -741,7 +798,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     cudaStream_t s = P.run[E::ST_AGC];
     need(E::ST_AGC, {E::ST_CHAN}, {E::ST_FD});
     bool anyAgc = false;
-    for (int c = ch0; c < ch0 + nch && !anyAgc; c++) {
+    for (int c = ch0; c < ch0 + nch && !anyAgc && fusedFilt < 0; c++) {
       anyAgc = e->hParams[c].agc_mode != 0;
     }
     if (anyAgc) {
@@ -760,14 +817,16 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     } else {
       need(E::ST_FD, {E::ST_AGC}, {E::ST_RDS, E::ST_AF /* the mono chain reads MPX */});
     }
-    Span sp(e, "freqdem", s);
-    if (carry) {
-      launchCarryF2(e->dY, e->yPitch, Y_OFF, ringEnd, ch0, nch, s);  // slot Y_OFF-1 <- last output
-      launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, ringEnd, ch0, nch, s);
-      e->launches += 2;
+    if (fusedFilt < 0) {
+      Span sp(e, "freqdem", s);
+      if (carry) {
+        launchCarryF2(e->dY, e->yPitch, Y_OFF, ringEnd, ch0, nch, s);  // slot Y_OFF-1 <- last output
+        launchCarryF32(e->dMpx, e->mpxPitch, H_MPX, ringEnd, ch0, nch, s);
+        e->launches += 2;
+      }
+      launchFreqDem(e->dY + t0, e->yPitch, e->dMpx + t0, e->mpxPitch, N, ch0, nch, e->k.fd_ref, s);
+      e->launches += 1;
     }
-    launchFreqDem(e->dY + t0, e->yPitch, e->dMpx + t0, e->mpxPitch, N, ch0, nch, e->k.fd_ref, s);
-    e->launches += 1;
   }
   done(E::ST_FD);
   // ---- RDS branch --------------------------------------------------------------------------
@@ -1305,6 +1364,9 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
     if (const char *fm = getenv("FMGPU_FIR_MODE")) {
       e->firMode = (atoi(fm) == 1 && e->pilTcOk && e->audTcOk) ? 1 : 0;
     }
+    if (const char *xm = getenv("FMGPU_DEMOD_MODE")) {
+      e->demodMode = (atoi(xm) == 1) ? 1 : 0;
+    }
     if (const char *dm = getenv("FMGPU_DECIM_MODE")) {
       e->decimMode = (atoi(dm) == 1 && e->decimTcOk) ? 1 : 0;
     }
@@ -1413,6 +1475,11 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
                   e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd,
                   e->dAudio2,  e->dGroups2, e->dStatus2, e->dNAudio2, e->dNGroups2, e->dR171,
                   e->dDecB,    e->dDecOffs, e->dPilB, e->dAudB};
+  for (auto &f : e->filters) {
+    if (f.dB) {
+      cudaFree(f.dB);
+    }
+  }
   for (void *p : ptrs) {
     if (p) {
       cudaFree(p);
@@ -1622,6 +1689,18 @@ int fmgpu_set_fir_mode(fmgpu_engine *e, int mode) {
 }
 
 int fmgpu_get_fir_mode(const fmgpu_engine *e) { return e ? e->firMode : FMGPU_EINVAL; }
+
+int fmgpu_set_demod_mode(fmgpu_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 1) {
+    return FMGPU_EINVAL;
+  }
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  syncPipes(e);
+  e->demodMode = mode;
+  return FMGPU_OK;
+}
+
+int fmgpu_get_demod_mode(const fmgpu_engine *e) { return e ? e->demodMode : FMGPU_EINVAL; }
 
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode) {
   if (!e || mode < 0 || mode > 2) {

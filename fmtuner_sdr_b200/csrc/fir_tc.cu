@@ -20,11 +20,12 @@
 // not bit-identical to it (k_fir_pair in kernels.cu stays the bit-exact flavour).
 //
 // No operand of the data ever sits in shared memory in MMA layout: the A operand lives in TENSOR
-// MEMORY. One persistent CTA per SM, ten warps:
+// MEMORY. One persistent CTA per SM, fourteen warps:
 //   warp 0     TMA producer: [128 rows x 32 floats] boxes of the input rows -> staging ring
 //   warp 1     allocates TMEM, issues the MMAs (one elected lane; A from TMEM, B from shared memory)
-//   warps 2-5  epilogue: tcgen05.ld the accumulator, recombine, stage in 128B-swizzled shared memory,
-//              one TMA store of [32 rows x 32 floats] per warp and tile; then zero the accumulator
+//   warps 2-5, 10-13  epilogue, two warps per TMEM lane quadrant (outputs 0..15 / 16..31 of the tile):
+//              tcgen05.ld the accumulator columns, recombine, stage in 64B-swizzled shared memory, one
+//              TMA store of [32 rows x 16 floats] per warp and tile; then zero the columns
 //              (tcgen05.st) so that every MMA accumulates
 //   warps 6-9  converters: staged floats -> fixed point -> three byte planes -> tcgen05.st into the
 //              TMEM ring of 32-sample sub-chunks (lane = row, 8 columns = 32 bytes of K per plane)
@@ -43,6 +44,7 @@
 #include <mutex>
 #include <vector>
 
+#include "fm_math.h"
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -65,9 +67,10 @@ constexpr int FT_MAX_KS = 12;
 constexpr int FT_B_BYTES = ((FT_MAX_KS + 3) / 4) * FT_BCHUNK;   // 36 KB
 constexpr int FT_NSTG = 4;                                 // float staging slots (16 KB each)
 constexpr int FT_STG_BYTES = FT_ROWS * FT_NO * 4;
-constexpr int FT_OUT_BYTES = 32 * FT_NO * 4;               // one epilogue warp's staging tile (4 KB)
-constexpr int FT_THREADS = 320;
-constexpr size_t FT_SMEM = 1024 + FT_B_BYTES + FT_NSTG * FT_STG_BYTES + 8 * FT_OUT_BYTES + 512;
+constexpr int FT_HALF = FT_NO / 2;                         // outputs per epilogue warp and tile
+constexpr int FT_OUT_BYTES = 32 * FT_HALF * 4;             // one epilogue warp's staging tile (2 KB)
+constexpr int FT_THREADS = 448;                            // 14 warps
+constexpr size_t FT_SMEM = 1024 + FT_B_BYTES + FT_NSTG * FT_STG_BYTES + 16 * FT_OUT_BYTES + 512;
 
 struct FirTcParams {
   int tiles_row;      // tiles per row = n_total / 32
@@ -79,6 +82,12 @@ struct FirTcParams {
   int off2, off3, off4;   // 2^23 * sum(hq) as limbs 2..4 (limbs 0, 1 are zero)
   float dscale;       // 2^data_shift: samples are quantised to 2^-data_shift
   float out_scale;    // scale / 2^(S + data_shift)
+  // complex form (channel filter + discriminator): rows are (channel, {I, Q}) pairs on adjacent lanes
+  int nch;            // channels of the call
+  float fd_ref;       // discriminator scale 1 / (2 pi kf)
+  const float2 *y_prev;   // [c * y_pitch]: the filter output in front of this block (discriminator r_prev)
+  float2 *y_last;         // [c * y_pitch]: this block's last filter output, for the next block
+  size_t y_pitch;
 };
 
 // CTA b owns tiles [lo, hi) of the (signal, row tile, time) sequence
@@ -88,16 +97,57 @@ __device__ __forceinline__ void tileRange(const FirTcParams &p, int *lo, int *hi
   *hi = static_cast<int>(t * (blockIdx.x + 1) / gridDim.x);
 }
 // the run of tiles starting at `cur` that stays inside one row tile: (signal, row tile, first tile, count)
-__device__ __forceinline__ void nextRun(const FirTcParams &p, int cur, int hi, int *sig, int *rt, int *t0,
-                                        int *nt) {
-  const int r = cur / p.tiles_row;
-  *t0 = cur - r * p.tiles_row;
-  *nt = min(hi - cur, p.tiles_row - *t0);
-  *sig = r / p.row_tiles;
-  *rt = r - *sig * p.row_tiles;
+struct Run {
+  int sig, rt, t0, nt;
+  int own;      // tiles of the CTA's range in this run (cur advances by this)
+  int primer;   // complex form: the run starts one tile early; that tile only yields the discriminator's
+                // previous sample (its outputs belong to another CTA)
+};
+template <bool CPLX>
+__device__ __forceinline__ Run nextRun(const FirTcParams &p, int cur, int hi) {
+  Run r;
+  const int row = cur / p.tiles_row;
+  r.t0 = cur - row * p.tiles_row;
+  r.own = min(hi - cur, p.tiles_row - r.t0);
+  r.nt = r.own;
+  r.sig = row / p.row_tiles;
+  r.rt = row - r.sig * p.row_tiles;
+  r.primer = 0;
+  if (CPLX && r.t0 > 0) {
+    r.primer = 1;
+    r.t0 -= 1;
+    r.nt += 1;
+  }
+  return r;
 }
 
-template <int KS, int RING, int NACC>
+// atan2 for the fused discriminator: branch-free, one reciprocal (MUFU.RCP + one Newton step on the
+// quotient) instead of fm_atan2f's two IEEE divisions; same Cephes polynomial. |error| <= 3 ulp of
+// the result (tests/test_gpu_chan_demod_tc.py compares the multiplex with the three-kernel form).
+__device__ __forceinline__ float atan2Fast(float y, float x) {
+  const float kPi = 3.14159265358979323846f;
+  const float kPi2 = 1.57079632679489661923f;
+  const float kPi4 = 0.78539816339744830962f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const bool big = mn > 0.4142135623730950f * mx;
+  const float num = big ? mn - mx : mn;
+  const float den = fmaxf(big ? mn + mx : mx, 1e-37f);
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));
+  float t = num * rc;
+  t = fmaf(fmaf(-den, t, num), rc, t);
+  const float z = t * t;
+  float pl = fmaf(z, 8.05374449538e-2f, -1.38776856032e-1f);
+  pl = fmaf(pl, z, 1.99777106478e-1f);
+  pl = fmaf(pl, z, -3.33329491539e-1f);
+  float r = (big ? kPi4 : 0.0f) + fmaf(pl * z, t, t);
+  r = (ay > ax) ? kPi2 - r : r;
+  r = (__float_as_int(x) < 0) ? kPi - r : r;
+  return copysignf(r, y);
+}
+
+template <int KS, int RING, int NACC, bool CPLX>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
          const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
@@ -110,7 +160,7 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
   const uint32_t sB = base;
   const uint32_t sStg = sB + FT_B_BYTES;
   const uint32_t sOut = sStg + FT_NSTG * FT_STG_BYTES;
-  const uint32_t sBar = sOut + 8 * FT_OUT_BYTES;
+  const uint32_t sBar = sOut + 16 * FT_OUT_BYTES;
   const uint32_t barSFull = sBar, barSEmpty = barSFull + 8 * FT_NSTG, barAFull = barSEmpty + 8 * FT_NSTG,
                  barAEmpty = barAFull + 8 * RING, barTFull = barAEmpty + 8 * RING,
                  barTEmpty = barTFull + 8 * NACC, sTmem = barTEmpty + 8 * NACC;
@@ -137,7 +187,7 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
     }
     for (int i = 0; i < NACC; i++) {
       mbarInit(barTFull + 8 * i, 1);    // tcgen05.commit
-      mbarInit(barTEmpty + 8 * i, 4);   // one arrival per epilogue warp
+      mbarInit(barTEmpty + 8 * i, 8);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -157,23 +207,30 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
     if (lane == 0) {
       uint32_t stg = 0, use = 0;
       for (int cur = lo; cur < hi;) {
-        int sig, rt, t0, nt;
-        nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
-        const CUtensorMap *map = sig ? &tm_in1 : &tm_in0;
-        const int nsub = nt + KS - 1;
+        const Run r = nextRun<CPLX>(p, cur, hi);
+        const CUtensorMap *map = r.sig ? &tm_in1 : &tm_in0;
+        const int nsub = r.nt + KS - 1;
         for (int g = 0; g < nsub; g++) {
           if (use > 0) {
             mbarWait(barSEmpty + 8 * stg, (use - 1) & 1);
           }
           mbarExpectTx(barSFull + 8 * stg, FT_STG_BYTES);
-          tmaLoad2d(sStg + stg * FT_STG_BYTES, map, barSFull + 8 * stg, p.in_x0 + FT_NO * (t0 + g),
-                    rt * FT_ROWS);
+          if (CPLX) {
+            // 32 complex samples of 64 channels: two boxes of [64 rows x 32 floats]
+            const int x = p.in_x0 + 2 * FT_NO * (r.t0 + g);
+            tmaLoad2d(sStg + stg * FT_STG_BYTES, map, barSFull + 8 * stg, x, r.rt * (FT_ROWS / 2));
+            tmaLoad2d(sStg + stg * FT_STG_BYTES + FT_STG_BYTES / 2, map, barSFull + 8 * stg, x + FT_NO,
+                      r.rt * (FT_ROWS / 2));
+          } else {
+            tmaLoad2d(sStg + stg * FT_STG_BYTES, map, barSFull + 8 * stg, p.in_x0 + FT_NO * (r.t0 + g),
+                      r.rt * FT_ROWS);
+          }
           if (++stg == FT_NSTG) {
             stg = 0;
             use++;
           }
         }
-        cur += nt;
+        cur += r.own;
       }
     }
   } else if (warp == 1) {
@@ -186,8 +243,8 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
     uint32_t win_slot = 0;        // ring slot of the window's first sub-chunk
     uint32_t wait_slot = 0, wait_use = 0;   // next sub-chunk to wait for
     for (int cur = lo; cur < hi;) {
-      int sig, rt, t0, nt;
-      nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
+      const Run r = nextRun<CPLX>(p, cur, hi);
+      const int nt = r.nt;
       int landed = 0;             // sub-chunks of this run known to be in TMEM
       for (int i = 0; i < nt; i++, tile_cnt++) {
         const uint32_t acc = tile_cnt % NACC;
@@ -234,15 +291,19 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
       if (win_slot >= RING) {
         win_slot -= RING;
       }
-      cur += nt;
+      cur += r.own;
     }
-  } else if (warp < 6) {
-    // ===== epilogue (warps 2..5 own TMEM lanes 32 * (warp % 4) ..) ==============================
+  } else if (warp < 6 || warp >= 10) {
+    // ===== epilogue (TMEM lanes 32 * (warp % 4) ..; half 0 = outputs 0..15 of a tile, half 1 = 16..31) ====
     const int q = warp & 3;
+    const int half = warp >= 10 ? 1 : 0;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < NACC * FT_ACC_COLS; c += 8) {
-      tmemSt8(tmem_base + lane_base + c, zero);
+    for (int a = 0; a < NACC; a++) {
+      for (int s = 0; s < FT_LIMBS; s++) {
+        tmemSt8(tmem_base + lane_base + a * FT_ACC_COLS + s * FT_NO + half * FT_HALF, zero);
+        tmemSt8(tmem_base + lane_base + a * FT_ACC_COLS + s * FT_NO + half * FT_HALF + 8, zero);
+      }
     }
     tmemWaitSt();
     tcFenceBefore();
@@ -252,13 +313,44 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
         mbarArrive(barTEmpty + 8 * i);
       }
     }
-    const uint32_t my_out = sOut + q * 2 * FT_OUT_BYTES;
+    const uint32_t my_out = sOut + (half * 4 + q) * 2 * FT_OUT_BYTES;
     uint32_t tile_cnt = 0;
+    // complex form: lanes (2 c, 2 c + 1) hold I and Q of channel c of the tile
+    const int comp = lane & 1;
+    const int ch_row = (q * 32 + lane) >> 1;          // channel inside the 64-channel tile
+    float prev_i = 0.0f, prev_q = 0.0f;               // half 0: the filter output in front of the next tile
+    // limbs -> float, most significant first (exact while the partial sums are below 2^24)
+    auto horner = [&](int d4, int d3, int d2, int d1, int d0) {
+      float f = static_cast<float>(d4 - p.off4);
+      f = fmaf(f, 256.0f, static_cast<float>(d3 - p.off3));
+      f = fmaf(f, 256.0f, static_cast<float>(d2 - p.off2));
+      f = fmaf(f, 256.0f, static_cast<float>(d1));
+      f = fmaf(f, 256.0f, static_cast<float>(d0));
+      return f * p.out_scale;
+    };
+    // output `col` (0..31) of this lane's row: one column of every limb set
+    auto oneOutput = [&](uint32_t taddr, int col) {
+      int32_t v[FT_LIMBS];
+#pragma unroll
+      for (int s = 0; s < FT_LIMBS; s++) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[s]) : "r"(taddr + s * FT_NO + col));
+      }
+      tmemWaitLd();
+      return horner(v[4], v[3], v[2], v[1], v[0]);
+    };
     for (int cur = lo; cur < hi;) {
-      int sig, rt, t0, nt;
-      nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
-      const CUtensorMap *map = sig ? &tm_out1 : &tm_out0;
-      for (int i = 0; i < nt; i++, tile_cnt++) {
+      const Run r = nextRun<CPLX>(p, cur, hi);
+      const CUtensorMap *map = r.sig ? &tm_out1 : &tm_out0;
+      const int ch = r.rt * (FT_ROWS / 2) + ch_row;   // complex form: channel of the call
+      if (CPLX && !r.primer && half == 0) {
+        float2 pv = make_float2(0.0f, 0.0f);
+        if (ch < p.nch) {
+          pv = p.y_prev[static_cast<size_t>(ch) * p.y_pitch];
+        }
+        prev_i = pv.x;
+        prev_q = pv.y;
+      }
+      for (int i = 0; i < r.nt; i++, tile_cnt++) {
         const uint32_t acc = tile_cnt % NACC;
         mbarWait(barTFull + 8 * acc, (tile_cnt / NACC) & 1);
         tcFenceAfter();
@@ -269,39 +361,92 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
         __syncwarp();
         const uint32_t buf = my_out + (tile_cnt & 1) * FT_OUT_BYTES;
         const uint32_t taddr = tmem_base + lane_base + acc * FT_ACC_COLS;
-#pragma unroll 1
-        for (int jg = 0; jg < FT_NO / 8; jg++) {
-          int32_t d[FT_LIMBS][8];
+        const bool skip = CPLX && r.primer && i == 0;   // a primer tile only yields its last output
+        float pi = prev_i, pq = prev_q;
+        if (CPLX && half == 1 && !skip) {
+          // the sample in front of output 16: output 15 of this tile
+          const float y15 = oneOutput(taddr, FT_HALF - 1);
+          const float o = __shfl_xor_sync(0xffffffffu, y15, 1);
+          pi = comp ? o : y15;
+          pq = comp ? y15 : o;
+        }
+        if (!skip) {
+          int32_t d[2][FT_LIMBS][8];
 #pragma unroll
-          for (int s = 0; s < FT_LIMBS; s++) {
-            tmemLd8(taddr + s * FT_NO + jg * 8, d[s]);
+          for (int g = 0; g < 2; g++) {
+#pragma unroll
+            for (int s = 0; s < FT_LIMBS; s++) {
+              tmemLd8(taddr + s * FT_NO + half * FT_HALF + g * 8, d[g][s]);
+            }
           }
           tmemWaitLd();
-          float y[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float f = static_cast<float>(d[4][j] - p.off4);
-            f = fmaf(f, 256.0f, static_cast<float>(d[3][j] - p.off3));
-            f = fmaf(f, 256.0f, static_cast<float>(d[2][j] - p.off2));
-            f = fmaf(f, 256.0f, static_cast<float>(d[1][j]));
-            f = fmaf(f, 256.0f, static_cast<float>(d[0][j]));
-            y[j] = f * p.out_scale;
+          for (int g = 0; g < 2; g++) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              y[j] = horner(d[g][4][j], d[g][3][j], d[g][2][j], d[g][1][j], d[g][0][j]);
+            }
+            if (CPLX) {
+              // quadrature discriminator: both lanes of a pair get I and Q of the group's eight samples;
+              // the even lane demodulates samples 0..3, the odd lane 4..7
+              float vi[9], vq[9];
+              vi[0] = pi;
+              vq[0] = pq;
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float o = __shfl_xor_sync(0xffffffffu, y[j], 1);
+                vi[j + 1] = comp ? o : y[j];
+                vq[j + 1] = comp ? y[j] : o;
+              }
+              pi = vi[8];
+              pq = vq[8];
+              float m[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; jj++) {
+                const float ai = comp ? vi[jj + 4] : vi[jj], aq = comp ? vq[jj + 4] : vq[jj];
+                const float ri = comp ? vi[jj + 5] : vi[jj + 1], rq = comp ? vq[jj + 5] : vq[jj + 1];
+                const float re = (ai * ri) + (aq * rq);
+                const float im = (ai * rq) - (aq * ri);
+                m[jj] = atan2Fast(im, re) * p.fd_ref;
+              }
+              // row lane / 2 of the warp's [16 rows x 64 bytes] tile, 16-byte unit 2 g + comp
+              const int rr = lane >> 1;
+              const uint32_t at = buf + rr * 64 + (static_cast<uint32_t>((2 * g + comp) ^ ((rr >> 1) & 3)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(at), "f"(m[0]), "f"(m[1]),
+                           "f"(m[2]), "f"(m[3])
+                           : "memory");
+            } else {
+              // row `lane` of the [32 rows x 64 bytes] tile, 16-byte units XOR-swizzled like the tensor map
+              const uint32_t row = buf + lane * 64;
+              const uint32_t u0 = static_cast<uint32_t>((2 * g) ^ ((lane >> 1) & 3)) << 4;
+              const uint32_t u1 = static_cast<uint32_t>((2 * g + 1) ^ ((lane >> 1) & 3)) << 4;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + u0), "f"(y[0]), "f"(y[1]),
+                           "f"(y[2]), "f"(y[3])
+                           : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + u1), "f"(y[4]), "f"(y[5]),
+                           "f"(y[6]), "f"(y[7])
+                           : "memory");
+            }
           }
-          // row `lane` of the [32 rows x 128 bytes] tile, 16-byte units XOR-swizzled like the tensor map
-          const uint32_t row = buf + lane * 128;
-          const uint32_t u0 = static_cast<uint32_t>((2 * jg) ^ (lane & 7)) << 4;
-          const uint32_t u1 = static_cast<uint32_t>((2 * jg + 1) ^ (lane & 7)) << 4;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + u0), "f"(y[0]), "f"(y[1]),
-                       "f"(y[2]), "f"(y[3])
-                       : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + u1), "f"(y[4]), "f"(y[5]),
-                       "f"(y[6]), "f"(y[7])
-                       : "memory");
         }
-        // every MMA accumulates: hand the accumulator back zeroed
+        if (CPLX && half == 0) {
+          // the sample in front of the next tile: output 31 of this one
+          const float y31 = oneOutput(taddr, FT_NO - 1);
+          const float o = __shfl_xor_sync(0xffffffffu, y31, 1);
+          prev_i = comp ? o : y31;
+          prev_q = comp ? y31 : o;
+        }
+        if (CPLX) {
+          // each warp of the pair has read one column of the other's half (outputs 15 / 31): nobody
+          // zeroes before both are done reading
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        }
+        // every MMA accumulates: hand this warp's columns back zeroed
 #pragma unroll
-        for (int c = 0; c < FT_ACC_COLS; c += 8) {
-          tmemSt8(taddr + c, zero);
+        for (int s = 0; s < FT_LIMBS; s++) {
+          tmemSt8(taddr + s * FT_NO + half * FT_HALF, zero);
+          tmemSt8(taddr + s * FT_NO + half * FT_HALF + 8, zero);
         }
         tmemWaitSt();
         tcFenceBefore();
@@ -309,11 +454,21 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) {
           mbarArrive(barTEmpty + 8 * acc);
-          tmaStore2d(map, buf, p.out_x0 + FT_NO * (t0 + i), rt * FT_ROWS + q * 32);
-          bulkCommit();
+          if (!skip) {
+            const int x = p.out_x0 + FT_NO * (r.t0 + i) + half * FT_HALF;
+            if (CPLX) {
+              tmaStore2d(map, buf, x, r.rt * (FT_ROWS / 2) + q * 16);
+            } else {
+              tmaStore2d(map, buf, x, r.rt * FT_ROWS + q * 32);
+            }
+          }
+          bulkCommit();   // (an empty group when nothing was stored: the wait counts groups)
+        }
+        if (CPLX && half == 1 && r.t0 + i == p.tiles_row - 1 && comp == 0 && ch < p.nch) {
+          p.y_last[static_cast<size_t>(ch) * p.y_pitch] = make_float2(pi, pq);
         }
       }
-      cur += nt;
+      cur += r.own;
     }
     if (lane == 0) {
       bulkWait<0>();
@@ -326,20 +481,38 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
     const float dscale = p.dscale;
     uint32_t stg = 0, stg_use = 0, slot = 0, slot_use = 0;
     for (int cur = lo; cur < hi;) {
-      int sig, rt, t0, nt;
-      nextRun(p, cur, hi, &sig, &rt, &t0, &nt);
-      const int nsub = nt + KS - 1;
+      const Run r = nextRun<CPLX>(p, cur, hi);
+      const int nsub = r.nt + KS - 1;
       for (int g = 0; g < nsub; g++) {
         mbarWait(barSFull + 8 * stg, stg_use & 1);
-        // my row of the [128 rows x 128 bytes] staging tile (128B-swizzled by the TMA)
-        const uint32_t src = sStg + stg * FT_STG_BYTES + row * 128;
         float x[FT_NO];
+        if (CPLX) {
+          // my component of my channel's 32 complex samples: two [64 rows x 128 bytes] boxes
+          const int chr = row >> 1, cmp = row & 1;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const uint32_t at = src + (static_cast<uint32_t>(u ^ (row & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(x[4 * u]), "=f"(x[4 * u + 1]), "=f"(x[4 * u + 2]), "=f"(x[4 * u + 3])
-                       : "r"(at));
+          for (int h = 0; h < 2; h++) {
+            const uint32_t src = sStg + stg * FT_STG_BYTES + h * (FT_STG_BYTES / 2) + chr * 128;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const uint32_t at = src + (static_cast<uint32_t>(u ^ (chr & 7)) << 4);
+              float a0, a1, a2, a3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                           : "r"(at));
+              x[16 * h + 2 * u] = cmp ? a1 : a0;
+              x[16 * h + 2 * u + 1] = cmp ? a3 : a2;
+            }
+          }
+        } else {
+          // my row of the [128 rows x 128 bytes] staging tile (128B-swizzled by the TMA)
+          const uint32_t src = sStg + stg * FT_STG_BYTES + row * 128;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const uint32_t at = src + (static_cast<uint32_t>(u ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[4 * u]), "=f"(x[4 * u + 1]), "=f"(x[4 * u + 2]), "=f"(x[4 * u + 3])
+                         : "r"(at));
+          }
         }
         __syncwarp();
         if (lane == 0) {
@@ -387,7 +560,7 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
           slot_use++;
         }
       }
-      cur += nt;
+      cur += r.own;
     }
   }
 
@@ -401,17 +574,18 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
 
 // float rows [rows][row_floats] with `pitch` floats between rows; boxes of 32 floats x box_rows, 128B swizzle
 bool encodeFloatRows(CUtensorMap *map, const float *base, uint64_t row_floats, uint64_t rows, uint64_t pitch,
-                     uint32_t box_rows) {
+                     uint32_t box_rows, uint32_t box_floats = FT_NO) {
   EncodeFn fn = encodeFn();
   if (!fn) {
     return false;
   }
   const cuuint64_t dims[2] = {row_floats, rows};
   const cuuint64_t strides[1] = {pitch * sizeof(float)};
-  const cuuint32_t box[2] = {FT_NO, box_rows};
+  const cuuint32_t box[2] = {box_floats, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
+            box_floats * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -435,6 +609,11 @@ int firTcKsteps(const float *h, int Lp) {
 bool firTcSupported(const float *h, int Lp, int in_off) {
   const int ks = firTcKsteps(h, Lp);
   return (ks == 5 || ks == 11 || ks == 12) && (ks - 1) * FT_NO <= in_off;
+}
+
+bool chanTcSupported(const float *h, int Lp, int in_off) {
+  const int ks = firTcKsteps(h, Lp);
+  return (ks == 4 || ks == 5) && (ks - 1) * FT_NO <= in_off;
 }
 
 // Host: integer taps, their digits, and the B image the way tcgen05.mma reads a K-major,
@@ -494,13 +673,13 @@ void firTcBuildTables(const float *h, int Lp, FirTcTables *t) {
   t->off[2] = static_cast<int32_t>(128 * h2);
 }
 
-cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
-                        const uint8_t *b_image_dev, int data_shift, int sm_count, cudaStream_t stream) {
+static cudaError_t firTcAttrs() {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    const void *fs[] = {(const void *)k_fir_tc<5, 8, 2>, (const void *)k_fir_tc<11, 14, 1>,
-                        (const void *)k_fir_tc<12, 14, 1>};
+    const void *fs[] = {(const void *)k_fir_tc<5, 8, 2, false>, (const void *)k_fir_tc<11, 14, 1, false>,
+                        (const void *)k_fir_tc<12, 14, 1, false>, (const void *)k_fir_tc<4, 8, 2, true>,
+                        (const void *)k_fir_tc<5, 8, 2, true>};
     for (const void *f : fs) {
       if (attr_err == cudaSuccess) {
         attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -508,6 +687,12 @@ cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTab
       }
     }
   });
+  return attr_err;
+}
+
+cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
+                        const uint8_t *b_image_dev, int data_shift, int sm_count, cudaStream_t stream) {
+  const cudaError_t attr_err = firTcAttrs();
   if (attr_err != cudaSuccess) {
     return attr_err;
   }
@@ -542,7 +727,7 @@ cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTab
     if (!encodeFloatRows(&tm_in[s], in, static_cast<uint64_t>(job.in_off + job.n_total),
                          static_cast<uint64_t>(nch), job.in_pitch, FT_ROWS) ||
         !encodeFloatRows(&tm_out[s], out, static_cast<uint64_t>(job.out_off + job.n_total),
-                         static_cast<uint64_t>(nch), job.out_pitch, 32)) {
+                         static_cast<uint64_t>(nch), job.out_pitch, 32, FT_HALF)) {
       return cudaErrorInvalidValue;
     }
   }
@@ -550,16 +735,74 @@ cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTab
   const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
   switch (t.ksteps) {
     case 5:
-      k_fir_tc<5, 8, 2><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      k_fir_tc<5, 8, 2, false><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
       break;
     case 11:
-      k_fir_tc<11, 14, 1><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      k_fir_tc<11, 14, 1, false><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
       break;
     case 12:
-      k_fir_tc<12, 14, 1><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      k_fir_tc<12, 14, 1, false><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
       break;
     default:
       return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// Channel filter + quadrature discriminator in one kernel (FMDemod::demodulateComplex,
+// /root/reference/src/fm_demod.cpp:194-199): x2 rows (DC-blocked complex samples, halo of in_off
+// samples in front) -> MPX rows. The pre-discriminator AGC between the two (fm_demod.cpp:196-198)
+// multiplies y[n] by a positive real gain, and arg(g y[n] conj(g' y[n-1])) = arg(y[n] conj(y[n-1])):
+// it does not change the discriminator's output and is left out. y_io[c * y_pitch + Y_OFF - 1] holds
+// the filter output in front of this block, y_io[c * y_pitch + Y_OFF + n_total - 1] receives the last one.
+cudaError_t launchChanDemodTc(const float2 *x2, size_t x2_pitch, int in_off, float2 *y_io, size_t y_pitch,
+                              float *mpx, size_t mpx_pitch, int mpx_off, int n_total, int ch0, int nch,
+                              float chan_scale, float fd_ref, const FirTcTables &t, const uint8_t *b_image_dev,
+                              int data_shift, int sm_count, cudaStream_t stream) {
+  const cudaError_t attr_err = firTcAttrs();
+  if (attr_err != cudaSuccess) {
+    return attr_err;
+  }
+  const int ws0 = (t.ksteps - 1) * FT_NO;
+  if (n_total % FT_NO != 0 || nch < 1 || ws0 > in_off || (t.ksteps != 4 && t.ksteps != 5)) {
+    return cudaErrorInvalidValue;
+  }
+  FirTcParams p{};
+  p.tiles_row = n_total / FT_NO;
+  p.row_tiles = (nch + FT_ROWS / 2 - 1) / (FT_ROWS / 2);
+  p.nsig = 1;
+  p.tiles_total = p.row_tiles * p.tiles_row;
+  p.in_x0 = 2 * (in_off - ws0);
+  p.out_x0 = mpx_off;
+  p.off2 = t.off[0];
+  p.off3 = t.off[1];
+  p.off4 = t.off[2];
+  p.dscale = static_cast<float>(std::ldexp(1.0, data_shift));
+  p.out_scale = static_cast<float>(std::ldexp(static_cast<double>(chan_scale), -(t.shift + data_shift)));
+  p.nch = nch;
+  p.fd_ref = fd_ref;
+  p.y_prev = y_io + static_cast<size_t>(ch0) * y_pitch + Y_OFF - 1;
+  p.y_last = y_io + static_cast<size_t>(ch0) * y_pitch + Y_OFF + n_total - 1;
+  p.y_pitch = y_pitch;
+  const float *in = reinterpret_cast<const float *>(x2 + static_cast<size_t>(ch0) * x2_pitch);
+  float *out = mpx + static_cast<size_t>(ch0) * mpx_pitch;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u) || (x2_pitch & 1u) ||
+      (mpx_pitch & 3u)) {
+    return cudaErrorInvalidValue;
+  }
+  CUtensorMap tm_in, tm_out;
+  if (!encodeFloatRows(&tm_in, in, 2ull * static_cast<uint64_t>(in_off + n_total), static_cast<uint64_t>(nch),
+                       2 * x2_pitch, FT_ROWS / 2) ||
+      !encodeFloatRows(&tm_out, out, static_cast<uint64_t>(mpx_off + n_total), static_cast<uint64_t>(nch),
+                       mpx_pitch, 16, FT_HALF)) {
+    return cudaErrorInvalidValue;
+  }
+  const int grid = std::min(sm_count, p.tiles_total);
+  const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
+  if (t.ksteps == 4) {
+    k_fir_tc<4, 8, 2, true><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in, tm_in, tm_out, tm_out, bi, p);
+  } else {
+    k_fir_tc<5, 8, 2, true><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in, tm_in, tm_out, tm_out, bi, p);
   }
   return cudaGetLastError();
 }

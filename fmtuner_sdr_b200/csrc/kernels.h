@@ -52,6 +52,13 @@ void firTcBuildTables(const float *h, int Lp, FirTcTables *t);
 // (larger values saturate)
 cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
                         const uint8_t *b_image_dev, int data_shift, int sm_count, cudaStream_t stream);
+// channel filter + discriminator fused (complex rows; the AGC between them cannot change the
+// discriminator's output and is left out); see fir_tc.cu
+bool chanTcSupported(const float *h, int Lp, int in_off);
+cudaError_t launchChanDemodTc(const float2 *x2, size_t x2_pitch, int in_off, float2 *y_io, size_t y_pitch,
+                              float *mpx, size_t mpx_pitch, int mpx_off, int n_total, int ch0, int nch,
+                              float chan_scale, float fd_ref, const FirTcTables &t, const uint8_t *b_image_dev,
+                              int data_shift, int sm_count, cudaStream_t stream);
 void launchConvertU8(const uint8_t *iq, size_t iq_stride, float2 *x1, size_t x1_pitch, int n,
                      int ch0, int nch, cudaStream_t stream);
 void launchRequantU8(const float2 *x1, size_t x1_pitch, uint8_t *out, size_t out_stride, int n, int ch0,

@@ -97,6 +97,8 @@ def load_library(build: bool = True):
     L.fmgpu_get_scan_mode.argtypes = [vp]
     L.fmgpu_set_fir_mode.argtypes = [vp, i32]
     L.fmgpu_get_fir_mode.argtypes = [vp]
+    L.fmgpu_set_demod_mode.argtypes = [vp, i32]
+    L.fmgpu_get_demod_mode.argtypes = [vp]
     L.fmgpu_set_pipeline_groups.argtypes = [vp, i32]
     L.fmgpu_set_stage_overlap.argtypes = [vp, i32]
     L.fmgpu_is_stereo.argtypes = [vp, i32]
@@ -262,6 +264,14 @@ class Engine:
 
     def fir_mode(self) -> int:
         return self.L.fmgpu_get_fir_mode(self.h)
+
+    def set_demod_mode(self, mode: int):
+        """0 = channel filter, AGC, discriminator as three kernels (bit-exact flavour); 1 = one
+        tensor-core kernel (integer channel filter + discriminator, AGC elided)."""
+        self._check(self.L.fmgpu_set_demod_mode(self.h, mode), "set_demod_mode")
+
+    def demod_mode(self) -> int:
+        return self.L.fmgpu_get_demod_mode(self.h)
 
     def set_pipeline_groups(self, groups: int):
         self._check(self.L.fmgpu_set_pipeline_groups(self.h, groups), "set_pipeline_groups")

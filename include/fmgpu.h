@@ -120,6 +120,16 @@ int fmgpu_get_scan_mode(const fmgpu_engine *e);
  * FMGPU_FIR_MODE sets the mode an engine starts in. */
 int fmgpu_set_fir_mode(fmgpu_engine *e, int mode);
 int fmgpu_get_fir_mode(const fmgpu_engine *e);
+/* Channel filter -> pre-discriminator AGC -> quadrature discriminator (FMDemod::demodulateComplex,
+ * fm_demod.cpp:194-199) of the batched path, all channels. 0: three kernels in the reference's
+ * arithmetic, bit-identical to the CPU oracle. 1: ONE tensor-core kernel — the channel filter as an
+ * exact integer contraction (24-bit fixed-point samples, 24-bit integer taps), the discriminator in
+ * its epilogue; the AGC multiplies y[n] by a positive real gain, which arg(y[n] conj(y[n-1])) does
+ * not see, so it is left out (its state is not advanced). Used for a call whose channels share one
+ * channel filter; otherwise, and for the stage-level entry points, mode 0's kernels run. MPX agrees
+ * with mode 0 to ~1e-6. FMGPU_DEMOD_MODE sets the mode an engine starts in. */
+int fmgpu_set_demod_mode(fmgpu_engine *e, int mode);
+int fmgpu_get_demod_mode(const fmgpu_engine *e);
 int fmgpu_set_blend_mode(fmgpu_engine *e, int channel, int mode);      /* StereoDecoder::setBlendMode */
 int fmgpu_set_force_mono(fmgpu_engine *e, int channel, int on);        /* StereoDecoder::setForceMono */
 int fmgpu_set_force_stereo(fmgpu_engine *e, int channel, int on);      /* StereoDecoder::setForceStereo */

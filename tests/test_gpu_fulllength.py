@@ -63,6 +63,7 @@ def test_config1_ten_seconds(orc_fm, rate, nblk, mode):
     eng.set_decimator_mode(mode)
     eng.set_scan_mode(mode)       # mode 1 = the engine's fast arithmetic, as bench.py runs it
     eng.set_fir_mode(mode)
+    eng.set_demod_mode(mode)
     audio, groups, status, dbg = run_engine_chunks(eng, iq.reshape(1, -1), nblk, 8, debug_channel=0)
     eng.close()
     a, g, st = audio[0], groups[0], status[0]
@@ -120,6 +121,7 @@ def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
             eng.set_decimator_mode(mode)
             eng.set_scan_mode(mode)
             eng.set_fir_mode(mode)
+    eng.set_demod_mode(mode)
             for i, c in enumerate(chans):
                 eng.set_blend_mode(c % 3, i)
             audio, groups, status, _ = run_engine_chunks(eng, np.stack([x[0] for x in cpu]), nblk, chunk)
@@ -194,7 +196,8 @@ def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
             audio_snr_db_min=min(r["audio_snr_db"] for r in b)))
     out = dict(config="BASELINE config 5: 320 channels x 3 s, SNR 10-40 dB, blend c%3, dsp_agc fast",
                reference_flavour=faith_lib.math,
-               arithmetic=("fast: tensor-core int8 decimator + scan de-emphasis (modes 1)" if mode else
+               arithmetic=("fast: tensor-core int8 decimator, fused tensor-core channel filter + discriminator "
+                           "(AGC elided), tensor-core pilot / low-pass FIRs, scans (modes 1)" if mode else
                            "reference order everywhere (modes 0)"),
                buckets=table)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
