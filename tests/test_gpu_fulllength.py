@@ -121,7 +121,7 @@ def test_config5_weak_signal_sweep_vs_faithful_reference(orc_fm, mode):
             eng.set_decimator_mode(mode)
             eng.set_scan_mode(mode)
             eng.set_fir_mode(mode)
-    eng.set_demod_mode(mode)
+            eng.set_demod_mode(mode)
             for i, c in enumerate(chans):
                 eng.set_blend_mode(c % 3, i)
             audio, groups, status, _ = run_engine_chunks(eng, np.stack([x[0] for x in cpu]), nblk, chunk)
