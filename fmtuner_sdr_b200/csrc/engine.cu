@@ -93,7 +93,7 @@ struct fmgpu_engine {
   uint8_t *dIq = nullptr, *dHistIq = nullptr;
   int *dHistValid = nullptr;
   float2 *dX1 = nullptr, *dX2 = nullptr, *dY = nullptr, *dRing = nullptr;
-  float *dR171 = nullptr;  // MPX resampled to 171 kHz (RDS branch), one call at a time
+  float *dR171 = nullptr;  // MPX resampled to 171 kHz (RDS branch): two buffers, by block parity
   size_t r171Pitch = 0;
   float *dMpx = nullptr, *dPilot = nullptr, *dLraw = nullptr, *dRraw = nullptr, *dLf = nullptr,
         *dRf = nullptr, *dAudio = nullptr, *dRdsHist = nullptr, *dMonoHist = nullptr;
@@ -105,6 +105,7 @@ struct fmgpu_engine {
   StereoState *dStereo = nullptr;
   AudioState *dAudioSt = nullptr;
   RdsState *dRds = nullptr;
+  RdsRsState *dRdsRs = nullptr;  // 171 kHz resampler bookkeeping (apart from RdsState, see engine.h)
   fmgpu_rds_group *dGroups = nullptr;
   fmgpu_block_status *dStatus = nullptr;
   uint32_t *dNAudio = nullptr, *dNGroups = nullptr;
@@ -129,7 +130,7 @@ struct fmgpu_engine {
   // block q - K + 1: they are the last readers of that slot (its tail is their halo).
   enum Stage {
     ST_H2D = 0, ST_DECIM, ST_DC, ST_CHAN, ST_AGC, ST_FD, ST_PILOT, ST_STEREO, ST_LPF, ST_AF, ST_RDS,
-    ST_D2H, ST_COUNT
+    ST_D2H, ST_RDSRS /* MPX -> 171 kHz, one block ahead of the RDS demodulator */, ST_COUNT
   };
   struct Pipe {
     cudaStream_t st[ST_COUNT] = {};   // the streams as created
@@ -577,7 +578,7 @@ void stageRds(fmgpu_engine *e, fmgpu_rds_group *groups, uint32_t gcap, fmgpu_blo
   (void)blk_len;
   launchRds(e->dMpx, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRing, e->dRdsBank, e->dRdsLpf,
             e->dMf, e->dDmf, e->dR171, e->r171Pitch, max171(e, n), e->dBits,
-            static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, s);
+            static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, RdsRsRef{e->dRdsRs, 0}, s);
   launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords, groups,
                   gcap, status, nblk, nblk, 0, ch0, nch, s);
   e->launches += 1;
@@ -767,9 +768,9 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     // sample into the y row); the AGC and discriminator stages of this block are empty
     cudaStream_t s = P.run[E::ST_CHAN];
     if (stereo) {
-      need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD, E::ST_PILOT, E::ST_STEREO, E::ST_RDS});
+      need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD, E::ST_PILOT, E::ST_STEREO, E::ST_RDS, E::ST_RDSRS});
     } else {
-      need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD, E::ST_RDS, E::ST_AF});
+      need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD, E::ST_RDS, E::ST_RDSRS, E::ST_AF});
     }
     Span sp(e, "chan_demod", s);
     if (carry) {
@@ -813,9 +814,9 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   {
     cudaStream_t s = P.run[E::ST_FD];
     if (stereo) {
-      need(E::ST_FD, {E::ST_AGC}, {E::ST_PILOT, E::ST_STEREO, E::ST_RDS});
+      need(E::ST_FD, {E::ST_AGC}, {E::ST_PILOT, E::ST_STEREO, E::ST_RDS, E::ST_RDSRS});
     } else {
-      need(E::ST_FD, {E::ST_AGC}, {E::ST_RDS, E::ST_AF /* the mono chain reads MPX */});
+      need(E::ST_FD, {E::ST_AGC}, {E::ST_RDS, E::ST_RDSRS, E::ST_AF /* the mono chain reads MPX */});
     }
     if (fusedFilt < 0) {
       Span sp(e, "freqdem", s);
@@ -830,28 +831,44 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
   }
   done(E::ST_FD);
   // ---- RDS branch --------------------------------------------------------------------------
+  // two stages: the 171 kHz resampler (tile kernel) of block q + 1 runs beside the demodulator
+  // (lane kernel) of block q; the 171 kHz rows and their counts are double-buffered by block parity
+  const RdsRsRef rr{e->dRdsRs, static_cast<int>(q & 1)};
+  float *r171 = e->dR171 + static_cast<size_t>(q & 1) * static_cast<size_t>(e->C) * e->r171Pitch;
+  {
+    cudaStream_t s = P.run[E::ST_RDSRS];
+    need(E::ST_RDSRS, {E::ST_FD}, {});
+    if (q >= 2) {
+      cudaStreamWaitEvent(s, ev(E::ST_RDS, q - 2), 0);   // the demodulator is done with this parity's rows
+    }
+    Span sp(e, "rds_resample", s);
+    launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step, 0, 0,
+                  2, 0, rr, s);
+    launchRdsResample(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, rr, e->dRdsBank, r171, e->r171Pitch,
+                      max171(e, N), ch0, nch, e->k, s);
+    launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
+    launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, rr, s);
+    e->launches += 4;
+  }
+  done(E::ST_RDSRS);
   {
     cudaStream_t s = P.run[E::ST_RDS];
-    need(E::ST_RDS, {E::ST_FD}, {});
-    {
-      Span sp(e, "rds_resample", s);  // tile kernel: MPX -> 171 kHz
-      launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step,
-                    e->k.rds_step, 0, 0, 1, first ? 1 : 0, s);
-      launchRdsResample(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, e->dRds, e->dRdsBank, e->dR171,
-                        e->r171Pitch, max171(e, N), ch0, nch, e->k, s);
-    }
+    need(E::ST_RDS, {E::ST_RDSRS}, {});
     {
       Span sp(e, "rds", s);  // lane kernel: 57 kHz mix ... bits
-      launchRdsDemod(e->dRds, e->dRing, e->dRdsLpf, e->dMf, e->dDmf, e->dR171, e->r171Pitch, e->dBits,
-                     static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, s);
+      if (first) {
+        launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step, 0,
+                      0, 3, 1, rr, s);   // the call's group / bit counters
+        e->launches += 1;
+      }
+      launchRdsDemod(e->dRds, e->dRing, e->dRdsLpf, e->dMf, e->dDmf, r171, e->r171Pitch, e->dBits,
+                     static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, rr, s);
     }
     e->launches += 1;
     {
       Span sp(e, "rds_sync", s);  // syndromes at every bit offset + block sync state machine
       launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords,
                       out.groups, out.gcap, status, nb, 1, b, ch0, nch, s);
-      launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
-      launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, s);
       if (last) {
         // the call's group counts, from the stream that owns RdsState::n_groups: the next call's
         // first k_prepare on this stream zeroes it again
@@ -860,7 +877,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
         e->launches += 1;
       }
     }
-    e->launches += 5;
+    e->launches += 1;
   }
   done(E::ST_RDS);
   // ---- audio branch ------------------------------------------------------------------------
@@ -929,7 +946,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       need(E::ST_AF, {E::ST_LPF}, {});
       Span sp(e, "afpost", sAf);
       launchPrepare(e->dAudioSt, e->dRds, status, nb, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
-                    1, 0, 0, first ? 1 : 0, sAf);
+                    1, 0, 0, first ? 1 : 0, RdsRsRef{e->dRdsRs, 0}, sAf);
       const int maxOut = static_cast<int>(std::min<size_t>(
           out.acap, static_cast<size_t>((static_cast<double>(N) * 16777216.0) / e->k.aud_step) + 2));
       launchResample(e->dLf + t0, e->dRf + t0, e->lfPitch, H_LF, nullptr, 0, out.audio, out.acap,
@@ -940,7 +957,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
         launchAudioIir(out.audio, out.acap, e->dAudioSt, e->dParams, ch0, nch, e->k.dc_a1_af, 0, 1, 0,
                        sAf);
       }
-      launchCommit(e->dAudioSt, e->dRds, ch0, nch, 1, 0, 0, sAf);
+      launchCommit(e->dAudioSt, e->dRds, ch0, nch, 1, 0, 0, RdsRsRef{e->dRdsRs, 0}, sAf);
       e->launches += 4;
     }
   } else {
@@ -949,7 +966,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     need(E::ST_AF, {E::ST_FD}, {});
     Span sp(e, "mono", sAf);
     launchPrepare(e->dAudioSt, e->dRds, status, nb, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step,
-                  0, 1, 0, first ? 1 : 0, sAf);
+                  0, 1, 0, first ? 1 : 0, RdsRsRef{e->dRdsRs, 0}, sAf);
     const int maxOut = static_cast<int>(std::min<size_t>(
         out.acap, static_cast<size_t>((static_cast<double>(N) * 16777216.0) / e->k.aud_step) + 2));
     launchResample(e->dMpx + t0, nullptr, e->mpxPitch, H_MPX, e->dMonoHist, 32, out.audio, out.acap,
@@ -958,7 +975,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
                    sAf);
     launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dMonoHist, 32, AUD_RS_LEN - 1, N, ch0, nch,
                    sAf);
-    launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 1, 0, sAf);
+    launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 1, 0, RdsRsRef{e->dRdsRs, 0}, sAf);
     e->launches += 5;
   }
   if (last) {
@@ -1385,7 +1402,9 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
   CKC(devAlloc(&e->dRf, C * e->lfPitch));
   CKC(devAlloc(&e->dAudio, C * 2 * e->acap));
   e->r171Pitch = roundUp(static_cast<size_t>(max171(e, static_cast<int>(e->nmax))) + 32, 32);
-  CKC(devAlloc(&e->dR171, C * e->r171Pitch));
+  CKC(devAlloc(&e->dR171, 2 * C * e->r171Pitch));
+  CKC(devAlloc(&e->dRdsRs, C));
+  CKC(cudaMemset(e->dRdsRs, 0, C * sizeof(RdsRsState)));
   CKC(devAlloc(&e->dRing, C * RDS_RING));
   CKC(devAlloc(&e->dRdsHist, C * 32));
   CKC(devAlloc(&e->dMonoHist, C * 32));
@@ -1474,7 +1493,7 @@ void fmgpu_engine_destroy(fmgpu_engine *e) {
                   e->dDemod,   e->dStereo, e->dAudioSt, e->dRds,    e->dGroups,  e->dStatus,
                   e->dNAudio,  e->dNGroups, e->dBits, e->dHistValid, e->dWords, e->dBitEnd,
                   e->dAudio2,  e->dGroups2, e->dStatus2, e->dNAudio2, e->dNGroups2, e->dR171,
-                  e->dDecB,    e->dDecOffs, e->dPilB, e->dAudB};
+                  e->dDecB,    e->dDecOffs, e->dPilB, e->dAudB, e->dRdsRs};
   for (auto &f : e->filters) {
     if (f.dB) {
       cudaFree(f.dB);
@@ -2279,7 +2298,7 @@ static size_t demodCommon(fmgpu_engine *e, int channel, const uint8_t *iq_u8, co
   }
   if (mono_out) {
     launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                  e->k.rds_step, 0, 1, 0, 1, s);
+                  e->k.rds_step, 0, 1, 0, 1, RdsRsRef{e->dRdsRs, 0}, s);
   }
   stageDemod(e, iq_u8 ? e->dIq : nullptr, e->iqPitch, nullptr, 1, ni, ni, channel, 1, s);
   if (mpx_out) {
@@ -2289,7 +2308,7 @@ static size_t demodCommon(fmgpu_engine *e, int channel, const uint8_t *iq_u8, co
   size_t produced = 0;
   if (mono_out) {
     stageMono(e, ni, 0, 0, channel, 1, s);
-    launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, s);
+    launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, RdsRsRef{e->dRdsRs, 0}, s);
     AudioState a{};
     cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
@@ -2325,9 +2344,9 @@ size_t fmgpu_downsample_mono(fmgpu_engine *e, int channel, const float *mpx, flo
   cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
                   n * sizeof(float), cudaMemcpyHostToDevice, s);
   launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                e->k.rds_step, 0, 1, 0, 1, s);
+                e->k.rds_step, 0, 1, 0, 1, RdsRsRef{e->dRdsRs, 0}, s);
   stageMono(e, ni, 0, 0, channel, 1, s);
-  launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, s);
+  launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 1, 0, RdsRsRef{e->dRdsRs, 0}, s);
   e->launches += 2;
   AudioState a{};
   cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
@@ -2392,9 +2411,9 @@ size_t fmgpu_afpost(fmgpu_engine *e, int channel, const float *in_left, const fl
   cudaMemcpyAsync(e->dRf + static_cast<size_t>(channel) * e->lfPitch + H_LF, in_right,
                   n_eff * sizeof(float), cudaMemcpyHostToDevice, s);
   launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                e->k.rds_step, 1, 0, 0, 1, s);
+                e->k.rds_step, 1, 0, 0, 1, RdsRsRef{e->dRdsRs, 0}, s);
   stageAfPost(e, ni, 0, channel, 1, s);
-  launchCommit(e->dAudioSt, e->dRds, channel, 1, 1, 0, 0, s);
+  launchCommit(e->dAudioSt, e->dRds, channel, 1, 1, 0, 0, RdsRsRef{e->dRdsRs, 0}, s);
   cudaMemcpyAsync(&a, e->dAudioSt + channel, sizeof(a), cudaMemcpyDeviceToHost, s);
   cudaStreamSynchronize(s);
   const size_t produced = std::min<size_t>({a.n_out, out_capacity, e->acap});
@@ -2418,9 +2437,9 @@ size_t fmgpu_rds(fmgpu_engine *e, int channel, const float *mpx, size_t n, fmgpu
   cudaMemcpyAsync(e->dMpx + static_cast<size_t>(channel) * e->mpxPitch + H_MPX, mpx,
                   n * sizeof(float), cudaMemcpyHostToDevice, s);
   launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, ni, ni, channel, 1, e->k.aud_step,
-                e->k.rds_step, 0, 0, 1, 1, s);
+                e->k.rds_step, 0, 0, 1, 1, RdsRsRef{e->dRdsRs, 0}, s);
   stageRds(e, e->dGroups, static_cast<uint32_t>(e->gcap), nullptr, 1, ni, ni, channel, 1, s);
-  launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 0, 1, s);
+  launchCommit(e->dAudioSt, e->dRds, channel, 1, 0, 0, 1, RdsRsRef{e->dRdsRs, 0}, s);
   e->launches += 2;
   RdsState r{};
   cudaMemcpyAsync(&r, e->dRds + channel, sizeof(r), cudaMemcpyDeviceToHost, s);

@@ -83,9 +83,19 @@ struct AudioState {   // AFPostProcessor (af_post_processor.h:27-32) + FMDemod m
   uint32_t mono_phase, mono_phase_next, mono_n_out;
 };
 
-struct RdsState {     // redsea SubcarrierSet + BlockStream (subcarrier.hh:38-90, block_sync.hh:67-79)
+// The 171 kHz resampler's bookkeeping lives apart from RdsState: in the block pipeline the resampler
+// of block q + 1 runs beside the demodulator of block q (which holds RdsState in registers and
+// writes all of it back). n171 / the 171 kHz rows are double-buffered by block parity.
+struct RdsRsState {
   uint32_t rs_phase, rs_phase_next;
-  uint32_t n171;      // 171 kHz samples this call will produce
+  uint32_t n171[2];   // 171 kHz samples the block of that parity produces
+};
+struct RdsRsRef {     // by value in kernel parameters
+  RdsRsState *st;
+  int par;
+};
+
+struct RdsState {     // redsea SubcarrierSet + BlockStream (subcarrier.hh:38-90, block_sync.hh:67-79)
   uint32_t theta, dtheta;
   float prev_f0_phase, phase0;
   uint32_t since_reset;

@@ -64,13 +64,18 @@ constexpr int FT_ACC_COLS = FT_LIMBS * FT_NO;              // 160 TMEM columns p
 constexpr int FT_SLOT_COLS = FT_PLANES * 8;                // 24 TMEM columns per sub-chunk slot
 constexpr int FT_BCHUNK = FT_N * 128;                      // bytes of one 128-byte K chunk of B (12 KB)
 constexpr int FT_MAX_KS = 12;
-constexpr int FT_B_BYTES = ((FT_MAX_KS + 3) / 4) * FT_BCHUNK;   // 36 KB
-constexpr int FT_NSTG = 4;                                 // float staging slots (16 KB each)
+constexpr int ftBBytes(int ks) { return ((ks + 3) / 4) * FT_BCHUNK; }   // 12 KB per 128 bytes of K
+constexpr int FT_NSTG_MAX = 4;                             // float staging slots (16 KB each): a launch parameter
+constexpr int FT_NSTG_DEFAULT = 3;
 constexpr int FT_STG_BYTES = FT_ROWS * FT_NO * 4;
 constexpr int FT_HALF = FT_NO / 2;                         // outputs per epilogue warp and tile
 constexpr int FT_OUT_BYTES = 32 * FT_HALF * 4;             // one epilogue warp's staging tile (2 KB)
 constexpr int FT_THREADS = 448;                            // 14 warps
-constexpr size_t FT_SMEM = 1024 + FT_B_BYTES + FT_NSTG * FT_STG_BYTES + 16 * FT_OUT_BYTES + 512;
+// shared memory of a CTA: B image, staging ring, 8 epilogue warps x 2 output tiles, barriers. Kept
+// small (89 .. 117 KB) so that the lane kernels' CTAs stay resident beside it.
+constexpr size_t ftSmemBytes(int ks, int nstg) {
+  return 1024 + ftBBytes(ks) + (size_t)nstg * FT_STG_BYTES + 16 * FT_OUT_BYTES + 512;
+}
 
 struct FirTcParams {
   int tiles_row;      // tiles per row = n_total / 32
@@ -83,6 +88,7 @@ struct FirTcParams {
   float dscale;       // 2^data_shift: samples are quantised to 2^-data_shift
   float out_scale;    // scale / 2^(S + data_shift)
   // complex form (channel filter + discriminator): rows are (channel, {I, Q}) pairs on adjacent lanes
+  int nstg;           // staging slots in use (2 .. FT_NSTG_MAX)
   int nch;            // channels of the call
   float fd_ref;       // discriminator scale 1 / (2 pi kf)
   const float2 *y_prev;   // [c * y_pitch]: the filter output in front of this block (discriminator r_prev)
@@ -158,10 +164,12 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smemAddr(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;
-  const uint32_t sStg = sB + FT_B_BYTES;
-  const uint32_t sOut = sStg + FT_NSTG * FT_STG_BYTES;
+  constexpr int B_BYTES = ((KS + 3) / 4) * FT_BCHUNK;
+  const uint32_t sStg = sB + B_BYTES;
+  const int NSTG = p.nstg;
+  const uint32_t sOut = sStg + NSTG * FT_STG_BYTES;
   const uint32_t sBar = sOut + 16 * FT_OUT_BYTES;
-  const uint32_t barSFull = sBar, barSEmpty = barSFull + 8 * FT_NSTG, barAFull = barSEmpty + 8 * FT_NSTG,
+  const uint32_t barSFull = sBar, barSEmpty = barSFull + 8 * FT_NSTG_MAX, barAFull = barSEmpty + 8 * FT_NSTG_MAX,
                  barAEmpty = barAFull + 8 * RING, barTFull = barAEmpty + 8 * RING,
                  barTEmpty = barTFull + 8 * NACC, sTmem = barTEmpty + 8 * NACC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -177,7 +185,7 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
     }
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < FT_NSTG; i++) {
+    for (int i = 0; i < FT_NSTG_MAX; i++) {
       mbarInit(barSFull + 8 * i, 1);
       mbarInit(barSEmpty + 8 * i, 4);   // one arrival per converter warp
     }
@@ -225,7 +233,7 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
             tmaLoad2d(sStg + stg * FT_STG_BYTES, map, barSFull + 8 * stg, p.in_x0 + FT_NO * (r.t0 + g),
                       r.rt * FT_ROWS);
           }
-          if (++stg == FT_NSTG) {
+          if (++stg == static_cast<uint32_t>(NSTG)) {
             stg = 0;
             use++;
           }
@@ -518,7 +526,7 @@ k_fir_tc(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUt
         if (lane == 0) {
           mbarArrive(barSEmpty + 8 * stg);
         }
-        if (++stg == FT_NSTG) {
+        if (++stg == static_cast<uint32_t>(NSTG)) {
           stg = 0;
           stg_use++;
         }
@@ -683,11 +691,20 @@ static cudaError_t firTcAttrs() {
     for (const void *f : fs) {
       if (attr_err == cudaSuccess) {
         attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(FT_SMEM));
+                                        static_cast<int>(ftSmemBytes(FT_MAX_KS, FT_NSTG_MAX)));
       }
     }
   });
   return attr_err;
+}
+
+// staging depth: FMGPU_FT_NSTG is a measurement override
+static int firTcStages() {
+  static const int n = [] {
+    const char *v = getenv("FMGPU_FT_NSTG");
+    return std::min(FT_NSTG_MAX, std::max(2, v ? atoi(v) : FT_NSTG_DEFAULT));
+  }();
+  return n;
 }
 
 cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
@@ -715,6 +732,8 @@ cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTab
   p.off4 = t.off[2];
   p.dscale = static_cast<float>(std::ldexp(1.0, data_shift));
   p.out_scale = static_cast<float>(std::ldexp(static_cast<double>(job.scale), -(t.shift + data_shift)));
+  p.nstg = firTcStages();
+  const size_t smem = ftSmemBytes(t.ksteps, p.nstg);
   CUtensorMap tm_in[2], tm_out[2];
   for (int s = 0; s < 2; s++) {
     const int ss = s < nsig ? s : 0;
@@ -735,13 +754,13 @@ cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTab
   const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
   switch (t.ksteps) {
     case 5:
-      k_fir_tc<5, 8, 2, false><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      k_fir_tc<5, 8, 2, false><<<grid, FT_THREADS, smem, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
       break;
     case 11:
-      k_fir_tc<11, 14, 1, false><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      k_fir_tc<11, 14, 1, false><<<grid, FT_THREADS, smem, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
       break;
     case 12:
-      k_fir_tc<12, 14, 1, false><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
+      k_fir_tc<12, 14, 1, false><<<grid, FT_THREADS, smem, stream>>>(tm_in[0], tm_in[1], tm_out[0], tm_out[1], bi, p);
       break;
     default:
       return cudaErrorInvalidValue;
@@ -780,6 +799,8 @@ cudaError_t launchChanDemodTc(const float2 *x2, size_t x2_pitch, int in_off, flo
   p.dscale = static_cast<float>(std::ldexp(1.0, data_shift));
   p.out_scale = static_cast<float>(std::ldexp(static_cast<double>(chan_scale), -(t.shift + data_shift)));
   p.nch = nch;
+  p.nstg = firTcStages();
+  const size_t smem = ftSmemBytes(t.ksteps, p.nstg);
   p.fd_ref = fd_ref;
   p.y_prev = y_io + static_cast<size_t>(ch0) * y_pitch + Y_OFF - 1;
   p.y_last = y_io + static_cast<size_t>(ch0) * y_pitch + Y_OFF + n_total - 1;
@@ -800,9 +821,9 @@ cudaError_t launchChanDemodTc(const float2 *x2, size_t x2_pitch, int in_off, flo
   const int grid = std::min(sm_count, p.tiles_total);
   const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
   if (t.ksteps == 4) {
-    k_fir_tc<4, 8, 2, true><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in, tm_in, tm_out, tm_out, bi, p);
+    k_fir_tc<4, 8, 2, true><<<grid, FT_THREADS, smem, stream>>>(tm_in, tm_in, tm_out, tm_out, bi, p);
   } else {
-    k_fir_tc<5, 8, 2, true><<<grid, FT_THREADS, FT_SMEM, stream>>>(tm_in, tm_in, tm_out, tm_out, bi, p);
+    k_fir_tc<5, 8, 2, true><<<grid, FT_THREADS, smem, stream>>>(tm_in, tm_in, tm_out, tm_out, bi, p);
   }
   return cudaGetLastError();
 }

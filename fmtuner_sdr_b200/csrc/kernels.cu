@@ -1374,7 +1374,9 @@ __device__ __forceinline__ uint32_t resampCount(uint32_t phase0, uint32_t step, 
 __global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *status,
                           int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch,
                           uint32_t aud_step, uint32_t rds_step, int do_audio, int do_mono,
-                          int do_rds, int first) {
+                          int do_rds, int first, RdsRsRef rr) {
+  // do_rds: 1 = resampler bookkeeping + (first block of a call) the call's counters; 2 = the
+  // bookkeeping only (resampler stage of the block pipeline); 3 = the counters only (its demodulator stage)
   const int lane = blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= nch) {
     return;
@@ -1406,11 +1408,14 @@ __global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *sta
       }
     }
   }
-  if (do_rds) {
-    RdsState *r = &rds[c];
+  if (do_rds == 1 || do_rds == 2) {
+    RdsRsState *q = &rr.st[c];
     uint32_t nx;
-    r->n171 = resampCount(r->rs_phase, rds_step, n_total, &nx);
-    r->rs_phase_next = nx;
+    q->n171[rr.par] = resampCount(q->rs_phase, rds_step, n_total, &nx);
+    q->rs_phase_next = nx;
+  }
+  if (do_rds == 1 || do_rds == 3) {
+    RdsState *r = &rds[c];
     if (first) {
       r->n_groups = 0;  // groups and bits accumulate over the logical blocks of one call
       r->n_bits = 0;
@@ -1420,7 +1425,7 @@ __global__ void k_prepare(AudioState *au, RdsState *rds, fmgpu_block_status *sta
 }
 
 __global__ void k_commit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
-                         int do_rds) {
+                         int do_rds, RdsRsRef rr) {
   const int lane = blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= nch) {
     return;
@@ -1435,7 +1440,7 @@ __global__ void k_commit(AudioState *au, RdsState *rds, int ch0, int nch, int do
     au[c].out_base += au[c].mono_n_out;
   }
   if (do_rds) {
-    rds[c].rs_phase = rds[c].rs_phase_next;
+    rr.st[c].rs_phase = rr.st[c].rs_phase_next;
   }
 }
 
@@ -1871,7 +1876,7 @@ constexpr int RDS_RS_SPAN = 2 * RDS_RS_OUT + RDS_RS_LEN + 8;
 
 __global__ void __launch_bounds__(128)
 k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restrict__ hist,
-               int hist_pitch, const RdsState *__restrict__ st, const float *__restrict__ g_bank,
+               int hist_pitch, RdsRsRef rr, const float *__restrict__ g_bank,
                float *__restrict__ r171, size_t r_pitch, uint32_t step, int ch0) {
   // Both operands of the 26-tap dot products come from shared memory: the 32 branch rows (128-bit
   // reads) and the input window of the CTA's 512 outputs, filled once with coalesced loads. (Storing
@@ -1882,7 +1887,7 @@ k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__r
   __shared__ __align__(16) float s_bank[32 * RDS_RS_ROW];
   __shared__ float s_x[RDS_RS_SPAN];
   const int c = blockIdx.y + ch0;
-  const uint32_t n171 = st[c].n171;
+  const uint32_t n171 = rr.st[c].n171[rr.par];
   const uint32_t k0 = blockIdx.x * RDS_RS_OUT;
   if (k0 >= n171) {
     return;
@@ -1892,7 +1897,7 @@ k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__r
     const int q = i - br * RDS_RS_ROW;
     s_bank[i] = (q < RDS_RS_LEN) ? g_bank[br * RDS_RS_LEN + q] : 0.0f;
   }
-  const unsigned long long phase = st[c].rs_phase;
+  const unsigned long long phase = rr.st[c].rs_phase;
   const uint32_t k_last = min(n171, k0 + RDS_RS_OUT) - 1;
   const long i_lo = (long)((phase + (unsigned long long)k0 * step) >> 24) - (RDS_RS_LEN - 1);
   const long i_hi = (long)((phase + (unsigned long long)k_last * step) >> 24);
@@ -1959,7 +1964,7 @@ __global__ void __launch_bounds__(32)
 k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring,
       const float *__restrict__ g_lpf, const float *__restrict__ g_mf,
       const float *__restrict__ g_dmf, uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end,
-      int ch0, int nch, EngineConst k) {
+      int ch0, int nch, EngineConst k, RdsRsRef rr) {
   __shared__ float s_lpf[RDS_LPF_LEN + 1];
   __shared__ float s_mf[32 * SS_LEN];
   __shared__ float s_dmf[32 * SS_LEN];
@@ -1983,8 +1988,9 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
   const int c = c0 + min(tl, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
   RdsState s = st[c];
+  const uint32_t my171 = rr.st[c].n171[rr.par];
   {
-    const uint32_t mine = (tl < nrows) ? s.n171 : 0u;
+    const uint32_t mine = (tl < nrows) ? my171 : 0u;
     const uint32_t mx = __reduce_max_sync(0xffffffffu, mine);
     if (threadIdx.x == 0) {
       s_nmax = mx;
@@ -2027,7 +2033,7 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
   }
 
   uint32_t produced = 0;
-  const uint32_t n171 = active ? s.n171 : 0u;
+  const uint32_t n171 = active ? my171 : 0u;
   const int nchunks = (int)((s_nmax + LT - 1) / LT);
   // tile element ii of chunk ck <-> 171 kHz sample ck*LT + ii (rows are padded to whole tiles)
   auto prefetch = [&](int ck) {
@@ -2709,15 +2715,15 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
 void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
                    int nblk, int blk_len, int n_total, int ch0, int nch, uint32_t aud_step,
                    uint32_t rds_step, int do_audio, int do_mono, int do_rds, int first,
-                   cudaStream_t stream) {
+                   RdsRsRef rr, cudaStream_t stream) {
   k_prepare<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, status, status_pitch, nblk, blk_len,
                                                   n_total, ch0, nch, aud_step, rds_step, do_audio,
-                                                  do_mono, do_rds, first);
+                                                  do_mono, do_rds, first, rr);
 }
 
 void launchCommit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
-                  int do_rds, cudaStream_t stream) {
-  k_commit<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, ch0, nch, do_audio, do_mono, do_rds);
+                  int do_rds, RdsRsRef rr, cudaStream_t stream) {
+  k_commit<<<(nch + 127) / 128, 128, 0, stream>>>(au, rds, ch0, nch, do_audio, do_mono, do_rds, rr);
 }
 
 void launchResample(const float *in0, const float *in1, size_t in_pitch, int in_off,
@@ -2762,28 +2768,30 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
 }
 
 void launchRdsResample(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch,
-                       const RdsState *st, const float *bank, float *r171, size_t r_pitch,
+                       RdsRsRef rr, const float *bank, float *r171, size_t r_pitch,
                        int max_171, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
   dim3 grid((max_171 + RDS_RS_OUT - 1) / RDS_RS_OUT, nch);
-  k_rds_resample<<<grid, 128, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch,
+  k_rds_resample<<<grid, 128, 0, stream>>>(mpx, mpx_pitch, hist, hist_pitch, rr, bank, r171, r_pitch,
                                            k.rds_step, ch0);
 }
 
 void launchRdsDemod(RdsState *st, float2 *ring, const float *lpf, const float *mf, const float *dmf,
                     const float *r171, size_t r_pitch, uint8_t *bits_out, uint32_t bits_cap,
-                    uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
+                    uint32_t *bit_end, int ch0, int nch, const EngineConst &k, RdsRsRef rr,
+                    cudaStream_t stream) {
   constexpr size_t smem = 2 * 32 * (LT + 4) * sizeof(float);
   k_rds<<<(nch + 31) / 32, 32, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
-                                              bits_cap, bit_end, ch0, nch, k);
+                                              bits_cap, bit_end, ch0, nch, k, rr);
 }
 
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
                float *r171, size_t r_pitch, int max_171, uint8_t *bits_out, uint32_t bits_cap,
-               uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  launchRdsResample(mpx, mpx_pitch, hist, hist_pitch, st, bank, r171, r_pitch, max_171, ch0, nch, k,
+               uint32_t *bit_end, int ch0, int nch, const EngineConst &k, RdsRsRef rr,
+               cudaStream_t stream) {
+  launchRdsResample(mpx, mpx_pitch, hist, hist_pitch, rr, bank, r171, r_pitch, max_171, ch0, nch, k,
                     stream);
-  launchRdsDemod(st, ring, lpf, mf, dmf, r171, r_pitch, bits_out, bits_cap, bit_end, ch0, nch, k,
+  launchRdsDemod(st, ring, lpf, mf, dmf, r171, r_pitch, bits_out, bits_cap, bit_end, ch0, nch, k, rr,
                  stream);
 }
 

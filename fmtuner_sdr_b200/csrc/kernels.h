@@ -95,9 +95,9 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
 void launchPrepare(AudioState *au, RdsState *rds, fmgpu_block_status *status, int status_pitch,
                    int nblk, int blk_len, int n_total, int ch0, int nch, uint32_t aud_step,
                    uint32_t rds_step, int do_audio, int do_mono, int do_rds, int first,
-                   cudaStream_t stream);
+                   RdsRsRef rr, cudaStream_t stream);
 void launchCommit(AudioState *au, RdsState *rds, int ch0, int nch, int do_audio, int do_mono,
-                  int do_rds, cudaStream_t stream);
+                  int do_rds, RdsRsRef rr, cudaStream_t stream);
 void launchResample(const float *in0, const float *in1, size_t in_pitch, int in_off,
                     const float *hist, int hist_pitch, float *out, size_t acap, const float *bank,
                     int sub_len, uint32_t step, const AudioState *au, int mono, int max_out,
@@ -113,15 +113,17 @@ void launchStoreCounts(const AudioState *au, const RdsState *rds, uint32_t *n_au
 // MPX -> 171 kHz (tile kernel) -> serial demodulator (lane kernel); max_171 >= every channel's
 // n171 of this call, r171 rows padded to whole 32-sample tiles
 void launchRdsResample(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch,
-                       const RdsState *st, const float *bank, float *r171, size_t r_pitch,
+                       RdsRsRef rr, const float *bank, float *r171, size_t r_pitch,
                        int max_171, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
 void launchRdsDemod(RdsState *st, float2 *ring, const float *lpf, const float *mf, const float *dmf,
                     const float *r171, size_t r_pitch, uint8_t *bits_out, uint32_t bits_cap,
-                    uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+                    uint32_t *bit_end, int ch0, int nch, const EngineConst &k, RdsRsRef rr,
+                    cudaStream_t stream);
 void launchRds(const float *mpx, size_t mpx_pitch, const float *hist, int hist_pitch, RdsState *st,
                float2 *ring, const float *bank, const float *lpf, const float *mf, const float *dmf,
                float *r171, size_t r_pitch, int max_171, uint8_t *bits_out, uint32_t bits_cap,
-               uint32_t *bit_end, int ch0, int nch, const EngineConst &k, cudaStream_t stream);
+               uint32_t *bit_end, int ch0, int nch, const EngineConst &k, RdsRsRef rr,
+               cudaStream_t stream);
 void launchBlockSync(const uint8_t *bits, uint32_t bits_cap, const uint32_t *bit_end, RdsState *st,
                      unsigned long long *words, fmgpu_rds_group *groups, uint32_t gcap,
                      fmgpu_block_status *status, int status_pitch, int nblk, int blk0, int ch0,
