@@ -670,6 +670,18 @@ void realign(fmgpu_engine *e) {
   e->headFresh = true;
 }
 
+// Measurement variant (build_variant with -DFMGPU_EXP_SKIP, never the shipped library): leave the
+// main kernel of the stages named in FMGPU_SKIP out of the block pipeline, to see what each one
+// costs the step beside the others. Results are WRONG with any stage skipped.
+#ifdef FMGPU_EXP_SKIP
+static bool expSkip(const char *name) {
+  static const std::string v = getenv("FMGPU_SKIP") ? getenv("FMGPU_SKIP") : "";
+  return v.find(name) != std::string::npos;
+}
+#else
+constexpr bool expSkip(const char *) { return false; }
+#endif
+
 // One logical block (global number q, block b of a call of nb blocks) of channels
 // [ch0, ch0 + nch) through the stage streams of pipe P. iq / stride: this block's bytes.
 void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint64_t q, int b, int nb,
@@ -713,7 +725,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     }
     {
       Span sp(e, "decimate", s);
-      runDecim(e, iq, stride, e->dX1 + t0, N, ch0, nch, s);
+      if (!expSkip("decimate")) runDecim(e, iq, stride, e->dX1 + t0, N, ch0, nch, s);
       launchCarryIq(e->dHistIq, e->dHistValid, iq, stride, static_cast<long>(N) * e->M, ch0, nch, s);
       e->launches += 2;
     }
@@ -735,7 +747,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     }
     if (e->scanMode == 1 && (xcf || decim)) {
       // float input: the two recursions as a warp-shuffle scan (fast arithmetic)
-      launchDcBlockScan(xcf ? xcf : e->dX1 + t0, xcf ? xcfStride : e->pitch, e->dX2 + t0, e->x2Pitch,
+      if (!expSkip("dcblock")) launchDcBlockScan(xcf ? xcf : e->dX1 + t0, xcf ? xcfStride : e->pitch, e->dX2 + t0, e->x2Pitch,
                         e->dDemod, status, nb, N, ch0, nch, e->k.dc_a1_iq, s);
     } else if (xcf) {
       // complex-float input at the DSP rate (FMDemod::processSplitComplex): read in place
@@ -779,7 +791,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       e->launches += 2;
     }
     const auto &f = e->filters[fusedFilt];
-    const cudaError_t err =
+    const cudaError_t err = expSkip("chan_demod") ? cudaSuccess :
         launchChanDemodTc(e->dX2 + t0, e->x2Pitch, H_X2, e->dY + t0, e->yPitch, e->dMpx + t0, e->mpxPitch,
                           H_MPX, N, ch0, nch, f.scale, e->k.fd_ref, f.tc, f.dB, 21, e->smCount, s);
     if (err != cudaSuccess) {
@@ -844,7 +856,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
     Span sp(e, "rds_resample", s);
     launchPrepare(e->dAudioSt, e->dRds, nullptr, 1, 1, N, N, ch0, nch, e->k.aud_step, e->k.rds_step, 0, 0,
                   2, 0, rr, s);
-    launchRdsResample(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, rr, e->dRdsBank, r171, e->r171Pitch,
+    if (!expSkip("rds_resample")) launchRdsResample(e->dMpx + t0, e->mpxPitch, e->dRdsHist, 32, rr, e->dRdsBank, r171, e->r171Pitch,
                       max171(e, N), ch0, nch, e->k, s);
     launchSaveTail(e->dMpx + t0, e->mpxPitch, H_MPX, e->dRdsHist, 32, RDS_HIST, N, ch0, nch, s);
     launchCommit(e->dAudioSt, e->dRds, ch0, nch, 0, 0, 1, rr, s);
@@ -861,13 +873,13 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
                       0, 3, 1, rr, s);   // the call's group / bit counters
         e->launches += 1;
       }
-      launchRdsDemod(e->dRds, e->dRing, e->dRdsLpf, e->dMf, e->dDmf, r171, e->r171Pitch, e->dBits,
+      if (!expSkip("rds_demod")) launchRdsDemod(e->dRds, e->dRing, e->dRdsLpf, e->dMf, e->dDmf, r171, e->r171Pitch, e->dBits,
                      static_cast<uint32_t>(e->bitsCap), e->dBitEnd, ch0, nch, e->k, rr, s);
     }
     e->launches += 1;
     {
       Span sp(e, "rds_sync", s);  // syndromes at every bit offset + block sync state machine
-      launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords,
+      if (!expSkip("rds_sync")) launchBlockSync(e->dBits, static_cast<uint32_t>(e->bitsCap), e->dBitEnd, e->dRds, e->dWords,
                       out.groups, out.gcap, status, nb, 1, b, ch0, nch, s);
       if (last) {
         // the call's group counts, from the stream that owns RdsState::n_groups: the next call's
@@ -898,7 +910,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       j.Lp = e->pilLp;
       j.scale = 1.0f;
       j.ch0 = ch0;
-      runFirReal(e, j, 1, nch, e->pilParam, e->pilTcOk, e->pilTc, e->dPilB, 22, s);
+      if (!expSkip("pilot_fir")) runFirReal(e, j, 1, nch, e->pilParam, e->pilTcOk, e->pilTc, e->dPilB, 22, s);
       e->launches += 1;
     }
     done(E::ST_PILOT);
@@ -911,7 +923,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
         launchCarryF32(e->dRraw, e->lrPitch, H_LR, ringEnd, ch0, nch, s);
         e->launches += 2;
       }
-      launchStereo(e->dMpx + t0, e->mpxPitch, e->dPilot + t0, e->pitch, e->dLraw + t0, e->dRraw + t0,
+      if (!expSkip("stereo_pll")) launchStereo(e->dMpx + t0, e->mpxPitch, e->dPilot + t0, e->pitch, e->dLraw + t0, e->dRraw + t0,
                    e->lrPitch, e->dStereo, e->dParams, status, nb, 1, N, N, ch0, nch, e->k, s);
       e->launches += 1;
     }
@@ -938,7 +950,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
       j.Lp = e->audLp;
       j.scale = e->k.aud_scale;
       j.ch0 = ch0;
-      runFirReal(e, j, 2, nch, e->audParam, e->audTcOk, e->audTc, e->dAudB, 20, s);
+      if (!expSkip("audio_lpf")) runFirReal(e, j, 2, nch, e->audParam, e->audTcOk, e->audTc, e->dAudB, 20, s);
       e->launches += 1;
     }
     done(E::ST_LPF);
@@ -949,7 +961,7 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
                     1, 0, 0, first ? 1 : 0, RdsRsRef{e->dRdsRs, 0}, sAf);
       const int maxOut = static_cast<int>(std::min<size_t>(
           out.acap, static_cast<size_t>((static_cast<double>(N) * 16777216.0) / e->k.aud_step) + 2));
-      launchResample(e->dLf + t0, e->dRf + t0, e->lfPitch, H_LF, nullptr, 0, out.audio, out.acap,
+      if (!expSkip("afpost")) launchResample(e->dLf + t0, e->dRf + t0, e->lfPitch, H_LF, nullptr, 0, out.audio, out.acap,
                      e->dAudBank, AUD_RS_LEN, e->k.aud_step, e->dAudioSt, 0, maxOut, ch0, nch, sAf);
       if (e->scanMode == 1) {
         launchAudioIirScan(out.audio, out.acap, e->dAudioSt, e->dParams, ch0, nch, e->k.dc_a1_af, 1, sAf);
