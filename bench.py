@@ -705,13 +705,14 @@ TILE_STAGES = ("decimate", "chanfir", "chan_demod", "freqdem", "pilot_fir", "aud
 LANE_STAGES = ("dcblock", "agc", "stereo_pll", "rds", "rds_sync")
 
 # DRAM bytes per DSP-rate sample (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu
-# --set full): decimate (tensor-core kernel) from profiles/r02_decim_tc_ncu.csv (commit "decim_tc:
-# elected-lane MMA issue"), decimate_fp32 and the others from the round-1 captures of the same
-# kernels (profiles/r01_top_kernels_ncu_default_10000ch.csv, r01_top_kernels_ncu.csv).
+# --set full).
 NCU_TRAFFIC_BYTES_PER_SAMPLE = {
-    "decimate": 27.7, "decimate_fp32": 27.8, "chanfir": 15.6, "pilot_fir": 7.6, "audio_lpf": 15.6,
-    "stereo_pll": 15.7, "dcblock": 12.1, "agc": 10.7, "freqdem": 9.3, "rds": 2.9, "rds_resample": 4.2,
-    "afpost": 9.5,
+    # fast flavour: profiles/r02_top_kernels_ncu.csv (the round-2 final capture, 81.92 M samples per launch)
+    "decimate": 29.0, "chan_demod": 11.9, "pilot_fir": 8.0, "audio_lpf": 15.8, "stereo_pll": 15.7,
+    "dcblock": 15.5, "rds": 3.0, "rds_resample": 6.5, "afpost": 10.7,
+    # reference-order flavour: the round-1 captures of the same FP32 kernels
+    "decimate_fp32": 27.8, "chanfir": 15.6, "pilot_fir_fp32": 7.6, "audio_lpf_fp32": 15.6, "agc": 10.7,
+    "freqdem": 9.3,
 }
 
 
@@ -738,7 +739,8 @@ def stage_figures(stage: str, stage_ms: float, C: int, B: int, peak_hbm: float, 
         # tensor-core forms (fir_tc.cu): the FP32 pipe is out of the picture, HBM is the roof
         "pilot_fir": (4.0 * n + 4.0 * n, 2.0 * 305 * n, "hbm" if decim_mode == "tc" else "fp32"),
         "audio_lpf": (8.0 * n + 8.0 * n, 2.0 * 2 * 121 * n, "hbm" if decim_mode == "tc" else "fp32"),
-        "rds_resample": (4.0 * n + 4.0 * n * 171.0 / 240.0, 2.0 * 26 * n * 171.0 / 240.0, "fp32"),
+        # bound by the shared-memory pipe (per-output branch rows + unaligned windows: one read per FMA)
+        "rds_resample": (4.0 * n + 4.0 * n * 171.0 / 240.0, 2.0 * 26 * n * 171.0 / 240.0, "lsu"),
         "afpost": (8.0 * n + 8.0 * n * 32.0 / 240.0, 2.0 * 2 * 24 * n * 32.0 / 240.0, "hbm"),
         "freqdem": (8.0 * n + 4.0 * n, 30.0 * n, "hbm"),
         "stereo_pll": (8.0 * n + 8.0 * n, 75.0 * n, "latency"),
@@ -751,7 +753,9 @@ def stage_figures(stage: str, stage_ms: float, C: int, B: int, peak_hbm: float, 
         return {"kernel": stage, "launch_ms": launch_ms}
     t = launch_ms * 1e-3
     gbs, tf = alg[0] / t / 1e9, alg[1] / t / 1e12
-    key = "decimate_fp32" if (stage == "decimate" and decim_mode != "tc") else stage
+    key = stage
+    if decim_mode != "tc" and stage in ("decimate", "pilot_fir", "audio_lpf"):
+        key = stage + "_fp32"
     traffic = NCU_TRAFFIC_BYTES_PER_SAMPLE.get(key)
     out = {"kernel": stage, "bound": alg[2], "launch_ms": launch_ms, "launches_per_step": B,
            "algorithmic_bytes": alg[0], "hbm_gbs": gbs, "hbm_frac": gbs / peak_hbm,
@@ -759,6 +763,16 @@ def stage_figures(stage: str, stage_ms: float, C: int, B: int, peak_hbm: float, 
            "traffic": traffic * n if traffic is not None else None}
     if alg[2] == "latency":
         out["lane_steps_per_s"] = n / t
+    if alg[2] == "lsu":
+        # algorithmic shared-memory wavefronts of the resampler: per warp of 32 outputs, 26 32-bit window
+        # reads (one wavefront each when conflict-free) + 7 128-bit branch-row reads (four wavefronts
+        # each); roof = one wavefront per SM and clock (148 SMs at the run's SM clock)
+        outs = n * 171.0 / 240.0
+        wf = outs / 32.0 * (26 + 7 * 4)
+        peak = 148 * 1.965e9
+        out["lsu_gwavefronts_s"] = wf / t / 1e9
+        out["lsu_peak_gwavefronts_s"] = peak / 1e9
+        out["lsu_frac"] = wf / t / peak
     return out
 
 
@@ -772,6 +786,11 @@ def roofline_record(acc: dict, C: int, B: int, fp32_peak: float, decim_mode: str
     if d["bound"] == "hbm":
         top = {"bound": "hbm", "achieved": d["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s",
                "frac": d["hbm_frac"], "peak_source": hbm_how}
+    elif d["bound"] == "lsu":
+        top = {"bound": "lsu", "achieved": d["lsu_gwavefronts_s"], "peak": d["lsu_peak_gwavefronts_s"],
+               "unit": "G shared-memory wavefronts/s", "frac": d["lsu_frac"],
+               "peak_source": "148 SMs x 1 wavefront per clock x 1.965 GHz (ncu of the same kernel: "
+                              "l1tex LSU data pipe 95 % busy, profiles/r02_top_kernels_ncu.csv)"}
     else:
         top = {"bound": "fp32", "achieved": d["fp32_tflops"], "peak": fp32_peak, "unit": "TFLOP/s",
                "frac": d["fp32_frac"],
