@@ -795,10 +795,13 @@ void launchBlock(fmgpu_engine *e, fmgpu_engine::Pipe &P, int ch0, int nch, uint6
         launchChanDemodTc(e->dX2 + t0, e->x2Pitch, H_X2, e->dY + t0, e->yPitch, e->dMpx + t0, e->mpxPitch,
                           H_MPX, N, ch0, nch, f.scale, e->k.fd_ref, f.tc, f.dB, 21, e->smCount, s);
     if (err != cudaSuccess) {
+      // refused before anything was launched (alignment, pitch): the three-kernel path takes the block
       e->lastError = std::string("tensor-core channel filter + discriminator: ") + cudaGetErrorString(err);
+      fusedFilt = -1;
     }
     e->launches += 1;
-  } else {
+  }
+  if (fusedFilt < 0) {
     cudaStream_t s = P.run[E::ST_CHAN];
     need(E::ST_CHAN, {E::ST_DC}, {E::ST_AGC, E::ST_FD});
     Span sp(e, "chanfir", s);
