@@ -1371,6 +1371,10 @@ int fmgpu_engine_create(const fmgpu_config *cfg, int n_channels, int device, fmg
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) {
       e->smCount = sms;
     }
+    e->k.sm_rot = e->smCount;
+    if (const char *sr = getenv("FMGPU_STEREO_ROT")) {   // measurement override: 0 = no rotation
+      e->k.sm_rot = atoi(sr);
+    }
     if (e->M > 1 && decimTcSupported(e->M, e->decL, e->N)) {
       std::vector<uint8_t> bimg;
       std::vector<int32_t> offs;

@@ -157,6 +157,8 @@ struct EngineConst {
   uint32_t rds_dtheta0;
   float rds_pll_alpha, rds_pll_beta;
   float ss_b0, ss_a1, ss_rate_adj;
+  // k_stereo: CTAs b, b + sm_rot, b + 2 sm_rot ... share an SM and rotate their warp roles (0 = off)
+  int sm_rot;
 };
 
 }  // namespace fmgpu

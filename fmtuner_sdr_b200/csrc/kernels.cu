@@ -1043,7 +1043,10 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   float *t_l = t_tgt + 2 * TS;      // 2: matrix -> mover
   float *t_r = t_l + 2 * TS;        // 2
   const int lane = threadIdx.x & 31;
-  const int role = threadIdx.x >> 5;  // 0 mover + blend + matrix, 1 PLL + envelopes, 2/3 target
+  // 0 mover + blend + matrix, 1 PLL + envelopes, 2/3 target. Warp w of a CTA sits on SM sub-partition
+  // w % 4, and the PLL role is the one that sets the pace: the CTAs that share an SM (block b, b + the
+  // SM count, ...) rotate the roles, so that their PLL warps land on different schedulers.
+  const int role = ((threadIdx.x >> 5) + (k.sm_rot > 0 ? (int)blockIdx.x / k.sm_rot : 0)) & 3;
   const int c0 = ch0 + blockIdx.x * 32;
   const int nrows = min(32, ch0 + nch - c0);
   const bool active = lane < nrows;
