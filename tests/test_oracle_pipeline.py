@@ -228,3 +228,23 @@ def test_agc_only_scales_the_discriminator_input(orc_libm, mode):
     on = orc.Channel(orc_libm, orc.make_config(dsp_agc=mode)).process(iq, debug=True)
     assert np.abs(off.mpx - on.mpx).max() < 2e-6
     assert np.abs(off.left - on.left).max() < 2e-6 and np.abs(off.right - on.right).max() < 2e-6
+
+
+@pytest.mark.parametrize("snr", [12.0, 25.0])
+def test_agc_elision_is_invisible_to_the_reference_itself(snr):
+    """The fused channel filter + discriminator of the engine's fast flavour (fmgpu_set_demod_mode 1)
+    leaves the pre-discriminator AGC out. Justification on the reference's OWN code (libfmref.so when
+    /root/reference was present at build time, else the libm restatement that equals it): FMDemod with
+    dsp_agc fast against dsp_agc off on weak, noisy channels — the multiplex agrees to one float ulp
+    and the RDS groups are the same; the audio moves by ~2e-5, which is what one ulp of MPX does to
+    the pilot PLL and blend, i.e. the reference's own sensitivity to rounding."""
+    lib = orc.OracleLib("ref") if orc.OracleLib.have_ref("ref") else orc.OracleLib("libm")
+    sig = orc.config3_signal(7, fs_iq=2_400_000)
+    sig.snr_db = snr
+    iq = sig.generate(24 * 8192 * 10)
+    off = orc.Channel(lib, orc.make_config(dsp_agc=0)).process(iq, debug=True)
+    on = orc.Channel(lib, orc.make_config(dsp_agc=1)).process(iq, debug=True)
+    assert np.abs(off.mpx - on.mpx).max() <= 2.4e-7
+    assert len(on.groups) >= 4 and len(on.groups) == len(off.groups)
+    assert all((on.groups[k] == off.groups[k]).all() for k in ("a", "b", "c", "d", "errors"))
+    assert np.abs(off.left - on.left).max() <= 1e-4 and np.abs(off.right - on.right).max() <= 1e-4
