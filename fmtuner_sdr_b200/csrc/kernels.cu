@@ -114,15 +114,13 @@ __device__ __forceinline__ float ncoPhaseDev(uint32_t theta) {
 }
 
 __device__ __forceinline__ float unwrapDev(float p) {
+  // branch-free (the if / else form compiled to a BSSY / BRA / BSYNC region per call, fourteen of
+  // them per sample group of k_rds); same values: each candidate is one IEEE addition
   const float kPi = 3.14159265358979323846f;
   const float k2Pi = 2.f * kPi;
-  if (p > kPi) {
-    return p - k2Pi;
-  }
-  if (p < -kPi) {
-    return p + k2Pi;
-  }
-  return p;
+  const float down = p - k2Pi;
+  const float up = p + k2Pi;
+  return (p > kPi) ? down : ((p < -kPi) ? up : p);
 }
 
 // Packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): acc.x = fma(h, x.x, acc.x) and
