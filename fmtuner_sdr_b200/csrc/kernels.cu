@@ -199,6 +199,20 @@ __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_
 template <int N> __device__ __forceinline__ void cpAsyncWait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// 128-bit shared-memory accesses through a 32-bit shared-window address computed ONCE: through a
+// generic float* the compiler re-derives the CTA's shared window base (S2UR SR_CgaCtaId + ULEA) in
+// front of the accesses of every loop iteration — ~20 % of the PLL warp's time in k_stereo.
+__device__ __forceinline__ uint32_t sharedAddr(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float4 ldsF4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stsF4(uint32_t a, const float4 &v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // tile[r][k] <- base[(c0 + r) * pitch + start + k],  r < nrows, k < len, as 16-byte
 // cp.async transfers: start, pitch and the row pitch TP are multiples of 4 floats; len is
@@ -272,6 +286,61 @@ __device__ __forceinline__ void tileStore(const float *tile, float *base, size_t
     const int r = idx / cpr;
     const int q = idx - r * cpr;
     const float4 v = *reinterpret_cast<const float4 *>(tile + r * TP + 4 * q);
+    *reinterpret_cast<float4 *>(base + (size_t)(c0 + r) * pitch + start + 4 * q) = v;
+  }
+}
+
+// The same tile movers on a 32-bit shared-window byte address (see sharedAddr): no generic -> shared
+// conversion per transfer.
+__device__ __forceinline__ void cpAsync16S(uint32_t saddr, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync4S(uint32_t saddr, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gmem) : "memory");
+}
+template <int TP, int FULL>
+__device__ __forceinline__ void tileLoadAsyncS(uint32_t tile, const float *base, size_t pitch, int c0,
+                                               int nrows, long start, int len, int lane) {
+  if (len == FULL) {
+    constexpr int cpr = (FULL + 3) / 4;
+    const int total = nrows * cpr;
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
+      const int r = idx / cpr;
+      const int q = idx - r * cpr;
+      cpAsync16S(tile + 4u * (r * TP + 4 * q), base + (size_t)(c0 + r) * pitch + start + 4 * q);
+    }
+    return;
+  }
+  const int cpr = (len + 3) >> 2;  // 16-byte chunks per row
+  const int total = nrows * cpr;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / cpr;
+    const int q = idx - r * cpr;
+    cpAsync16S(tile + 4u * (r * TP + 4 * q), base + (size_t)(c0 + r) * pitch + start + 4 * q);
+  }
+}
+template <int TP, int LEN>
+__device__ __forceinline__ void tileLoadAsync4S(uint32_t tile, const float *base, size_t pitch, int c0,
+                                                int nrows, long start, int len, int lane) {
+  const int total = nrows * LEN;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / LEN;
+    const int q = idx - r * LEN;
+    if (q < len) {
+      cpAsync4S(tile + 4u * (r * TP + q), base + (size_t)(c0 + r) * pitch + start + q);
+    }
+  }
+}
+template <int TP, int FULL>
+__device__ __forceinline__ void tileStoreS(uint32_t tile, float *base, size_t pitch, int c0, int nrows,
+                                           long start, int len, int lane) {
+  const int cpr = (len == FULL) ? (FULL + 3) / 4 : (len + 3) >> 2;
+  const int total = nrows * cpr;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / cpr;
+    const int q = idx - r * cpr;
+    const float4 v = ldsF4(tile + 4u * (r * TP + 4 * q));
     *reinterpret_cast<float4 *>(base + (size_t)(c0 + r) * pitch + start + 4 * q) = v;
   }
 }
@@ -1040,6 +1109,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   float *t_tgt = t_s2 + 2 * TS;     // 2: target -> matrix
   float *t_l = t_tgt + 2 * TS;      // 2: matrix -> mover
   float *t_r = t_l + 2 * TS;        // 2
+  const uint32_t sm_base = sharedAddr(sm_st);   // byte address of sm_st in the shared window
+  auto sa = [&](const float *p) { return sm_base + 4u * static_cast<uint32_t>(p - sm_st); };
   const int lane = threadIdx.x & 31;
   // 0 mover + blend + matrix, 1 PLL + envelopes, 2/3 target. Warp w of a CTA sits on SM sub-partition
   // w % 4, and the PLL role is the one that sets the pace: the CTAs that share an SM (block b, b + the
@@ -1079,8 +1150,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   const int nchunks = (n_total + ST - 1) / ST;
   auto clen = [&](int ck) { return min(ST, n_total - ck * ST); };
   if (role == 0 && nchunks > 0) {
-    tileLoadAsync<TP, ST>(t_pil, pilot, pilot_pitch, c0, nrows, 0, clen(0), lane);
-    tileLoadAsync<TP, ST>(t_mpx, mpx, mpx_pitch, c0, nrows, H_MPX, clen(0), lane);
+    tileLoadAsyncS<TP, ST>(sa(t_pil), pilot, pilot_pitch, c0, nrows, 0, clen(0), lane);
+    tileLoadAsyncS<TP, ST>(sa(t_mpx), mpx, mpx_pitch, c0, nrows, H_MPX, clen(0), lane);
     cpAsyncCommit();
     cpAsyncWait<0>();
   }
@@ -1094,21 +1165,21 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   for (int kk = 0; kk <= nchunks + 2; kk++) {
     if (role == 0) {
       if (kk + 1 < nchunks) {
-        tileLoadAsync<TP, ST>(t_pil + ((kk + 1) & 1) * TS, pilot, pilot_pitch, c0, nrows,
-                          (long)(kk + 1) * ST, clen(kk + 1), lane);
-        tileLoadAsync<TP, ST>(t_mpx + ((kk + 1) & 1) * TS, mpx, mpx_pitch, c0, nrows,
-                          H_MPX + (long)(kk + 1) * ST, clen(kk + 1), lane);
+        tileLoadAsyncS<TP, ST>(sa(t_pil + ((kk + 1) & 1) * TS), pilot, pilot_pitch, c0, nrows,
+                               (long)(kk + 1) * ST, clen(kk + 1), lane);
+        tileLoadAsyncS<TP, ST>(sa(t_mpx + ((kk + 1) & 1) * TS), mpx, mpx_pitch, c0, nrows,
+                               H_MPX + (long)(kk + 1) * ST, clen(kk + 1), lane);
       }
       if (kk >= 1 && kk - 1 < nchunks) {
         const int j = kk - 1;
-        tileLoadAsync4<TP, ST>(t_dly + (j & 1) * TS, mpx, mpx_pitch, c0, nrows,
-                               H_MPX + (long)j * ST - k.delay, clen(j), lane);
+        tileLoadAsync4S<TP, ST>(sa(t_dly + (j & 1) * TS), mpx, mpx_pitch, c0, nrows,
+                                H_MPX + (long)j * ST - k.delay, clen(j), lane);
       }
       cpAsyncCommit();
       if (kk >= 3) {
         const int j = kk - 3;
-        tileStore<TP, ST>(t_l + (j & 1) * TS, lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
-        tileStore<TP, ST>(t_r + (j & 1) * TS, rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+        tileStoreS<TP, ST>(sa(t_l + (j & 1) * TS), lraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
+        tileStoreS<TP, ST>(sa(t_r + (j & 1) * TS), rraw, lr_pitch, c0, nrows, H_LR + (long)j * ST, clen(j), lane);
       }
       // ... and, while its copies are in flight, the blend recursion and the L-R matrix
       if (active && kk >= 2 && kk - 2 < nchunks) {
@@ -1131,17 +1202,18 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
           o_r = monoNorm + ((stereoRight - monoNorm) * blend);
         };
         int i = 0;
+        const uint32_t a_td = sa(td), a_c2 = sa(tc2), a_tt = sa(tt), a_tl = sa(tl), a_tr = sa(tr);
         for (; i + 4 <= len; i += 4) {
-          const float4 dv = *reinterpret_cast<const float4 *>(td + i);
-          const float4 cv = *reinterpret_cast<const float4 *>(tc2 + i);
-          const float4 tv = *reinterpret_cast<const float4 *>(tt + i);
+          const float4 dv = ldsF4(a_td + 4u * i);
+          const float4 cv = ldsF4(a_c2 + 4u * i);
+          const float4 tv = ldsF4(a_tt + 4u * i);
           float4 lv, rv;
           matrix(dv.x, cv.x, tv.x, lv.x, rv.x);
           matrix(dv.y, cv.y, tv.y, lv.y, rv.y);
           matrix(dv.z, cv.z, tv.z, lv.z, rv.z);
           matrix(dv.w, cv.w, tv.w, lv.w, rv.w);
-          *reinterpret_cast<float4 *>(tl + i) = lv;
-          *reinterpret_cast<float4 *>(tr + i) = rv;
+          stsF4(a_tl + 4u * i, lv);
+          stsF4(a_tr + 4u * i, rv);
         }
         for (; i < len; i++) {
           matrix(td[i], tc2[i], tt[i], tl[i], tr[i]);
@@ -1159,6 +1231,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
         float *tpb = t_pbm + ro;
         float *tmm = t_mm + ro;
         float *ts2 = t_s2 + ro;
+        const uint32_t a_tp = sa(tp), a_tm = sa(tm), a_tc2 = sa(tc2), a_tf = sa(tf), a_tpb = sa(tpb),
+                       a_tmm = sa(tmm), a_ts2 = sa(ts2);
         // one sample: envelopes with the VCO phase BEFORE this sample's update
         // (stereo_decoder.cpp:176-186), then the PLL step
         auto sample = [&](float pil, float x, float &o_frq, float &o_pbm, float &o_mm, float &o_s2,
@@ -1198,18 +1272,18 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
             // four samples per 128-bit shared-memory access: a lane's row is 16-byte aligned, so a
             // warp's access is conflict-free (the 32-bit form hits 8 banks: 4-way conflicts)
             for (; q + 4 <= run; q += 4, i += 4) {
-              const float4 pv = *reinterpret_cast<const float4 *>(tp + i);
-              const float4 xv = *reinterpret_cast<const float4 *>(tm + i);
+              const float4 pv = ldsF4(a_tp + 4u * i);
+              const float4 xv = ldsF4(a_tm + 4u * i);
               float4 of, ob, om, os, oc;
               sample(pv.x, xv.x, of.x, ob.x, om.x, os.x, oc.x);
               sample(pv.y, xv.y, of.y, ob.y, om.y, os.y, oc.y);
               sample(pv.z, xv.z, of.z, ob.z, om.z, os.z, oc.z);
               sample(pv.w, xv.w, of.w, ob.w, om.w, os.w, oc.w);
-              *reinterpret_cast<float4 *>(tf + i) = of;
-              *reinterpret_cast<float4 *>(tpb + i) = ob;
-              *reinterpret_cast<float4 *>(tmm + i) = om;
-              *reinterpret_cast<float4 *>(ts2 + i) = os;
-              *reinterpret_cast<float4 *>(tc2 + i) = oc;
+              stsF4(a_tf + 4u * i, of);
+              stsF4(a_tpb + 4u * i, ob);
+              stsF4(a_tmm + 4u * i, om);
+              stsF4(a_ts2 + 4u * i, os);
+              stsF4(a_tc2 + 4u * i, oc);
             }
           }
           for (; q < run; q++, i++) {  // ragged ends (a logical block ending inside the tile)
@@ -1322,17 +1396,18 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
           }
           return target;
         };
+        const uint32_t a_s2 = sa(ts2), a_pb = sa(tpb), a_mm = sa(tmm), a_f = sa(tf), a_t = sa(tt);
         for (int i = i0; i < i1; i += 4) {
-          const float4 sv = *reinterpret_cast<const float4 *>(ts2 + i);
-          const float4 bv = *reinterpret_cast<const float4 *>(tpb + i);
-          const float4 mv = *reinterpret_cast<const float4 *>(tmm + i);
-          const float4 fv = *reinterpret_cast<const float4 *>(tf + i);
+          const float4 sv = ldsF4(a_s2 + 4u * i);
+          const float4 bv = ldsF4(a_pb + 4u * i);
+          const float4 mv = ldsF4(a_mm + 4u * i);
+          const float4 fv = ldsF4(a_f + 4u * i);
           float4 tv;
           tv.x = targetOf(sv.x, bv.x, mv.x, fv.x);
           tv.y = targetOf(sv.y, bv.y, mv.y, fv.y);
           tv.z = targetOf(sv.z, bv.z, mv.z, fv.z);
           tv.w = targetOf(sv.w, bv.w, mv.w, fv.w);
-          *reinterpret_cast<float4 *>(tt + i) = tv;
+          stsF4(a_t + 4u * i, tv);
         }
       }
     }
