@@ -123,6 +123,19 @@ __device__ __forceinline__ float unwrapDev(float p) {
   return (p > kPi) ? down : ((p < -kPi) ? up : p);
 }
 
+// a / 57000 without the IEEE-division sequence (its slow-path call sits in a BSSY / BRA / BSYNC
+// region: seven of them per sample group of k_rds): q = a y, r = fma(-q, c, a), q + r y with
+// y = RN(1 / c). Bit-identical to a / 57000.f for every finite float except |a| <= 9.39e-38 and -0
+// (tools/div_const_proof.cpp compares all 4.28e9 of them); its argument here is 57000 x a difference
+// of two NCO phases ((float)uint32 * 2 pi / 2^32): +0 or >= 5.7e-12 in magnitude.
+__device__ __forceinline__ float divBy57000(float a) {
+  constexpr float c = 57000.0f;
+  constexpr float y = 1.0f / c;
+  const float q = __fmul_rn(a, y);
+  const float r = __fmaf_rn(-q, c, a);
+  return __fmaf_rn(r, y, q);
+}
+
 // Packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): acc.x = fma(h, x.x, acc.x) and
 // acc.y = fma(h, x.y, acc.y) in ONE instruction, each half an IEEE round-to-nearest fma, so the
 // result is bit-identical to two fmaf() calls. ptxas folds the {h, h} pair into a scalar
@@ -2159,7 +2172,7 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
 #pragma unroll
       for (int q = 1; q < 8; q++) {
         const float delta = unwrapDev(pn[q] - pn[q - 1]);
-        const float x = (delta * 57000.f) / 57000.f;
+        const float x = divBy57000(delta * 57000.f);
         ph0[q] = x;
       }
 #pragma unroll
@@ -2309,7 +2322,7 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
         const float pnl = ncoPhaseDev(s.theta);
         const float delta = unwrapDev(pnl - s.prev_f0_phase);
         s.prev_f0_phase = pnl;
-        s.phase0 = unwrapDev(s.phase0 + ((delta * 57000.f) / 57000.f));
+        s.phase0 = unwrapDev(s.phase0 + (divBy57000(delta * 57000.f)));
         s.since_reset += (uint32_t)m;
         ii += m;
       }
