@@ -10,7 +10,9 @@
 //
 //   D[channel][(limb, j, iq)] = sum_k A[channel][k] * B[(limb, j, iq)][k]       (tcgen05.mma kind::i8,
 //                                                                               u8 x s8 -> s32 in TMEM)
-//   k = byte offset inside the tile's window, j = 0..7 the tile's outputs, iq = byte parity.
+//   k = byte offset inside the tile's window, j = 0..15 the tile's outputs, iq = byte parity
+//   (N = 128 columns per MMA: sixteen outputs per tile, 28 K-steps for /10 instead of 2 x 23 with
+//   eight-output tiles: 0.60 -> 0.565 ms per launch).
 //
 // The int32 sums are exact; the epilogue recombines the limbs, removes the 127.5 offset in integer
 // arithmetic (255 * sum of the taps that see real samples) and rounds ONCE to float. The result is
@@ -20,9 +22,10 @@
 //
 // One CTA per SM, persistent over (128-channel row tile, time segment) work items:
 //   warp 0     TMA producer: 16 KB chunks (128 rows x 128 B) into a ring of shared-memory slots
-//   warp 1     allocates TMEM, issues the MMAs (one elected lane), frees ring slots with tcgen05.commit
-//   warps 2-5  epilogue: tcgen05.ld the 64 accumulator columns of a tile, recombine, store float2
-// Window of tile t (8 outputs): block-relative bytes [ADV*t - WS0, ADV*t - WS0 + 32*KS), ADV = 16*M,
+//   warp 1     allocates TMEM, copies every chunk into the TMEM A ring (tcgen05.cp) and issues the MMAs
+//              with the A operand in TMEM (one elected lane); tcgen05.commit frees the ring slots
+//   warps 2-5  epilogue: tcgen05.ld the 128 accumulator columns of a tile, recombine, store float2
+// Window of tile t (16 outputs): block-relative bytes [ADV*t - WS0, ADV*t - WS0 + 32*KS), ADV = 32*M,
 // WS0 = roundup(2L - 2, 32); the bytes in front of the block come from the per-channel history
 // buffer (hist tensor map), invalid history is byte 0 and is compensated in the offset term.
 #include <cuda.h>
@@ -46,27 +49,25 @@ namespace {
 using namespace tc;
 
 constexpr int TC_ROWS = 128;          // channels per tile (UMMA M)
-constexpr int TC_NO = 8;              // outputs per tile
+constexpr int TC_NO = 16;             // outputs per tile
 constexpr int TC_LIMBS = 4;
-constexpr int TC_N = TC_NO * 2 * TC_LIMBS;   // 64 accumulator columns (UMMA N)
+constexpr int TC_N = TC_NO * 2 * TC_LIMBS;   // 128 accumulator columns (UMMA N)
 constexpr int TC_CHUNK = 128;         // bytes of K per ring slot row (one 128B swizzle atom)
 constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
-constexpr int TC_B_CHUNKS = 6;        // K extent of B: 6 * 128 = 768 bytes >= 32 * KS
-constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 48 KB
+constexpr int TC_B_CHUNKS = 7;        // K extent of B: 7 * 128 = 896 bytes >= 32 * KS
+constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 112 KB
 // A ring slots of 16 KB in shared memory: TcParams::ring, a launch parameter. With the A operand in
 // shared memory a tile's window touches up to 7 slots (default 10: three in flight); with the A
 // operand in TMEM a slot is free again as soon as its four tcgen05.cp retire, so the ring only covers
 // the TMA latency and the CTA leaves shared memory to the kernels that run beside it.
-constexpr int TC_RING_SMEM_A = 10;
 constexpr int TC_RING_TMEM_A = 5;
-constexpr int TC_RING_MAX = 10;
+constexpr int TC_RING_MAX = 6;
 constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns (A operand from shared memory)
 // A operand from TMEM: columns [0, 256) hold a ring of eight chunks (32 columns = 128 bytes of K
 // per lane), columns [256, 512) four accumulator slots
-constexpr bool TC_ATMEM_DEFAULT = true;
 constexpr int TC_A_SLOTS = 8;
 constexpr int TC_A_COLS = 32;
-constexpr int TC_ACC_TS = 4;
+constexpr int TC_ACC_TS = 2;
 constexpr int TC_THREADS = 192;
 constexpr int TC_SHIFT = 26;          // taps are quantised to 2^-26
 constexpr size_t tcSmemBytes(int ring) { return 1024 + TC_B_BYTES + (size_t)ring * TC_CHUNK_BYTES + 512; }
@@ -98,8 +99,8 @@ __device__ __forceinline__ int windowStart(const TcParams &p, int t) {
   return p.adv * t - p.ws0 + TC_CHUNK * p.halo_chunks;   // >= 0
 }
 
-constexpr int TC_MAX_KSTEPS = 4 * TC_B_CHUNKS;   // 24
-constexpr int TC_WIN_CHUNKS = 7;                 // a 768-byte window starting anywhere touches <= 7 chunks
+constexpr int TC_MAX_KSTEPS = 4 * TC_B_CHUNKS;   // 28
+constexpr int TC_WIN_CHUNKS = 8;                 // an 896-byte window starting at a 32-byte phase touches <= 8 chunks
 
 // The MMAs of one tile, fully unrolled for the window's phase PH (its start inside a chunk, in
 // 32-byte steps): every shared-memory offset is then an immediate. cb[r] / eb[r]: descriptor low
@@ -347,45 +348,50 @@ k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CU
         const uint32_t acc = tile_cnt % NACC;
         mbarWait(barTFull + 8 * acc, (tile_cnt / NACC) & 1);
         tcFenceAfter();
-        int32_t d[TC_N];
         const uint32_t taddr = tmem_base + lane_base + ACC_COL0 + acc * TC_N;
-        tmemLd16(taddr, d);
-        tmemLd16(taddr + 16, d + 16);
-        tmemLd16(taddr + 32, d + 32);
-        tmemLd16(taddr + 48, d + 48);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tcFenceBefore();
-        __syncwarp();
-        if (lane == 0) {
-          mbarArrive(barTEmpty + 8 * acc);
-        }
         const int n0 = (t0 + i) * TC_NO;
-        float2 y[TC_NO];
+        // four outputs at a time: the eight columns (j, iq) of each of the four limbs
+#pragma unroll 1
+        for (int jg = 0; jg < TC_NO / 4; jg++) {
+          int32_t d[TC_LIMBS][8];
 #pragma unroll
-        for (int j = 0; j < TC_NO; j++) {
-          // taps in front of the first real sample multiply byte 0: leave them out of the offset
-          int2 off = off_all;
-          const int missing = need_hist - p.M * (n0 + j) - valid;
-          if (missing > 0) {
-            off = __ldg(offs + min(missing, p.L));
+          for (int l = 0; l < TC_LIMBS; l++) {
+            tmemLd8(taddr + l * (2 * TC_NO) + 8 * jg, d[l]);
           }
-          float v[2];
-#pragma unroll
-          for (int iq = 0; iq < 2; iq++) {
-            const int col = j * 2 + iq;   // column of limb l: l * 16 + col, limb 0 = most significant
-            const int hi = (d[col] << 7) + d[16 + col];
-            const int lo = (d[32 + col] << 7) + d[48 + col];
-            const int ph = 2 * hi - off.x;   // offset term 255 * sum(hq) split the same way
-            const int pl = 2 * lo - off.y;
-            v[iq] = fmaf(static_cast<float>(ph), 16384.0f, static_cast<float>(pl)) * p.out_scale;
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (jg == TC_NO / 4 - 1) {   // the whole accumulator has been read
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) {
+              mbarArrive(barTEmpty + 8 * acc);
+            }
           }
-          y[j] = make_float2(v[0], v[1]);
-        }
-        if (live) {
-          float4 *o4 = reinterpret_cast<float4 *>(out + n0);
+          float2 y[4];
 #pragma unroll
-          for (int j = 0; j < TC_NO; j += 2) {
-            o4[j >> 1] = make_float4(y[j].x, y[j].y, y[j + 1].x, y[j + 1].y);
+          for (int jj = 0; jj < 4; jj++) {
+            const int j = 4 * jg + jj;
+            // taps in front of the first real sample multiply byte 0: leave them out of the offset
+            int2 off = off_all;
+            const int missing = need_hist - p.M * (n0 + j) - valid;
+            if (missing > 0) {
+              off = __ldg(offs + min(missing, p.L));
+            }
+            float v[2];
+#pragma unroll
+            for (int iq = 0; iq < 2; iq++) {
+              const int col = jj * 2 + iq;   // limb 0 = most significant
+              const int hi = (d[0][col] << 7) + d[1][col];
+              const int lo = (d[2][col] << 7) + d[3][col];
+              const int ph = 2 * hi - off.x;   // offset term 255 * sum(hq) split the same way
+              const int pl = 2 * lo - off.y;
+              v[iq] = fmaf(static_cast<float>(ph), 16384.0f, static_cast<float>(pl)) * p.out_scale;
+            }
+            y[jj] = make_float2(v[0], v[1]);
+          }
+          if (live) {
+            float4 *o4 = reinterpret_cast<float4 *>(out + n0 + 4 * jg);
+            o4[0] = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+            o4[1] = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
           }
         }
       }
@@ -457,7 +463,7 @@ void decimTcBuildTables(int M, const std::vector<float> &hrev, std::vector<uint8
         // sample i of output j's window is block-relative byte 2 (M (8 t + j) - (L - 1) + i) + iq
         const int k = ws0 + 2 * (M * j - (L - 1) + i) + iq;   // byte inside the tile's window
         for (int l = 0; l < TC_LIMBS; l++) {
-          const int n = l * 16 + j * 2 + iq;
+          const int n = l * (2 * TC_NO) + j * 2 + iq;
           const int kc = k / TC_CHUNK, kk = k % TC_CHUNK;
           const size_t at = static_cast<size_t>(kc) * TC_N * TC_CHUNK + static_cast<size_t>(n) * TC_CHUNK +
                             static_cast<size_t>(((kk >> 4) ^ (n & 7)) << 4) + (kk & 15);
@@ -490,9 +496,8 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
       return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(tcSmemBytes(TC_RING_MAX)));
     };
-    const void *fs[] = {(const void *)k_decim_tc<false, 23>, (const void *)k_decim_tc<false, 18>,
-                        (const void *)k_decim_tc<false, 0>,  (const void *)k_decim_tc<true, 23>,
-                        (const void *)k_decim_tc<true, 18>,  (const void *)k_decim_tc<true, 0>};
+    const void *fs[] = {(const void *)k_decim_tc<true, 28>, (const void *)k_decim_tc<true, 22>,
+                        (const void *)k_decim_tc<true, 0>};
     for (const void *f : fs) {
       if (attr_err == cudaSuccess) {
         attr_err = set(f);
@@ -526,39 +531,24 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
     return cudaErrorInvalidValue;
   }
   const int grid = std::min(sm_count, p.row_tiles * p.n_seg);
-  // FMGPU_TC_ATMEM / FMGPU_TC_RING: measurement overrides (A operand from shared memory; ring depth)
-  static const bool a_from_tmem = [] {
-    const char *v = getenv("FMGPU_TC_ATMEM");
-    return v ? atoi(v) != 0 : TC_ATMEM_DEFAULT;
-  }();
+  // FMGPU_TC_RING: measurement override of the shared-memory ring depth
   static const int ring_slots = [] {
     const char *v = getenv("FMGPU_TC_RING");
-    const int dflt = a_from_tmem ? TC_RING_TMEM_A : TC_RING_SMEM_A;
-    const int r = v ? atoi(v) : dflt;
-    return std::min(TC_RING_MAX, std::max(a_from_tmem ? 2 : 8, r));
+    const int r = v ? atoi(v) : TC_RING_TMEM_A;
+    return std::min(TC_RING_MAX, std::max(2, r));
   }();
   p.ring = ring_slots;
   const size_t smem_bytes = tcSmemBytes(ring_slots);
   const uint4 *bi = reinterpret_cast<const uint4 *>(b_image_dev);
   const int2 *of = reinterpret_cast<const int2 *>(offs_dev);
-#define FMGPU_TC_LAUNCH(AT, KSV)                                                                          \
-  k_decim_tc<AT, KSV><<<grid, TC_THREADS, smem_bytes, stream>>>(tm_iq, tm_hist, bi, of, hist_valid, x1, x1_pitch, p)
-  if (a_from_tmem) {
-    if (p.ksteps == 23) {
-      FMGPU_TC_LAUNCH(true, 23);
-    } else if (p.ksteps == 18) {
-      FMGPU_TC_LAUNCH(true, 18);
-    } else {
-      FMGPU_TC_LAUNCH(true, 0);
-    }
+#define FMGPU_TC_LAUNCH(KSV)                                                                              \
+  k_decim_tc<true, KSV><<<grid, TC_THREADS, smem_bytes, stream>>>(tm_iq, tm_hist, bi, of, hist_valid, x1, x1_pitch, p)
+  if (p.ksteps == 28) {          // /10 at 2.4 MS/s
+    FMGPU_TC_LAUNCH(28);
+  } else if (p.ksteps == 22) {   // /8 at 2.048 MS/s
+    FMGPU_TC_LAUNCH(22);
   } else {
-    if (p.ksteps == 23) {
-      FMGPU_TC_LAUNCH(false, 23);
-    } else if (p.ksteps == 18) {
-      FMGPU_TC_LAUNCH(false, 18);
-    } else {
-      FMGPU_TC_LAUNCH(false, 0);
-    }
+    FMGPU_TC_LAUNCH(0);
   }
 #undef FMGPU_TC_LAUNCH
   return cudaGetLastError();

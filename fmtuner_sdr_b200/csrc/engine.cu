@@ -396,7 +396,7 @@ int fillStateField(fmgpu_engine *e, S *base, size_t fieldOffset, const void *val
 // the decimating FIR of n_out outputs per channel into x1 (history in dHistIq), either flavour
 void runDecim(fmgpu_engine *e, const uint8_t *iq, size_t stride, float2 *x1, int n_out, int ch0,
               int nch, cudaStream_t s) {
-  if (e->decimMode == 1 && e->decimTcOk && n_out % 8 == 0 && (stride & 15u) == 0 &&
+  if (e->decimMode == 1 && e->decimTcOk && n_out % 16 == 0 && (stride & 15u) == 0 &&
       (reinterpret_cast<uintptr_t>(iq) & 15u) == 0) {
     const cudaError_t err =
         launchDecimTc(e->M, e->decL, iq, stride, static_cast<size_t>(n_out) * e->M * 2, e->dHistIq,
