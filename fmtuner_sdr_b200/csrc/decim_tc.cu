@@ -56,15 +56,14 @@ constexpr int TC_CHUNK = 128;         // bytes of K per ring slot row (one 128B 
 constexpr int TC_CHUNK_BYTES = TC_ROWS * TC_CHUNK;   // 16 KB
 constexpr int TC_B_CHUNKS = 7;        // K extent of B: 7 * 128 = 896 bytes >= 32 * KS
 constexpr int TC_B_BYTES = TC_B_CHUNKS * TC_N * TC_CHUNK;   // 112 KB
-// A ring slots of 16 KB in shared memory: TcParams::ring, a launch parameter. With the A operand in
-// shared memory a tile's window touches up to 7 slots (default 10: three in flight); with the A
-// operand in TMEM a slot is free again as soon as its four tcgen05.cp retire, so the ring only covers
-// the TMA latency and the CTA leaves shared memory to the kernels that run beside it.
+// A ring slots of 16 KB in shared memory: TcParams::ring, a launch parameter. The A operand lives in
+// TMEM: a slot is free again as soon as its four tcgen05.cp retire, so the ring only covers the TMA
+// latency (five slots; B takes 112 KB of the CTA's 194 KB).
 constexpr int TC_RING_TMEM_A = 5;
 constexpr int TC_RING_MAX = 6;
-constexpr int TC_ACC = 8;             // TMEM accumulator slots of 64 columns (A operand from shared memory)
-// A operand from TMEM: columns [0, 256) hold a ring of eight chunks (32 columns = 128 bytes of K
-// per lane), columns [256, 512) four accumulator slots
+constexpr int TC_ACC = 2;             // (the form with the A operand in shared memory is not built any more)
+// TMEM: columns [0, 256) hold a ring of eight chunks (32 columns = 128 bytes of K per lane; a tile's
+// window touches up to eight), columns [256, 512) two accumulators of 128 columns
 constexpr int TC_A_SLOTS = 8;
 constexpr int TC_A_COLS = 32;
 constexpr int TC_ACC_TS = 2;
@@ -170,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_decim_tc(const __grid_constant__ CUtensorMap tm_iq, const __grid_constant__ CUtensorMap tm_hist,
            const uint4 *__restrict__ b_image, const int2 *__restrict__ offs, const int *__restrict__ hist_valid,
            float2 *__restrict__ x1, size_t x1_pitch, const TcParams p) {
+  static_assert(ATMEM, "the A operand lives in TMEM: with 16-output tiles B (112 KB) leaves no room for a ten-slot ring");
   constexpr int NACC = ATMEM ? TC_ACC_TS : TC_ACC;
   constexpr uint32_t ACC_COL0 = ATMEM ? TC_A_SLOTS * TC_A_COLS : 0;   // first accumulator column
   extern __shared__ uint8_t smem_raw[];
