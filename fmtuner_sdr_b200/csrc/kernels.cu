@@ -2049,7 +2049,7 @@ k_rds_resample(const float *__restrict__ mpx, size_t mpx_pitch, const float *__r
 // separate mover warp would hold this kernel's 160+ registers per thread a second time for the
 // whole kernel, and what the lane kernels cost the step is the registers and shared memory they
 // keep from the FIR kernels running beside them, not their issue slots.
-__global__ void __launch_bounds__(32)
+__global__ void __maxnreg__(255)
 k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring,
       const float *__restrict__ g_lpf, const float *__restrict__ g_mf,
       const float *__restrict__ g_dmf, uint8_t *bits_out, uint32_t bits_cap, uint32_t *bit_end,
