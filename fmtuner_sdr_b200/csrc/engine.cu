@@ -2629,6 +2629,12 @@ int fmgpu_get_stage_times(fmgpu_engine *e, const char **names, float *ms, int ca
   return n;
 }
 
+size_t fmgpu_fir_tc_host_model(const float *taps, int n_taps, float scale, int data_shift, const float *x,
+                               size_t n_hist, size_t n, float *y) {
+  const int lp = static_cast<int>(roundUp(static_cast<size_t>(std::max(n_taps, 1)), 8));
+  return firTcHostModel(taps, n_taps, lp, scale, data_shift, x, n_hist, n, y);
+}
+
 size_t fmgpu_design_host(const fmgpu_config *cfg, int which, int bw_hz, float *out, size_t cap,
                          float *scale) {
   if (!cfg || cfg->iq_rate < 1 || cfg->decimation < 1) {

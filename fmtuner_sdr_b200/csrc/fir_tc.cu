@@ -768,6 +768,67 @@ cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTab
   return cudaGetLastError();
 }
 
+// Host-only model of the kernel's arithmetic, from the SAME tables the kernel uses (include/fmgpu.h:
+// fmgpu_fir_tc_host_model): every digit is read back out of the B image through the operand layout,
+// the five limb sets are summed in 64-bit integers, and the epilogue's float recombination is
+// repeated operation for operation. The CPU test-suite checks it against a float64 FIR: the table
+// builder, the digit split, the offset limbs and the bound on the result need no GPU to be tested.
+size_t firTcHostModel(const float *taps, int n_taps, int lp, float scale, int data_shift, const float *x,
+                      size_t n_hist, size_t n, float *y) {
+  if (!taps || !x || !y || n_taps < 1 || lp < n_taps || lp > MAX_TAPS || n % FT_NO != 0) {
+    return 0;
+  }
+  std::vector<float> h(static_cast<size_t>(lp), 0.0f);   // reversed, padded in front (engine.cu: padFront)
+  for (int i = 0; i < n_taps; i++) {
+    h[lp - n_taps + i] = taps[n_taps - 1 - i];
+  }
+  FirTcTables t;
+  firTcBuildTables(h.data(), lp, &t);
+  const int ws0 = (t.ksteps - 1) * FT_NO;
+  if (static_cast<size_t>(ws0) > n_hist) {
+    return 0;
+  }
+  const float dscale = static_cast<float>(std::ldexp(1.0, data_shift));
+  const float out_scale = static_cast<float>(std::ldexp(static_cast<double>(scale), -(t.shift + data_shift)));
+  const float *xs = x + n_hist;   // xs[s], s >= -n_hist
+  for (size_t n0 = 0; n0 < n; n0 += FT_NO) {
+    long long D[FT_LIMBS][FT_NO] = {};
+    for (int k = 0; k < t.ksteps * FT_NO; k++) {
+      const float v = xs[static_cast<long>(n0) - ws0 + k];
+      float tq = v * dscale;
+      tq = std::fmin(std::fmax(tq, -8388608.0f), 8388607.0f);
+      const uint32_t q = static_cast<uint32_t>(static_cast<int32_t>(std::nearbyint(tq)) + 8388608);
+      const int kc = k / 128, kk = k % 128;
+      for (int col = 0; col < FT_N; col++) {
+        const size_t at = static_cast<size_t>(kc) * FT_BCHUNK + static_cast<size_t>(col) * 128 +
+                          static_cast<size_t>(((kk >> 4) ^ (col & 7)) << 4) + (kk & 15);
+        const int dg = static_cast<int8_t>(t.b_image[at]);
+        if (dg == 0) {
+          continue;
+        }
+        const int l = col / FT_NO, j = col % FT_NO;
+        for (int a = 0; a < FT_PLANES; a++) {
+          D[a + l][j] += static_cast<long long>((q >> (8 * a)) & 0xffu) * dg;
+        }
+      }
+    }
+    for (int j = 0; j < FT_NO; j++) {
+      for (int s2 = 0; s2 < FT_LIMBS; s2++) {
+        if (D[s2][j] > 2147483647LL || D[s2][j] < -2147483648LL) {
+          return 0;   // an int32 accumulator of the kernel would have overflowed
+        }
+      }
+      float f = static_cast<float>(static_cast<int32_t>(D[4][j]) - t.off[2]);
+      f = std::fmaf(f, 256.0f, static_cast<float>(static_cast<int32_t>(D[3][j]) - t.off[1]));
+      f = std::fmaf(f, 256.0f, static_cast<float>(static_cast<int32_t>(D[2][j]) - t.off[0]));
+      f = std::fmaf(f, 256.0f, static_cast<float>(static_cast<int32_t>(D[1][j])));
+      f = std::fmaf(f, 256.0f, static_cast<float>(static_cast<int32_t>(D[0][j])));
+      y[n0 + j] = f * out_scale;
+    }
+  }
+  return n;
+}
+
 // Channel filter + quadrature discriminator in one kernel (FMDemod::demodulateComplex,
 // /root/reference/src/fm_demod.cpp:194-199): x2 rows (DC-blocked complex samples, halo of in_off
 // samples in front) -> MPX rows. The pre-discriminator AGC between the two (fm_demod.cpp:196-198)

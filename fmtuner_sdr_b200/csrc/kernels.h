@@ -52,6 +52,8 @@ void firTcBuildTables(const float *h, int Lp, FirTcTables *t);
 // (larger values saturate)
 cudaError_t launchFirTc(const FirRealJob &job, int nsig, int nch, const FirTcTables &t,
                         const uint8_t *b_image_dev, int data_shift, int sm_count, cudaStream_t stream);
+size_t firTcHostModel(const float *taps, int n_taps, int lp, float scale, int data_shift, const float *x,
+                      size_t n_hist, size_t n, float *y);
 // channel filter + discriminator fused (complex rows; the AGC between them cannot change the
 // discriminator's output and is left out); see fir_tc.cu
 bool chanTcSupported(const float *h, int Lp, int in_off);

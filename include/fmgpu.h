@@ -318,6 +318,16 @@ size_t fmgpu_get_design(fmgpu_engine *e, int which, int channel, float *out, siz
  * and setBandwidthHz(bw_hz). */
 size_t fmgpu_design_host(const fmgpu_config *cfg, int which, int bw_hz, float *out, size_t cap,
                          float *scale);
+/* HOST-ONLY model of the tensor-core FIR's arithmetic (fmgpu_set_fir_mode 1; fir_tc.cu), evaluated
+ * from the same tables the kernel uses: taps (design order, n_taps of them, padded like the engine
+ * pads them) as 24-bit integers in three signed digits read back out of the operand image, samples as
+ * 24-bit fixed point with quantum 2^-data_shift, 64-bit limb sums, the epilogue's float
+ * recombination. x holds n_hist history samples followed by n samples (n a multiple of 32, n_hist
+ * at least the filter's reach rounded up to 32); y receives n outputs. Returns n, or 0 when the
+ * arguments do not fit or an int32 accumulator of the kernel would have overflowed. Needs no device:
+ * the CPU test-suite uses it to check the table builder and the error bound against a float64 FIR. */
+size_t fmgpu_fir_tc_host_model(const float *taps, int n_taps, float scale, int data_shift, const float *x,
+                               size_t n_hist, size_t n, float *y);
 /* Intermediate device buffers of the last fmgpu_process_* call, copied to the host:
  * which: 0 decimated cf32 (2 floats/sample), 1 MPX, 2 stereo left at the DSP rate,
  * 3 stereo right, 4 pilot band-pass output, 5 / 6 the matrix outputs L / R in front of the 15 kHz
