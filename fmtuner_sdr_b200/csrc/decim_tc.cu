@@ -484,6 +484,58 @@ void decimTcBuildTables(int M, const std::vector<float> &hrev, std::vector<uint8
   }
 }
 
+// Host-only model of the kernel's arithmetic from the SAME tables (include/fmgpu.h:
+// fmgpu_decim_tc_host_model): digits read back out of the B image through the operand layout, exact
+// 64-bit limb sums, the epilogue's integer offset removal and single float rounding. `valid` = real
+// sample pairs in front of the block (the rest of the window is byte 0, as after a reset).
+size_t decimTcHostModel(int M, const std::vector<float> &hrev, float scale, const uint8_t *iq, int valid,
+                        int n_out, float *out) {
+  const int L = static_cast<int>(hrev.size());
+  if (!decimTcSupported(M, L, n_out) || !iq || !out || valid < 0 || valid > L - 1) {
+    return 0;
+  }
+  std::vector<uint8_t> b_image;
+  std::vector<int32_t> offs;
+  decimTcBuildTables(M, hrev, &b_image, &offs);
+  const int ws0 = ((2 * L - 2) + 31) / 32 * 32;
+  const int ksteps = (ws0 + 2 * M * (TC_NO - 1) + 2 + 31) / 32;
+  const int adv = 2 * M * TC_NO;
+  const float out_scale = static_cast<float>(static_cast<double>(scale) / (255.0 * static_cast<double>(1 << TC_SHIFT)));
+  // iq: `valid` pairs of history, then n_out * M pairs; byte b of the block sits at iq[2 * valid + b]
+  auto byteAt = [&](long b) -> int {   // block-relative byte; in front of the history: 0
+    const long at = 2L * valid + b;
+    return at < 0 ? 0 : iq[at];
+  };
+  for (int t = 0; t < n_out / TC_NO; t++) {
+    long long D[TC_N] = {};
+    for (int k = 0; k < 32 * ksteps; k++) {
+      const int a = byteAt(static_cast<long>(adv) * t - ws0 + k);
+      if (a == 0) {
+        continue;
+      }
+      const int kc = k / TC_CHUNK, kk = k % TC_CHUNK;
+      for (int n = 0; n < TC_N; n++) {
+        const size_t at = static_cast<size_t>(kc) * TC_N * TC_CHUNK + static_cast<size_t>(n) * TC_CHUNK +
+                          static_cast<size_t>(((kk >> 4) ^ (n & 7)) << 4) + (kk & 15);
+        D[n] += static_cast<long long>(a) * static_cast<int8_t>(b_image[at]);
+      }
+    }
+    for (int j = 0; j < TC_NO; j++) {
+      const int missing = (L - 1) - M * (t * TC_NO + j) - valid;
+      const int m = missing > 0 ? std::min(missing, L) : 0;
+      for (int q = 0; q < 2; q++) {
+        const int col = j * 2 + q;
+        const int hi = static_cast<int>((D[col] << 7) + D[2 * TC_NO + col]);
+        const int lo = static_cast<int>((D[4 * TC_NO + col] << 7) + D[6 * TC_NO + col]);
+        const int ph = 2 * hi - offs[2 * m];
+        const int pl = 2 * lo - offs[2 * m + 1];
+        out[2 * (t * TC_NO + j) + q] = std::fmaf(static_cast<float>(ph), 16384.0f, static_cast<float>(pl)) * out_scale;
+      }
+    }
+  }
+  return static_cast<size_t>(n_out);
+}
+
 cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, size_t iq_row_bytes,
                           const uint8_t *hist, const int *hist_valid, int total_rows, float2 *x1,
                           size_t x1_pitch, int n_out, int ch0, int nch, float scale,

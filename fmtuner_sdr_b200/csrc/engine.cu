@@ -2629,6 +2629,16 @@ int fmgpu_get_stage_times(fmgpu_engine *e, const char **names, float *ms, int ca
   return n;
 }
 
+size_t fmgpu_decim_tc_host_model(int decimation, const float *taps, int n_taps, float scale,
+                                 const unsigned char *iq, int valid_history, int n_out, float *out) {
+  if (!taps || n_taps < 1) {
+    return 0;
+  }
+  std::vector<float> hrev(taps, taps + n_taps);
+  std::reverse(hrev.begin(), hrev.end());
+  return decimTcHostModel(decimation, hrev, scale, iq, valid_history, n_out, out);
+}
+
 size_t fmgpu_fir_tc_host_model(const float *taps, int n_taps, float scale, int data_shift, const float *x,
                                size_t n_hist, size_t n, float *y) {
   const int lp = static_cast<int>(roundUp(static_cast<size_t>(std::max(n_taps, 1)), 8));

@@ -30,6 +30,8 @@ void launchDecim(int M, const uint8_t *iq, size_t iq_stride, const uint8_t *hist
 bool decimTcSupported(int M, int L, int n_out);
 void decimTcBuildTables(int M, const std::vector<float> &hrev, std::vector<uint8_t> *b_image,
                         std::vector<int32_t> *offs);
+size_t decimTcHostModel(int M, const std::vector<float> &hrev, float scale, const uint8_t *iq, int valid,
+                        int n_out, float *out);
 cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, size_t iq_row_bytes,
                           const uint8_t *hist, const int *hist_valid, int total_rows, float2 *x1,
                           size_t x1_pitch, int n_out, int ch0, int nch, float scale,

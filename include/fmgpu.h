@@ -328,6 +328,13 @@ size_t fmgpu_design_host(const fmgpu_config *cfg, int which, int bw_hz, float *o
  * the CPU test-suite uses it to check the table builder and the error bound against a float64 FIR. */
 size_t fmgpu_fir_tc_host_model(const float *taps, int n_taps, float scale, int data_shift, const float *x,
                                size_t n_hist, size_t n, float *y);
+/* The same for the tensor-core decimator (fmgpu_set_decimator_mode 1; decim_tc.cu): taps in design
+ * order (fmgpu_design_host, which = 0) and their scale; iq = valid_history sample pairs of history
+ * (0 .. n_taps - 1; what is missing of the window counts as byte 0, as after a reset) followed by
+ * n_out * decimation pairs; out receives n_out complex floats. Returns n_out, or 0 when the factor /
+ * tap count / n_out has no tensor-core form. Host only. */
+size_t fmgpu_decim_tc_host_model(int decimation, const float *taps, int n_taps, float scale,
+                                 const unsigned char *iq, int valid_history, int n_out, float *out);
 /* Intermediate device buffers of the last fmgpu_process_* call, copied to the host:
  * which: 0 decimated cf32 (2 floats/sample), 1 MPX, 2 stereo left at the DSP rate,
  * 3 stereo right, 4 pilot band-pass output, 5 / 6 the matrix outputs L / R in front of the 15 kHz

@@ -78,3 +78,34 @@ def test_saturation_and_refusals():
     assert n == 64 and np.abs(y - want).max() <= 1e-6
     assert _model(taps, scale, 22, hist, np.zeros(33, np.float32))[0] == 0     # not a multiple of 32
     assert _model(taps, scale, 22, np.zeros(64, np.float32), np.zeros(64, np.float32))[0] == 0   # history too short
+
+
+@pytest.mark.parametrize("rates,valid_full", [((2_400_000, 10), True), ((2_400_000, 10), False),
+                                              ((2_048_000, 8), True), ((1_024_000, 4), True)])
+def test_integer_decimator_model_against_float64(rates, valid_full):
+    """decim_tc.cu's tables: taps quantised to 2^-26 in four base-128 limbs, I/Q de-interleave inside B,
+    the 127.5 offset removed in integers (the table of partial tap sums when the window starts inside
+    the zeros after a reset), one float rounding: within 1.5e-7 of the float64 FIR."""
+    iq_rate, decim = rates
+    L = fm.load_library()
+    taps, scale = _design(0, iq_rate, decim)
+    n_out = 256
+    valid = taps.size - 1 if valid_full else 37
+    rng = np.random.default_rng(3)
+    iq = rng.integers(0, 256, 2 * (valid + n_out * decim), dtype=np.uint8)
+    iq[200:260] = 255
+    out = np.zeros(2 * n_out, np.float32)
+    L.fmgpu_decim_tc_host_model.restype = C.c_size_t
+    L.fmgpu_decim_tc_host_model.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p]
+    n = L.fmgpu_decim_tc_host_model(decim, taps.ctypes.data, taps.size, scale, iq.ctypes.data, valid, n_out,
+                                    out.ctypes.data)
+    assert n == n_out
+    x = (iq.astype(np.float64).reshape(-1, 2) - 127.5) / 127.5
+    x = x[:, 0] + 1j * x[:, 1]
+    # what is missing of the first windows is ZERO SAMPLES (a reset), not byte 0
+    xp = np.concatenate([np.zeros(taps.size - 1 - valid, np.complex128), x])
+    idx = (np.arange(n_out) * decim)[:, None] + np.arange(taps.size)[None, :]
+    want = scale * (xp[idx] @ taps[::-1].astype(np.float64))
+    got = out.view(np.complex64).astype(np.complex128)
+    assert np.abs(got - want).max() <= 1.5e-7, np.abs(got - want).max()
