@@ -419,6 +419,74 @@ __global__ void k_save_tail(const float *src, size_t src_pitch, int src_off, flo
 // Input bytes are fetched as 128-bit words from the 16-byte aligned virtual stream
 // hist ++ input.
 // ---------------------------------------------------------------------------
+// Measurement variant (build_variant with -DFMGPU_EXP_FUSED_LEVEL, never the shipped library): the
+// RF level meter's sums (k_siglevel below; signal_level.cpp:145-178) taken inside the FP32
+// decimator's tile fill, from the bytes the fill holds in registers anyway — SURVEY §8(f) row 2 as
+// worded. Every sample of the call is counted by exactly one tile (the one whose NEW samples it
+// belongs to); totals per channel accumulate in one fmgpu_level_sums each. In the shipped library
+// LevelAcc is empty and every call below compiles to nothing.
+#ifdef FMGPU_EXP_FUSED_LEVEL
+#define FMGPU_LVL_PARAM , fmgpu_level_sums *lvl
+#define FMGPU_LVL_ARG , expLevelBuf()
+struct LevelAcc {
+  uint32_t si = 0, sq = 0, sii = 0, sqq = 0, hard = 0, nearc = 0, cnt = 0;
+  __device__ __forceinline__ void word(uint32_t w) {  // two samples: bytes I0, Q0, I1, Q1
+    si = __dp4a(w, 0x00010001u, si);
+    sq = __dp4a(w, 0x01000100u, sq);
+    sii = __dp4a(w, w & 0x00ff00ffu, sii);
+    sqq = __dp4a(w, w & 0xff00ff00u, sqq);
+    const uint32_t t = ((w & 0x7f7f7f7fu) + 0x09090909u) ^ (w & 0x80808080u);
+    if ((t - 0x12121212u) & ~t & 0x80808080u) {
+      const uint32_t i0 = w & 0xffu, q0 = (w >> 8) & 0xffu, i1 = (w >> 16) & 0xffu, q1 = w >> 24;
+      hard += (i0 <= 1u || i0 >= 254u || q0 <= 1u || q0 >= 254u) ? 1u : 0u;
+      hard += (i1 <= 1u || i1 >= 254u || q1 <= 1u || q1 >= 254u) ? 1u : 0u;
+      nearc += (i0 <= 8u || i0 >= 247u || q0 <= 8u || q0 >= 247u) ? 1u : 0u;
+      nearc += (i1 <= 8u || i1 >= 247u || q1 <= 8u || q1 >= 247u) ? 1u : 0u;
+    }
+    cnt += 2;
+  }
+  __device__ __forceinline__ void one(uint32_t w16) {  // one sample: bytes I, Q
+    const uint32_t vi = w16 & 0xffu, vq = (w16 >> 8) & 0xffu;
+    si += vi;
+    sq += vq;
+    sii += vi * vi;
+    sqq += vq * vq;
+    hard += (vi <= 1u || vi >= 254u || vq <= 1u || vq >= 254u) ? 1u : 0u;
+    nearc += (vi <= 8u || vi >= 247u || vq <= 8u || vq >= 247u) ? 1u : 0u;
+    cnt++;
+  }
+  // a CTA sees (T + Pp) * M samples at most: every partial stays far below 2^32 across a warp
+  __device__ __forceinline__ void flush(fmgpu_level_sums *o) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      si += __shfl_down_sync(0xffffffffu, si, d);
+      sq += __shfl_down_sync(0xffffffffu, sq, d);
+      sii += __shfl_down_sync(0xffffffffu, sii, d);
+      sqq += __shfl_down_sync(0xffffffffu, sqq, d);
+      hard += __shfl_down_sync(0xffffffffu, hard, d);
+      nearc += __shfl_down_sync(0xffffffffu, nearc, d);
+      cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_i), (unsigned long long)si);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_q), (unsigned long long)sq);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_ii), (unsigned long long)sii);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&o->sum_qq), (unsigned long long)sqq);
+      atomicAdd(&o->hard_clip, hard);
+      atomicAdd(&o->near_clip, nearc);
+      atomicAdd(&o->n_samples, cnt);
+    }
+  }
+};
+#else
+#define FMGPU_LVL_PARAM
+#define FMGPU_LVL_ARG
+struct LevelAcc {
+  __device__ __forceinline__ void word(uint32_t) {}
+  __device__ __forceinline__ void one(uint32_t) {}
+};
+#endif
+
 #ifndef FMGPU_DECIM_NT
 #define FMGPU_DECIM_NT 128
 #endif
@@ -433,7 +501,7 @@ template <int M, bool PACK>
 __global__ void __launch_bounds__(DECIM_NT)
 k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restrict__ hist,
         const int *__restrict__ hist_valid, float2 *__restrict__ x1, size_t x1_pitch, int n_out,
-        int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps) {
+        int ch0, int Pp, float scale, const __grid_constant__ TapsParam taps FMGPU_LVL_PARAM) {
   constexpr int R = 4;
   constexpr int T = DECIM_NT * R;
   constexpr int RM = R * M;
@@ -467,6 +535,9 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
     const int a_hist = (int)max(0L, min((long)tile_len, (long)H_IQ - v0));
     const unsigned short *p_hist = hist_c + v0;
     const unsigned short *p_in = in_c + (v0 - H_IQ);
+    // level sums (measurement variant only): this tile's NEW samples start at element a_own
+    [[maybe_unused]] LevelAcc lv;
+    [[maybe_unused]] const int a_own = max((Pp - 1) * M, a_hist);
     auto fill = [&](auto fast_tag) {
       constexpr bool FAST = decltype(fast_tag)::value;  // whole tile inside the input row
 #pragma unroll DECIM_FILL_UNROLL
@@ -485,6 +556,9 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
         if (!FAST && !ok) {
           f = make_float2(0.0f, 0.0f);
         }
+        if (ok && (int)a >= a_own) {
+          lv.one(w);
+        }
         xs[a + SK * (a / RM)] = f;
       }
     };
@@ -492,18 +566,56 @@ k_decim(const uint8_t *__restrict__ iq, size_t iq_stride, const uint8_t *__restr
       if (M % 2 == 0) {
         // even M: tile_len, RM and the skew are even, so elements (a, a + 1), a even, are one
         // 16-byte aligned pair in shared memory: two 16-bit loads, one 128-bit store per lane
+#ifdef FMGPU_EXP_FUSED_LEVEL
+        // measurement variant: the loads of DECIM_FILL_UNROLL iterations first (the clip counters'
+        // branch would otherwise keep the compiler from batching them: 3.46 instead of 2.01 ms per
+        // launch in the first form), then convert + store + level sums
+        constexpr int U = DECIM_FILL_UNROLL;
+        for (unsigned a0 = 2 * t; a0 < (unsigned)tile_len; a0 += 2 * DECIM_NT * U) {
+          uint32_t w0[U], w1[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned a = a0 + u * 2 * DECIM_NT;
+            const bool in = a < (unsigned)tile_len;
+            w0[u] = in ? (uint32_t)__ldg(p_in + a) : 0u;
+            w1[u] = in ? (uint32_t)__ldg(p_in + a + 1) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned a = a0 + u * 2 * DECIM_NT;
+            if (a < (unsigned)tile_len) {
+              const float2 f0 = iqBytesToFloat(w0[u]);
+              const float2 f1 = iqBytesToFloat(w1[u]);
+              *reinterpret_cast<float4 *>(xs + a + SK * (a / RM)) = make_float4(f0.x, f0.y, f1.x, f1.y);
+              if ((int)a >= a_own) {  // a_own is even here: a pair is owned whole or not at all
+                lv.word(w0[u] | (w1[u] << 16));
+              }
+            }
+          }
+        }
+#else
 #pragma unroll DECIM_FILL_UNROLL
         for (unsigned a = 2 * t; a < (unsigned)tile_len; a += 2 * DECIM_NT) {
           const float2 f0 = iqBytesToFloat(__ldg(p_in + a));
           const float2 f1 = iqBytesToFloat(__ldg(p_in + a + 1));
           *reinterpret_cast<float4 *>(xs + a + SK * (a / RM)) = make_float4(f0.x, f0.y, f1.x, f1.y);
         }
+#endif
       } else {
         fill(std::true_type{});
       }
     } else {
       fill(std::false_type{});
     }
+#ifdef FMGPU_EXP_FUSED_LEVEL
+    // the last M - 1 samples of the call lie behind the newest sample of the last output
+    if (blockIdx.x == gridDim.x - 1) {
+      for (long s2 = o + tile_len + t; s2 < n_in; s2 += DECIM_NT) {
+        lv.one(in_c[s2]);
+      }
+    }
+    lv.flush(lvl + c);
+#endif
   }
   __syncthreads();
 
@@ -1095,6 +1207,17 @@ k_fir_real(FirRealJob job, const __grid_constant__ TapsParam taps) {
 // ---------------------------------------------------------------------------
 constexpr int STEREO_TILES = 23;
 constexpr int STEREO_THREADS = 128;
+// channels per CTA of the two lane kernels (one lane each; lanes past it idle). These kernels are
+// bound by dependent-issue latency, not by lanes: fewer channels per warp = more chains per scheduler.
+#ifndef FMGPU_STEREO_CPC
+#define FMGPU_STEREO_CPC 32
+#endif
+#ifndef FMGPU_RDS_CPC
+#define FMGPU_RDS_CPC 32
+#endif
+constexpr int STEREO_CPC = FMGPU_STEREO_CPC;
+constexpr int RDS_CPC = FMGPU_RDS_CPC;
+static_assert(STEREO_CPC >= 1 && STEREO_CPC <= 32 && RDS_CPC >= 1 && RDS_CPC <= 32, "one lane per channel");
 #ifndef FMGPU_STEREO_MINB
 #define FMGPU_STEREO_MINB 6  // at most 85 registers per thread
 #endif
@@ -1108,7 +1231,7 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   // 16-byte aligned rows, read and written by their lane four samples at a time; a pitch of ST + 4
   // floats is odd in 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups
   constexpr int TP = ST + 4;
-  constexpr int TS = 32 * TP;  // floats per tile
+  constexpr int TS = STEREO_CPC * TP;  // floats per tile
   extern __shared__ float sm_st[];
   // chunk j of a ring of n sits in slot j % n
   float *t_pil = sm_st;             // 2: mover -> PLL
@@ -1129,8 +1252,8 @@ k_stereo(const float *__restrict__ mpx, size_t mpx_pitch, const float *__restric
   // w % 4, and the PLL role is the one that sets the pace: the CTAs that share an SM (block b, b + the
   // SM count, ...) rotate the roles, so that their PLL warps land on different schedulers.
   const int role = ((threadIdx.x >> 5) + (k.sm_rot > 0 ? (int)blockIdx.x / k.sm_rot : 0)) & 3;
-  const int c0 = ch0 + blockIdx.x * 32;
-  const int nrows = min(32, ch0 + nch - c0);
+  const int c0 = ch0 + blockIdx.x * STEREO_CPC;
+  const int nrows = min(STEREO_CPC, ch0 + nch - c0);
   const bool active = lane < nrows;
   const int c = c0 + min(lane, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
@@ -2071,8 +2194,8 @@ k_rds(const float *__restrict__ r171, size_t r_pitch, RdsState *st, float2 *ring
   constexpr int TPR = LT + 4;  // 16-byte aligned rows
   extern __shared__ float sm_rds[];
   float *t_in[2] = {sm_rds, sm_rds + 32 * TPR};
-  const int c0 = ch0 + blockIdx.x * 32;
-  const int nrows = min(32, ch0 + nch - c0);
+  const int c0 = ch0 + blockIdx.x * RDS_CPC;
+  const int nrows = min(RDS_CPC, ch0 + nch - c0);
   const bool active = tl < nrows;
   const int c = c0 + min(tl, nrows - 1);
   constexpr float kPi = 3.14159265358979323846f;
@@ -2559,6 +2682,30 @@ static bool usePackedFma() {
   return v != 0;
 }
 
+#ifdef FMGPU_EXP_FUSED_LEVEL
+// measurement variant: per-channel totals of the fused level sums, read back by the check script
+constexpr int EXP_LEVEL_CH = 65536;
+static fmgpu_level_sums *expLevelBuf() {
+  static fmgpu_level_sums *buf = nullptr;
+  if (!buf) {
+    cudaMalloc(&buf, EXP_LEVEL_CH * sizeof(fmgpu_level_sums));
+    cudaMemset(buf, 0, EXP_LEVEL_CH * sizeof(fmgpu_level_sums));
+  }
+  return buf;
+}
+extern "C" int fmgpu_exp_fused_level_read(fmgpu_level_sums *out, int n_channels, int reset) {
+  if (n_channels > EXP_LEVEL_CH) {
+    return -1;
+  }
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, expLevelBuf(), n_channels * sizeof(fmgpu_level_sums), cudaMemcpyDeviceToHost);
+  if (reset) {
+    cudaMemset(expLevelBuf(), 0, EXP_LEVEL_CH * sizeof(fmgpu_level_sums));
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#endif
+
 #define FMGPU_DECIM_CASE(MM)                                                                     \
   case MM: {                                                                                     \
     constexpr int T = 4 * DECIM_NT;                                                                     \
@@ -2575,10 +2722,10 @@ static bool usePackedFma() {
     dim3 grid((n_out + T - 1) / T, nch);                                                         \
     if (usePackedFma()) {                                                                        \
       k_decim<MM, true><<<grid, DECIM_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,        \
-                                                     x1_pitch, n_out, ch0, Pp, scale, taps);     \
+                                                     x1_pitch, n_out, ch0, Pp, scale, taps FMGPU_LVL_ARG); \
     } else {                                                                                     \
       k_decim<MM, false><<<grid, DECIM_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,       \
-                                                      x1_pitch, n_out, ch0, Pp, scale, taps);    \
+                                                      x1_pitch, n_out, ch0, Pp, scale, taps FMGPU_LVL_ARG); \
     }                                                                                            \
     break;                                                                                       \
   }
@@ -2790,13 +2937,13 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   float *lraw, float *rraw, size_t lr_pitch, StereoState *st, const ChanParams *cp,
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
-  constexpr size_t smem = STEREO_TILES * 32 * (STEREO_ST + 4) * sizeof(float);  // tiles of [32][ST + 4]
+  constexpr size_t smem = STEREO_TILES * STEREO_CPC * (STEREO_ST + 4) * sizeof(float);  // tiles of [CPC][ST + 4]
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_stereo<<<(nch + 31) / 32, STEREO_THREADS, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
+  k_stereo<<<(nch + STEREO_CPC - 1) / STEREO_CPC, STEREO_THREADS, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
                                                  lr_pitch, st, cp, status, status_pitch, nblk,
                                                  blk_len, n_total, ch0, nch, k);
 }
@@ -2869,7 +3016,7 @@ void launchRdsDemod(RdsState *st, float2 *ring, const float *lpf, const float *m
                     uint32_t *bit_end, int ch0, int nch, const EngineConst &k, RdsRsRef rr,
                     cudaStream_t stream) {
   constexpr size_t smem = 2 * 32 * (LT + 4) * sizeof(float);
-  k_rds<<<(nch + 31) / 32, 32, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
+  k_rds<<<(nch + RDS_CPC - 1) / RDS_CPC, 32, smem, stream>>>(r171, r_pitch, st, ring, lpf, mf, dmf, bits_out,
                                               bits_cap, bit_end, ch0, nch, k, rr);
 }
 
