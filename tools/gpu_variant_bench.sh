@@ -1,10 +1,10 @@
-# channels per CTA of the lane kernels (k_stereo, k_rds): build variants with 16 / 8 channels per warp
-# (more dependent chains per scheduler) against the shipped 32. usage: bash tools/gpu_cpc.sh <variant> ...
+# usage: bash tools/gpu_variant_bench.sh <variant> ... : the quick default bench with the shipped library and
+# with build/libfmgpu_<variant>.so (fmtuner_sdr_b200.build.build_variant), step + stage times alone
 mkdir -p gpurun_out
 run() {
   name=$1; shift
-  env "$@" timeout 120 python bench.py --no-cpu-baseline --no-e2e --no-extras > gpurun_out/cpc_$name.json 2> gpurun_out/cpc_$name.err
-  python - gpurun_out/cpc_$name.json $name <<'PY'
+  env "$@" timeout 120 python bench.py --no-cpu-baseline --no-e2e --no-extras > gpurun_out/var_$name.json 2> gpurun_out/var_$name.err
+  python - gpurun_out/var_$name.json $name <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
