@@ -47,6 +47,7 @@
 
 #include "../../include/fmgpu.h"
 #include "design.h"
+#include "device_once.h"
 
 struct fmgpu_channelizer {
   int device = 0;
@@ -399,11 +400,8 @@ int fmgpu_channelizer_process(fmgpu_channelizer *z, const uint8_t *iq_dev, size_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long n_out = static_cast<long>(n_in / static_cast<size_t>(z->D));
   const size_t smem = static_cast<size_t>((TM - 1) * z->D + z->L) * sizeof(float2);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_channelize, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  static fmgpu::DeviceOnce attrs;  // per device: device_once.h
+  attrs.run([] { return cudaFuncSetAttribute(k_channelize, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
   if (smem > 200 * 1024) {
     z->lastError = "channelizer: filter too long for the shared-memory tile";
     return FMGPU_ERANGE;
@@ -411,11 +409,8 @@ int fmgpu_channelizer_process(fmgpu_channelizer *z, const uint8_t *iq_dev, size_
   const size_t pp_smem = (static_cast<size_t>((PP_TM - 1) * z->D + z->L) + static_cast<size_t>(z->P) * (PP_TM + 1) +
                           static_cast<size_t>(z->P)) * sizeof(float2) + static_cast<size_t>(z->L) * sizeof(float);
   if (z->polyphase && pp_smem <= 200 * 1024) {
-    static bool pp_attr_done = false;
-    if (!pp_attr_done) {
-      cudaFuncSetAttribute(k_channelize_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      pp_attr_done = true;
-    }
+    static fmgpu::DeviceOnce pp_attrs;
+    pp_attrs.run([] { return cudaFuncSetAttribute(k_channelize_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     k_channelize_pp<<<static_cast<unsigned>((n_out + PP_TM - 1) / PP_TM), PP_THREADS, pp_smem, s>>>(
         iq_dev, z->dHist, z->histValid, static_cast<long>(n_in), z->dTaps, z->dRot, z->dTw, z->L, z->D, z->P,
         z->rotPeriod, ch_first, ch_count, z->outCount, n_out, reinterpret_cast<float2 *>(out_cf32_dev),

@@ -39,6 +39,7 @@
 #include <mutex>
 #include <vector>
 
+#include "device_once.h"
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -541,20 +542,18 @@ cudaError_t launchDecimTc(int M, int L, const uint8_t *iq, size_t iq_stride, siz
                           size_t x1_pitch, int n_out, int ch0, int nch, float scale,
                           const uint8_t *b_image_dev, const int32_t *offs_dev, int sm_count,
                           cudaStream_t stream) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    auto set = [](const void *f) {
-      return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(tcSmemBytes(TC_RING_MAX)));
-    };
+  static DeviceOnce attrs;  // per device: device_once.h
+  const cudaError_t attr_err = attrs.run([] {
     const void *fs[] = {(const void *)k_decim_tc<true, 28>, (const void *)k_decim_tc<true, 22>,
                         (const void *)k_decim_tc<true, 0>};
+    cudaError_t err = cudaSuccess;
     for (const void *f : fs) {
-      if (attr_err == cudaSuccess) {
-        attr_err = set(f);
+      if (err == cudaSuccess) {
+        err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(tcSmemBytes(TC_RING_MAX)));
       }
     }
+    return err;
   });
   if (attr_err != cudaSuccess) {
     return attr_err;

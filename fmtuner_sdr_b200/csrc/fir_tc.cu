@@ -44,6 +44,7 @@
 #include <mutex>
 #include <vector>
 
+#include "device_once.h"
 #include "fm_math.h"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -682,20 +683,20 @@ void firTcBuildTables(const float *h, int Lp, FirTcTables *t) {
 }
 
 static cudaError_t firTcAttrs() {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
+  static DeviceOnce attrs;  // per device: device_once.h
+  return attrs.run([] {
     const void *fs[] = {(const void *)k_fir_tc<5, 8, 2, false>, (const void *)k_fir_tc<11, 14, 1, false>,
                         (const void *)k_fir_tc<12, 14, 1, false>, (const void *)k_fir_tc<4, 8, 2, true>,
                         (const void *)k_fir_tc<5, 8, 2, true>};
+    cudaError_t err = cudaSuccess;
     for (const void *f : fs) {
-      if (attr_err == cudaSuccess) {
-        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(ftSmemBytes(FT_MAX_KS, FT_NSTG_MAX)));
+      if (err == cudaSuccess) {
+        err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(ftSmemBytes(FT_MAX_KS, FT_NSTG_MAX)));
       }
     }
+    return err;
   });
-  return attr_err;
 }
 
 // staging depth: FMGPU_FT_NSTG is a measurement override

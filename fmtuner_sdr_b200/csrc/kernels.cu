@@ -12,6 +12,7 @@
 //    spread over all SMs.
 // Compiled with -fmad=false: only explicit fmaf() fuses.
 #include "kernels.h"
+#include "device_once.h"
 
 #include <type_traits>
 
@@ -2711,14 +2712,13 @@ extern "C" int fmgpu_exp_fused_level_read(fmgpu_level_sums *out, int n_channels,
     constexpr int T = 4 * DECIM_NT;                                                                     \
     const int tile_len = (T + Pp - 1) * MM;                                                      \
     const size_t smem = (size_t)(tile_len + 2 * (tile_len / (4 * MM)) + 4) * sizeof(float2);     \
-    static bool attr_done = false;                                                               \
-    if (!attr_done) {                                                                            \
+    static DeviceOnce attrs; /* per device: device_once.h */                                     \
+    attrs.run([] {                                                                               \
       cudaFuncSetAttribute(k_decim<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                            160 * 1024);                                                          \
-      cudaFuncSetAttribute(k_decim<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                           160 * 1024);                                                          \
-      attr_done = true;                                                                          \
-    }                                                                                            \
+      return cudaFuncSetAttribute(k_decim<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  160 * 1024);                                                   \
+    });                                                                                          \
     dim3 grid((n_out + T - 1) / T, nch);                                                         \
     if (usePackedFma()) {                                                                        \
       k_decim<MM, true><<<grid, DECIM_NT, smem, stream>>>(iq, iq_stride, hist, hist_valid, x1,        \
@@ -2782,11 +2782,8 @@ void launchDcBlock(const float2 *x1, size_t x1_pitch, const uint8_t *iq_u8, size
                    int status_pitch, int nblk, int blk_len, int n_total, int ch0, int nch, float a1,
                    cudaStream_t stream) {
   constexpr size_t smem = 3 * 32 * (2 * LT + 4) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_dcblock, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static DeviceOnce attrs;  // per device: device_once.h
+  attrs.run([] { return cudaFuncSetAttribute(k_dcblock, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   k_dcblock<<<(nch + 31) / 32, 32, smem, stream>>>(x1, x1_pitch, iq_u8, iq_stride, x2, x2_pitch, st,
                                                status, status_pitch, nblk, blk_len, n_total, ch0,
                                                nch, a1);
@@ -2818,11 +2815,8 @@ void launchChanFir(const float2 *x2, size_t x2_pitch, float2 *ybuf, size_t y_pit
 void launchAgc(float2 *ybuf, size_t y_pitch, DemodState *st, const ChanParams *cp, int n_total,
                int ch0, int nch, cudaStream_t stream) {
   constexpr size_t smem = 2 * 32 * (2 * LT + 4) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_agc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static DeviceOnce attrs;  // per device: device_once.h
+  attrs.run([] { return cudaFuncSetAttribute(k_agc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   k_agc<<<(nch + 31) / 32, 32, smem, stream>>>(ybuf, y_pitch, st, cp, n_total, ch0, nch);
 }
 
@@ -2938,11 +2932,8 @@ void launchStereo(const float *mpx, size_t mpx_pitch, const float *pilot, size_t
                   fmgpu_block_status *status, int status_pitch, int nblk, int blk_len, int n_total,
                   int ch0, int nch, const EngineConst &k, cudaStream_t stream) {
   constexpr size_t smem = STEREO_TILES * STEREO_CPC * (STEREO_ST + 4) * sizeof(float);  // tiles of [CPC][ST + 4]
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static DeviceOnce attrs;  // per device: device_once.h
+  attrs.run([] { return cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   k_stereo<<<(nch + STEREO_CPC - 1) / STEREO_CPC, STEREO_THREADS, smem, stream>>>(mpx, mpx_pitch, pilot, pilot_pitch, lraw, rraw,
                                                  lr_pitch, st, cp, status, status_pitch, nblk,
                                                  blk_len, n_total, ch0, nch, k);
