@@ -824,6 +824,16 @@ def roofline_record(acc: dict, C: int, B: int, fp32_peak: float, decim_mode: str
                "hbm_frac": n_iq_step * BYTES_PER_IQ_SAMPLE_ALG / (step_ms * 1e-3) / 1e9 / peak_hbm,
                "fp32_tflops": n_iq_step * FLOP_PER_IQ_SAMPLE_ALG / (step_ms * 1e-3) / 1e12,
                "fp32_frac": n_iq_step * FLOP_PER_IQ_SAMPLE_ALG / (step_ms * 1e-3) / 1e12 / fp32_peak}}
+    # the same record in the contract's own vocabulary (bound "hbm", GB/s against MEASURED_PEAKS.json)
+    # for the largest HBM-bound tile kernel, whichever kernel is named above
+    hbm_tiles = [k for k in tiles if figs[k]["bound"] == "hbm"]
+    if hbm_tiles:
+        h = max(hbm_tiles, key=acc.get)
+        rec["largest_hbm_bound_kernel"] = {
+            "kernel": h, "bound": "hbm", "achieved": figs[h]["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s",
+            "frac": figs[h]["hbm_frac"], "traffic": figs[h]["traffic"],
+            "algorithmic_bytes": figs[h]["algorithmic_bytes"], "launch_ms": figs[h]["launch_ms"],
+            "step_share": acc[h] / serial}
     if "freqdem" in figs:
         f = figs["freqdem"]
         rec["streaming_kernels"].append({"kernel": "freqdem", "bytes_per_launch": f["algorithmic_bytes"],
