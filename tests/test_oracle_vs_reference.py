@@ -64,6 +64,20 @@ def test_config1_identical(orc_libm, ref, rate):
     assert a.status["stereo"][-1] == 1 and len(a.groups) >= 3
 
 
+@pytest.mark.parametrize("rate,nblk", [("240k", 293), ("256k", 313)])
+def test_config1_ten_seconds_identical(orc_libm, ref, rate, nblk):
+    """The full 10 s of BASELINE configs 1 / 2 (293 blocks at 240 k, 313 at 256 k): resampler phases
+    drifting over seconds, > 110 RDS groups, the stereo lock held for the whole run. The restated
+    oracle and the reference's own sources must still agree on every float, bit and group."""
+    iq_rate, decim = rates(rate)
+    iq = orc.config1_signal(fs_iq=iq_rate).generate(nblk * 8192 * decim)
+    cfg = dict(iq_rate=iq_rate, decimation=decim)
+    _, a, ab = run(orc_libm, cfg, iq)
+    _, b, bb = run(ref, cfg, iq)
+    assert_identical(a, b, ab, bb)
+    assert len(a.groups) > 100 and a.status["stereo"][-1] == 1
+
+
 @pytest.mark.parametrize("c", [0, 3, 7, 11, 100, 255])
 def test_config3_channels_identical(orc_libm, ref, c):
     """BASELINE config 3: varied deviation / SNR / tones / RDS payloads."""
