@@ -31,6 +31,35 @@ def test_golden_fixture(orc_fm, name, rate):
     assert np.array_equal(ch.rds_bits(), g["rds_bits"])
 
 
+@pytest.mark.parametrize("name,kind,c", [("reference_config1_240k", "config1", None),
+                                         ("reference_config3_ch7", "config3", 7)])
+def test_reference_made_fixture(orc_libm, name, kind, c):
+    """Fixtures written by the REFERENCE'S OWN SOURCES run in the build container
+    (oracle/_ref/libfmref.so; tests/golden/make_golden.py main_reference): the restated oracle in its
+    faithful (libm) flavour must reproduce them wherever the tests run, /root/reference present or not.
+    Bit for bit on the image they were made on; a host whose libm rounds sinf / cosf / expf / atan2f
+    differently may move floats by an ulp, which the fallback bound allows (integers stay exact)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    iq_rate, decim = rates("240k")
+    sig = orc.config1_signal(fs_iq=iq_rate) if kind == "config1" else orc.config3_signal(c, fs_iq=iq_rate)
+    iq = sig.generate(14 * 8192 * decim)
+    assert np.array_equal(np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8),
+                          g["iq_sha256"])
+    ch = orc.Channel(orc_libm, orc.make_config(iq_rate=iq_rate, decimation=decim))
+    ch.enable_bits_tap()
+    r = ch.process(iq, debug=True)
+    pairs = [(r.dec[::64], g["dec_every64"]), (r.mpx[::16], g["mpx_every16"]), (r.left, g["left"]),
+             (r.right, g["right"])]
+    assert all(a.shape == b.shape for a, b in pairs)
+    if not all(np.array_equal(a, b) for a, b in pairs):
+        assert max(float(np.abs(a - b).max()) for a, b in pairs) < 5e-6
+    assert np.array_equal(r.status["stereo"], g["status"]["stereo"])
+    assert np.array_equal(r.status["n_audio"], g["status"]["n_audio"])
+    assert np.abs(r.status["pilot_tenths"].astype(int) - g["status"]["pilot_tenths"].astype(int)).max() <= 1
+    assert groups_equal(r.groups, g["groups"]) and len(r.groups) >= 2
+    assert np.array_equal(ch.rds_bits(), g["rds_bits"])
+
+
 @pytest.fixture(scope="module")
 def config1(orc_libm):
     iq_rate, decim = rates("240k")
