@@ -5,6 +5,11 @@
 // dependency of the reference (CMakeLists.txt:122-147) and is absent from this
 // image, so its published algorithms are restated here. PARITY UNPINNED against
 // a real liquid-dsp build: no golden vectors exist in the reference.
+// Everything ABOVE this file is pinned: the reference's own wrapper and class code is
+// compiled unmodified over oracle/liquid_shim (which forwards to these objects) and
+// compared bit for bit with oracle/pipeline.hpp (tests/test_oracle_vs_reference.py);
+// independent float64 models (scipy / numpy, tests/test_oracle_design.py,
+// tests/test_oracle_pipeline.py) check the structure of what is restated here.
 //
 // Reference call sites restated (all under /root/reference):
 //   src/dsp/liquid_primitives.cpp:29-54   agc_crcf
